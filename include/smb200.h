@@ -1,0 +1,176 @@
+/*
+ * smb200.h -- C ABI of libsmb200.so: the B200 (sm_100a) engine behind
+ * simpleMath's elementwise hot path.
+ *
+ * This is the drop-in boundary.  The reference has no ABI of its own (it is a
+ * header-only C++20 template library); these entry points are exactly what its
+ * three hot-path function templates and its array storage would bind to.  Each
+ * declaration cites the reference interface it replaces (paths relative to the
+ * reference repo root).  The C++ headers under include/sm/ keep the reference's
+ * names and signatures and forward to this ABI; INTEGRATION.md shows the same
+ * bindings as a patch a reference maintainer would apply.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  No torch / CUDA types in any signature
+ *     (`stream` is a cudaStream_t passed as void*).
+ *   - Strides and shapes are in ELEMENTS, uint64_t, never negative
+ *     (include/SMArray.h:357-364), rank <= SMB_MAX_NDIM (include/math/helpers.h:4).
+ *   - Operand / result pointers may be device, managed, pinned-host or plain
+ *     host memory, and may be interior pointers of a larger block (views,
+ *     include/SMArray.h:397-437).  Host operands are staged through HBM by the
+ *     library (chunked, copy/compute overlapped).
+ *   - stream == NULL: the call is synchronous -- the result is complete when it
+ *     returns, like the reference.  stream != NULL: the
+ *     work is enqueued on that stream (device / managed / pinned memory only)
+ *     and the caller synchronises.
+ *   - Return value 0 on success, non-zero on error; smb_last_error() then
+ *     returns a thread-local message.  The C++ wrappers rethrow it as
+ *     std::runtime_error, the reference's error convention (include/SMUtils.h:77).
+ *   - There is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with SMB_ERR_NO_DEVICE.
+ */
+#ifndef SMB200_H
+#define SMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMB_MAX_NDIM 6 /* include/math/helpers.h:4 (MAX_NDIM) */
+
+/* Op tags: one per reference Op struct. */
+enum {
+    SMB_OP_ADD = 0, /* AddOp<T>       include/math/add.h:5-14        */
+    SMB_OP_SUB = 1, /* SubtractOp<T>  include/math/subtract.h:5-14   */
+    SMB_OP_MUL = 2, /* MultiplyOp<T>  include/math/multiply.h:7-16   */
+    SMB_OP_DIV = 3, /* DivideOp<T>    include/math/division.h:8-17,67-70 */
+    SMB_OP_POW = 4  /* PowOp<T>       include/math/pow.h:6-14, math/simd/crafted_pow.h:54-103 */
+};
+
+/* Element types: exactly the SimdTraits<T> specialisations of the reference
+ * (include/math/helpers.h:23-119). */
+enum { SMB_F32 = 0, SMB_F64 = 1, SMB_I32 = 2 };
+
+/* Memory kinds for smb_alloc. */
+enum {
+    SMB_MEM_DEVICE = 0,  /* HBM only (cudaMalloc), pooled                          */
+    SMB_MEM_MANAGED = 1, /* host-dereferenceable, HBM-preferred (cudaMallocManaged) */
+    SMB_MEM_PINNED = 2   /* page-locked host memory (cudaHostAlloc)                 */
+};
+
+/* Error codes. */
+enum {
+    SMB_OK = 0,
+    SMB_ERR_INVALID = 1,   /* bad op / dtype / rank / null pointer */
+    SMB_ERR_NO_DEVICE = 2, /* no CUDA device: there is no CPU fallback */
+    SMB_ERR_CUDA = 3,      /* a CUDA runtime call failed            */
+    SMB_ERR_OOM = 4
+};
+
+/* Options for smb_set_option. */
+enum {
+    /* 1 (default): sm::pow(arr, y) with y in {0, 1, 2, 0.5, -1} uses the exact
+     * single-instruction form (x*x, sqrt, 1/x ...); 0: always run the general
+     * exp2(y*log2 x) kernel (what bench.py reports as the headline). */
+    SMB_OPT_POW_SPECIALISE = 0,
+    /* Bytes per staging chunk of the host-operand pipeline (default 64 MiB). */
+    SMB_OPT_STAGE_CHUNK_BYTES = 1,
+    /* Kernel variant override for tuning sweeps (0 = library default). */
+    SMB_OPT_CONTIG_VARIANT = 2,
+    SMB_OPT_BCAST_VARIANT = 3
+};
+
+/* ---- the hot path ------------------------------------------------------- */
+
+/* Replaces element_wise_op<T, Operation>(a, stride_a, b, stride_b, n, result,
+ * shape) -- include/math/calculate.h:5-99.  `stride_a` / `stride_b` are the
+ * broadcast stride tables sm::broadcast() returns (0 on broadcast dims),
+ * `shape` the result shape, n == prod(shape); `out` receives the dense
+ * row-major result.  The fast-path dispatch (calculate.h:10-13), dimension
+ * coalescing and the N-d index -> offset math all happen inside. */
+int smb_elementwise(int op, int dtype,
+                    const void *a, const uint64_t *stride_a,
+                    const void *b, const uint64_t *stride_b,
+                    const uint64_t *shape, int ndim, uint64_t n,
+                    void *out, void *stream);
+
+/* Same computation restricted to the flat output range
+ * [lin_begin, lin_begin + lin_count) of the broadcast result -- the unit of
+ * multi-GPU sharding.  `a` and `b` address the FULL operands;
+ * `out` addresses the shard: out[0] is flat element lin_begin. */
+int smb_elementwise_range(int op, int dtype,
+                          const void *a, const uint64_t *stride_a,
+                          const void *b, const uint64_t *stride_b,
+                          const uint64_t *shape, int ndim,
+                          uint64_t lin_begin, uint64_t lin_count,
+                          void *out, void *stream);
+
+/* Replaces handle_contiguous_arrays<T, Operation>(a, b, result, n) --
+ * include/math/calculate.h:101-134: three dense streams. */
+int smb_contiguous(int op, int dtype, const void *a, const void *b, void *out,
+                   uint64_t n, void *stream);
+
+/* Replaces array_scalar_op<T, Operation>(a, value, n, result) --
+ * include/math/calculate.h:137-169.  `scalar` points at one host T; it is the
+ * RIGHT operand (calculate.h:159,167).  sm::pow(arr, e) is op == SMB_OP_POW
+ * (include/UserFunctions.h:42-48). */
+int smb_array_scalar(int op, int dtype, const void *a, const void *scalar,
+                     uint64_t n, void *out, void *stream);
+
+/* ---- storage: replaces `new T[n]` / `delete[]` of SMArray<T>::data ------- */
+/* include/SMArray.h:33-34,70-76,219,342-346; include/UserFunctions.h:8-40.
+ * Pooled (size-class caching) so a fresh result block per operator call costs
+ * no cudaMalloc.  smb_free accepts only pointers smb_alloc returned;
+ * smb_owns accepts any address, including interior ones. */
+void *smb_alloc(size_t bytes, int kind);
+int smb_free(void *ptr);
+int smb_owns(const void *ptr);
+int smb_pool_trim(void);
+/* stats[0]=bytes in use, [1]=bytes cached, [2]=cudaMalloc-class calls, [3]=pool hits */
+int smb_pool_stats(uint64_t stats[4]);
+
+/* Replaces std::fill_n in sm::ones / sm::zeros (include/UserFunctions.h:18-40):
+ * fills n elements with *value on the device that owns `out`. */
+int smb_fill(int dtype, void *out, const void *value, uint64_t n, void *stream);
+
+/* Migrate a managed block to `device` (>= 0) or to the host (-1). */
+int smb_prefetch(const void *ptr, size_t bytes, int device, void *stream);
+
+/* ---- device / runtime ----------------------------------------------------- */
+int smb_device_count(void);
+int smb_set_device(int device);
+int smb_get_device(void);
+int smb_sync(void);
+int smb_set_option(int key, int64_t value);
+int64_t smb_get_option(int key);
+/* Kernels launched by this library in this process so far. */
+uint64_t smb_launch_count(void);
+/* Name of the kernel variant the last compute call on this thread launched. */
+const char *smb_last_kernel(void);
+const char *smb_last_error(void);
+const char *smb_version(void);
+
+/* ---- planning, exposed for host-side tests (no GPU needed) ---------------- */
+/* Runs the host planner only: dimension coalescing + kernel choice for an
+ * smb_elementwise call.  Writes the coalesced rank / shape / strides and
+ * returns the kernel kind (>= 0: 0 contiguous, 1 row-broadcast, 2 generic
+ * strided) or a negative error. */
+int smb_plan_elementwise(const uint64_t *stride_a, const uint64_t *stride_b,
+                         const uint64_t *shape, int ndim, int elem_size,
+                         int *out_ndim, uint64_t *out_shape,
+                         uint64_t *out_stride_a, uint64_t *out_stride_b);
+
+/* ---- bench / test support -------------------------------------------------- */
+/* Counter-based generator: out[i] = lo + (hi-lo) * U(seed, first+i), the same
+ * arithmetic as oracle/oracle.c:orc_fill_uniform_f32, so inputs larger than
+ * PCIe can comfortably carry are produced in HBM and re-derived on the CPU. */
+int smb_fill_uniform_f32(void *out, uint64_t first, uint64_t n, uint64_t seed,
+                         float lo, float hi, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMB200_H */

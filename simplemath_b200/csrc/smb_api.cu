@@ -1,0 +1,845 @@
+// smb_api.cu -- the C ABI of libsmb200.so (declared in include/smb200.h):
+// device runtime, pooled storage, planner, launchers and the host-operand
+// staging pipeline.  See DESIGN.md for the data-flow picture.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <algorithm>
+
+#include "../../include/smb200.h"
+#include "smb_alloc.h"
+#include "smb_kernels.cuh"
+#include "smb_plan.h"
+
+namespace smb {
+
+// ------------------------------------------------------------------ errors --
+static thread_local std::string g_err;
+static thread_local const char *g_last_kernel = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define SMB_CK(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            cudaGetLastError();                                                                   \
+            return fail(e_ == cudaErrorMemoryAllocation ? SMB_ERR_OOM : SMB_ERR_CUDA, "%s: %s",   \
+                        #call, cudaGetErrorString(e_));                                           \
+        }                                                                                         \
+    } while (0)
+
+// ------------------------------------------------------------ options -------
+static std::atomic<int64_t> g_opt_pow_specialise{1};
+static std::atomic<int64_t> g_opt_chunk_bytes{64ll << 20};
+static std::atomic<int64_t> g_opt_contig_variant{0};
+static std::atomic<int64_t> g_opt_bcast_variant{0};
+
+// ------------------------------------------------------ device context ------
+constexpr int kSlots = 3; // staging pipeline depth (H2D | kernel | D2H in flight)
+struct DeviceCtx {
+    bool ready = false;
+    int sm_count = 0;
+    cudaStream_t main = nullptr;
+    cudaStream_t slot[kSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev = nullptr;
+};
+static DeviceCtx g_ctx[64];
+static std::mutex g_ctx_mu;
+
+// There is no CPU fallback: every compute entry point goes through here and
+// fails loudly when no CUDA device is usable.
+static int current_ctx(DeviceCtx **out) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(SMB_ERR_NO_DEVICE, "no CUDA device available (%s); libsmb200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    int dev = 0;
+    SMB_CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(SMB_ERR_INVALID, "device index %d out of range", dev);
+    DeviceCtx &c = g_ctx[dev];
+    if (!c.ready) {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        if (!c.ready) {
+            SMB_CK(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
+            SMB_CK(cudaStreamCreateWithFlags(&c.main, cudaStreamNonBlocking));
+            for (int i = 0; i < kSlots; ++i) SMB_CK(cudaStreamCreateWithFlags(&c.slot[i], cudaStreamNonBlocking));
+            SMB_CK(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+            c.ready = true;
+        }
+    }
+    *out = &c;
+    return SMB_OK;
+}
+
+// ------------------------------------------------------------------ pool ----
+cudaError_t Pool::raw_alloc(void **p, size_t bytes, int kind) {
+    ++driver_calls_;
+    if (kind == SMB_MEM_DEVICE) return cudaMalloc(p, bytes);
+    if (kind == SMB_MEM_MANAGED) return cudaMallocManaged(p, bytes, cudaMemAttachGlobal);
+    return cudaHostAlloc(p, bytes, cudaHostAllocPortable);
+}
+void Pool::raw_free(const Block &b) {
+    if (b.kind == SMB_MEM_PINNED) { cudaFreeHost(b.base); return; }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (b.device >= 0 && b.device != cur) cudaSetDevice(b.device);
+    cudaFree(b.base);
+    if (b.device >= 0 && b.device != cur) cudaSetDevice(cur);
+}
+void *Pool::alloc(size_t bytes, int kind, int device, cudaError_t *err) {
+    const size_t sz = bucket(bytes);
+    const Key key{kind == SMB_MEM_PINNED ? -1 : device, kind, sz};
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = free_.find(key);
+    if (it != free_.end() && !it->second.empty()) {
+        void *p = it->second.back();
+        it->second.pop_back();
+        auto c = cached_.find((uintptr_t)p);
+        Block b = c->second;
+        cached_.erase(c);
+        live_[(uintptr_t)p] = b;
+        cached_bytes_ -= sz;
+        in_use_ += sz;
+        ++hits_;
+        *err = cudaSuccess;
+        return p;
+    }
+    void *p = nullptr;
+    cudaError_t e = raw_alloc(&p, sz, kind);
+    if (e == cudaErrorMemoryAllocation) { // give cached blocks back to the driver and retry once
+        cudaGetLastError();
+        for (auto &kv : cached_) raw_free(kv.second);
+        cached_.clear();
+        free_.clear();
+        cached_bytes_ = 0;
+        e = raw_alloc(&p, sz, kind);
+    }
+    *err = e;
+    if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    live_[(uintptr_t)p] = Block{p, sz, key.device, kind};
+    in_use_ += sz;
+    return p;
+}
+bool Pool::free(void *ptr) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = live_.find((uintptr_t)ptr);
+    if (it == live_.end()) return false;
+    Block b = it->second;
+    live_.erase(it);
+    in_use_ -= b.bytes;
+    cached_[(uintptr_t)ptr] = b;
+    cached_bytes_ += b.bytes;
+    free_[Key{b.device, b.kind, b.bytes}].push_back(ptr);
+    return true;
+}
+bool Pool::owns(const void *ptr, Block *out) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = live_.upper_bound((uintptr_t)ptr);
+    if (it == live_.begin()) return false;
+    --it;
+    const Block &b = it->second;
+    if ((uintptr_t)ptr >= (uintptr_t)b.base + b.bytes) return false;
+    if (out) *out = b;
+    return true;
+}
+void Pool::trim() {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto &kv : cached_) raw_free(kv.second);
+    cached_.clear();
+    free_.clear();
+    cached_bytes_ = 0;
+}
+void Pool::stats(uint64_t s[4]) {
+    std::lock_guard<std::mutex> lk(mu_);
+    s[0] = in_use_;
+    s[1] = cached_bytes_;
+    s[2] = driver_calls_;
+    s[3] = hits_;
+}
+
+// Scoped device scratch block from the pool.
+struct Scratch {
+    void *p = nullptr;
+    ~Scratch() { if (p) Pool::instance().free(p); }
+    int get(size_t bytes, int device) {
+        cudaError_t e;
+        p = Pool::instance().alloc(bytes, SMB_MEM_DEVICE, device, &e);
+        if (!p) return fail(e == cudaErrorMemoryAllocation ? SMB_ERR_OOM : SMB_ERR_CUDA, "scratch alloc of %zu bytes: %s",
+                            bytes, cudaGetErrorString(e));
+        return SMB_OK;
+    }
+};
+
+// ------------------------------------------------------- pointer kinds ------
+enum MemType { MT_HOST = 0, MT_PINNED = 1, MT_DEVICE = 2, MT_MANAGED = 3 };
+static MemType mem_type(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return MT_HOST; }
+    switch (at.type) {
+        case cudaMemoryTypeDevice: return MT_DEVICE;
+        case cudaMemoryTypeManaged: return MT_MANAGED;
+        case cudaMemoryTypeHost: return MT_PINNED;
+        default: return MT_HOST;
+    }
+}
+static inline bool on_host(MemType t) { return t == MT_HOST || t == MT_PINNED; }
+
+static void prefetch_managed(const void *p, size_t bytes, cudaStream_t s) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaMemPrefetchAsync(p, bytes, dev, s) != cudaSuccess) cudaGetLastError(); // best effort
+}
+
+// ----------------------------------------------------------- launchers ------
+static inline size_t esize(int dtype) { return dtype == SMB_F64 ? 8 : 4; }
+
+// Library defaults for the dense-stream kernel (chosen by tools/sweep on B200,
+// see profiles/): bytes per vector access and vectors in flight per thread.
+#ifndef SMB_STREAM_VB
+#define SMB_STREAM_VB 16
+#endif
+#ifndef SMB_STREAM_UNROLL
+#define SMB_STREAM_UNROLL 4
+#endif
+constexpr int kThreads = 256;
+
+static unsigned grid_for(uint64_t work_items, uint64_t items_per_block, int sm_count, int64_t ctas_per_sm) {
+    uint64_t blocks = (work_items + items_per_block - 1) / items_per_block;
+    if (blocks == 0) blocks = 1;
+    if (ctas_per_sm > 0) blocks = std::min<uint64_t>(blocks, (uint64_t)sm_count * (uint64_t)ctas_per_sm);
+    return (unsigned)std::min<uint64_t>(blocks, 0x7fffffffull);
+}
+
+template<typename T, typename Fn, bool HAS_B>
+static int launch_stream(const DeviceCtx &c, const T *a, const T *b, T *out, uint64_t n, uint64_t first, Fn fn,
+                         cudaStream_t s) {
+    if (n == 0) return SMB_OK;
+    constexpr int VB = SMB_STREAM_VB, UNROLL = SMB_STREAM_UNROLL;
+    const uintptr_t ma = (uintptr_t)a % VB, mb = HAS_B ? (uintptr_t)b % VB : ma, mo = (uintptr_t)out % VB;
+    const int64_t cps = g_opt_contig_variant.load();
+    if (ma == mb && ma == mo && ma % sizeof(T) == 0) {
+        uint64_t head = ma ? (VB - ma) / sizeof(T) : 0;
+        if (head > n) head = n;
+        if (head) { // peel up to the first common vector boundary (views give interior pointers)
+            k_stream_unaligned<T, Fn, HAS_B><<<1, kThreads, 0, s>>>(a, b, out, head, first, fn);
+            ++g_launches;
+        }
+        const uint64_t rest = n - head;
+        if (rest) {
+            constexpr uint64_t per_block = (uint64_t)kThreads * UNROLL * (VB / sizeof(T));
+            const unsigned grid = grid_for(rest, per_block, c.sm_count, cps);
+            k_stream<T, Fn, HAS_B, VB, UNROLL><<<grid, kThreads, 0, s>>>(a + head, HAS_B ? b + head : nullptr, out + head,
+                                                                       rest, first + head, fn);
+            ++g_launches;
+            g_last_kernel = HAS_B ? "k_stream<binary>" : "k_stream<scalar>";
+        }
+    } else {
+        const unsigned grid = grid_for(n, kThreads, c.sm_count, 32);
+        k_stream_unaligned<T, Fn, HAS_B><<<grid, kThreads, 0, s>>>(a, b, out, n, first, fn);
+        ++g_launches;
+        g_last_kernel = "k_stream_unaligned";
+    }
+    SMB_CK(cudaGetLastError());
+    return SMB_OK;
+}
+
+template<typename T>
+static int contiguous_t(const DeviceCtx &c, int op, const T *a, const T *b, T *out, uint64_t n, uint64_t first,
+                        uint64_t lane_end, cudaStream_t s) {
+    switch (op) {
+        case SMB_OP_ADD: return launch_stream<T, BinaryFn<OP_ADD, T>, true>(c, a, b, out, n, first, {lane_end}, s);
+        case SMB_OP_SUB: return launch_stream<T, BinaryFn<OP_SUB, T>, true>(c, a, b, out, n, first, {lane_end}, s);
+        case SMB_OP_MUL: return launch_stream<T, BinaryFn<OP_MUL, T>, true>(c, a, b, out, n, first, {lane_end}, s);
+        case SMB_OP_DIV: return launch_stream<T, BinaryFn<OP_DIV, T>, true>(c, a, b, out, n, first, {lane_end}, s);
+        case SMB_OP_POW: return launch_stream<T, BinaryFn<OP_POW, T>, true>(c, a, b, out, n, first, {lane_end}, s);
+    }
+    return fail(SMB_ERR_INVALID, "unknown op %d", op);
+}
+
+// array (op) scalar.  `first` is the absolute flat index of a[0] (staging
+// chunks), lane_end the absolute end of the reference's SIMD region.
+template<typename T>
+static int scalar_t(const DeviceCtx &c, int op, const T *a, T v, T *out, uint64_t n, uint64_t first, uint64_t lane_end,
+                    cudaStream_t s);
+
+template<>
+int scalar_t<float>(const DeviceCtx &c, int op, const float *a, float v, float *out, uint64_t n, uint64_t first,
+                    uint64_t lane_end, cudaStream_t s) {
+    using T = float;
+    switch (op) {
+        case SMB_OP_ADD: return launch_stream<T, ScalarFn<OP_ADD, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_SUB: return launch_stream<T, ScalarFn<OP_SUB, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_MUL: return launch_stream<T, ScalarFn<OP_MUL, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_DIV: return launch_stream<T, ScalarFn<OP_DIV, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_POW: {
+            if (g_opt_pow_specialise.load()) {
+                if (v == 2.0f) return launch_stream<T, PowSpecialFn<POWS_SQUARE, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
+                if (v == -1.0f) return launch_stream<T, PowSpecialFn<POWS_RECIP, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
+                if (v == 0.5f) return launch_stream<T, PowSpecialFn<POWS_SQRT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
+                if (v == 1.0f) return launch_stream<T, PowSpecialFn<POWS_IDENT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
+            }
+            return launch_stream<T, ScalarFn<OP_POW, T>, false>(c, a, nullptr, out, n, first, {classify_exp(v), lane_end}, s);
+        }
+    }
+    return fail(SMB_ERR_INVALID, "unknown op %d", op);
+}
+template<>
+int scalar_t<double>(const DeviceCtx &c, int op, const double *a, double v, double *out, uint64_t n, uint64_t first,
+                     uint64_t lane_end, cudaStream_t s) {
+    using T = double;
+    switch (op) {
+        case SMB_OP_ADD: return launch_stream<T, ScalarFn<OP_ADD, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_SUB: return launch_stream<T, ScalarFn<OP_SUB, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_MUL: return launch_stream<T, ScalarFn<OP_MUL, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_DIV: return launch_stream<T, ScalarFn<OP_DIV, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_POW: {
+            if (g_opt_pow_specialise.load()) {
+                if (v == 2.0) return launch_stream<T, PowSpecialFn<POWS_SQUARE, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
+                if (v == -1.0) return launch_stream<T, PowSpecialFn<POWS_RECIP, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
+                if (v == 0.5) return launch_stream<T, PowSpecialFn<POWS_SQRT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
+                if (v == 1.0) return launch_stream<T, PowSpecialFn<POWS_IDENT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
+            }
+            return launch_stream<T, ScalarFn<OP_POW, T>, false>(c, a, nullptr, out, n, first, {classify_exp(v), lane_end}, s);
+        }
+    }
+    return fail(SMB_ERR_INVALID, "unknown op %d", op);
+}
+template<>
+int scalar_t<int32_t>(const DeviceCtx &c, int op, const int32_t *a, int32_t v, int32_t *out, uint64_t n, uint64_t first,
+                      uint64_t lane_end, cudaStream_t s) {
+    using T = int32_t;
+    switch (op) {
+        case SMB_OP_ADD: return launch_stream<T, ScalarFn<OP_ADD, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_SUB: return launch_stream<T, ScalarFn<OP_SUB, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_MUL: return launch_stream<T, ScalarFn<OP_MUL, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_DIV: return launch_stream<T, ScalarFn<OP_DIV, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+        case SMB_OP_POW: return launch_stream<T, ScalarFn<OP_POW, T>, false>(c, a, nullptr, out, n, first, {v, lane_end}, s);
+    }
+    return fail(SMB_ERR_INVALID, "unknown op %d", op);
+}
+
+// ---- broadcast launch -------------------------------------------------------
+static BcastTable make_table(const ElementwisePlan &p, uint64_t lin_base, uint64_t count, uint64_t lane_base, bool *wide) {
+    BcastTable t;
+    memset(&t, 0, sizeof t);
+    t.ndim = p.ndim;
+    bool w = lin_base + count > (1ull << 31);
+    for (int k = 0; k < SMB_MAX_NDIM; ++k) {
+        const uint64_t d = k < p.ndim ? p.shape[k] : 1;
+        if (d >= (1ull << 31)) w = true;
+        t.shape64[k] = d;
+        t.sa[k] = k < p.ndim ? p.sa[k] : 0;
+        t.sb[k] = k < p.ndim ? p.sb[k] : 0;
+        const FastDiv32 f = make_fastdiv32((uint32_t)std::min<uint64_t>(d, 0x7fffffffull));
+        t.shape[k] = f.d;
+        t.mul[k] = f.mul;
+        t.shr[k] = f.shr;
+    }
+    t.lin_base = lin_base;
+    t.count = count;
+    t.lane_base = lane_base;
+    *wide = w;
+    return t;
+}
+
+static bool operand_reused(const ElementwisePlan &p, const uint64_t *s) {
+    for (int k = 0; k < p.ndim; ++k)
+        if (s[k] == 0 && p.shape[k] > 1) return true;
+    return false;
+}
+
+// Largest vector width (bytes) the row kernel may use for this plan / pointers.
+template<typename T>
+static int row_vector_bytes(const ElementwisePlan &p, const T *a, const T *b, const T *out, uint64_t lin_base,
+                            uint64_t count) {
+    const int candidates[2] = {16, (int)sizeof(T)};
+    for (int vb : candidates) {
+        const uint64_t epv = vb / sizeof(T);
+        if (epv == 1) return vb;
+        const int m = p.ndim;
+        if (p.shape[m - 1] % epv || lin_base % epv || count % epv) continue;
+        if ((uintptr_t)out % vb) continue;
+        bool ok = true;
+        const uint64_t *ss[2] = {p.sa, p.sb};
+        const void *pp[2] = {a, b};
+        for (int o = 0; o < 2 && ok; ++o) {
+            if (ss[o][m - 1] != 1) continue; // inner-broadcast operand: scalar loads, no constraint
+            if ((uintptr_t)pp[o] % vb) ok = false;
+            for (int k = 0; k < m - 1 && ok; ++k)
+                if (ss[o][k] % epv) ok = false;
+        }
+        if (ok) return vb;
+    }
+    return (int)sizeof(T);
+}
+
+template<typename T, typename Fn>
+static int launch_bcast(const DeviceCtx &c, const ElementwisePlan &p, const T *a, const T *b, T *out, uint64_t lin_base,
+                        uint64_t count, uint64_t lane_base, Fn fn, cudaStream_t s) {
+    if (count == 0) return SMB_OK;
+    bool wide = false;
+    const BcastTable t = make_table(p, lin_base, count, lane_base, &wide);
+    if (p.kind == PLAN_GENERIC) {
+        const unsigned grid = grid_for(count, kThreads, c.sm_count, 32);
+        if (wide) k_generic<T, Fn, true><<<grid, kThreads, 0, s>>>(a, b, out, t, fn);
+        else k_generic<T, Fn, false><<<grid, kThreads, 0, s>>>(a, b, out, t, fn);
+        g_last_kernel = wide ? "k_generic<wide>" : "k_generic";
+    } else {
+        const int vb = row_vector_bytes<T>(p, a, b, out, lin_base, count);
+        const int ar = operand_reused(p, p.sa), br = operand_reused(p, p.sb);
+        const uint64_t nvec = count / (vb / sizeof(T));
+        const unsigned grid = grid_for(nvec, kThreads, c.sm_count, 0);
+        if (vb == 16) {
+            if (wide) k_row<T, Fn, 16, true><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, fn);
+            else k_row<T, Fn, 16, false><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, fn);
+            g_last_kernel = wide ? "k_row<vec16,wide>" : "k_row<vec16>";
+        } else {
+            if (wide) k_row<T, Fn, (int)sizeof(T), true><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, fn);
+            else k_row<T, Fn, (int)sizeof(T), false><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, fn);
+            g_last_kernel = wide ? "k_row<scalar,wide>" : "k_row<scalar>";
+        }
+    }
+    ++g_launches;
+    SMB_CK(cudaGetLastError());
+    return SMB_OK;
+}
+
+template<typename T>
+static int bcast_t(const DeviceCtx &c, int op, const ElementwisePlan &p, const T *a, const T *b, T *out, uint64_t lin_base,
+                   uint64_t count, uint64_t lane_base, uint64_t lane_end, cudaStream_t s) {
+    switch (op) {
+        case SMB_OP_ADD: return launch_bcast<T, BinaryFn<OP_ADD, T>>(c, p, a, b, out, lin_base, count, lane_base, {lane_end}, s);
+        case SMB_OP_SUB: return launch_bcast<T, BinaryFn<OP_SUB, T>>(c, p, a, b, out, lin_base, count, lane_base, {lane_end}, s);
+        case SMB_OP_MUL: return launch_bcast<T, BinaryFn<OP_MUL, T>>(c, p, a, b, out, lin_base, count, lane_base, {lane_end}, s);
+        case SMB_OP_DIV: return launch_bcast<T, BinaryFn<OP_DIV, T>>(c, p, a, b, out, lin_base, count, lane_base, {lane_end}, s);
+        case SMB_OP_POW: return launch_bcast<T, BinaryFn<OP_POW, T>>(c, p, a, b, out, lin_base, count, lane_base, {lane_end}, s);
+    }
+    return fail(SMB_ERR_INVALID, "unknown op %d", op);
+}
+
+// One elementwise launch on DEVICE-ACCESSIBLE operands.  `a`/`b` address the
+// operands of plan `p`; the launch produces flat elements
+// [lin_base, lin_base+count) of the plan's result into out[0..count).
+static int elementwise_device(const DeviceCtx &c, int op, int dtype, const ElementwisePlan &p, const void *a, const void *b,
+                              void *out, uint64_t lin_base, uint64_t count, uint64_t lane_base, uint64_t lane_end,
+                              cudaStream_t s) {
+    if (p.kind == PLAN_CONTIGUOUS) {
+        switch (dtype) {
+            case SMB_F32: return contiguous_t<float>(c, op, (const float *)a + lin_base, (const float *)b + lin_base, (float *)out, count, lane_base, lane_end, s);
+            case SMB_F64: return contiguous_t<double>(c, op, (const double *)a + lin_base, (const double *)b + lin_base, (double *)out, count, lane_base, lane_end, s);
+            case SMB_I32: return contiguous_t<int32_t>(c, op, (const int32_t *)a + lin_base, (const int32_t *)b + lin_base, (int32_t *)out, count, lane_base, lane_end, s);
+        }
+    } else {
+        switch (dtype) {
+            case SMB_F32: return bcast_t<float>(c, op, p, (const float *)a, (const float *)b, (float *)out, lin_base, count, lane_base, lane_end, s);
+            case SMB_F64: return bcast_t<double>(c, op, p, (const double *)a, (const double *)b, (double *)out, lin_base, count, lane_base, lane_end, s);
+            case SMB_I32: return bcast_t<int32_t>(c, op, p, (const int32_t *)a, (const int32_t *)b, (int32_t *)out, lin_base, count, lane_base, lane_end, s);
+        }
+    }
+    return fail(SMB_ERR_INVALID, "unknown dtype %d", dtype);
+}
+
+static int scalar_device(const DeviceCtx &c, int op, int dtype, const void *a, const void *scalar, void *out, uint64_t n,
+                         uint64_t first, uint64_t lane_end, cudaStream_t s) {
+    switch (dtype) {
+        case SMB_F32: return scalar_t<float>(c, op, (const float *)a, *(const float *)scalar, (float *)out, n, first, lane_end, s);
+        case SMB_F64: return scalar_t<double>(c, op, (const double *)a, *(const double *)scalar, (double *)out, n, first, lane_end, s);
+        case SMB_I32: return scalar_t<int32_t>(c, op, (const int32_t *)a, *(const int32_t *)scalar, (int32_t *)out, n, first, lane_end, s);
+    }
+    return fail(SMB_ERR_INVALID, "unknown dtype %d", dtype);
+}
+
+// Where the reference's AVX2 loops stop and scalar Op::apply takes over; only
+// int pow can tell (smb_math.cuh).  handle_contiguous_arrays: `i + 8 <= n`
+// stepping by simd_width (calculate.h:116-121); array_scalar_op:
+// n - n % simd_width (calculate.h:139-140).
+static uint64_t contiguous_lane_end(int dtype, uint64_t n) {
+    const uint64_t w = dtype == SMB_F64 ? 4 : 8;
+    uint64_t i = 0;
+    if (n >= 8) i = ((n - 8) / w + 1) * w;
+    return i;
+}
+static uint64_t scalar_lane_end(int dtype, uint64_t n) {
+    const uint64_t w = dtype == SMB_F64 ? 4 : 8;
+    return n - n % w;
+}
+// The reference's own fast-path predicate on the UN-coalesced tables
+// (calculate.h:10-11, helpers.h:130-139): decides lane vs scalar int-pow
+// semantics, nothing else.
+static bool reference_takes_contiguous_path(const uint64_t *sa, const uint64_t *sb, const uint64_t *shape, int ndim) {
+    if (ndim == 1) return true;
+    if (sa[ndim - 1] != 1 || sb[ndim - 1] != 1) return false;
+    uint64_t expected = 1;
+    for (int i = ndim - 1; i >= 0; --i) {
+        if (sa[i] != sb[i] || sa[i] != expected) return false;
+        expected *= shape[i];
+    }
+    return true;
+}
+
+// --------------------------------------------------- host-operand staging ---
+// Operands in host memory are streamed through HBM in slabs along the leading
+// coalesced dim: slab i uses slot i % kSlots (own stream + scratch), so the H2D
+// copy of slab i+1, the kernel of slab i and the D2H copy of slab i-1 overlap.
+// An operand that does not vary along the leading dim (stride 0 there) is
+// uploaded once.  Device/managed operands are used in place.
+static int elementwise_staged(DeviceCtx &c, int op, int dtype, const ElementwisePlan &p, const void *a, MemType ta,
+                              const void *b, MemType tb, void *out, MemType to, uint64_t lane_end) {
+    const size_t es = esize(dtype);
+    int dev = 0;
+    SMB_CK(cudaGetDevice(&dev));
+    const uint64_t rows = p.shape[0];
+    const uint64_t inner = p.n / rows; // result elements per leading index
+    const bool a_var = p.ndim > 1 ? p.sa[0] != 0 : p.sa[0] != 0;
+    const bool b_var = p.sb[0] != 0;
+    // extent of one leading-index slice of each operand (elements)
+    auto slice_extent = [&](const uint64_t *s) {
+        uint64_t e = 1;
+        for (int k = 1; k < p.ndim; ++k) e += (p.shape[k] - 1) * s[k];
+        return e;
+    };
+    const uint64_t ea1 = slice_extent(p.sa), eb1 = slice_extent(p.sb);
+    const uint64_t chunk_bytes = (uint64_t)std::max<int64_t>(g_opt_chunk_bytes.load(), 1 << 16);
+    uint64_t chunk_rows = std::max<uint64_t>(1, chunk_bytes / std::max<uint64_t>(1, inner * es));
+    chunk_rows = std::min(chunk_rows, rows);
+    const uint64_t nchunks = (rows + chunk_rows - 1) / chunk_rows;
+    const int nslots = (int)std::min<uint64_t>(kSlots, nchunks);
+
+    // invariant operands: upload once on slot 0, everyone else waits on the event
+    Scratch inv_a, inv_b;
+    const void *da_inv = a, *db_inv = b;
+    bool need_ev = false;
+    if (on_host(ta) && !a_var) {
+        if (int rc = inv_a.get(p.extent_a * es, dev)) return rc;
+        SMB_CK(cudaMemcpyAsync(inv_a.p, a, p.extent_a * es, cudaMemcpyHostToDevice, c.slot[0]));
+        da_inv = inv_a.p;
+        need_ev = true;
+    }
+    if (on_host(tb) && !b_var) {
+        if (int rc = inv_b.get(p.extent_b * es, dev)) return rc;
+        SMB_CK(cudaMemcpyAsync(inv_b.p, b, p.extent_b * es, cudaMemcpyHostToDevice, c.slot[0]));
+        db_inv = inv_b.p;
+        need_ev = true;
+    }
+    if (need_ev) {
+        SMB_CK(cudaEventRecord(c.ev, c.slot[0]));
+        for (int i = 1; i < nslots; ++i) SMB_CK(cudaStreamWaitEvent(c.slot[i], c.ev, 0));
+    }
+    const uint64_t slab_ea = a_var ? (chunk_rows - 1) * p.sa[0] + ea1 : 0;
+    const uint64_t slab_eb = b_var ? (chunk_rows - 1) * p.sb[0] + eb1 : 0;
+    Scratch sa_[kSlots], sb_[kSlots], so_[kSlots];
+    for (int i = 0; i < nslots; ++i) {
+        if (on_host(ta) && a_var) if (int rc = sa_[i].get(slab_ea * es, dev)) return rc;
+        if (on_host(tb) && b_var) if (int rc = sb_[i].get(slab_eb * es, dev)) return rc;
+        if (on_host(to)) if (int rc = so_[i].get(chunk_rows * inner * es, dev)) return rc;
+    }
+    for (uint64_t ci = 0; ci < nchunks; ++ci) {
+        const int sl = (int)(ci % kSlots);
+        cudaStream_t s = c.slot[sl];
+        const uint64_t r0 = ci * chunk_rows, r = std::min(chunk_rows, rows - r0);
+        ElementwisePlan sub = p;
+        sub.shape[0] = r;
+        sub.n = r * inner;
+        const char *pa = (const char *)da_inv, *pb = (const char *)db_inv;
+        if (a_var) {
+            const char *src = (const char *)a + r0 * p.sa[0] * es;
+            if (on_host(ta)) {
+                SMB_CK(cudaMemcpyAsync(sa_[sl].p, src, ((r - 1) * p.sa[0] + ea1) * es, cudaMemcpyHostToDevice, s));
+                pa = (const char *)sa_[sl].p;
+            } else pa = src;
+        }
+        if (b_var) {
+            const char *src = (const char *)b + r0 * p.sb[0] * es;
+            if (on_host(tb)) {
+                SMB_CK(cudaMemcpyAsync(sb_[sl].p, src, ((r - 1) * p.sb[0] + eb1) * es, cudaMemcpyHostToDevice, s));
+                pb = (const char *)sb_[sl].p;
+            } else pb = src;
+        }
+        char *po = on_host(to) ? (char *)so_[sl].p : (char *)out + r0 * inner * es;
+        if (int rc = elementwise_device(c, op, dtype, sub, pa, pb, po, 0, sub.n, r0 * inner, lane_end, s)) return rc;
+        if (on_host(to))
+            SMB_CK(cudaMemcpyAsync((char *)out + r0 * inner * es, po, sub.n * es, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < nslots; ++i) SMB_CK(cudaStreamSynchronize(c.slot[i]));
+    if (need_ev && nslots == 0) SMB_CK(cudaStreamSynchronize(c.slot[0]));
+    return SMB_OK;
+}
+
+static int scalar_staged(DeviceCtx &c, int op, int dtype, const void *a, MemType ta, const void *scalar, void *out,
+                         MemType to, uint64_t n, uint64_t lane_end) {
+    const size_t es = esize(dtype);
+    int dev = 0;
+    SMB_CK(cudaGetDevice(&dev));
+    const uint64_t chunk_bytes = (uint64_t)std::max<int64_t>(g_opt_chunk_bytes.load(), 1 << 16);
+    const uint64_t chunk = std::min<uint64_t>(n, std::max<uint64_t>(1, chunk_bytes / es));
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    const int nslots = (int)std::min<uint64_t>(kSlots, nchunks);
+    Scratch sa_[kSlots], so_[kSlots];
+    for (int i = 0; i < nslots; ++i) {
+        if (on_host(ta)) if (int rc = sa_[i].get(chunk * es, dev)) return rc;
+        if (on_host(to)) if (int rc = so_[i].get(chunk * es, dev)) return rc;
+    }
+    for (uint64_t ci = 0; ci < nchunks; ++ci) {
+        const int sl = (int)(ci % kSlots);
+        cudaStream_t s = c.slot[sl];
+        const uint64_t i0 = ci * chunk, cnt = std::min(chunk, n - i0);
+        const char *pa = (const char *)a + i0 * es;
+        if (on_host(ta)) {
+            SMB_CK(cudaMemcpyAsync(sa_[sl].p, pa, cnt * es, cudaMemcpyHostToDevice, s));
+            pa = (const char *)sa_[sl].p;
+        }
+        char *po = on_host(to) ? (char *)so_[sl].p : (char *)out + i0 * es;
+        if (int rc = scalar_device(c, op, dtype, pa, scalar, po, cnt, i0, lane_end, s)) return rc;
+        if (on_host(to)) SMB_CK(cudaMemcpyAsync((char *)out + i0 * es, po, cnt * es, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < nslots; ++i) SMB_CK(cudaStreamSynchronize(c.slot[i]));
+    return SMB_OK;
+}
+
+static int check_args(int op, int dtype) {
+    if (op < SMB_OP_ADD || op > SMB_OP_POW) return fail(SMB_ERR_INVALID, "unknown op %d", op);
+    if (dtype < SMB_F32 || dtype > SMB_I32) return fail(SMB_ERR_INVALID, "unknown dtype %d (float, double, int32 only)", dtype);
+    return SMB_OK;
+}
+
+static int elementwise_entry(int op, int dtype, const void *a, const uint64_t *stride_a, const void *b,
+                             const uint64_t *stride_b, const uint64_t *shape, int ndim, uint64_t lin_begin,
+                             uint64_t lin_count, bool whole, void *out, void *stream) {
+    if (int rc = check_args(op, dtype)) return rc;
+    if (ndim < 1 || ndim > SMB_MAX_NDIM) return fail(SMB_ERR_INVALID, "rank %d outside 1..%d", ndim, SMB_MAX_NDIM);
+    if (!stride_a || !stride_b || !shape) return fail(SMB_ERR_INVALID, "null shape / stride table");
+    DeviceCtx *c = nullptr;
+    if (int rc = current_ctx(&c)) return rc;
+    const ElementwisePlan p = make_plan(stride_a, stride_b, shape, ndim);
+    if (whole) { lin_begin = 0; lin_count = p.n; }
+    if (lin_begin > p.n || lin_count > p.n - lin_begin) return fail(SMB_ERR_INVALID, "flat range outside the result");
+    if (lin_count == 0) return SMB_OK;
+    if (!a || !b || !out) return fail(SMB_ERR_INVALID, "null operand pointer");
+    uint64_t lane_end = 0;
+    if (op == SMB_OP_POW && dtype == SMB_I32 && reference_takes_contiguous_path(stride_a, stride_b, shape, ndim))
+        lane_end = contiguous_lane_end(dtype, p.n);
+    const MemType ta = mem_type(a), tb = mem_type(b), to = mem_type(out);
+    const size_t es = esize(dtype);
+    if (on_host(ta) || on_host(tb) || on_host(to)) {
+        if (lin_begin != 0 || lin_count != p.n) {
+            // partial range with host operands: stage the touched operands whole
+            int dev = 0;
+            SMB_CK(cudaGetDevice(&dev));
+            Scratch da, db, dout;
+            const void *pa = a, *pb = b;
+            void *po = out;
+            cudaStream_t s = c->main;
+            if (on_host(ta)) { if (int rc = da.get(p.extent_a * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(da.p, a, p.extent_a * es, cudaMemcpyHostToDevice, s)); pa = da.p; }
+            if (on_host(tb)) { if (int rc = db.get(p.extent_b * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(db.p, b, p.extent_b * es, cudaMemcpyHostToDevice, s)); pb = db.p; }
+            if (on_host(to)) { if (int rc = dout.get(lin_count * es, dev)) return rc; po = dout.p; }
+            if (int rc = elementwise_device(*c, op, dtype, p, pa, pb, po, lin_begin, lin_count, lin_begin, lane_end, s)) return rc;
+            if (on_host(to)) SMB_CK(cudaMemcpyAsync(out, po, lin_count * es, cudaMemcpyDeviceToHost, s));
+            SMB_CK(cudaStreamSynchronize(s));
+            return SMB_OK;
+        }
+        return elementwise_staged(*c, op, dtype, p, a, ta, b, tb, out, to, lane_end);
+    }
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
+    if (ta == MT_MANAGED) prefetch_managed(a, p.extent_a * es, s);
+    if (tb == MT_MANAGED) prefetch_managed(b, p.extent_b * es, s);
+    if (to == MT_MANAGED) prefetch_managed(out, lin_count * es, s);
+    if (int rc = elementwise_device(*c, op, dtype, p, a, b, out, lin_begin, lin_count, lin_begin, lane_end, s)) return rc;
+    if (!stream) SMB_CK(cudaStreamSynchronize(s));
+    return SMB_OK;
+}
+
+} // namespace smb
+
+using namespace smb;
+
+// =============================================================== C ABI =====
+extern "C" {
+
+int smb_elementwise(int op, int dtype, const void *a, const uint64_t *stride_a, const void *b, const uint64_t *stride_b,
+                    const uint64_t *shape, int ndim, uint64_t n, void *out, void *stream) {
+    if (shape && ndim >= 1 && ndim <= SMB_MAX_NDIM) {
+        uint64_t prod = 1;
+        for (int k = 0; k < ndim; ++k) prod *= shape[k];
+        if (prod != n) return fail(SMB_ERR_INVALID, "n (%llu) != prod(shape) (%llu)", (unsigned long long)n, (unsigned long long)prod);
+    }
+    return elementwise_entry(op, dtype, a, stride_a, b, stride_b, shape, ndim, 0, 0, true, out, stream);
+}
+
+int smb_elementwise_range(int op, int dtype, const void *a, const uint64_t *stride_a, const void *b,
+                          const uint64_t *stride_b, const uint64_t *shape, int ndim, uint64_t lin_begin,
+                          uint64_t lin_count, void *out, void *stream) {
+    return elementwise_entry(op, dtype, a, stride_a, b, stride_b, shape, ndim, lin_begin, lin_count, false, out, stream);
+}
+
+int smb_contiguous(int op, int dtype, const void *a, const void *b, void *out, uint64_t n, void *stream) {
+    const uint64_t one = 1, shape = n;
+    return elementwise_entry(op, dtype, a, &one, b, &one, &shape, 1, 0, 0, true, out, stream);
+}
+
+int smb_array_scalar(int op, int dtype, const void *a, const void *scalar, uint64_t n, void *out, void *stream) {
+    if (int rc = check_args(op, dtype)) return rc;
+    if (!scalar) return fail(SMB_ERR_INVALID, "null scalar pointer");
+    DeviceCtx *c = nullptr;
+    if (int rc = current_ctx(&c)) return rc;
+    if (n == 0) return SMB_OK;
+    if (!a || !out) return fail(SMB_ERR_INVALID, "null operand pointer");
+    const uint64_t lane_end = scalar_lane_end(dtype, n);
+    const MemType ta = mem_type(a), to = mem_type(out);
+    const size_t es = esize(dtype);
+    if (on_host(ta) || on_host(to)) return scalar_staged(*c, op, dtype, a, ta, scalar, out, to, n, lane_end);
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
+    if (ta == MT_MANAGED) prefetch_managed(a, n * es, s);
+    if (to == MT_MANAGED) prefetch_managed(out, n * es, s);
+    if (int rc = scalar_device(*c, op, dtype, a, scalar, out, n, 0, lane_end, s)) return rc;
+    if (!stream) SMB_CK(cudaStreamSynchronize(s));
+    return SMB_OK;
+}
+
+void *smb_alloc(size_t bytes, int kind) {
+    if (kind < SMB_MEM_DEVICE || kind > SMB_MEM_PINNED) { fail(SMB_ERR_INVALID, "unknown memory kind %d", kind); return nullptr; }
+    DeviceCtx *c = nullptr;
+    if (current_ctx(&c)) return nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e;
+    void *p = Pool::instance().alloc(bytes, kind, dev, &e);
+    if (!p) fail(e == cudaErrorMemoryAllocation ? SMB_ERR_OOM : SMB_ERR_CUDA, "smb_alloc(%zu, kind %d): %s", bytes, kind, cudaGetErrorString(e));
+    return p;
+}
+
+int smb_free(void *ptr) {
+    if (!ptr) return SMB_OK;
+    if (!Pool::instance().free(ptr)) return fail(SMB_ERR_INVALID, "smb_free: %p was not returned by smb_alloc", ptr);
+    return SMB_OK;
+}
+
+int smb_owns(const void *ptr) { return ptr && Pool::instance().owns(ptr) ? 1 : 0; }
+
+int smb_pool_trim(void) {
+    cudaDeviceSynchronize();
+    Pool::instance().trim();
+    return SMB_OK;
+}
+
+int smb_pool_stats(uint64_t stats[4]) {
+    if (!stats) return fail(SMB_ERR_INVALID, "null stats");
+    Pool::instance().stats(stats);
+    return SMB_OK;
+}
+
+int smb_fill(int dtype, void *out, const void *value, uint64_t n, void *stream) {
+    if (dtype < SMB_F32 || dtype > SMB_I32) return fail(SMB_ERR_INVALID, "unknown dtype %d", dtype);
+    DeviceCtx *c = nullptr;
+    if (int rc = current_ctx(&c)) return rc;
+    if (n == 0) return SMB_OK;
+    if (!out || !value) return fail(SMB_ERR_INVALID, "null pointer");
+    const MemType to = mem_type(out);
+    if (on_host(to)) return fail(SMB_ERR_INVALID, "smb_fill needs device or managed memory");
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
+    if (to == MT_MANAGED) prefetch_managed(out, n * esize(dtype), s);
+    const unsigned grid = grid_for(n, kThreads * 4, c->sm_count, 16);
+    if (dtype == SMB_F64) k_fill<double><<<grid, kThreads, 0, s>>>((double *)out, n, *(const double *)value);
+    else k_fill<uint32_t><<<grid, kThreads, 0, s>>>((uint32_t *)out, n, *(const uint32_t *)value);
+    ++g_launches;
+    SMB_CK(cudaGetLastError());
+    if (!stream) SMB_CK(cudaStreamSynchronize(s));
+    return SMB_OK;
+}
+
+int smb_prefetch(const void *ptr, size_t bytes, int device, void *stream) {
+    DeviceCtx *c = nullptr;
+    if (int rc = current_ctx(&c)) return rc;
+    if (mem_type(ptr) != MT_MANAGED) return SMB_OK; // nothing to migrate
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
+    SMB_CK(cudaMemPrefetchAsync(ptr, bytes, device < 0 ? cudaCpuDeviceId : device, s));
+    if (!stream) SMB_CK(cudaStreamSynchronize(s));
+    return SMB_OK;
+}
+
+int smb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int smb_set_device(int device) {
+    SMB_CK(cudaSetDevice(device));
+    return SMB_OK;
+}
+int smb_get_device(void) {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return d;
+}
+int smb_sync(void) {
+    SMB_CK(cudaDeviceSynchronize());
+    return SMB_OK;
+}
+
+int smb_set_option(int key, int64_t value) {
+    switch (key) {
+        case SMB_OPT_POW_SPECIALISE: g_opt_pow_specialise = value ? 1 : 0; return SMB_OK;
+        case SMB_OPT_STAGE_CHUNK_BYTES: g_opt_chunk_bytes = value; return SMB_OK;
+        case SMB_OPT_CONTIG_VARIANT: g_opt_contig_variant = value; return SMB_OK;
+        case SMB_OPT_BCAST_VARIANT: g_opt_bcast_variant = value; return SMB_OK;
+    }
+    return fail(SMB_ERR_INVALID, "unknown option %d", key);
+}
+int64_t smb_get_option(int key) {
+    switch (key) {
+        case SMB_OPT_POW_SPECIALISE: return g_opt_pow_specialise;
+        case SMB_OPT_STAGE_CHUNK_BYTES: return g_opt_chunk_bytes;
+        case SMB_OPT_CONTIG_VARIANT: return g_opt_contig_variant;
+        case SMB_OPT_BCAST_VARIANT: return g_opt_bcast_variant;
+    }
+    return -1;
+}
+
+uint64_t smb_launch_count(void) { return g_launches.load(); }
+const char *smb_last_kernel(void) { return g_last_kernel; }
+const char *smb_last_error(void) { return g_err.c_str(); }
+const char *smb_version(void) { return "smb200 0.1 (sm_100a)"; }
+
+int smb_plan_elementwise(const uint64_t *stride_a, const uint64_t *stride_b, const uint64_t *shape, int ndim, int elem_size,
+                         int *out_ndim, uint64_t *out_shape, uint64_t *out_stride_a, uint64_t *out_stride_b) {
+    (void)elem_size;
+    if (ndim < 1 || ndim > SMB_MAX_NDIM || !stride_a || !stride_b || !shape) return -SMB_ERR_INVALID;
+    const ElementwisePlan p = make_plan(stride_a, stride_b, shape, ndim);
+    if (out_ndim) *out_ndim = p.ndim;
+    for (int k = 0; k < p.ndim; ++k) {
+        if (out_shape) out_shape[k] = p.shape[k];
+        if (out_stride_a) out_stride_a[k] = p.sa[k];
+        if (out_stride_b) out_stride_b[k] = p.sb[k];
+    }
+    return p.kind;
+}
+
+int smb_fill_uniform_f32(void *out, uint64_t first, uint64_t n, uint64_t seed, float lo, float hi, void *stream) {
+    DeviceCtx *c = nullptr;
+    if (int rc = current_ctx(&c)) return rc;
+    if (n == 0) return SMB_OK;
+    if (!out || on_host(mem_type(out))) return fail(SMB_ERR_INVALID, "smb_fill_uniform_f32 needs device or managed memory");
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
+    const unsigned grid = grid_for(n, kThreads * 4, c->sm_count, 16);
+    k_fill_uniform_f32<<<grid, kThreads, 0, s>>>((float *)out, first, n, seed, lo, hi);
+    ++g_launches;
+    SMB_CK(cudaGetLastError());
+    if (!stream) SMB_CK(cudaStreamSynchronize(s));
+    return SMB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,363 @@
+// smb_kernels.cuh -- the sm_100a kernels that replace the reference's three CPU
+// loops (include/math/calculate.h):
+//
+//   k_stream   <- handle_contiguous_arrays (:101-134) and array_scalar_op (:137-169)
+//                 dense streams, 128/256-bit vector loads+stores, grid-stride.
+//   k_row      <- element_wise_op general loop (:47-98) when, after coalescing,
+//                 both operands have inner stride 0 or 1: vectorised along the
+//                 inner dim, outer index -> offset by fast-divmod.
+//   k_generic  <- the same loop for arbitrary element strides (scalar gathers,
+//                 coalesced stores).
+//
+// All are HBM-bound (0.08-0.25 flop/byte); no tensor cores, no TMEM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "smb_math.cuh"
+#include "smb_plan.h"
+
+namespace smb {
+
+// ---------------------------------------------------------------------------
+// 16-byte and 32-byte global vector access with streaming cache hints.
+// 256-bit LDG/STG is new with sm_100 (SASS LDG.E.256 / STG.E.256).
+// Streaming operands are read once: L1 no-allocate + L2 evict-first keep them
+// from displacing reused (broadcast) operands.
+template<int BYTES> struct alignas(BYTES) RawVec { uint32_t w[BYTES / 4]; };
+
+template<int BYTES, bool STREAMING> struct VecIO;
+
+template<> struct VecIO<16, true> {
+    static __device__ __forceinline__ RawVec<16> load(const void *p) {
+        RawVec<16> v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p));
+        return v;
+    }
+    static __device__ __forceinline__ void store(void *p, const RawVec<16> &v) {
+        asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]) : "memory");
+    }
+};
+template<> struct VecIO<16, false> {
+    static __device__ __forceinline__ RawVec<16> load(const void *p) {
+        RawVec<16> v;
+        asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p));
+        return v;
+    }
+    static __device__ __forceinline__ void store(void *p, const RawVec<16> &v) {
+        asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]) : "memory");
+    }
+};
+template<> struct VecIO<32, true> {
+    static __device__ __forceinline__ RawVec<32> load(const void *p) {
+        RawVec<32> v;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]),
+                       "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7]) : "l"(p));
+        return v;
+    }
+    static __device__ __forceinline__ void store(void *p, const RawVec<32> &v) {
+        asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :: "l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]),
+                        "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7]) : "memory");
+    }
+};
+template<> struct VecIO<32, false> {
+    static __device__ __forceinline__ RawVec<32> load(const void *p) {
+        RawVec<32> v;
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]),
+                       "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7]) : "l"(p));
+        return v;
+    }
+    static __device__ __forceinline__ void store(void *p, const RawVec<32> &v) {
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :: "l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]),
+                        "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7]) : "memory");
+    }
+};
+
+template<typename T, int BYTES> union Pack {
+    RawVec<BYTES> raw;
+    T e[BYTES / sizeof(T)];
+    __device__ __forceinline__ Pack() {}
+};
+
+// ---------------------------------------------------------------------------
+// Functors: what a launch applies to (a[i], b[i]).  `lane` tells the i32 pow
+// instantiation whether flat element i is one the reference computes in an
+// AVX2 lane (wrapping) or with scalar Op::apply (through double); see
+// smb_math.cuh.  Every other (Op, T) ignores it.
+template<int OP, typename T> struct BinaryFn {
+    uint64_t lane_end; // elements with flat index < lane_end use lane semantics
+    __device__ __forceinline__ T operator()(T a, T b, uint64_t) const { return DevOp<OP, T>::apply(a, b); }
+};
+template<> struct BinaryFn<OP_POW, int32_t> {
+    uint64_t lane_end;
+    __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b, uint64_t i) const {
+        return i < lane_end ? powi_lane(a, b) : powi_scalar(a, b);
+    }
+};
+
+// array (op) scalar: the scalar is the RIGHT operand (calculate.h:159,167).
+template<int OP, typename T> struct ScalarFn {
+    T v;
+    uint64_t lane_end;
+    __device__ __forceinline__ T operator()(T a, T, uint64_t) const { return DevOp<OP, T>::apply(a, v); }
+};
+template<> struct ScalarFn<OP_POW, int32_t> {
+    int32_t v;
+    uint64_t lane_end;
+    __device__ __forceinline__ int32_t operator()(int32_t a, int32_t, uint64_t i) const {
+        return i < lane_end ? powi_lane(a, v) : powi_scalar(a, v);
+    }
+};
+template<> struct ScalarFn<OP_POW, float> {
+    PowExpF32 pe; // exponent classified once on the host
+    uint64_t lane_end;
+    __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return pow_f32(a, pe); }
+};
+template<> struct ScalarFn<OP_POW, double> {
+    PowExpF64 pe;
+    uint64_t lane_end;
+    __device__ __forceinline__ double operator()(double a, double, uint64_t) const { return pow_f64(a, pe); }
+};
+
+// Exact special forms of sm::pow(arr, y) for y in {2, 0.5, -1, 1}: one correctly
+// rounded instruction instead of exp2(y*log2 x).  Chosen on the host
+// (SMB_OPT_POW_SPECIALISE); the C99 special-case table still holds:
+//   y = 2  : x*x            (pow(-0,2)=+0, pow(+-inf,2)=+inf, NaN -> NaN)
+//   y = -1 : 1/x            (pow(+-0,-1)=+-inf, pow(+-inf,-1)=+-0)
+//   y = 0.5: sqrt(x) except pow(-0,.5)=+0 and pow(-inf,.5)=+inf
+//   y = 1  : x
+enum { POWS_SQUARE = 0, POWS_RECIP = 1, POWS_SQRT = 2, POWS_IDENT = 3 };
+template<int WHICH, typename T> struct PowSpecialFn {
+    uint64_t lane_end;
+    __device__ __forceinline__ T operator()(T a, T, uint64_t) const {
+        if (WHICH == POWS_SQUARE) return DevOp<OP_MUL, T>::apply(a, a);
+        if (WHICH == POWS_RECIP) return DevOp<OP_DIV, T>::apply((T)1, a);
+        if (WHICH == POWS_SQRT) {
+            if (a == (T)0) return (T)0;                 // +-0 -> +0
+            if (a == -(T)INFINITY) return (T)INFINITY;  // -inf -> +inf
+            if constexpr (sizeof(T) == 4) return __fsqrt_rn(a);
+            else return __dsqrt_rn(a);
+        }
+        return a;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// k_stream: out[i] = fn(a[i], b[i]) over dense streams.
+//   VB     bytes per vector access (16 or 32)
+//   UNROLL independent vectors in flight per thread per operand
+//   HAS_B  false for array (op) scalar
+// Work is cut into tiles of blockDim*UNROLL vectors; tile t is handled by block
+// t mod gridDim (grid-stride), thread j of the block touching vectors
+// j, j+blockDim, ... so every warp access is one fully coalesced 512 B / 1 KiB run.
+// All loads of a tile are issued before the first use (memory-level parallelism).
+// The ragged end (< one vector) is done by the last threads with scalar accesses.
+template<typename T, typename Fn, bool HAS_B, int VB, int UNROLL, bool GUARD>
+__device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
+                                            uint64_t v0, uint64_t nvec, uint64_t first, const Fn &fn) {
+    constexpr int EPV = VB / (int)sizeof(T);
+    Pack<T, VB> pa[UNROLL], pb[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const uint64_t v = v0 + (uint64_t)u * blockDim.x;
+        if (!GUARD || v < nvec) {
+            pa[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(a) + v);
+            if (HAS_B) pb[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(b) + v);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const uint64_t v = v0 + (uint64_t)u * blockDim.x;
+        if (!GUARD || v < nvec) {
+            Pack<T, VB> r;
+#pragma unroll
+            for (int k = 0; k < EPV; ++k)
+                r.e[k] = fn(pa[u].e[k], HAS_B ? pb[u].e[k] : pa[u].e[k], first + v * EPV + k);
+            VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v, r.raw);
+        }
+    }
+}
+
+template<typename T, typename Fn, bool HAS_B, int VB, int UNROLL>
+__global__ void __launch_bounds__(256) k_stream(const T *__restrict__ a, const T *__restrict__ b,
+                                               T *__restrict__ out, uint64_t n, uint64_t first, Fn fn) {
+    constexpr int EPV = VB / (int)sizeof(T); // elements per vector
+    const uint64_t nvec = n / EPV;
+    const uint64_t tile_vecs = (uint64_t)blockDim.x * UNROLL;
+    const uint64_t full_tiles = nvec / tile_vecs;
+    // full tiles: no bounds checks in the loop body
+#pragma unroll 1
+    for (uint64_t tile = blockIdx.x; tile < full_tiles; tile += gridDim.x)
+        stream_tile<T, Fn, HAS_B, VB, UNROLL, false>(a, b, out, tile * tile_vecs + threadIdx.x, nvec, first, fn);
+    // the ragged last tile goes to the block whose turn it would be
+    if (full_tiles * tile_vecs < nvec && blockIdx.x == full_tiles % gridDim.x)
+        stream_tile<T, Fn, HAS_B, VB, UNROLL, true>(a, b, out, full_tiles * tile_vecs + threadIdx.x, nvec, first, fn);
+    // tail: n % EPV elements
+    const uint64_t tail0 = nvec * EPV;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid < n - tail0) {
+        const uint64_t i = tail0 + gtid;
+        out[i] = fn(a[i], HAS_B ? b[i] : a[i], first + i);
+    }
+}
+
+// Scalar-access variant for operands whose addresses do not share an alignment
+// (views hand us interior pointers): element i by thread i, fully coalesced
+// 4/8-byte accesses.
+template<typename T, typename Fn, bool HAS_B>
+__global__ void __launch_bounds__(256) k_stream_unaligned(const T *__restrict__ a, const T *__restrict__ b,
+                                                         T *__restrict__ out, uint64_t n, uint64_t first, Fn fn) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = fn(a[i], HAS_B ? b[i] : a[i], first + i);
+}
+
+// ---------------------------------------------------------------------------
+// Broadcast stride table.  Passed BY VALUE as a __grid_constant__ kernel
+// parameter: kernel parameters live in the constant bank (c[0x0][...]), so every
+// lane reads shape / stride / magic through the constant cache with uniform
+// (broadcast) access -- the "stride table in constant memory" of the design --
+// without a cudaMemcpyToSymbol round trip and without a global __constant__
+// symbol that concurrent launches on different streams would race on.
+struct BcastTable {
+    int ndim;                        // coalesced rank >= 1
+    uint32_t shape[SMB_MAX_NDIM];    // valid when !WIDE (all < 2^31)
+    uint32_t mul[SMB_MAX_NDIM];      // fast-divmod magic per dim (divisor = shape[k])
+    uint32_t shr[SMB_MAX_NDIM];
+    uint64_t shape64[SMB_MAX_NDIM];
+    uint64_t sa[SMB_MAX_NDIM];       // element strides, 0 on broadcast dims
+    uint64_t sb[SMB_MAX_NDIM];
+    uint64_t lin_base;               // first flat output index of this launch (sharding)
+    uint64_t count;                  // elements this launch produces
+    uint64_t lane_base;              // absolute flat index of lin_base (differs when a slab is staged)
+};
+
+__device__ __forceinline__ uint32_t fastdiv(uint32_t x, uint32_t d, uint32_t mul, uint32_t shr) {
+    return d == 1 ? x : (__umulhi(x, mul) >> shr);
+}
+
+// flat index (relative to the full result) -> operand element offsets.
+// Dims are peeled from the innermost outwards: idx_k = lin mod shape_k.
+template<bool WIDE>
+__device__ __forceinline__ void offsets_of(const BcastTable &t, uint64_t lin, uint64_t &oa, uint64_t &ob) {
+    oa = 0;
+    ob = 0;
+    if (WIDE) {
+        uint64_t rem = lin;
+#pragma unroll
+        for (int k = SMB_MAX_NDIM - 1; k >= 0; --k) {
+            if (k < t.ndim) {
+                uint64_t idx;
+                if (k == 0) idx = rem;
+                else { uint64_t q = rem / t.shape64[k]; idx = rem - q * t.shape64[k]; rem = q; }
+                oa += idx * t.sa[k];
+                ob += idx * t.sb[k];
+            }
+        }
+    } else {
+        uint32_t rem = (uint32_t)lin;
+#pragma unroll
+        for (int k = SMB_MAX_NDIM - 1; k >= 0; --k) {
+            if (k < t.ndim) {
+                uint32_t idx;
+                if (k == 0) idx = rem;
+                else { uint32_t q = fastdiv(rem, t.shape[k], t.mul[k], t.shr[k]); idx = rem - q * t.shape[k]; rem = q; }
+                oa += (uint64_t)idx * t.sa[k];
+                ob += (uint64_t)idx * t.sb[k];
+            }
+        }
+    }
+}
+
+// k_row: inner strides in {0,1}.  Each thread produces EPV consecutive outputs
+// of one row (host guarantees inner length, lin_base and the row bases are
+// multiples of EPV and 16/32-byte aligned when EPV > 1).  An operand with inner
+// stride 1 is read with one vector load; with inner stride 0 with one scalar
+// load that is splat.  Operands with any zero stride are re-read by other
+// threads, so they use the default (caching) load path; pure streams use the
+// streaming hints.
+template<typename T, typename Fn, int VB, bool WIDE>
+__global__ void __launch_bounds__(256) k_row(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
+                                            const __grid_constant__ BcastTable t, int a_reused, int b_reused, Fn fn) {
+    constexpr int EPV = VB / (int)sizeof(T);
+    const uint64_t nvec = t.count / EPV; // host guarantees count % EPV == 0 when EPV > 1
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int m = t.ndim;
+    const bool ia = t.sa[m - 1] != 0, ib = t.sb[m - 1] != 0;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const uint64_t lin = t.lin_base + v * EPV;
+        uint64_t oa, ob;
+        offsets_of<WIDE>(t, lin, oa, ob);
+        Pack<T, VB> pa, pb, r;
+        if constexpr (EPV == 1) {
+            pa.e[0] = a[oa];
+            pb.e[0] = b[ob];
+        } else {
+            if (ia) pa.raw = a_reused ? VecIO<VB, false>::load(a + oa) : VecIO<VB, true>::load(a + oa);
+            else {
+                const T s = a[oa];
+#pragma unroll
+                for (int k = 0; k < EPV; ++k) pa.e[k] = s;
+            }
+            if (ib) pb.raw = b_reused ? VecIO<VB, false>::load(b + ob) : VecIO<VB, true>::load(b + ob);
+            else {
+                const T s = b[ob];
+#pragma unroll
+                for (int k = 0; k < EPV; ++k) pb.e[k] = s;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa.e[k], pb.e[k], t.lane_base + v * EPV + k);
+        if constexpr (EPV == 1) out[v] = r.e[0];
+        else VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v, r.raw);
+    }
+}
+
+// k_generic: arbitrary element strides; one output element per thread per
+// iteration, coalesced stores, gathered loads.
+template<typename T, typename Fn, bool WIDE>
+__global__ void __launch_bounds__(256) k_generic(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
+                                                const __grid_constant__ BcastTable t, Fn fn) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.count; i += stride) {
+        const uint64_t lin = t.lin_base + i;
+        uint64_t oa, ob;
+        offsets_of<WIDE>(t, lin, oa, ob);
+        out[i] = fn(a[oa], b[ob], t.lane_base + i);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fill (sm::ones / sm::zeros) and the counter-based uniform generator.
+template<typename T>
+__global__ void __launch_bounds__(256) k_fill(T *__restrict__ out, uint64_t n, T v) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// Same arithmetic as oracle/oracle.c:orc_fill_uniform_f32 (two roundings, no FMA).
+__global__ void __launch_bounds__(256) k_fill_uniform_f32(float *__restrict__ out, uint64_t first, uint64_t n,
+                                                         uint64_t seed, float lo, float hi) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const float span = __fsub_rn(hi, lo);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t h = splitmix64(seed * 0xD1342543DE82EF95ull + first + i);
+        const float u = __fmul_rn((float)(uint32_t)(h >> 40), 1.0f / 16777216.0f);
+        out[i] = __fadd_rn(lo, __fmul_rn(span, u));
+    }
+}
+
+} // namespace smb

@@ -1,0 +1,625 @@
+// smb_math.cuh -- device bodies of the reference's Op structs.
+//
+// One functor per (Op, T): the `apply_device` specialisation each reference Op
+// struct gains (AddOp add.h:5-14, SubtractOp subtract.h:5-14, MultiplyOp
+// multiply.h:7-16, DivideOp division.h:8-17,67-70, PowOp pow.h:6-14 and
+// math/simd/crafted_pow.h:54-103).
+//
+// Semantics:
+//   f32/f64 + - * / : IEEE-754 round-to-nearest-even, denormals kept, no FMA
+//                     contraction (explicit _rn intrinsics, and the file is
+//                     compiled with -fmad=false) -> bit-exact vs Op::apply.
+//   i32 + - *       : two's-complement wrap (what _mm256_{add,sub,mullo}_epi32 do).
+//   i32 /           : C truncation toward zero (/0 and INT_MIN/-1 trap on x86,
+//                     are undefined in the reference and return an unspecified
+//                     value here; no test feeds them).
+//   i32 pow         : two flavours, because the reference has two (see below).
+//   f32/f64 pow     : exp2(y * log2 x), correctly range-reduced, full C99 Annex F
+//                     special-case table; ULP-bounded vs std::pow.
+//
+// The functions are SMB_HD so tests/hostcheck can compile this same source for
+// the host and sweep the pow kernels' accuracy without a GPU.  That build is a
+// test artefact; the shipped library has no host execution path.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define SMB_HD __host__ __device__ __forceinline__
+#define SMB_D __device__ __forceinline__
+#else
+#define SMB_HD inline
+#define SMB_D inline
+#endif
+
+namespace smb {
+
+enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3, OP_POW = 4 };
+enum { DT_F32 = 0, DT_F64 = 1, DT_I32 = 2 };
+
+// ---- bit casts and exact single-rounding primitives, host and device -------
+SMB_HD uint32_t f2u(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(x);
+#else
+    uint32_t u; __builtin_memcpy(&u, &x, 4); return u;
+#endif
+}
+SMB_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float x; __builtin_memcpy(&x, &u, 4); return x;
+#endif
+}
+SMB_HD uint64_t d2u(double x) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t u; __builtin_memcpy(&u, &x, 8); return u;
+#endif
+}
+SMB_HD double u2d(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double x; __builtin_memcpy(&x, &u, 8); return x;
+#endif
+}
+SMB_HD float fadd(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+SMB_HD float fsub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+SMB_HD float fmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+SMB_HD float ffma(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return __builtin_fmaf(a, b, c);
+#endif
+}
+SMB_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+SMB_HD double dsub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+SMB_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+SMB_HD double dfma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+
+// ============================================================ integer pow ===
+// Lane semantics: __sm256_powi_ps, math/simd/crafted_pow.h:54-103 -- what every
+// element produced by an AVX2 apply_simd lane gets.  |exp| as
+// _mm256_abs_epi32 + logical shifts see it (INT_MIN -> 0x80000000), wrapping
+// mullo (:72,:76); 0^(exp>0) -> 0 (:81-84); exp<0 -> 0 except base 1 -> 1 and
+// base -1 -> (exp odd ? -1 : 1) (:85-102).  The exponent is warp-uniform on the
+// sm::pow path, so the loop does not diverge there.
+SMB_HD int32_t powi_lane(int32_t base, int32_t exp) {
+    if (exp < 0) {
+        if (base == 1) return 1;
+        if (base == -1) return (exp & 1) ? -1 : 1;
+        return 0;
+    }
+    uint32_t e = (uint32_t)exp, cur = (uint32_t)base, res = 1u;
+    while (e) {
+        if (e & 1u) res *= cur;
+        cur *= cur;
+        e >>= 1;
+    }
+    return (int32_t)res; // base==0 && exp>0 already yields 0
+}
+
+// Scalar semantics: PowOp<int>::apply, math/pow.h:8-10 -- std::pow in double,
+// converted back to int on return (cvttsd2si on x86-64: anything outside
+// (-2^31-1, 2^31) -- including +inf from 0^negative -- becomes 0x80000000).
+// Reached by the tail elements of the AVX loops (calculate.h:130-133,166-168)
+// and by every element of the general strided loop (calculate.h:96).
+// libm's pow is exact whenever the true result is a representable integer of
+// this size, so the double detour is reproduced with integers only: exact
+// magnitude by squaring, saturating once it passes 2^31.
+SMB_HD int32_t powi_scalar(int32_t base, int32_t exp) {
+    const int32_t indefinite = (int32_t)0x80000000u;
+    if (exp < 0) {
+        if (base == 0) return indefinite; // pow(+0, negative) = +inf
+        if (base == 1) return 1;
+        if (base == -1) return (exp & 1) ? -1 : 1;
+        return 0; // |result| < 1 truncates to 0
+    }
+    const uint64_t cap = 0x80000001ull; // any magnitude > 2^31 behaves alike
+    uint64_t cur = base < 0 ? (uint64_t)0 - (uint64_t)(int64_t)base : (uint64_t)base;
+    uint64_t res = 1;
+    uint32_t e = (uint32_t)exp;
+    while (e) {
+        if (e & 1u) { res *= cur; if (res > cap) res = cap; }
+        e >>= 1;
+        if (e) { cur *= cur; if (cur > cap) cur = cap; }
+    }
+    if (res >= 0x80000000ull) return indefinite; // -2^31 exactly is the same bits
+    const bool neg = base < 0 && (exp & 1);
+    return neg ? -(int32_t)res : (int32_t)res;
+}
+
+// =============================================================== float pow ===
+// Exponent facts that are uniform over a launch (the exponent of sm::pow is one
+// scalar, UserFunctions.h:42-48) are classified once on the host.
+struct PowExpF32 {
+    float y;
+    int y_is_int;   // y is an integer value (includes |y| >= 2^24)
+    int y_is_odd;   // y is an odd integer
+    int y_class;    // 0 finite non-zero, 1 zero, 2 +inf, 3 -inf, 4 NaN
+};
+struct PowExpF64 {
+    double y;
+    int y_is_int;
+    int y_is_odd;
+    int y_class;
+};
+
+SMB_HD PowExpF32 classify_exp(float y) {
+    PowExpF32 p;
+    p.y = y;
+    uint32_t u = f2u(y) & 0x7fffffffu;
+    p.y_class = 0;
+    if (u == 0) p.y_class = 1;
+    else if (u == 0x7f800000u) p.y_class = (f2u(y) >> 31) ? 3 : 2;
+    else if (u > 0x7f800000u) p.y_class = 4;
+    p.y_is_int = 0;
+    p.y_is_odd = 0;
+    if (p.y_class == 0 || p.y_class == 1) {
+        int e = (int)(u >> 23) - 127; // unbiased exponent
+        if (u == 0) { p.y_is_int = 1; }
+        else if (e >= 24) { p.y_is_int = 1; }            // even: ulp >= 2
+        else if (e >= 0) {
+            uint32_t frac_mask = (1u << (23 - e)) - 1u;
+            if (e == 23) frac_mask = 0;
+            if ((u & frac_mask) == 0) {
+                p.y_is_int = 1;
+                p.y_is_odd = (int)((u >> (23 - e)) & 1u);
+            }
+        }
+    }
+    return p;
+}
+SMB_HD PowExpF64 classify_exp(double y) {
+    PowExpF64 p;
+    p.y = y;
+    uint64_t u = d2u(y) & 0x7fffffffffffffffull;
+    p.y_class = 0;
+    if (u == 0) p.y_class = 1;
+    else if (u == 0x7ff0000000000000ull) p.y_class = (d2u(y) >> 63) ? 3 : 2;
+    else if (u > 0x7ff0000000000000ull) p.y_class = 4;
+    p.y_is_int = 0;
+    p.y_is_odd = 0;
+    if (p.y_class == 0 || p.y_class == 1) {
+        int e = (int)(u >> 52) - 1023;
+        if (u == 0) { p.y_is_int = 1; }
+        else if (e >= 53) { p.y_is_int = 1; }
+        else if (e >= 0) {
+            uint64_t frac_mask = e == 52 ? 0ull : ((1ull << (52 - e)) - 1ull);
+            if ((u & frac_mask) == 0) {
+                p.y_is_int = 1;
+                p.y_is_odd = (int)((u >> (52 - e)) & 1ull);
+            }
+        }
+    }
+    return p;
+}
+
+// ---- log2 / exp2 kernels in double, used for f32 pow -----------------------
+// For a float result the double pipeline leaves < 2^-30 relative error before
+// the single final rounding, i.e. the result is the correctly rounded value in
+// all but ~1 in 2^6 * 2^-... near-tie cases: <= 0.5 + 2^-6 ULP.
+//
+// log2(x), x a positive finite double (any float converts to a NORMAL double, so
+// float denormals need no special path):
+//   x = 2^e * m, m in [sqrt(1/2), sqrt(2));  p = (m-1)/(m+1), |p| <= 0.1716;
+//   log2(m) = (2/ln2) * atanh(p) = p * (c0 + s*(c1 + ... )), s = p*p.
+// Truncating after the s^6 term leaves 2 * 0.02944^7 / 15 / (2 * 0.1716...) ->
+// relative 2^-38.
+SMB_HD double log2_pos(double x) {
+    uint64_t ux = d2u(x);
+    // choose e so that m = x * 2^-e lies in [sqrt(1/2), sqrt(2))
+    int64_t hi = (int64_t)(ux >> 32);
+    int64_t eadj = (hi - 0x3fe6a09e) >> 20; // floor((hi - hi(sqrt(1/2))) / 2^20)
+    double m = u2d(ux - ((uint64_t)eadj << 52));
+    double num = dsub(m, 1.0);
+    double den = dadd(m, 1.0);
+    // reciprocal: float seed + one Newton step in double (relative 2^-44)
+#if defined(__CUDA_ARCH__)
+    double r = (double)__frcp_rn((float)den);
+#else
+    double r = (double)(1.0f / (float)den);
+#endif
+    double err = dfma(-den, r, 1.0);
+    r = dfma(r, err, r);
+    double p = dmul(num, r);
+    // one correction of p itself: p += r * (num - p*den)
+    p = dfma(r, dfma(-p, den, num), p);
+    double s = dmul(p, p);
+    // (2/ln2) / (2k+1)
+    const double c0 = 2.8853900817779268147;  // 2/ln2
+    const double c1 = 0.96179669392597560491; // 2/(3 ln2)
+    const double c2 = 0.57707801635558536295; // 2/(5 ln2)
+    const double c3 = 0.41219858311113240210; // 2/(7 ln2)
+    const double c4 = 0.32059889797532520164; // 2/(9 ln2)
+    const double c5 = 0.26230818925253880134; // 2/(11 ln2)
+    const double c6 = 0.22195308321368667805; // 2/(13 ln2)
+    double q = dfma(s, c6, c5);
+    q = dfma(s, q, c4);
+    q = dfma(s, q, c3);
+    q = dfma(s, q, c2);
+    q = dfma(s, q, c1);
+    q = dfma(s, q, c0);
+    return dfma(p, q, (double)eadj);
+}
+
+// exp2(t) for |t| <= ~1100, returned as a double: n = rint(t), f = t - n in
+// [-0.5, 0.5], 2^f by a degree-10 Taylor polynomial in f*ln2 folded into the
+// coefficients (truncation (0.3466)^11/11! = 2^-42), scaled by 2^n through the
+// exponent field.
+SMB_HD double exp2_d(double t) {
+    const double shifter = 6755399441055744.0; // 1.5 * 2^52
+    double tn = dadd(t, shifter);
+    int32_t n = (int32_t)(uint32_t)d2u(tn); // low word holds rint(t)
+    double fn = dsub(tn, shifter);
+    double f = dsub(t, fn);
+    const double k1 = 6.93147180559945309417e-01;
+    const double k2 = 2.40226506959100712334e-01;
+    const double k3 = 5.55041086648215799532e-02;
+    const double k4 = 9.61812910762847716197e-03;
+    const double k5 = 1.33335581464284434234e-03;
+    const double k6 = 1.54035303933816099544e-04;
+    const double k7 = 1.52527338040598402800e-05;
+    const double k8 = 1.32154867901443094884e-06;
+    const double k9 = 1.01780860092396997275e-07;
+    const double k10 = 7.05491162080112332987e-09;
+    double q = dfma(f, k10, k9);
+    q = dfma(f, q, k8);
+    q = dfma(f, q, k7);
+    q = dfma(f, q, k6);
+    q = dfma(f, q, k5);
+    q = dfma(f, q, k4);
+    q = dfma(f, q, k3);
+    q = dfma(f, q, k2);
+    q = dfma(f, q, k1);
+    q = dfma(f, q, 1.0);
+    return u2d(d2u(q) + ((uint64_t)(int64_t)n << 52));
+}
+
+// The special-case table of C99 Annex F.10.4.4 / IEEE 754-2008 pow, shared by
+// f32 and f64.  Returns true and sets *out when (x, y) is a special pair;
+// otherwise x is finite and non-zero, y finite and non-zero, and the caller
+// computes |x|^y and applies `negate`.
+template<typename F, typename PE>
+SMB_HD bool pow_special(F x, const PE &pe, F *out, bool *negate) {
+    const F one = (F)1, zero = (F)0;
+    const F inf = (F)INFINITY;
+    *negate = false;
+    if (pe.y_class == 1) { *out = one; return true; }            // pow(x, +-0) = 1, even for NaN
+    if (x == one) { *out = one; return true; }                   // pow(+1, y) = 1, even for NaN
+    if (x != x || pe.y_class == 4) { *out = x + pe.y; return true; } // NaN propagates
+    const bool xneg = signbit(x);
+    const F ax = xneg ? -x : x;
+    if (pe.y_class == 2 || pe.y_class == 3) {                    // y = +-inf
+        if (ax == one) { *out = one; return true; }              // pow(-1, +-inf) = 1
+        const bool grow = (ax > one) == (pe.y_class == 2);
+        *out = grow ? inf : zero;
+        return true;
+    }
+    const bool yneg = pe.y < zero;
+    if (ax == zero) {                                            // pow(+-0, y)
+        F r = yneg ? inf : zero;                                 // (divide-by-zero flag not modelled)
+        *out = (xneg && pe.y_is_odd) ? -r : r;
+        return true;
+    }
+    if (ax == inf) {                                             // pow(+-inf, y)
+        F r = yneg ? zero : inf;
+        *out = (xneg && pe.y_is_odd) ? -r : r;
+        return true;
+    }
+    if (xneg) {
+        if (!pe.y_is_int) { *out = (F)NAN; return true; }        // negative finite ^ non-integer
+        *negate = pe.y_is_odd != 0;
+    }
+    return false;
+}
+
+// f32 pow, general path.
+SMB_HD float pow_f32(float x, const PowExpF32 &pe) {
+    // Fast classification: positive, finite, non-zero x (normal or denormal) and
+    // finite non-zero y need no table lookup.
+    const uint32_t ux = f2u(x);
+    bool negate = false;
+    if (!(pe.y_class == 0 && (ux - 1u) < 0x7f7fffffu)) {
+        float sp;
+        if (pow_special<float, PowExpF32>(x, pe, &sp, &negate)) return sp;
+    }
+    const double ax = (double)u2f(ux & 0x7fffffffu);
+    double t = dmul((double)pe.y, log2_pos(ax));
+    // float range: 2^128 overflows, below 2^-150 rounds to zero.  Clamp so the
+    // exponent arithmetic in exp2_d stays in range; the clamped values still
+    // round to inf / 0 in the final conversion.
+    t = t > 200.0 ? 200.0 : t;
+    t = t < -200.0 ? -200.0 : t;
+    float r = (float)exp2_d(t); // one rounding, gradual underflow included
+    return negate ? -r : r;
+}
+
+// ============================================================== double pow ===
+// Double-double (hi + lo, |lo| <= ulp(hi)/2) helpers built on FMA.
+struct dd { double hi, lo; };
+SMB_HD dd two_sum(double a, double b) {
+    double s = dadd(a, b);
+    double bb = dsub(s, a);
+    double e = dadd(dsub(a, dsub(s, bb)), dsub(b, bb));
+    return dd{s, e};
+}
+SMB_HD dd fast_two_sum(double a, double b) { // |a| >= |b|
+    double s = dadd(a, b);
+    double e = dsub(b, dsub(s, a));
+    return dd{s, e};
+}
+SMB_HD dd two_prod(double a, double b) {
+    double p = dmul(a, b);
+    double e = dfma(a, b, -p);
+    return dd{p, e};
+}
+SMB_HD dd dd_mul(dd a, dd b) {
+    dd p = two_prod(a.hi, b.hi);
+    p.lo = dfma(a.hi, b.lo, dfma(a.lo, b.hi, p.lo));
+    return fast_two_sum(p.hi, p.lo);
+}
+SMB_HD dd dd_mul_d(dd a, double b) {
+    dd p = two_prod(a.hi, b);
+    p.lo = dfma(a.lo, b, p.lo);
+    return fast_two_sum(p.hi, p.lo);
+}
+SMB_HD dd dd_add(dd a, dd b) {
+    dd s = two_sum(a.hi, b.hi);
+    s.lo = dadd(s.lo, dadd(a.lo, b.lo));
+    return fast_two_sum(s.hi, s.lo);
+}
+SMB_HD dd dd_add_d(dd a, double b) {
+    dd s = two_sum(a.hi, b);
+    s.lo = dadd(s.lo, a.lo);
+    return fast_two_sum(s.hi, s.lo);
+}
+
+// log2 of a positive finite NORMALISED-OR-DENORMAL double, as a double-double
+// with relative error < 2^-68:
+//   m in [sqrt(1/2), sqrt(2)), p = (m-1)/(m+1) as a double-double quotient,
+//   log2(m) = C0*p + p^3 * Q(s): the leading term in double-double, the tail
+//   (<= 2^-6.7 of the total) needs 2^-62 relative: s in double-double only for
+//   the p^3*c1 term, the rest in plain double.
+SMB_HD dd log2_dd(double x) {
+    uint64_t ux = d2u(x);
+    int64_t eoff = 0;
+    if ((ux >> 52) == 0) { // denormal: scale by 2^54 (exact)
+        x = dmul(x, 18014398509481984.0);
+        ux = d2u(x);
+        eoff = -54;
+    }
+    int64_t hi = (int64_t)(ux >> 32);
+    int64_t eadj = (hi - 0x3fe6a09e) >> 20;
+    double m = u2d(ux - ((uint64_t)eadj << 52));
+    const double e = (double)(eadj + eoff);
+    double num = dsub(m, 1.0);            // exact (Sterbenz)
+    dd den = two_sum(m, 1.0);             // m + 1 exactly, as hi + lo
+    // p = num / den to ~2^-100: p_hi = num * r, two residual corrections.
+    double r = 1.0 / den.hi;
+    double p_hi = dmul(num, r);
+    // residual = num - p_hi * (den.hi + den.lo), evaluated exactly enough with FMA
+    double res = dfma(-p_hi, den.hi, num);
+    res = dfma(-p_hi, den.lo, res);
+    double p_lo = dmul(res, r);
+    dd p = fast_two_sum(p_hi, p_lo);
+    // s = p^2 (double-double), plain-double copy for the tail polynomial
+    dd s = dd_mul(p, p);
+    const double sd = s.hi;
+    // tail: Q(s) = c2 + s*(c3 + ...), coefficients (2/ln2)/(2k+1), k = 2..
+    // truncation: need s^k/(2k+1) < 2^-70 relative: 0.02944^13 = 2^-66 -> k up to 14.
+    const double c2 = 0.57707801635558536295;
+    const double c3 = 0.41219858311113240210;
+    const double c4 = 0.32059889797532520164;
+    const double c5 = 0.26230818925253880134;
+    const double c6 = 0.22195308321368667805;
+    const double c7 = 0.19235933878519512098;
+    const double c8 = 0.16972882833987804793;
+    const double c9 = 0.15186263588304877972;
+    const double c10 = 0.13739952770371080070;
+    const double c11 = 0.12545174268599681802;
+    const double c12 = 0.11541560327111707259;
+    const double c13 = 0.10686629932510840055;
+    const double c14 = 0.09949620971648024;
+    const double c15 = 0.09307709941219118757;
+    double q = dfma(sd, c15, c14);
+    q = dfma(sd, q, c13);
+    q = dfma(sd, q, c12);
+    q = dfma(sd, q, c11);
+    q = dfma(sd, q, c10);
+    q = dfma(sd, q, c9);
+    q = dfma(sd, q, c8);
+    q = dfma(sd, q, c7);
+    q = dfma(sd, q, c6);
+    q = dfma(sd, q, c5);
+    q = dfma(sd, q, c4);
+    q = dfma(sd, q, c3);
+    q = dfma(sd, q, c2);
+    // c1 + s*q in double-double (c1 = 2/(3 ln2) split hi/lo)
+    const dd c1 = dd{0.9617966939259756, 5.0577616648125907e-17};
+    dd t1 = dd_add(c1, dd_mul_d(s, q));
+    // c0 + s*t1 in double-double (c0 = 2/ln2 split hi/lo)
+    const dd c0 = dd{2.8853900817779268, 4.0710547481862066e-17};
+    dd t0 = dd_add(c0, dd_mul(s, t1));
+    dd l = dd_mul(p, t0);
+    return dd_add(dd{e, 0.0}, l);
+}
+
+// exp2 of a double-double argument t = th + tl, |t| <= 1100, result as double
+// with < 0.5 + 2^-10 ULP error before scaling; scaling handles gradual underflow
+// with a single final rounding.
+SMB_HD double exp2_from_dd(dd t) {
+    const double shifter = 6755399441055744.0;
+    double tn = dadd(t.hi, shifter);
+    int32_t n = (int32_t)(uint32_t)d2u(tn);
+    double fn = dsub(tn, shifter);
+    // f = (th - n) + tl, |f| <= 0.5 (+tiny)
+    dd f = fast_two_sum(dsub(t.hi, fn), t.lo);
+    // z = f * ln2 in double-double
+    const dd ln2 = dd{0.6931471805599453, 2.3190468138462996e-17};
+    dd z = dd_mul(f, ln2);
+    // e^z = 1 + z + z^2/2 + z^3 * R(z): |z| <= 0.3466.  Leading terms in
+    // double-double, R in double (Taylor through z^15: 0.3466^16/16! = 2^-69).
+    const double zh = z.hi;
+    double r = 1.0 / 1307674368000.0;            // 1/15!
+    r = dfma(zh, r, 1.0 / 87178291200.0);        // 1/14!
+    r = dfma(zh, r, 1.0 / 6227020800.0);         // 1/13!
+    r = dfma(zh, r, 1.0 / 479001600.0);          // 1/12!
+    r = dfma(zh, r, 1.0 / 39916800.0);           // 1/11!
+    r = dfma(zh, r, 1.0 / 3628800.0);            // 1/10!
+    r = dfma(zh, r, 1.0 / 362880.0);             // 1/9!
+    r = dfma(zh, r, 1.0 / 40320.0);              // 1/8!
+    r = dfma(zh, r, 1.0 / 5040.0);               // 1/7!
+    r = dfma(zh, r, 1.0 / 720.0);                // 1/6!
+    r = dfma(zh, r, 1.0 / 120.0);                // 1/5!
+    r = dfma(zh, r, 1.0 / 24.0);                 // 1/4!
+    r = dfma(zh, r, 1.0 / 6.0);                  // 1/3!
+    // z^2/2 + z^3*r = z^2 * (0.5 + z*r)
+    dd z2 = dd_mul(z, z);
+    dd w = dd_mul_d(z2, dfma(zh, r, 0.5));       // relative 2^-53 of a term <= 0.07 of total
+    dd sum = dd_add(z, w);
+    sum = dd_add_d(sum, 1.0);                    // 1 + z + ...
+    // scale by 2^n with one rounding: for results in the normal range add to the
+    // exponent; near underflow do it in two exact steps on hi+lo.
+    if (n > -1000) {
+        double h = dadd(sum.hi, sum.lo);
+        if (n > 1000) { // overflow side: split the scaling to stay finite until the end
+            h = u2d(d2u(h) + ((uint64_t)(int64_t)(n - 100) << 52));
+            return dmul(h, 1.2676506002282294e30); // 2^100
+        }
+        return u2d(d2u(h) + ((uint64_t)(int64_t)n << 52));
+    }
+    // n <= -1000: result may be denormal.  Scale hi and lo by 2^(n+200) exactly
+    // (still normal), then one multiply by 2^-200 performs the only rounding on
+    // hi; lo's contribution is folded in first with an FMA-free exact add since
+    // |lo| << ulp(hi) after scaling can still decide a tie.
+    double hs = u2d(d2u(sum.hi) + ((uint64_t)(int64_t)(n + 200) << 52));
+    double ls = sum.lo == 0.0 ? 0.0 : u2d(d2u(sum.lo) + ((uint64_t)(int64_t)(n + 200) << 52));
+    const double tiny = 6.223015277861142e-61; // 2^-200
+    return dfma(hs, tiny, dmul(ls, tiny));
+}
+
+SMB_HD double pow_f64(double x, const PowExpF64 &pe) {
+    const uint64_t ux = d2u(x);
+    bool negate = false;
+    if (!(pe.y_class == 0 && (ux - 1ull) < 0x7fefffffffffffffull)) {
+        double sp;
+        if (pow_special<double, PowExpF64>(x, pe, &sp, &negate)) return sp;
+    }
+    const double ax = u2d(ux & 0x7fffffffffffffffull);
+    dd l = log2_dd(ax);
+    // |y * log2 x| beyond ~1100 is a certain overflow / underflow; clamp y*l.hi
+    // first so the double-double product cannot produce inf - inf.
+    double rough = dmul(pe.y, l.hi);
+    double r;
+    if (!(rough < 1100.0)) r = (double)INFINITY;
+    else if (!(rough > -1100.0)) r = 0.0;
+    else {
+        dd t = dd_mul_d(l, pe.y);
+        // y itself can be huge while l is tiny; the product above is exact to
+        // 2^-100 relative, fine.
+        r = exp2_from_dd(t);
+    }
+    return negate ? -r : r;
+}
+
+// ========================================================= the Op functors ===
+// DevOp<OP, T>::apply(a, b [, lane]) -- `lane` only matters for i32 pow.
+template<int OP, typename T> struct DevOp;
+
+template<> struct DevOp<OP_ADD, float> { static SMB_HD float apply(float a, float b) { return fadd(a, b); } };
+template<> struct DevOp<OP_SUB, float> { static SMB_HD float apply(float a, float b) { return fsub(a, b); } };
+template<> struct DevOp<OP_MUL, float> { static SMB_HD float apply(float a, float b) { return fmul(a, b); } };
+template<> struct DevOp<OP_DIV, float> {
+    static SMB_HD float apply(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fdiv_rn(a, b);
+#else
+        return a / b;
+#endif
+    }
+};
+template<> struct DevOp<OP_ADD, double> { static SMB_HD double apply(double a, double b) { return dadd(a, b); } };
+template<> struct DevOp<OP_SUB, double> { static SMB_HD double apply(double a, double b) { return dsub(a, b); } };
+template<> struct DevOp<OP_MUL, double> { static SMB_HD double apply(double a, double b) { return dmul(a, b); } };
+template<> struct DevOp<OP_DIV, double> {
+    static SMB_HD double apply(double a, double b) {
+#if defined(__CUDA_ARCH__)
+        return __ddiv_rn(a, b);
+#else
+        return a / b;
+#endif
+    }
+};
+template<> struct DevOp<OP_ADD, int32_t> { static SMB_HD int32_t apply(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); } };
+template<> struct DevOp<OP_SUB, int32_t> { static SMB_HD int32_t apply(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); } };
+template<> struct DevOp<OP_MUL, int32_t> { static SMB_HD int32_t apply(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); } };
+template<> struct DevOp<OP_DIV, int32_t> {
+    static SMB_HD int32_t apply(int32_t a, int32_t b) {
+        // /0 and INT_MIN/-1 are undefined in the reference (division.h:69); keep
+        // the host build of this header from trapping on them.
+#if !defined(__CUDA_ARCH__)
+        if (b == 0 || (a == (int32_t)0x80000000u && b == -1)) return 0;
+#endif
+        return a / b;
+    }
+};
+// array ^ array pow (README.md:119-133 recipe): per-element exponent.
+template<> struct DevOp<OP_POW, float> {
+    static SMB_HD float apply(float a, float b) { return pow_f32(a, classify_exp(b)); }
+};
+template<> struct DevOp<OP_POW, double> {
+    static SMB_HD double apply(double a, double b) { return pow_f64(a, classify_exp(b)); }
+};
+template<> struct DevOp<OP_POW, int32_t> {
+    static SMB_HD int32_t apply(int32_t a, int32_t b) { return powi_scalar(a, b); }
+    static SMB_HD int32_t apply_lane(int32_t a, int32_t b) { return powi_lane(a, b); }
+};
+
+} // namespace smb

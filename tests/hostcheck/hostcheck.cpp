@@ -1,0 +1,31 @@
+// hostcheck.cpp -- TEST ARTEFACT: compiles the device math header
+// (simplemath_b200/csrc/smb_math.cuh) for the host so the pow / powi bodies can
+// be swept for accuracy on the CPU-only build container.  Built into
+// tests/hostcheck/libsmb_hostcheck.so by __graft_entry__.build(); never linked
+// into libsmb200.so -- the product has no host execution path.
+#include "../../simplemath_b200/csrc/smb_math.cuh"
+#include <cstdint>
+using namespace smb;
+extern "C" {
+void hc_pow_f32(const float *x, float y, uint64_t n, float *out) {
+    PowExpF32 pe = classify_exp(y);
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = pow_f32(x[i], pe);
+}
+void hc_pow_f32_pair(const float *x, const float *y, uint64_t n, float *out) {
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = DevOp<OP_POW, float>::apply(x[i], y[i]);
+}
+void hc_pow_f64(const double *x, double y, uint64_t n, double *out) {
+    PowExpF64 pe = classify_exp(y);
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = pow_f64(x[i], pe);
+}
+void hc_pow_f64_pair(const double *x, const double *y, uint64_t n, double *out) {
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = DevOp<OP_POW, double>::apply(x[i], y[i]);
+}
+void hc_powi(const int32_t *b, const int32_t *e, uint64_t n, int lane, int32_t *out) {
+    for (uint64_t i = 0; i < n; ++i) out[i] = lane ? powi_lane(b[i], e[i]) : powi_scalar(b[i], e[i]);
+}
+}
