@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement (BASELINE.json metric, config C5).
+
+Workload "C5": float32, n = 2^30 elements (4 GiB per array), contiguous:
+    step = { out = a + b            (element_wise_op<float, AddOp>,   12 B/elem)
+             pw  = pow(x, 2.5)      (sm::pow -> array_scalar_op<PowOp>, 8 B/elem,
+                                     general exp2(y*log2 x) kernel) }
+sharded across the N GPUs by flat output index range (rank g owns
+shard_range(n, g, N)); no collective on the data path.  Total work is fixed as N
+grows -> "scaling": "strong".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]       this repo's CUDA path
+    python bench.py --impl reference ...                      the reference's own CPU
+                                                              implementation (oracle/_ref)
+
+For N > 1 the driver launches one rank per GPU with torch.distributed.run.
+Rank 0 prints ONE JSON line.  `value` = algorithmic GB/s of the whole job with
+inputs resident in HBM; `e2e` = the same metric through the C ABI with pinned
+HOST buffers (H2D + D2H inside the timed region); `roofline` = the dominant
+kernel (contiguous add) timed alone with CUDA events against the measured HBM
+peak; `cpu_baseline` = the compiled reference timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "elementwise algorithmic GB/s, f32 add + pow on 4 GiB arrays (C5)"
+UNIT = "GB/s"
+N_TOTAL = 1 << 30
+POW_Y = 2.5
+ADD_BYTES_PER_ELEM = 12  # 2 reads + 1 write  
+POW_BYTES_PER_ELEM = 8   # 1 read + 1 write
+L2_BYTES = 126 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="smb200", choices=["smb200", "reference"])
+    ap.add_argument("--elems", type=int, default=N_TOTAL, help="total elements (default 2^30 = config C5)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-elems", type=int, default=1 << 26, help="bounded CPU sample (elements)")
+    return ap.parse_args()
+
+
+def measured_peak():
+    """HBM roofline denominator: MEASURED_PEAKS.json (driver-written), else the
+    profiling recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json: torch copy_ 1 Gi bf16)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during a timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------ reference arm
+def cpu_reference(elems: int, steps: int, warmup: int):
+    """The reference's own CPU implementation of the step (SMArray operator+ and
+    sm::pow as shipped, incl. the per-call result new[]), all host threads."""
+    import numpy as np
+    import oracle
+    ref = oracle.reference()
+    kind = "reference"
+    if ref is None:  # oracle/_ref never built: fall back to the C restatement
+        ref, kind = oracle.c_oracle(), "port"
+    orc = oracle.c_oracle()
+    a = orc.fill_uniform_f32(0, elems, 1, -1.0, 1.0)
+    b = orc.fill_uniform_f32(0, elems, 2, -1.0, 1.0)
+    x = orc.fill_uniform_f32(0, elems, 3, 0.01, 100.0)
+    cores = ref.threads() if kind == "reference" else (os.cpu_count() or 1)
+
+    def step():
+        if kind == "reference":
+            ref.smarray_binary("add", a, b, want_result=False)
+            ref.smarray_scalar("pow", x, POW_Y, want_result=False)
+        else:
+            ref.elementwise("add", a, [1], b, [1], [elems])
+            ref.array_scalar("pow", x, POW_Y)
+
+    for _ in range(warmup):
+        step()
+    t_add = t_pow = 0.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    # per-op split (one extra pass each)
+    t1 = time.perf_counter()
+    if kind == "reference":
+        ref.smarray_binary("add", a, b, want_result=False)
+    else:
+        ref.elementwise("add", a, [1], b, [1], [elems])
+    t_add = time.perf_counter() - t1
+    t_pow = max(dt - t_add, 0.0)
+    bytes_step = elems * (ADD_BYTES_PER_ELEM + POW_BYTES_PER_ELEM)
+    return {
+        "value": bytes_step / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+        "sample": f"{elems} f32 elements per array ({elems / N_TOTAL:.4g} of C5), {steps} steps, operators as shipped "
+                  f"(alloc included); add runs the reference's single-threaded contiguous path (calculate.h:101-134), "
+                  f"pow its OpenMP array_scalar_op with libm powf",
+        "ms_per_step": dt * 1e3, "add_gbs": elems * ADD_BYTES_PER_ELEM / max(t_add, 1e-9) / 1e9,
+        "pow_gbs": elems * POW_BYTES_PER_ELEM / max(t_pow, 1e-9) / 1e9,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference(args.cpu_elems, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C5: f32 add + pow(x,2.5), contiguous; bounded CPU sample of the 2^30-element job",
+                   "elements": args.cpu_elems, "pow_exponent": POW_Y},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ops": {"add_gbs": res["add_gbs"], "pow_gbs": res["pow_gbs"]},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------ our arm
+def run_smb(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import simplemath_b200 as smb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the smb200 arm has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local)
+    smb.lib().smb_set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.elems
+    lo, hi = smb.shard_range(n, rank, world, align=4096)
+    m = hi - lo  # this rank's shard
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    a = torch.empty(m, dtype=torch.float32, device=dev)
+    b = torch.empty(m, dtype=torch.float32, device=dev)
+    x = torch.empty(m, dtype=torch.float32, device=dev)
+    out = torch.empty(m, dtype=torch.float32, device=dev)
+    pw = torch.empty(m, dtype=torch.float32, device=dev)
+    # counter-based generator of the FLAT index: every rank produces exactly its slice of the global arrays
+    smb.fill_uniform_f32_ptr(a.data_ptr(), lo, m, 1, -1.0, 1.0, sp)
+    smb.fill_uniform_f32_ptr(b.data_ptr(), lo, m, 2, -1.0, 1.0, sp)
+    smb.fill_uniform_f32_ptr(x.data_ptr(), lo, m, 3, 0.01, 100.0, sp)
+    smb.set_option(smb.OPT_POW_SPECIALISE, 0)  # headline = the general pow kernel
+
+    def step():
+        smb.contiguous_ptr(smb.OP_ADD, smb.F32, a.data_ptr(), b.data_ptr(), out.data_ptr(), m, sp)
+        smb.array_scalar_ptr(smb.OP_POW, smb.F32, x.data_ptr(), POW_Y, m, pw.data_ptr(), sp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1)  # ms, on the launching stream
+
+    def max_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = smb.launch_count()
+    ms_total = timed(step, args.steps)
+    launches = smb.launch_count() - l0
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    bytes_step_all = n * (ADD_BYTES_PER_ELEM + POW_BYTES_PER_ELEM)
+    value = bytes_step_all / (ms_step * 1e-3) / 1e9
+
+    # ---- per-kernel timing (each kernel alone, CUDA events on its stream) -> roofline
+    def add_only():
+        smb.contiguous_ptr(smb.OP_ADD, smb.F32, a.data_ptr(), b.data_ptr(), out.data_ptr(), m, sp)
+
+    def pow_only():
+        smb.array_scalar_ptr(smb.OP_POW, smb.F32, x.data_ptr(), POW_Y, m, pw.data_ptr(), sp)
+
+    reps = max(args.steps, 10)
+    add_only(); pow_only()
+    barrier()
+    ms_add = max_ranks(timed(add_only, reps)) / reps
+    barrier()
+    ms_pow = max_ranks(timed(pow_only, reps)) / reps
+    barrier()
+    peak, peak_src = measured_peak()
+    add_bytes_launch = m * ADD_BYTES_PER_ELEM   # algorithmic bytes one launch (this rank) moves
+    pow_bytes_launch = m * POW_BYTES_PER_ELEM
+    add_gbs = add_bytes_launch / (ms_add * 1e-3) / 1e9
+    pow_gbs = pow_bytes_launch / (ms_pow * 1e-3) / 1e9
+    traffic = ncu_traffic() or {}
+    roofline = {"bound": "hbm", "kernel": "k_stream<float, BinaryFn<ADD>> (contiguous add)", "achieved": add_gbs,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": add_gbs / peak,
+                "frac_of_nominal_8000": add_gbs / 8000.0,
+                "algorithmic_bytes_per_launch": add_bytes_launch, "ms_per_launch": ms_add,
+                "traffic": traffic.get("add_dram_bytes_per_launch")}
+    roofline_pow = {"bound": "hbm", "kernel": "k_stream<float, ScalarFn<POW>> (pow y=2.5, general)", "achieved": pow_gbs,
+                    "peak": peak, "unit": "GB/s", "frac": pow_gbs / peak, "frac_of_nominal_8000": pow_gbs / 8000.0,
+                    "algorithmic_bytes_per_launch": pow_bytes_launch, "ms_per_launch": ms_pow,
+                    "traffic": traffic.get("pow_dram_bytes_per_launch")}
+
+    # ---- extra pow variants (reference benchmark exponent y=2; specialised form)
+    extras = {}
+
+    def pow_y(yv, spec):
+        smb.set_option(smb.OPT_POW_SPECIALISE, spec)
+        fn = lambda: smb.array_scalar_ptr(smb.OP_POW, smb.F32, x.data_ptr(), yv, m, pw.data_ptr(), sp)
+        fn()
+        barrier()
+        ms = max_ranks(timed(fn, reps)) / reps
+        smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+        return pow_bytes_launch / (ms * 1e-3) / 1e9
+    extras["pow_y2_general_gbs_per_gpu"] = pow_y(2.0, 0)
+    extras["pow_y2_specialised_gbs_per_gpu"] = pow_y(2.0, 1)
+
+    # ---- verification (outside every timed region): windows vs the oracle on rank 0,
+    # per-shard checksums all-gathered over NCCL
+    ok = True
+    checksum = int(out.view(torch.int32).to(torch.int64).sum().item()) ^ int(pw.view(torch.int32).to(torch.int64).sum().item())
+    sums = [checksum]
+    if world > 1:
+        t = torch.tensor([checksum], dtype=torch.int64, device=dev)
+        allc = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allc, t)
+        sums = [int(c.item()) for c in allc]
+    if rank == 0:
+        try:
+            import oracle
+            orc = oracle.c_oracle()
+            w = min(1 << 18, m)
+            for start in (0, max(0, m - w)):
+                ha, hb = orc.fill_uniform_f32(lo + start, w, 1, -1.0, 1.0), orc.fill_uniform_f32(lo + start, w, 2, -1.0, 1.0)
+                hx = orc.fill_uniform_f32(lo + start, w, 3, 0.01, 100.0)
+                ok &= bool(np.array_equal(out[start:start + w].cpu().numpy(), orc.elementwise("add", ha, [1], hb, [1], [w])))
+                err = oracle.ulp_error_f32(pw[start:start + w].cpu().numpy(), orc.pow_ref_f32(hx, POW_Y))
+                ok &= bool(err.max() <= 1.0)
+        except Exception as e:  # the oracle is a checker; its absence must not hide the measurement
+            ok = f"not checked: {e}"
+
+    # ---- e2e: the same step through the C ABI with pinned HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        lib = smb.lib()
+        nbytes = m * 4
+        hp = [lib.smb_alloc(nbytes, smb.MEM_PINNED) for _ in range(5)]
+        if all(hp):
+            ha, hb, hx, hout, hpw = hp
+            def host_view(ptr):
+                return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(m,))
+            for dst, src in ((ha, a), (hb, b), (hx, x)):
+                torch.from_numpy(host_view(dst)).copy_(src)  # D2H, outside the timed region
+
+            def e2e_step():
+                # host operands: the library stages H2D -> kernel -> D2H in overlapped slabs and
+                # returns when the result is in host memory
+                smb.contiguous_ptr(smb.OP_ADD, smb.F32, ha, hb, hout, m)
+                smb.array_scalar_ptr(smb.OP_POW, smb.F32, hx, POW_Y, m, hpw)
+            e2e_step()
+            barrier()
+            l1 = smb.launch_count()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) * 1e3
+            e2e_launches = smb.launch_count() - l1
+            barrier()
+            dt = max_ranks(dt) / args.e2e_steps
+            # spot-check the host result
+            hres = host_view(hout)
+            e2e_ok = bool(np.array_equal(hres[:4096], out[:4096].cpu().numpy()))
+            e2e = {"value": bytes_step_all / (dt * 1e-3) / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": 3 * nbytes * 1, "d2h_bytes_per_step": 2 * nbytes,
+                   "ms_per_step": dt, "steps": args.e2e_steps, "launches_per_step": e2e_launches / args.e2e_steps,
+                   "bytes_are": "per rank", "timer": "host perf_counter around synchronous C-ABI calls, max over ranks",
+                   "result_checked": e2e_ok}
+            for p in hp:
+                lib.smb_free(p)
+        else:
+            e2e = {"value": None, "unit": UNIT, "error": "pinned host allocation failed"}
+            for p in hp:
+                if p:
+                    lib.smb_free(p)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            r = cpu_reference(args.cpu_elems, 5, 1)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu["add_gbs"], cpu["pow_gbs"] = r["add_gbs"], r["pow_gbs"]
+        except Exception as e:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "C5: f32 contiguous add (a+b) + pow(x, 2.5) on 2^30-element (4 GiB) arrays, sharded by "
+                                   "flat output index range", "elements": n, "elements_per_gpu": m, "pow_exponent": POW_Y,
+                       "pow_kernel": "general exp2(y*log2 x), specialisation off", "parallelism": f"flat-range shards x{world}",
+                       "l2": f"inputs larger than L2 ({m * 4 >> 20} MiB per array per GPU vs 126 MiB L2)",
+                       "inputs": "splitmix64 counter generator of the flat index, produced in HBM"},
+            "elements_per_s": n / (ms_step * 1e-3),
+            "frac_hbm_measured": value / world / peak, "frac_hbm_nominal_8000": value / world / 8000.0,
+            "roofline": roofline, "roofline_pow": roofline_pow, "ops": extras,
+            "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "verified": ok, "shard_checksums": sums,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_smb(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,6 @@
+// sm/sm.h -- umbrella header, drop-in for the reference's include/sm.h:2-3.
+// Build user code with  -I<repo>/include -I<repo>/include/sm  and link
+// -L<repo>/simplemath_b200 -lsmb200.
+#pragma once
+#include "SMArray.h"
+#include "UserFunctions.h"

@@ -1,0 +1,177 @@
+// dropin_test.cpp -- C++ acceptance test of the drop-in headers (include/sm/)
+// over libsmb200.so.  Written against the reference's PUBLIC API only, in the
+// style of its own tests (tests/add.cpp ... tests/pow.cpp), and covering what
+// those tests leave unpinned: non-trivial float values,
+// scalar-operand operators, transposed operands, scalar ops on views, rank 6,
+// float/double pow, the pool allocator.  Expected values come from plain scalar
+// C++ (the definition of Op::apply) evaluated here on the host.
+#include <gtest/gtest.h>
+#include <cmath>
+#include <cstdint>
+#include <random>
+#include "sm.h"
+
+namespace {
+template<typename T> T urand(std::mt19937 &g, double lo, double hi) {
+    return static_cast<T>(std::uniform_real_distribution<double>(lo, hi)(g));
+}
+} // namespace
+
+TEST(DropIn, ContiguousFloatOpsBitExact) {
+    std::mt19937 g(1);
+    const int n = 100003; // odd length: vector body + ragged tail
+    auto a = sm::empty<float>(n);
+    auto b = sm::empty<float>(n);
+    for (int i = 0; i < n; ++i) { a.data[i] = urand<float>(g, -1e3, 1e3); b.data[i] = urand<float>(g, 0.1, 7.0); }
+    auto s = a + b; auto d = a - b; auto m = a * b; auto q = a / b;
+    for (int i = 0; i < n; ++i) {
+        volatile float x = a.data[i], y = b.data[i];
+        volatile float es = x + y, ed = x - y, em = x * y, eq = x / y;
+        ASSERT_EQ(s.data[i], es); ASSERT_EQ(d.data[i], ed); ASSERT_EQ(m.data[i], em); ASSERT_EQ(q.data[i], eq);
+    }
+}
+
+TEST(DropIn, ScalarOperandOperators) {
+    auto a = sm::empty<double>(4, 5);
+    for (size_t i = 0; i < a.totalSize; ++i) a.data[i] = 0.37 * double(i) - 3.0;
+    auto r1 = a + 1.5; auto r2 = a - 1.5; auto r3 = a * 1.5; auto r4 = a / 1.5;
+    for (size_t i = 0; i < a.totalSize; ++i) {
+        EXPECT_EQ(r1.data[i], a.data[i] + 1.5); EXPECT_EQ(r2.data[i], a.data[i] - 1.5);
+        EXPECT_EQ(r3.data[i], a.data[i] * 1.5); EXPECT_EQ(r4.data[i], a.data[i] / 1.5);
+    }
+    std::vector<size_t> want = {4, 5};
+    EXPECT_EQ(r1.shape(), want);
+}
+
+TEST(DropIn, IntWrapAndTruncation) {
+    sm::SMArray<int> a = {2147483647, -2147483647 - 1, 7, -7, 100000, -100000};
+    sm::SMArray<int> b = {1, -1, 2, 2, 100000, 3};
+    auto s = a + b; auto m = a * b; auto q = a / sm::SMArray<int>{3, 5, 2, 2, -7, 3};
+    EXPECT_EQ(s(0), -2147483647 - 1); EXPECT_EQ(s(1), 2147483647);
+    EXPECT_EQ(m(4), (int) (uint32_t) (100000u * 100000u)); EXPECT_EQ(m(5), -300000);
+    EXPECT_EQ(q(2), 3); EXPECT_EQ(q(3), -3); EXPECT_EQ(q(4), -14285); EXPECT_EQ(q(5), -33333);
+}
+
+TEST(DropIn, RowColumnAndOuterBroadcast) {
+    const size_t R = 37, C = 52;
+    auto a = sm::empty<float>(R, C);
+    auto row = sm::empty<float>(1, C);
+    auto col = sm::empty<float>(R, 1);
+    for (size_t i = 0; i < R; ++i) for (size_t j = 0; j < C; ++j) a(i, j) = float(i) * 0.5f - float(j) * 0.25f;
+    for (size_t j = 0; j < C; ++j) row(0, j) = float(j) + 0.125f;
+    for (size_t i = 0; i < R; ++i) col(i, 0) = 3.0f - float(i);
+    auto r1 = a + row; auto r2 = a * col; auto r3 = col - row;
+    std::vector<size_t> want = {R, C};
+    EXPECT_EQ(r3.shape(), want);
+    for (size_t i = 0; i < R; ++i)
+        for (size_t j = 0; j < C; ++j) {
+            ASSERT_EQ(r1(i, j), a(i, j) + row(0, j));
+            ASSERT_EQ(r2(i, j), a(i, j) * col(i, 0));
+            ASSERT_EQ(r3(i, j), col(i, 0) - row(0, j));
+        }
+}
+
+TEST(DropIn, RankSixAndRankPadding) {
+    auto a = sm::empty<int>(2, 3, 2, 3, 2, 3);
+    auto b = sm::empty<int>(3, 1, 3);
+    for (size_t i = 0; i < a.totalSize; ++i) a.data[i] = int(i);
+    for (size_t i = 0; i < b.totalSize; ++i) b.data[i] = int(i) * 1000;
+    auto r = a + b;
+    EXPECT_EQ(r.totalSize, a.totalSize);
+    for (size_t i0 = 0; i0 < 2; ++i0) for (size_t i1 = 0; i1 < 3; ++i1) for (size_t i2 = 0; i2 < 2; ++i2)
+        for (size_t i3 = 0; i3 < 3; ++i3) for (size_t i4 = 0; i4 < 2; ++i4) for (size_t i5 = 0; i5 < 3; ++i5)
+            ASSERT_EQ(r(i0, i1, i2, i3, i4, i5), a(i0, i1, i2, i3, i4, i5) + b(i3, 0, i5));
+}
+
+TEST(DropIn, TransposedOperandAndViews) {
+    auto a = sm::empty<float>(6, 4);
+    auto b = sm::empty<float>(4, 6);
+    for (size_t i = 0; i < 24; ++i) { a.data[i] = float(i); b.data[i] = float(100 + i); }
+    auto at = a.transpose();                // shape {4,6}, strides {1,4}
+    auto r = at + b;
+    for (size_t i = 0; i < 4; ++i) for (size_t j = 0; j < 6; ++j) ASSERT_EQ(r(i, j), a(j, i) + b(i, j));
+    // interior-pointer view of a larger block, scalar op on the (non-dense) view
+    auto big = sm::empty<float>(5, 6, 7);
+    for (size_t i = 0; i < big.totalSize; ++i) big.data[i] = float(i) * 0.5f;
+    auto v = big(2, SLICE_ALL);             // shape {6,7}, base pointer inside big
+    auto w = v * 3.0f;
+    for (size_t i = 0; i < 6; ++i) for (size_t j = 0; j < 7; ++j) ASSERT_EQ(w(i, j), big(2, i, j) * 3.0f);
+    auto vt = v.transpose() + 1.0f;         // strided view (op) scalar honours strides
+    for (size_t i = 0; i < 7; ++i) for (size_t j = 0; j < 6; ++j) ASSERT_EQ(vt(i, j), big(2, j, i) + 1.0f);
+}
+
+TEST(DropIn, FloatPowWithinOneUlpOfStdPowInDouble) {
+    std::mt19937 g(3);
+    auto a = sm::empty<float>(300, 211);
+    for (size_t i = 0; i < a.totalSize; ++i) a.data[i] = urand<float>(g, 0.01, 100.0);
+    for (float y: {2.0f, 2.5f, -1.0f, 0.5f, 3.0f, -0.3333f, 7.25f}) {
+        auto r = sm::pow(a, y);
+        for (size_t i = 0; i < a.totalSize; ++i) {
+            const double want = std::pow(double(a.data[i]), double(y));
+            const float w32 = float(want);
+            const double ulp = std::fabs(double(std::nextafter(w32, INFINITY)) - double(w32));
+            ASSERT_TRUE(std::fabs(double(r.data[i]) - want) <= 1.0 * ulp);
+        }
+    }
+}
+
+TEST(DropIn, DoublePowWithinOneUlpOfPowl) {
+    std::mt19937 g(4);
+    auto a = sm::empty<double>(20000);
+    for (size_t i = 0; i < a.totalSize; ++i) a.data[i] = urand<double>(g, 0.01, 100.0);
+    for (double y: {2.0, 2.5, -1.0, 0.5, 1.0 / 3.0, 11.0}) {
+        auto r = sm::pow(a, y);
+        for (size_t i = 0; i < a.totalSize; ++i) {
+            const long double want = powl((long double) a.data[i], (long double) y);
+            const double w = double(want);
+            const double ulp = std::nextafter(w, INFINITY) - w;
+            ASSERT_TRUE(fabsl((long double) r.data[i] - want) <= 1.0L * ulp);
+        }
+    }
+}
+
+TEST(DropIn, PowSpecialValues) {
+    sm::SMArray<float> x = {0.0f, -0.0f, 1.0f, -1.0f, -8.0f, INFINITY, -INFINITY, NAN, 4.0f};
+    auto p0 = sm::pow(x, 0.0f);
+    for (int i = 0; i < 9; ++i) EXPECT_EQ(p0(i), 1.0f);                 // x^0 == 1, even NaN^0
+    auto p3 = sm::pow(x, 3.0f);
+    EXPECT_EQ(p3(4), -512.0f); EXPECT_EQ(p3(6), -INFINITY); EXPECT_TRUE(std::isnan(p3(7)));
+    EXPECT_TRUE(std::signbit(p3(1)) && p3(1) == 0.0f);                   // (-0)^3 == -0
+    auto ph = sm::pow(x, 0.5f);
+    EXPECT_TRUE(std::isnan(ph(3)) && std::isnan(ph(4)));                 // negative ^ non-integer
+    EXPECT_EQ(ph(8), 2.0f); EXPECT_EQ(ph(6), INFINITY); EXPECT_TRUE(!std::signbit(ph(1)));
+    auto pm = sm::pow(x, -1.0f);
+    EXPECT_EQ(pm(0), INFINITY); EXPECT_EQ(pm(1), -INFINITY); EXPECT_EQ(pm(8), 0.25f);
+    auto pn = sm::pow(x, -2.5f);
+    EXPECT_EQ(pn(0), INFINITY); EXPECT_EQ(pn(5), 0.0f); EXPECT_EQ(pn(8), 0.03125f);
+}
+
+TEST(DropIn, IncompatibleShapesThrowLikeTheReference) {
+    sm::SMArray<float> a = {{1, 2, 3}, {4, 5, 6}};
+    sm::SMArray<float> b = {{1, 2}, {3, 4}};
+    bool threw = false;
+    try { auto r = a + b; (void) r; } catch (const std::runtime_error &e) {
+        threw = std::string(e.what()) == "Cannot broadcast shapes: incompatible dimensions";
+    }
+    EXPECT_TRUE(threw);
+}
+
+TEST(DropIn, ResultBlocksComeFromThePool) {
+    auto a = sm::ones<float>(1000000);
+    auto b = sm::ones<float>(1000000);
+    uint64_t before[4], after[4];
+    { auto warm = a + b; (void) warm; }
+    smb_pool_stats(before);
+    for (int i = 0; i < 50; ++i) { auto r = a + b; ASSERT_EQ(r.data[i], 2.0f); }
+    smb_pool_stats(after);
+    EXPECT_EQ(after[2], before[2]);          // no new driver allocations: million_check reuses one block
+    EXPECT_TRUE(after[3] >= before[3] + 50); // every iteration was a pool hit
+}
+
+TEST(DropIn, AdoptedForeignBlockIsAcceptedAndReleased) {
+    float *raw = new float[64];
+    for (int i = 0; i < 64; ++i) raw[i] = float(i);
+    sm::SMArray<float> a(raw, {8, 8});      // plain new[] memory, as reference user code may pass
+    auto r = a + a;
+    for (int i = 0; i < 64; ++i) ASSERT_EQ(r.data[i], 2.0f * float(i));
+}

@@ -1,0 +1,31 @@
+"""Drop-in acceptance on the GPU box: the reference's own tests/*.cpp, compiled
+UNMODIFIED against include/sm + libsmb200.so (binaries prebuilt by
+__graft_entry__.build() where /root/reference exists), plus this repo's own C++
+acceptance test.  All 32 reference tests must pass on the CUDA path."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "tests", "dropin", "bin")
+
+
+def _run(name):
+    path = os.path.join(BIN, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} was not prebuilt")
+    r = subprocess.run([path], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return int(r.stdout.strip().splitlines()[-1].split()[0])
+
+
+def test_reference_tests_pass_on_the_drop_in_headers():
+    total = sum(_run(f"ref_{t}") for t in ("add", "subtract", "multiply", "division", "pow"))
+    assert total == 32
+
+
+def test_own_cpp_acceptance():
+    assert _run("dropin_test") >= 12

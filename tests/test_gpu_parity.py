@@ -1,0 +1,401 @@
+"""Parity tests proper (need a B200): the CUDA path, called through the C ABI,
+against the oracle / golden vectors.
+
+Bars: bit-exact for int32 and for float/double + - * /; float/double pow within
+the stated ULP bound of std::pow computed in higher precision
+(f32 <= 1 ULP vs double, f64 <= 1 ULP vs long double).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+import simplemath_b200 as smb
+from conftest import assert_same_bits
+
+pytestmark = pytest.mark.gpu
+
+F32_POW_ULP_BOUND = 1.0
+F64_POW_ULP_BOUND = 1.0
+
+
+def _pow_close(got, a, y, dtype, orc):
+    if dtype == np.float32:
+        yv = np.asarray(y, np.float32)
+        if yv.ndim == 0:
+            err = oracle.ulp_error_f32(got.ravel(), orc.pow_ref_f32(a.ravel(), float(yv)))
+        else:
+            with np.errstate(all="ignore"):
+                ref = np.power(a.astype(np.float64), np.broadcast_to(yv, got.shape).astype(np.float64))
+            err = oracle.ulp_error_f32(got.ravel(), np.broadcast_to(ref, got.shape).ravel())
+        return err.max() <= F32_POW_ULP_BOUND, err.max()
+    yv = np.asarray(y, np.float64)
+    if yv.ndim == 0:
+        hi, lo = orc.pow_ref_f64(a.ravel(), float(yv))
+        err = oracle.ulp_error_f64(got.ravel(), hi, lo)
+        return err.max() <= F64_POW_ULP_BOUND, err.max()
+    ref = np.power(np.broadcast_to(a, got.shape).astype(np.longdouble), np.broadcast_to(yv, got.shape).astype(np.longdouble))
+    err = np.abs((got.astype(np.longdouble) - ref) / np.spacing(np.abs(ref.astype(np.float64)))).astype(np.float64)
+    return err.max() <= F64_POW_ULP_BOUND + 0.5, err.max()
+
+
+def test_every_golden_vector_through_the_c_abi(golden, orc):
+    """All committed fixtures (produced by the unmodified reference)."""
+    for c in golden.cases:
+        a, b = c["a"], c["b"]
+        es = a.dtype.itemsize
+        dt = smb.dtype_code(a.dtype)
+        out = np.empty(c["out"].shape, a.dtype)
+        if c["kind"] == "elementwise":
+            smb.elementwise_ptr(smb.OPS[c["op"]], dt, a.ctypes.data, c["sa"], b.ctypes.data, c["sb"], c["shape"], out.ctypes.data)
+        else:
+            smb.array_scalar_ptr(smb.OPS[c["op"]], dt, a.ctypes.data, b[0].item(), a.size, out.ctypes.data)
+        what = f"golden case {c['idx']} ({c['kind']} {c['op']} {a.dtype})"
+        if c["op"] == "pow" and a.dtype.kind == "f":
+            if c["kind"] == "scalar":
+                ok, worst = _pow_close(out, a, b[0], a.dtype.type, orc)
+            else:
+                av = np.lib.stride_tricks.as_strided(a, c["shape"], [s * es for s in c["sa"]])
+                bv = np.lib.stride_tricks.as_strided(b, c["shape"], [s * es for s in c["sb"]])
+                ok, worst = _pow_close(out, av, bv, a.dtype.type, orc)
+            assert ok, (what, worst)
+        else:
+            assert_same_bits(out, c["out"], what)
+
+
+SHAPES = [((1,), (1,)), ((1000,), (1000,)), ((100_003,), (100_003,)), ((33, 65), (1, 65)), ((33, 65), (33, 1)),
+          ((33, 1), (1, 65)), ((12, 1, 40), (1, 9, 40)), ((5, 6, 7, 3), (1, 6, 1, 3)), ((2, 3, 4, 5, 6, 7), (2, 1, 4, 1, 6, 1)),
+          ((400, 300), (300,)), ((64, 1024), (64, 1024)), ((3, 1, 4, 1, 5), (2, 1, 6, 1)), ((257, 129), (257, 129))]
+
+
+def _operands(rng, dtype, op, s1, s2):
+    if dtype == np.int32:
+        lo, hi = (-2**31, 2**31) if op in ("add", "sub", "mul") else (-1000, 1001)
+        a = rng.integers(lo, hi, size=s1, dtype=np.int64).astype(np.int32)
+        if op == "div":
+            b = (rng.integers(1, 98, size=s2) * rng.choice([-1, 1], size=s2)).astype(np.int32)
+        elif op == "pow":
+            a = rng.integers(-12, 13, size=s1).astype(np.int32)
+            b = rng.integers(-4, 34, size=s2).astype(np.int32)
+        else:
+            b = rng.integers(lo, hi, size=s2, dtype=np.int64).astype(np.int32)
+        return a, b
+    if op == "pow":
+        return rng.uniform(0.01, 50, size=s1).astype(dtype), rng.uniform(-4, 4, size=s2).astype(dtype)
+    a = (rng.standard_normal(s1) * 10.0 ** rng.integers(-30, 30, size=s1)).astype(dtype)
+    b = (rng.standard_normal(s2) * 10.0 ** rng.integers(-30, 30, size=s2)).astype(dtype)
+    return a, b
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32])
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div", "pow"])
+def test_random_broadcast_vs_oracle(orc, dtype, op):
+    rng = np.random.default_rng(hash((op, np.dtype(dtype).name, 1)) % 2**32)
+    for s1, s2 in SHAPES:
+        a, b = _operands(rng, dtype, op, s1, s2)
+        got = smb.binary(op, a, b)
+        if op == "pow" and dtype != np.int32:
+            ok, worst = _pow_close(got, np.broadcast_to(a, got.shape), np.broadcast_to(b, got.shape), dtype, orc)
+            assert ok, (op, s1, s2, worst)
+        else:
+            assert_same_bits(got, orc.binary(op, a, b), f"{op} {np.dtype(dtype).name} {s1}x{s2} [{smb.last_kernel()}]")
+        v = b.ravel()[0].item()
+        got = smb.scalar(op, a, v)
+        if op == "pow" and dtype != np.int32:
+            ok, worst = _pow_close(got, a, np.asarray(v, dtype), dtype, orc)
+            assert ok, (op, s1, worst)
+        else:
+            assert_same_bits(got, orc.array_scalar(op, a, v), f"{op} scalar {np.dtype(dtype).name} {s1}")
+
+
+def test_views_interior_pointers_and_transposes(orc):
+    rng = np.random.default_rng(5)
+    big = rng.standard_normal((4, 30, 20, 3)).astype(np.float32)
+    small = rng.standard_normal((1, 30, 1, 3)).astype(np.float32)
+    for k in range(4):
+        v = big[k]                                   # interior pointer, parent strides
+        assert_same_bits(smb.binary("add", v, small), orc.binary("add", v, small), f"view {k}")
+    m = rng.standard_normal((37, 53)).astype(np.float32)
+    n = rng.standard_normal((53, 37)).astype(np.float32)
+    assert_same_bits(smb.binary("mul", m.T, n), orc.binary("mul", m.T, n), "transposed operand")
+    assert smb.last_kernel().startswith("k_generic")
+    w = rng.standard_normal((64, 100)).astype(np.float32)
+    sl = w[:, 3:67]                                  # misaligned rows: inner stride 1, odd base offset
+    assert_same_bits(smb.binary("sub", sl, sl), orc.binary("sub", sl, sl), "misaligned slice")
+    odd = rng.standard_normal(4099).astype(np.float32)
+    assert_same_bits(smb.binary("add", odd[1:], odd[:-1]), orc.binary("add", odd[1:], odd[:-1]), "operands misaligned differently")
+    assert_same_bits(smb.binary("add", odd[3:], odd[3:]), orc.binary("add", odd[3:], odd[3:]), "common misalignment (peeled head)")
+
+
+def test_reference_broadcast_test_shape(orc):
+    """tests/add.cpp:59-92 at full size: ones(32,224,224,3)(0, SLICE_ALL) + {1,224,1,3}."""
+    big = np.ones((2, 224, 224, 3), np.float32)
+    two = np.full((1, 224, 1, 3), 3, np.float32)
+    got = smb.binary("add", big[0], two)
+    assert got.shape == (1, 224, 224, 3)
+    assert_same_bits(got, np.full((1, 224, 224, 3), 4, np.float32))
+
+
+def test_reference_int_pow_tests(orc):
+    """tests/pow.cpp:46-99 through the C ABI."""
+    a = np.full(2_000_000, 5, np.int32)
+    assert_same_bits(smb.pow(a, 3), np.full(2_000_000, 125, np.int32))
+    alt = np.where(np.arange(5000) % 2 == 0, 5, -5).astype(np.int32)
+    assert_same_bits(smb.pow(alt, 3), (alt.astype(np.int64) ** 3).astype(np.int32))
+    assert_same_bits(smb.pow(alt, -2), np.zeros(5000, np.int32))
+
+
+def test_int_pow_lane_and_tail_semantics(orc):
+    bases = np.array([0, 1, -1, 2, -2, 3, -3, 5, -5, 7, 10, -10, 46340, 46341, -46341, 65536, 2**31 - 1, -2**31, 123, -77], np.int32)
+    for e in (0, 1, 2, 3, 5, 13, 20, 31, 32, 33, 62, -1, -2, -31, 2**31 - 1, -2**31):
+        for n in (1, 7, 8, 11, 16, 20, 1000, 1003):
+            a = np.resize(bases, n).astype(np.int32)
+            assert_same_bits(smb.pow(a, e), orc.array_scalar("pow", a, e), f"i32 pow e={e} n={n}")
+
+
+@pytest.mark.parametrize("y", [2.0, 2.5, 0.5, -1.0, 3.0, -2.5, 1 / 3, 17.0, 100.5, -77.7, 1e-3, 0.1])
+def test_pow_f32_ulp_general_kernel(orc, y):
+    rng = np.random.default_rng(int(abs(y) * 1000) % 2**31)
+    x = np.concatenate([rng.uniform(0.01, 100, 1 << 21).astype(np.float32),
+                        rng.integers(1, 0x7f800000, 1 << 21, dtype=np.uint32).view(np.float32)])
+    smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+    try:
+        got = smb.pow(x, y)
+    finally:
+        smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+    err = oracle.ulp_error_f32(got, orc.pow_ref_f32(x, y))
+    assert err.max() <= F32_POW_ULP_BOUND, (y, err.max(), x[err.argmax()], got[err.argmax()])
+    if y in (2.0, 0.5, -1.0):  # the specialised exact forms agree within the same bound
+        err = oracle.ulp_error_f32(smb.pow(x, y), orc.pow_ref_f32(x, y))
+        assert err.max() <= 0.5 + 1e-6, (y, err.max())
+
+
+@pytest.mark.parametrize("y", [2.0, 2.5, 0.5, -1.0, 1 / 3, 17.0, -77.7, 1e-3])
+def test_pow_f64_ulp_general_kernel(orc, y):
+    rng = np.random.default_rng(int(abs(y) * 1000) % 2**31 + 7)
+    x = np.concatenate([rng.uniform(0.01, 100, 1 << 19), rng.integers(1, 0x7ff0000000000000, 1 << 19, dtype=np.uint64).view(np.float64)])
+    smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+    try:
+        got = smb.pow(x, y)
+    finally:
+        smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+    hi, lo = orc.pow_ref_f64(x, y)
+    err = oracle.ulp_error_f64(got, hi, lo)
+    assert err.max() <= F64_POW_ULP_BOUND, (y, err.max(), x[err.argmax()])
+
+
+def test_pow_special_case_table_on_device(orc):
+    xs = np.array([0.0, -0.0, 1.0, -1.0, 2.0, -2.0, 0.5, -0.5, 3.0, -3.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 3.4e38,
+                   -3.4e38, 1.17549435e-38, 0.99999994, 1.0000001], np.float32)
+    ys = [0.0, -0.0, 1.0, -1.0, 2.0, -2.0, 3.0, -3.0, 0.5, -0.5, 2.5, -2.5, np.inf, -np.inf, np.nan, 1e30, -1e30, 16777216.0,
+          16777217.0, 4294967296.0, 1e-30, 127.0, -149.0, 1 / 3]
+    for spec in (0, 1):
+        smb.set_option(smb.OPT_POW_SPECIALISE, spec)
+        for y in ys:
+            got = smb.pow(xs, np.float32(y))
+            want64 = orc.pow_ref_f32(xs, float(np.float32(y)))
+            with np.errstate(all="ignore"):
+                want = want64.astype(np.float32)
+            for xi, g, w, w64 in zip(xs, got, want, want64):
+                if np.isnan(w):
+                    assert np.isnan(g), (xi, y, g)
+                elif np.isinf(w) or w == 0 or np.isinf(g) or g == 0:
+                    ok = g == w and np.signbit(g) == np.signbit(w)
+                    assert ok or oracle.ulp_error_f32(np.array([g]), np.array([w64]))[0] <= 1, (xi, y, g, w)
+                else:
+                    assert oracle.ulp_error_f32(np.array([g]), np.array([w64]))[0] <= 1, (xi, y, g, w)
+    smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+
+
+def test_float_specials_bit_exact(orc):
+    sp = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1.1754942e-38, 3.4028235e38, -3.4028235e38, 1.0, -1.5,
+                   5.9e-39, 1e-40], np.float32)
+    A, B = [np.ascontiguousarray(v.ravel()) for v in np.meshgrid(sp, sp, indexing="ij")]
+    for op in ("add", "sub", "mul", "div"):
+        assert_same_bits(smb.binary(op, A, B), orc.binary(op, A, B), f"f32 specials {op}")
+        assert_same_bits(smb.binary(op, A.astype(np.float64), B.astype(np.float64)),
+                         orc.binary(op, A.astype(np.float64), B.astype(np.float64)), f"f64 specials {op}")
+
+
+def test_empty_and_rejects():
+    e = np.empty((0, 5), np.float32)
+    assert smb.binary("add", e, np.ones((1, 5), np.float32)).shape == (0, 5)
+    assert smb.scalar("mul", np.empty(0, np.int32), 3).size == 0
+    with pytest.raises(smb.SmbError, match="Cannot broadcast"):
+        smb.binary("add", np.ones((2, 3), np.float32), np.ones((4, 3), np.float32))
+    with pytest.raises(smb.SmbError, match="unsupported element type"):
+        smb.binary("add", np.ones(4, np.int64), np.ones(4, np.int64))
+    with pytest.raises(smb.SmbError):
+        smb.elementwise_ptr(9, smb.F32, 0, [1], 0, [1], [4], 0)
+
+
+def test_staging_pipeline_many_chunks(orc):
+    """Host operands larger than the staging chunk: slabs overlap on 3 streams."""
+    rng = np.random.default_rng(9)
+    smb.set_option(smb.OPT_STAGE_CHUNK_BYTES, 1 << 16)
+    try:
+        a = rng.standard_normal((301, 1000)).astype(np.float32)
+        row = rng.standard_normal((1, 1000)).astype(np.float32)
+        col = rng.standard_normal((301, 1)).astype(np.float32)
+        assert_same_bits(smb.binary("add", a, a[::-1].copy()), orc.binary("add", a, a[::-1].copy()), "chunked contiguous")
+        assert_same_bits(smb.binary("mul", a, row), orc.binary("mul", a, row), "chunked row broadcast")
+        assert_same_bits(smb.binary("sub", col, row), orc.binary("sub", col, row), "chunked outer")
+        x = rng.integers(-9, 10, size=100_003).astype(np.int32)
+        assert_same_bits(smb.pow(x, 5), orc.array_scalar("pow", x, 5), "chunked i32 pow keeps lane/tail split")
+        ia = rng.integers(-1000, 1000, size=(40, 1, 256)).astype(np.int32)
+        ib = rng.integers(1, 98, size=(1, 50, 256)).astype(np.int32)
+        assert_same_bits(smb.binary("div", ia, ib), orc.binary("div", ia, ib), "chunked 3-D")
+    finally:
+        smb.set_option(smb.OPT_STAGE_CHUNK_BYTES, 64 << 20)
+
+
+# ---- device-resident operands (torch owns the memory; the C ABI gets raw addresses) ----
+def _torch():
+    import torch
+    return torch
+
+
+def test_device_pointers_and_flat_range_sharding(orc):
+    torch = _torch()
+    rng = np.random.default_rng(12)
+    a = rng.standard_normal((96, 1, 64)).astype(np.float32)
+    b = rng.standard_normal((1, 40, 64)).astype(np.float32)
+    want = orc.binary("mul", a, b).ravel()
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    shape, sa, sb, n = smb.broadcast(a.shape, smb.row_major_strides(a.shape), b.shape, smb.row_major_strides(b.shape))
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    smb.elementwise_ptr(smb.OP_MUL, smb.F32, da.data_ptr(), sa, db.data_ptr(), sb, shape, out.data_ptr())
+    assert_same_bits(out.cpu().numpy(), want, "device operands")
+    # the same result assembled from 1, 2, 3, 8 flat-range shards (multi-GPU unit of work)
+    for world in (1, 2, 3, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = smb.shard_range(n, r, world, align=256)
+            part = torch.empty(hi - lo, dtype=torch.float32, device="cuda")
+            smb.elementwise_range_ptr(smb.OP_MUL, smb.F32, da.data_ptr(), sa, db.data_ptr(), sb, shape, lo, hi - lo, part.data_ptr())
+            parts.append(part)
+        assert_same_bits(torch.cat(parts).cpu().numpy(), want, f"{world} shards")
+    # unaligned range boundaries fall back to the scalar row kernel
+    part = torch.empty(1001, dtype=torch.float32, device="cuda")
+    smb.elementwise_range_ptr(smb.OP_MUL, smb.F32, da.data_ptr(), sa, db.data_ptr(), sb, shape, 777, 1001, part.data_ptr())
+    assert_same_bits(part.cpu().numpy(), want[777:1778], "odd range")
+
+
+def test_async_stream_and_generator(orc):
+    torch = _torch()
+    n = 1 << 20
+    s = torch.cuda.Stream()
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    y = torch.empty(n, dtype=torch.float32, device="cuda")
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    smb.fill_uniform_f32_ptr(x.data_ptr(), 0, n, 1, -1.0, 1.0, s.cuda_stream)
+    smb.fill_uniform_f32_ptr(y.data_ptr(), 0, n, 2, -1.0, 1.0, s.cuda_stream)
+    smb.contiguous_ptr(smb.OP_ADD, smb.F32, x.data_ptr(), y.data_ptr(), out.data_ptr(), n, s.cuda_stream)
+    s.synchronize()
+    hx, hy = orc.fill_uniform_f32(0, n, 1, -1.0, 1.0), orc.fill_uniform_f32(0, n, 2, -1.0, 1.0)
+    assert_same_bits(x.cpu().numpy(), hx, "generator matches the oracle's")
+    assert_same_bits(out.cpu().numpy(), orc.elementwise("add", hx, [1], hy, [1], [n]), "async add")
+
+
+def test_pool_allocator_and_managed_memory(orc):
+    lib = smb.lib()
+    stats = (ctypes.c_uint64 * 4)()
+    p = lib.smb_alloc(1 << 20, smb.MEM_MANAGED)
+    assert p and lib.smb_owns(p) and lib.smb_owns(p + 4096) and not lib.smb_owns(p + (4 << 20))
+    n = (1 << 20) // 4
+    host = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_float)), shape=(n,))
+    host[:] = np.arange(n, dtype=np.float32)           # written through the host mapping
+    q = lib.smb_alloc(1 << 20, smb.MEM_MANAGED)
+    smb.array_scalar_ptr(smb.OP_MUL, smb.F32, p, 0.5, n, q)
+    res = np.ctypeslib.as_array(ctypes.cast(q, ctypes.POINTER(ctypes.c_float)), shape=(n,))
+    assert_same_bits(res.copy(), np.arange(n, dtype=np.float32) * np.float32(0.5), "managed in/out")
+    # interior pointer of a managed block as an operand (what a view hands over)
+    smb.array_scalar_ptr(smb.OP_ADD, smb.F32, p + 4 * 1000, 1.0, 5000, q)
+    assert_same_bits(res[:5000].copy(), np.arange(1000, 6000, dtype=np.float32) + 1, "interior pointer")
+    assert lib.smb_free(p) == 0 and lib.smb_free(q) == 0
+    lib.smb_pool_stats(stats)
+    calls = stats[2]
+    p2 = lib.smb_alloc(1 << 20, smb.MEM_MANAGED)       # recycled, no driver call
+    lib.smb_pool_stats(stats)
+    assert p2 in (p, q) and stats[2] == calls and stats[3] >= 1
+    lib.smb_free(p2)
+    assert lib.smb_free(12345) != 0                    # foreign pointer refused
+
+
+# ---- BASELINE.json configs at full size: oracle on samples + size-independent properties ----
+def test_config_c1_million_check(orc):
+    a = np.ones(1_000_000, np.float32)
+    assert_same_bits(smb.binary("add", a, a), np.full(1_000_000, 2, np.float32), "C1 as in benchmark/add.cpp:21-29")
+    rng = np.random.default_rng(1)
+    a, b = rng.uniform(-1, 1, 1_000_000).astype(np.float32), rng.uniform(-1, 1, 1_000_000).astype(np.float32)
+    assert_same_bits(smb.binary("add", a, b), orc.binary("add", a, b), "C1 random")
+
+
+def test_config_c2_row_broadcast_full(orc):
+    rng = np.random.default_rng(1)
+    a = rng.uniform(-1, 1, (4096, 4096)).astype(np.float32)
+    b = np.random.default_rng(2).uniform(-1, 1, (1, 4096)).astype(np.float32)
+    got = smb.binary("add", a, b)
+    assert smb.last_kernel().startswith("k_row<vec16")
+    assert_same_bits(got, orc.binary("add", a, b), "C2 full")
+
+
+def test_config_c4_int_3d_broadcast_full(orc):
+    torch = _torch()
+    rng = np.random.default_rng(4)
+    a = rng.integers(-1000, 1001, size=(512, 1, 1024)).astype(np.int32)
+    bm = rng.integers(-2**31, 2**31, size=(1, 512, 1024), dtype=np.int64).astype(np.int32)
+    bd = rng.integers(1, 98, size=(1, 512, 1024)).astype(np.int32)
+    shape, sa, sb, n = smb.broadcast(a.shape, smb.row_major_strides(a.shape), bm.shape, smb.row_major_strides(bm.shape))
+    assert n == 268435456
+    da = torch.from_numpy(a).cuda()
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    for op, b in ((smb.OP_MUL, bm), (smb.OP_DIV, bd)):
+        db = torch.from_numpy(b).cuda()
+        smb.elementwise_ptr(op, smb.I32, da.data_ptr(), sa, db.data_ptr(), sb, shape, out.data_ptr())
+        o3 = out.view(512, 512, 1024)
+        # sampled slabs against the oracle, bit-exact
+        for i in (0, 1, 255, 511):
+            want = orc.binary("mul" if op == smb.OP_MUL else "div", a[i:i + 1], b)
+            assert_same_bits(o3[i:i + 1].cpu().numpy(), want, f"C4 slab {i}")
+        # whole-output property: torch's own integer ops on the broadcast views agree everywhere
+        ta, tb = da.view(512, 1, 1024), db.view(1, 512, 1024)
+        ref = ta * tb if op == smb.OP_MUL else torch.div(ta, tb, rounding_mode="trunc")
+        assert bool((o3 == ref).all())
+        del ref
+
+
+def test_config_c3_c5_large_pow_and_add_properties(orc):
+    """256M-element f32 pow (C3) and 1 Gi-element add (C5 per-GPU at N=1 is 4 GiB
+    arrays): sampled windows against the oracle + linear-time whole-array
+    properties."""
+    torch = _torch()
+    n = 268_435_456
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    smb.fill_uniform_f32_ptr(x.data_ptr(), 0, n, 3, 0.01, 100.0)
+    smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+    try:
+        for y in (2.0, 2.5):
+            smb.array_scalar_ptr(smb.OP_POW, smb.F32, x.data_ptr(), y, n, out.data_ptr())
+            for start in (0, 123_456_789, n - (1 << 20)):
+                w = orc.fill_uniform_f32(start, 1 << 20, 3, 0.01, 100.0)
+                got = out[start:start + (1 << 20)].cpu().numpy()
+                err = oracle.ulp_error_f32(got, orc.pow_ref_f32(w, y))
+                assert err.max() <= F32_POW_ULP_BOUND, (y, start, err.max())
+            # monotone in x for y > 0: sorting inputs sorts outputs (whole array, on device)
+            idx = torch.argsort(x[: 1 << 24])
+            assert bool((out[: 1 << 24][idx].diff() >= 0).all())
+    finally:
+        smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+    # pow(x, 2) specialised == x*x exactly, everywhere
+    smb.array_scalar_ptr(smb.OP_POW, smb.F32, x.data_ptr(), 2.0, n, out.data_ptr())
+    assert bool((out == x * x).all())
+    # add: (a + b) - b' == exact torch result everywhere (same IEEE op), checksum of the whole output
+    y = torch.empty(n, dtype=torch.float32, device="cuda")
+    smb.fill_uniform_f32_ptr(y.data_ptr(), 0, n, 4, -1.0, 1.0)
+    smb.contiguous_ptr(smb.OP_ADD, smb.F32, x.data_ptr(), y.data_ptr(), out.data_ptr(), n)
+    assert bool((out == x + y).all())
+    w = orc.fill_uniform_f32(n - 4096, 4096, 3, 0.01, 100.0), orc.fill_uniform_f32(n - 4096, 4096, 4, -1.0, 1.0)
+    assert_same_bits(out[n - 4096:].cpu().numpy(), orc.elementwise("add", w[0], [1], w[1], [1], [4096]), "C5 add tail window")
