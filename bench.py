@@ -312,6 +312,8 @@ def run_smb(args):
     extras["pow_y2_general_gbs_per_gpu"] = pow_y(2.0, 0)
     extras["pow_y2_specialised_gbs_per_gpu"] = pow_y(2.0, 1)
 
+    step()  # leave out / pw holding the step's results for verification
+    torch.cuda.synchronize()
     # ---- verification (outside every timed region): windows vs the oracle on rank 0,
     # per-shard checksums all-gathered over NCCL
     ok = True

@@ -225,6 +225,10 @@ def binary(op, a: np.ndarray, b: np.ndarray) -> np.ndarray:
     if len(shape) > MAX_NDIM:
         raise SmbError(f"rank {len(shape)} > MAX_NDIM {MAX_NDIM}")
     out = np.empty(shape, dtype=a.dtype)
+    if total and (a.size == 0 or b.size == 0):
+        # sm::broadcast lets a 0-sized dim meet a 1 (result dim max(0,1) = 1, SMUtils.h:76-80) and the reference
+        # then reads element 0 of an empty block; refuse instead of reading out of bounds
+        raise SmbError("empty operand cannot be broadcast to a non-empty result")
     if total:
         elementwise_ptr(op, dt, a.ctypes.data, sa, b.ctypes.data, sb, shape, out.ctypes.data)
     return out

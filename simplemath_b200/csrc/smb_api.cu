@@ -216,7 +216,7 @@ static inline size_t esize(int dtype) { return dtype == SMB_F64 ? 8 : 4; }
 #ifndef SMB_STREAM_UNROLL
 #define SMB_STREAM_UNROLL 4
 #endif
-constexpr int kThreads = 256;
+constexpr int kThreads = kBlock;
 
 static unsigned grid_for(uint64_t work_items, uint64_t items_per_block, int sm_count, int64_t ctas_per_sm) {
     uint64_t blocks = (work_items + items_per_block - 1) / items_per_block;
@@ -293,7 +293,15 @@ int scalar_t<float>(const DeviceCtx &c, int op, const float *a, float v, float *
                 if (v == 0.5f) return launch_stream<T, PowSpecialFn<POWS_SQRT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
                 if (v == 1.0f) return launch_stream<T, PowSpecialFn<POWS_IDENT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
             }
-            return launch_stream<T, ScalarFn<OP_POW, T>, false>(c, a, nullptr, out, n, first, {classify_exp(v), lane_end}, s);
+            {
+                ScalarFn<OP_POW, T> fn;
+                fn.pe = classify_exp(v);
+                fn.lane_end = lane_end;
+                fn.fast = pow_f32_fast_ok(fn.pe) ? 1 : 0;
+                fn.tab_log = nullptr; // set per CTA from shared memory
+                fn.tab_exp = nullptr;
+                return launch_stream<T, ScalarFn<OP_POW, T>, false>(c, a, nullptr, out, n, first, fn, s);
+            }
         }
     }
     return fail(SMB_ERR_INVALID, "unknown op %d", op);

@@ -13,10 +13,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "smb_math.cuh"
 #include "smb_plan.h"
 
 namespace smb {
+
+constexpr int kBlock = 256; // threads per CTA of every kernel in this file
 
 // ---------------------------------------------------------------------------
 // 16-byte and 32-byte global vector access with streaming cache hints.
@@ -115,16 +118,48 @@ template<> struct ScalarFn<OP_POW, int32_t> {
         return i < lane_end ? powi_lane(a, v) : powi_scalar(a, v);
     }
 };
+// sm::pow(arr, y) for float: pairs of elements go through the table-driven
+// packed core (smb_math.cuh); whatever it declines -- specials, denormal inputs,
+// results near overflow / underflow -- takes the FP64 reference-accuracy path,
+// kept out of line so the hot loop stays small.
+__device__ __noinline__ float pow_f32_slow(float x, PowExpF32 pe) { return pow_f32(x, pe); }
+
+static __device__ const PowTabLog d_pow_log_tab[SMB_POW_LOG_ENTRIES] = SMB_POW_LOG_TABLE_INIT;
+static __device__ const PowTabExp d_pow_exp_tab[SMB_POW_EXP_ENTRIES] = SMB_POW_EXP_TABLE_INIT;
+
 template<> struct ScalarFn<OP_POW, float> {
-    PowExpF32 pe; // exponent classified once on the host
+    static constexpr bool PAIRWISE = true;    // stream_tile feeds two elements per call
+    static constexpr bool POW_TABLES = true;  // k_stream stages the lookup tables in shared memory
+    PowExpF32 pe;  // exponent classified once on the host
     uint64_t lane_end;
-    __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return pow_f32(a, pe); }
+    int fast;      // pow_f32_fast_ok(pe), evaluated on the host
+    const PowTabLog *tab_log;
+    const PowTabExp *tab_exp;
+    __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return pow_f32_slow(a, pe); }
+    // NP pairs (one vector) at once: branch-free fast core, then ONE check; a vector
+    // with any declined element is redone whole on the slow path (rare).
+    template<int NP>
+    __device__ __forceinline__ void pairs(const float *in, float *out) const {
+        bool ok = fast != 0;
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+            ok &= pow_f32_pair_fast(in[2 * k], in[2 * k + 1], pe, tab_log, tab_exp, &out[2 * k], &out[2 * k + 1]);
+        if (!ok) {
+#pragma unroll
+            for (int k = 0; k < 2 * NP; ++k) out[k] = pow_f32_slow(in[k], pe);
+        }
+    }
 };
 template<> struct ScalarFn<OP_POW, double> {
     PowExpF64 pe;
     uint64_t lane_end;
     __device__ __forceinline__ double operator()(double a, double, uint64_t) const { return pow_f64(a, pe); }
 };
+
+template<typename Fn, typename = void> struct fn_pairwise : std::false_type {};
+template<typename Fn> struct fn_pairwise<Fn, std::void_t<decltype(Fn::PAIRWISE)>> : std::bool_constant<Fn::PAIRWISE> {};
+template<typename Fn, typename = void> struct fn_pow_tables : std::false_type {};
+template<typename Fn> struct fn_pow_tables<Fn, std::void_t<decltype(Fn::POW_TABLES)>> : std::bool_constant<Fn::POW_TABLES> {};
 
 // Exact special forms of sm::pow(arr, y) for y in {2, 0.5, -1, 1}: one correctly
 // rounded instruction instead of exp2(y*log2 x).  Chosen on the host
@@ -166,7 +201,7 @@ __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__
     Pack<T, VB> pa[UNROLL], pb[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-        const uint64_t v = v0 + (uint64_t)u * blockDim.x;
+        const uint64_t v = v0 + (uint64_t)u * kBlock;
         if (!GUARD || v < nvec) {
             pa[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(a) + v);
             if (HAS_B) pb[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(b) + v);
@@ -174,12 +209,16 @@ __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-        const uint64_t v = v0 + (uint64_t)u * blockDim.x;
+        const uint64_t v = v0 + (uint64_t)u * kBlock;
         if (!GUARD || v < nvec) {
             Pack<T, VB> r;
+            if constexpr (fn_pairwise<Fn>::value && !HAS_B && (EPV % 2 == 0)) {
+                fn.template pairs<EPV / 2>(pa[u].e, r.e);
+            } else {
 #pragma unroll
-            for (int k = 0; k < EPV; ++k)
-                r.e[k] = fn(pa[u].e[k], HAS_B ? pb[u].e[k] : pa[u].e[k], first + v * EPV + k);
+                for (int k = 0; k < EPV; ++k)
+                    r.e[k] = fn(pa[u].e[k], HAS_B ? pb[u].e[k] : pa[u].e[k], first + v * EPV + k);
+            }
             VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v, r.raw);
         }
     }
@@ -187,10 +226,20 @@ __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__
 
 template<typename T, typename Fn, bool HAS_B, int VB, int UNROLL>
 __global__ void __launch_bounds__(256) k_stream(const T *__restrict__ a, const T *__restrict__ b,
-                                               T *__restrict__ out, uint64_t n, uint64_t first, Fn fn) {
+                                               T *__restrict__ out, uint64_t n, uint64_t first, Fn fn_in) {
     constexpr int EPV = VB / (int)sizeof(T); // elements per vector
+    Fn fn = fn_in;
+    if constexpr (fn_pow_tables<Fn>::value) { // 2.5 KB of lookup tables, L2 -> shared memory once per CTA
+        __shared__ PowTabLog s_log[SMB_POW_LOG_ENTRIES];
+        __shared__ PowTabExp s_exp[SMB_POW_EXP_ENTRIES];
+        for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES; i += kBlock) s_log[i] = d_pow_log_tab[i];
+        for (int i = threadIdx.x; i < SMB_POW_EXP_ENTRIES; i += kBlock) s_exp[i] = d_pow_exp_tab[i];
+        __syncthreads();
+        fn.tab_log = s_log;
+        fn.tab_exp = s_exp;
+    }
     const uint64_t nvec = n / EPV;
-    const uint64_t tile_vecs = (uint64_t)blockDim.x * UNROLL;
+    constexpr uint64_t tile_vecs = (uint64_t)kBlock * UNROLL; // launches always use kBlock threads
     const uint64_t full_tiles = nvec / tile_vecs;
     // full tiles: no bounds checks in the loop body
 #pragma unroll 1

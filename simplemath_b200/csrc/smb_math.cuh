@@ -23,6 +23,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include "smb_pow_tables.h"
 
 #if defined(__CUDACC__)
 #define SMB_HD __host__ __device__ __forceinline__
@@ -360,13 +361,13 @@ SMB_HD bool pow_special(F x, const PE &pe, F *out, bool *negate) {
     return false;
 }
 
-// f32 pow, general path.
+// f32 pow, reference-accuracy path (FP64 pipe, <= 0.5002 ULP): every special
+// case, denormal inputs, per-element exponents (array ^ array) and the rare
+// elements the fast core below declines.
 SMB_HD float pow_f32(float x, const PowExpF32 &pe) {
-    // Fast classification: positive, finite, non-zero x (normal or denormal) and
-    // finite non-zero y need no table lookup.
     const uint32_t ux = f2u(x);
     bool negate = false;
-    if (!(pe.y_class == 0 && (ux - 1u) < 0x7f7fffffu)) {
+    if (!(pe.y_class == 0 && (ux - 1u) < 0x7f7fffffu)) { // not (positive finite non-zero x, finite non-zero y)
         float sp;
         if (pow_special<float, PowExpF32>(x, pe, &sp, &negate)) return sp;
     }
@@ -379,6 +380,153 @@ SMB_HD float pow_f32(float x, const PowExpF32 &pe) {
     t = t < -200.0 ? -200.0 : t;
     float r = (float)exp2_d(t); // one rounding, gradual underflow included
     return negate ? -r : r;
+}
+
+// ---- table-driven f32 pow core on the FP32 pipe, two elements per instruction --
+// The double core runs on the half-rate FP64 pipe and made sm::pow compute-bound
+// at a third of the HBM rate (2.15 TB/s measured on B200).  This core keeps the
+// arithmetic on the FP32 pipe and issues it as packed fma.rn.f32x2 (SASS FFMA2,
+// new with sm_100): two elements per instruction, which is what lets ~35
+// floating-point operations per element fit under the memory roofline.
+//
+//   x = 2^e * m, m in [sqrt(1/2), sqrt(2)); the top 7 bits of m's offset select a
+//   table entry {c, L_hi, L_lo}, log2(c) = L_hi + L_lo, c = 1 exactly around m = 1
+//   (so x near 1 keeps full RELATIVE accuracy);
+//   p = (m-c)/(m+c), |p| <= 0.0059, as p_hi + p_lo (MUFU.RCP seed + two FMA
+//   residual steps; m-c is exact, m+c is carried with its rounding error);
+//   log2 x = (e + L_hi) + [C0*p + L_lo + p^3*(C1 + C2 p^2)]  -- e + L_hi is exact
+//   because L_hi is a multiple of 2^-15; the bracket is kept as two floats;
+//   t = y*log2 x as th + tl; k = rint(64 t): 2^t = 2^n * T[j] * 2^f, n = k >> 6,
+//   j = k & 63, |f| <= 2^-7, T[j] = 2^(j/64) as T_hi + T_lo,
+//   2^f - 1 = f*(E1 + f*(E2 + f*E3)).
+// Error: <= 0.5 (final rounding) + ~0.05 ULP typical; tests bound it by 1 ULP.
+// The core declines (returns false) anything that is not "normal positive
+// magnitude, result comfortably inside the normal range"; the caller then uses
+// pow_f32 above for that element.
+struct f2 { float x, y; };
+SMB_HD f2 f2_make(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
+SMB_HD f2 f2_splat(float a) { return f2_make(a, a); }
+SMB_HD f2 f2_fma(f2 a, f2 b, f2 c) {
+#if defined(__CUDA_ARCH__)
+    const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+    return f2_make(r.x, r.y);
+#else
+    return f2_make(ffma(a.x, b.x, c.x), ffma(a.y, b.y, c.y));
+#endif
+}
+SMB_HD f2 f2_mul(f2 a, f2 b) {
+#if defined(__CUDA_ARCH__)
+    const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return f2_make(r.x, r.y);
+#else
+    return f2_make(fmul(a.x, b.x), fmul(a.y, b.y));
+#endif
+}
+SMB_HD f2 f2_add(f2 a, f2 b) {
+#if defined(__CUDA_ARCH__)
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return f2_make(r.x, r.y);
+#else
+    return f2_make(fadd(a.x, b.x), fadd(a.y, b.y));
+#endif
+}
+// Negation is free: FFMA2 / FADD2 / FMUL2 take a per-operand negate modifier.
+SMB_HD f2 f2_neg(f2 a) { return f2_make(-a.x, -a.y); }
+SMB_HD f2 f2_sub(f2 a, f2 b) { return f2_add(a, f2_neg(b)); }
+SMB_HD f2 f2_fnma(f2 a, f2 b, f2 c) { return f2_fma(f2_neg(a), b, c); } // c - a*b, one rounding
+
+struct PowTabLog { float c, l_hi, l_lo, pad; };
+struct PowTabExp { float t_hi, t_lo; };
+
+#ifndef SMB_RCP_PERTURB
+#define SMB_RCP_PERTURB(r) (r)
+#endif
+SMB_HD float rcp_seed(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return SMB_RCP_PERTURB(1.0f / x);
+#endif
+}
+
+// Host-side facts about the (uniform) exponent that gate the fast core.
+SMB_HD bool pow_f32_fast_ok(const PowExpF32 &pe) {
+    const uint32_t ay = f2u(pe.y) & 0x7fffffffu;
+    // finite, non-zero, |y| < 2^64 (so y*log2 x cannot overflow), not so tiny that y*log2 x is denormal
+    return pe.y_class == 0 && ay < 0x5f800000u && ay > 0x1f800000u;
+}
+
+// Two elements at once, branch-free.  Returns true when BOTH results are valid;
+// false when either element needs pow_f32 (the values written are then garbage,
+// but every table index and operation along the way is safe).  The caller
+// accumulates the flag over a whole vector and branches once.
+SMB_HD bool pow_f32_pair_fast(float x0, float x1, const PowExpF32 &pe, const PowTabLog *tab_log,
+                              const PowTabExp *tab_exp, float *r0, float *r1) {
+    const uint32_t u0 = f2u(x0), u1 = f2u(x1);
+    const uint32_t a0 = u0 & 0x7fffffffu, a1 = u1 & 0x7fffffffu;
+    // normal finite magnitude; negative bases only with an integer exponent
+    const uint32_t neg_ok = pe.y_is_int ? 0u : 0x80000000u; // sign bits that disqualify
+    bool ok = (a0 - 0x00800000u) < 0x7f000000u && (a1 - 0x00800000u) < 0x7f000000u && ((u0 | u1) & neg_ok) == 0u;
+    // ---- log2 |x| -------------------------------------------------------------
+    const int32_t d0 = (int32_t)(a0 - 0x3f3504f3u), d1 = (int32_t)(a1 - 0x3f3504f3u);
+    const f2 m = f2_make(u2f(a0 - ((uint32_t)d0 & 0xff800000u)), u2f(a1 - ((uint32_t)d1 & 0xff800000u)));
+    const PowTabLog t0 = tab_log[(d0 >> 16) & 127], t1 = tab_log[(d1 >> 16) & 127];
+    const f2 c = f2_make(t0.c, t1.c);
+    const f2 num = f2_sub(m, c);                       // exact (Sterbenz)
+    const f2 den = f2_add(m, c);
+    const f2 den_lo = f2_sub(m, f2_sub(den, c));       // den + den_lo == m + c exactly
+    const f2 r = f2_make(rcp_seed(den.x), rcp_seed(den.y));
+    const f2 p_hi = f2_mul(num, r);
+    f2 res = f2_fnma(p_hi, den, num);
+    res = f2_fnma(p_hi, den_lo, res);
+    const f2 p_lo = f2_mul(res, r);
+    const f2 s = f2_mul(p_hi, p_hi);
+    const f2 q = f2_fma(s, f2_splat(0.5767093896865845f), f2_splat(0.9617967009544373f));
+    const f2 u = f2_mul(p_hi, s);
+    const f2 c0h = f2_splat(2.885390043258667f), c0l = f2_splat(3.851926067000022e-08f); // 2/ln2 = c0h + c0l
+    const f2 lh = f2_mul(c0h, p_hi);
+    f2 ll = f2_fma(c0h, p_hi, f2_neg(lh));
+    ll = f2_fma(c0l, p_hi, ll);
+    ll = f2_fma(c0h, p_lo, ll);
+    ll = f2_fma(u, q, ll);
+    // e + L_hi is exact (integer + multiple of 2^-15, magnitude <= 150.5); scalar adds, the
+    // table words are used once and packing them would cost more than it saves
+    const f2 h1 = f2_make(fadd((float)(d0 >> 23), t0.l_hi), fadd((float)(d1 >> 23), t1.l_hi));
+    const f2 h2 = f2_add(h1, lh);                          // fast two-sum: |h1| >= |lh| or h1 == 0
+    const f2 l2 = f2_add(f2_sub(h1, h2), lh);
+    const f2 lo_raw = f2_add(f2_make(fadd(t0.l_lo, l2.x), fadd(t1.l_lo, l2.y)), ll);
+    // renormalise: L_lo alone can reach 2^-16, too coarse a tail once multiplied by a large y
+    const f2 h3 = f2_add(h2, lo_raw);
+    const f2 lo = f2_add(f2_sub(h2, h3), lo_raw);
+    // ---- t = y * log2|x| as th + tl ---------------------------------------------
+    const f2 y2 = f2_splat(pe.y);
+    const f2 th = f2_mul(y2, h3);
+    f2 tl = f2_fma(y2, h3, f2_neg(th));
+    tl = f2_fma(y2, lo, tl);
+    // results outside the comfortable normal range (incl. overflow / underflow) go to the slow path
+    ok = ok && fabsf(th.x) < 125.0f && fabsf(th.y) < 125.0f;
+    // ---- 2^t --------------------------------------------------------------------
+    const f2 shifter = f2_splat(12582912.0f);              // 1.5 * 2^23
+    const f2 tk = f2_fma(th, f2_splat(64.0f), shifter);    // low mantissa bits hold k = rint(64 th)
+    const uint32_t k0 = f2u(tk.x), k1 = f2u(tk.y);         // biased by 0x4b400000, a multiple of 64
+    const f2 kf = f2_sub(tk, shifter);
+    f2 f = f2_fma(kf, f2_splat(-0.015625f), th);           // th - k/64, exact
+    f = f2_add(f, tl);
+    const PowTabExp e0 = tab_exp[k0 & 63u], e1 = tab_exp[k1 & 63u];
+    f2 g = f2_fma(f, f2_splat(0.05547422543168068f), f2_splat(0.24022682011127472f));
+    g = f2_fma(f, g, f2_splat(0.6931471824645996f));
+    const f2 w = f2_mul(f, g);                             // 2^f - 1
+    const f2 thi = f2_make(e0.t_hi, e1.t_hi);
+    const f2 v = f2_make(ffma(thi.x, w.x, e0.t_lo), ffma(thi.y, w.y, e1.t_lo));
+    const f2 z = f2_add(thi, v);                           // in [0.99, 2.01): 2^(j/64 + f)
+    // scale by 2^n, n = k >> 6, through the exponent field (|n| <= 125 keeps the result normal):
+    // (k << 17) & 0xff800000 == n << 23 (the bias 0x4b400000 << 17 vanishes mod 2^32); restore the sign
+    const uint32_t odd = pe.y_is_odd ? 0x80000000u : 0u;
+    *r0 = u2f((f2u(z.x) + ((k0 << 17) & 0xff800000u)) | (u0 & odd));
+    *r1 = u2f((f2u(z.y) + ((k1 << 17) & 0xff800000u)) | (u1 & odd));
+    return ok;
 }
 
 // ============================================================== double pow ===

@@ -12,6 +12,27 @@ void hc_pow_f32(const float *x, float y, uint64_t n, float *out) {
     #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = pow_f32(x[i], pe);
 }
+static const PowTabLog kLog[SMB_POW_LOG_ENTRIES] = SMB_POW_LOG_TABLE_INIT;
+static const PowTabExp kExp[SMB_POW_EXP_ENTRIES] = SMB_POW_EXP_TABLE_INIT;
+// The fast (table-driven, packed) core exactly as ScalarFn<OP_POW,float>::pair uses it:
+// pairs of elements, pow_f32 for whatever the core declines.  *declined counts those.
+void hc_pow_f32_fast(const float *x, float y, uint64_t n, float *out, uint64_t *declined) {
+    PowExpF32 pe = classify_exp(y);
+    const bool fast = pow_f32_fast_ok(pe);
+    uint64_t dec = 0;
+    #pragma omp parallel for schedule(static) reduction(+:dec)
+    for (int64_t i = 0; i < (int64_t)(n / 2); ++i) {
+        float r0, r1;
+        if (pow_f32_pair_fast(x[2 * i], x[2 * i + 1], pe, kLog, kExp, &r0, &r1) && fast) {
+            out[2 * i] = r0; out[2 * i + 1] = r1;
+        } else {
+            out[2 * i] = pow_f32(x[2 * i], pe); out[2 * i + 1] = pow_f32(x[2 * i + 1], pe);
+            dec += 2;
+        }
+    }
+    if (n & 1) out[n - 1] = pow_f32(x[n - 1], pe);
+    if (declined) *declined = dec;
+}
 void hc_pow_f32_pair(const float *x, const float *y, uint64_t n, float *out) {
     #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = DevOp<OP_POW, float>::apply(x[i], y[i]);

@@ -220,7 +220,9 @@ def test_float_specials_bit_exact(orc):
 
 def test_empty_and_rejects():
     e = np.empty((0, 5), np.float32)
-    assert smb.binary("add", e, np.ones((1, 5), np.float32)).shape == (0, 5)
+    assert smb.binary("add", e, e).shape == (0, 5)
+    with pytest.raises(smb.SmbError, match="empty operand"):
+        smb.binary("add", e, np.ones((1, 5), np.float32))  # the reference would read a[0] of an empty block
     assert smb.scalar("mul", np.empty(0, np.int32), 3).size == 0
     with pytest.raises(smb.SmbError, match="Cannot broadcast"):
         smb.binary("add", np.ones((2, 3), np.float32), np.ones((4, 3), np.float32))

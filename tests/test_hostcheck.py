@@ -4,7 +4,8 @@ bit-exact against the oracle, float/double pow within the stated ULP bounds
 against std::pow evaluated in higher precision.
 
 Stated bounds (also enforced on the GPU in test_gpu_parity.py):
-    f32 pow: <= 1 ULP  vs std::pow computed in double   (measured <= 0.5002)
+    f32 pow: <= 1 ULP  vs std::pow computed in double   (measured: fast FFMA2 core <= 0.54,
+                                                          FP64 reference-accuracy path <= 0.5002)
     f64 pow: <= 1 ULP  vs powl in long double            (measured <= 0.56)
 """
 import ctypes
@@ -44,6 +45,15 @@ def hc_pow32(hc, x, y):
     out = np.empty_like(x)
     hc.hc_pow_f32(_p(x), ctypes.c_float(y), ctypes.c_uint64(x.size), _p(out))
     return out
+
+
+def hc_pow32_fast(hc, x, y):
+    """The kernel's own path: table-driven packed core for pairs, pow_f32 for declined elements."""
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    dec = ctypes.c_uint64(0)
+    hc.hc_pow_f32_fast(_p(x), ctypes.c_float(y), ctypes.c_uint64(x.size), _p(out), ctypes.byref(dec))
+    return out, dec.value / max(x.size, 1)
 
 
 def hc_pow64(hc, x, y):
@@ -86,6 +96,59 @@ def test_pow_f32_ulp_all_magnitudes(hc, orc, y):
     x = rng.integers(1, 0x7f800000, 1 << 20, dtype=np.uint32).view(np.float32)  # every positive finite incl. denormals
     err = oracle.ulp_error_f32(hc_pow32(hc, x, y), orc.pow_ref_f32(x, y))
     assert err.max() <= F32_POW_ULP_BOUND, (y, err.max(), x[err.argmax()])
+
+
+@pytest.mark.parametrize("y", [2.0, 2.5, 0.5, -1.0, 3.0, -2.5, 1 / 3, 17.0, 1e-3, 0.1, -0.0625, 31.0])
+def test_pow_f32_fast_core_ulp(hc, orc, y):
+    """The table-driven FFMA2 core (what the GPU kernel runs for ordinary data):
+    uniform values, every magnitude, signed bases, and all 128 table-entry edges."""
+    rng = np.random.default_rng(int(abs(y) * 977) % 2**31)
+    edges = []
+    for j in range(128):
+        for d in (-2, -1, 0, 1, 2):
+            edges += [0x3F3504F3 + (j << 16) + d, 0x3F3504F3 + (j << 16) + 0xFFFF + d]
+    xe = np.array(edges, dtype=np.uint32).view(np.float32)
+    xe = np.concatenate([xe * np.float32(2.0 ** k) for k in (-20, -3, -1, 0, 1, 2, 7, 30)])
+    x = np.concatenate([rng.uniform(0.01, 100, 1 << 20).astype(np.float32),
+                        rng.integers(1, 0x7F800000, 1 << 20, dtype=np.uint32).view(np.float32),
+                        -rng.uniform(0.01, 100, 1 << 18).astype(np.float32), xe])
+    x = x[: x.size // 2 * 2]
+    got, declined = hc_pow32_fast(hc, x, y)
+    ref = orc.pow_ref_f32(x, float(np.float32(y)))
+    err = oracle.ulp_error_f32(got, ref)
+    assert err.max() <= F32_POW_ULP_BOUND, (y, err.max(), x[err.argmax()], got[err.argmax()])
+    if y in (2.0, 2.5, 0.5, -1.0):  # ordinary data must stay on the fast core
+        g2, d2 = hc_pow32_fast(hc, rng.uniform(0.01, 100, 1 << 16).astype(np.float32), y)
+        assert d2 == 0.0
+
+
+def test_pow_f32_fast_core_near_one_huge_exponents(hc, orc):
+    rng = np.random.default_rng(16)
+    x = (1 + rng.uniform(-2e-2, 2e-2, 1 << 20)).astype(np.float32)
+    for y in (1e4, -3e4, 12345.678, 3000.0, -5000.5, 700.25):
+        got, _ = hc_pow32_fast(hc, x, y)
+        err = oracle.ulp_error_f32(got, orc.pow_ref_f32(x, float(np.float32(y))))
+        assert err.max() <= F32_POW_ULP_BOUND, (y, err.max(), x[err.argmax()])
+
+
+def test_pow_f32_fast_core_special_values_fall_back(hc, orc):
+    x = np.array(SPECIAL_X + [7.0], np.float32)
+    x = np.resize(x, (x.size // 2) * 2)
+    for y in SPECIAL_Y:
+        got, _ = hc_pow32_fast(hc, x, np.float32(y))
+        assert_same_bits(got, hc_pow32(hc, x, np.float32(y)), f"fast path vs reference path, y={y}") if not (
+            np.isfinite(np.float32(y)) and y != 0) else None
+        want64 = orc.pow_ref_f32(x, float(np.float32(y)))
+        with np.errstate(all="ignore"):
+            want = want64.astype(np.float32)
+        for xi, g, w, w64 in zip(x, got, want, want64):
+            if np.isnan(w):
+                assert np.isnan(g), (xi, y, g)
+            elif np.isinf(w) or w == 0 or np.isinf(g) or g == 0:
+                ok = g == w and np.signbit(g) == np.signbit(w)
+                assert ok or oracle.ulp_error_f32(np.array([g]), np.array([w64]))[0] <= 1, (xi, y, g, w)
+            else:
+                assert oracle.ulp_error_f32(np.array([g]), np.array([w64]))[0] <= F32_POW_ULP_BOUND, (xi, y, g, w)
 
 
 def test_pow_f32_near_one_huge_exponents(hc, orc):
