@@ -231,7 +231,10 @@ static int launch_stream(const DeviceCtx &c, const T *a, const T *b, T *out, uin
     if (n == 0) return SMB_OK;
     constexpr int VB = SMB_STREAM_VB, UNROLL = SMB_STREAM_UNROLL;
     const uintptr_t ma = (uintptr_t)a % VB, mb = HAS_B ? (uintptr_t)b % VB : ma, mo = (uintptr_t)out % VB;
-    const int64_t cps = g_opt_contig_variant.load();
+    int64_t cps = g_opt_contig_variant.load();
+    // kernels that stage lookup tables in shared memory (f32 pow) amortise the 24 KB fill over a
+    // persistent grid; plain streams run one tile per CTA (tools/sweep: fastest on B200)
+    if (fn_pow_tables<Fn>::value && cps == 0) cps = 8;
     if (ma == mb && ma == mo && ma % sizeof(T) == 0) {
         uint64_t head = ma ? (VB - ma) / sizeof(T) : 0;
         if (head > n) head = n;
@@ -294,13 +297,10 @@ int scalar_t<float>(const DeviceCtx &c, int op, const float *a, float v, float *
                 if (v == 1.0f) return launch_stream<T, PowSpecialFn<POWS_IDENT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
             }
             {
-                ScalarFn<OP_POW, T> fn;
-                fn.pe = classify_exp(v);
-                fn.lane_end = lane_end;
-                fn.fast = pow_f32_fast_ok(fn.pe) ? 1 : 0;
-                fn.tab_log = nullptr; // set per CTA from shared memory
-                fn.tab_exp = nullptr;
-                return launch_stream<T, ScalarFn<OP_POW, T>, false>(c, a, nullptr, out, n, first, fn, s);
+                const PowExpF32 pe = classify_exp(v);
+                if (pow_f32_small_y(pe))
+                    return launch_stream<T, PowF32Fn<true>, false>(c, a, nullptr, out, n, first, PowF32Fn<true>::make(v, lane_end), s);
+                return launch_stream<T, PowF32Fn<false>, false>(c, a, nullptr, out, n, first, PowF32Fn<false>::make(v, lane_end), s);
             }
         }
     }

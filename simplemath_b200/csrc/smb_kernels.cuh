@@ -20,6 +20,9 @@
 namespace smb {
 
 constexpr int kBlock = 256; // threads per CTA of every kernel in this file
+#ifndef SMB_POW_MIN_BLOCKS
+#define SMB_POW_MIN_BLOCKS 1 // no register cap: 74 regs, 3 CTAs/SM measured fastest (tools/sweep, caps 3/4/5 were slower)
+#endif
 
 // ---------------------------------------------------------------------------
 // 16-byte and 32-byte global vector access with streaming cache hints.
@@ -127,29 +130,34 @@ __device__ __noinline__ float pow_f32_slow(float x, PowExpF32 pe) { return pow_f
 static __device__ const PowTabLog d_pow_log_tab[SMB_POW_LOG_ENTRIES] = SMB_POW_LOG_TABLE_INIT;
 static __device__ const PowTabExp d_pow_exp_tab[SMB_POW_EXP_ENTRIES] = SMB_POW_EXP_TABLE_INIT;
 
-template<> struct ScalarFn<OP_POW, float> {
-    static constexpr bool PAIRWISE = true;    // stream_tile feeds two elements per call
+template<bool SMALL_Y> struct PowF32Fn {
+    static constexpr bool PAIRWISE = true;    // stream_vec feeds two elements per call
     static constexpr bool POW_TABLES = true;  // k_stream stages the lookup tables in shared memory
     PowExpF32 pe;  // exponent classified once on the host
     uint64_t lane_end;
-    int fast;      // pow_f32_fast_ok(pe), evaluated on the host
+    int fast;              // pow_f32_fast_ok(pe)
+    uint32_t sign_reject;  // 0x80000000 when negative bases must take the slow path (non-integer y)
+    uint32_t odd_mask;     // 0x80000000 when y is an odd integer (result keeps the base's sign)
     const PowTabLog *tab_log;
     const PowTabExp *tab_exp;
     __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return pow_f32_slow(a, pe); }
-    // NP pairs (one vector) at once: branch-free fast core, then ONE check; a vector
-    // with any declined element is redone whole on the slow path (rare).
-    template<int NP>
-    __device__ __forceinline__ void pairs(const float *in, float *out) const {
-        bool ok = fast != 0;
-#pragma unroll
-        for (int k = 0; k < NP; ++k)
-            ok &= pow_f32_pair_fast(in[2 * k], in[2 * k + 1], pe, tab_log, tab_exp, &out[2 * k], &out[2 * k + 1]);
-        if (!ok) {
-#pragma unroll
-            for (int k = 0; k < 2 * NP; ++k) out[k] = pow_f32_slow(in[k], pe);
-        }
+    // Two elements through the branch-free fast core; false = redo on the slow path.
+    __device__ __forceinline__ bool pair(float a0, float a1, float &r0, float &r1) const {
+        return pow_f32_pair_fast<SMALL_Y>(a0, a1, pe.y, sign_reject, odd_mask, tab_log, tab_exp, &r0, &r1) && fast != 0;
+    }
+    static PowF32Fn make(float y, uint64_t lane_end_) {
+        PowF32Fn fn;
+        fn.pe = classify_exp(y);
+        fn.lane_end = lane_end_;
+        fn.fast = pow_f32_fast_ok(fn.pe) ? 1 : 0;
+        fn.sign_reject = pow_f32_sign_reject(fn.pe);
+        fn.odd_mask = pow_f32_odd_mask(fn.pe);
+        fn.tab_log = nullptr; // set per CTA from shared memory
+        fn.tab_exp = nullptr;
+        return fn;
     }
 };
+template<> struct ScalarFn<OP_POW, float> : PowF32Fn<false> {};
 template<> struct ScalarFn<OP_POW, double> {
     PowExpF64 pe;
     uint64_t lane_end;
@@ -194,6 +202,27 @@ template<int WHICH, typename T> struct PowSpecialFn {
 // j, j+blockDim, ... so every warp access is one fully coalesced 512 B / 1 KiB run.
 // All loads of a tile are issued before the first use (memory-level parallelism).
 // The ragged end (< one vector) is done by the last threads with scalar accesses.
+// One vector of results from one vector (or two) of operands.
+template<typename T, typename Fn, bool HAS_B, int VB>
+__device__ __forceinline__ void stream_vec(const Pack<T, VB> &pa, const Pack<T, VB> &pb, Pack<T, VB> &r, uint64_t first_elem,
+                                           const Fn &fn) {
+    constexpr int EPV = VB / (int)sizeof(T);
+    if constexpr (fn_pairwise<Fn>::value && !HAS_B && (EPV % 2 == 0)) {
+        // Pairwise functors (f32 pow): branch-free fast core on every pair, ONE check per vector;
+        // a vector with any declined element is redone whole on the slow path (rare).
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < EPV; k += 2) ok &= fn.pair(pa.e[k], pa.e[k + 1], r.e[k], r.e[k + 1]);
+        if (!ok) {
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa.e[k], pa.e[k], 0);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa.e[k], HAS_B ? pb.e[k] : pa.e[k], first_elem + k);
+    }
+}
+
 template<typename T, typename Fn, bool HAS_B, int VB, int UNROLL, bool GUARD>
 __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
                                             uint64_t v0, uint64_t nvec, uint64_t first, const Fn &fn) {
@@ -212,39 +241,68 @@ __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__
         const uint64_t v = v0 + (uint64_t)u * kBlock;
         if (!GUARD || v < nvec) {
             Pack<T, VB> r;
-            if constexpr (fn_pairwise<Fn>::value && !HAS_B && (EPV % 2 == 0)) {
-                fn.template pairs<EPV / 2>(pa[u].e, r.e);
-            } else {
-#pragma unroll
-                for (int k = 0; k < EPV; ++k)
-                    r.e[k] = fn(pa[u].e[k], HAS_B ? pb[u].e[k] : pa[u].e[k], first + v * EPV + k);
-            }
+            stream_vec<T, Fn, HAS_B, VB>(pa[u], pb[u], r, first + v * EPV, fn);
             VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v, r.raw);
         }
     }
 }
 
 template<typename T, typename Fn, bool HAS_B, int VB, int UNROLL>
-__global__ void __launch_bounds__(256) k_stream(const T *__restrict__ a, const T *__restrict__ b,
+__global__ void __launch_bounds__(256, fn_pow_tables<Fn>::value ? SMB_POW_MIN_BLOCKS : 1) k_stream(const T *__restrict__ a, const T *__restrict__ b,
                                                T *__restrict__ out, uint64_t n, uint64_t first, Fn fn_in) {
     constexpr int EPV = VB / (int)sizeof(T); // elements per vector
     Fn fn = fn_in;
-    if constexpr (fn_pow_tables<Fn>::value) { // 2.5 KB of lookup tables, L2 -> shared memory once per CTA
-        __shared__ PowTabLog s_log[SMB_POW_LOG_ENTRIES];
-        __shared__ PowTabExp s_exp[SMB_POW_EXP_ENTRIES];
-        for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES; i += kBlock) s_log[i] = d_pow_log_tab[i];
-        for (int i = threadIdx.x; i < SMB_POW_EXP_ENTRIES; i += kBlock) s_exp[i] = d_pow_exp_tab[i];
+    if constexpr (fn_pow_tables<Fn>::value) {
+        // Lookup tables, L2 -> shared memory once per CTA, each entry replicated across the lanes
+        // of a wavefront (24 KB) so the per-lane lookups never conflict; see smb_math.cuh.
+        __shared__ __align__(16) PowTabLog s_log[SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE];
+        __shared__ __align__(16) PowTabExp s_exp[SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE];
+        for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE; i += kBlock)
+            s_log[i] = d_pow_log_tab[i / SMB_POW_LOG_STRIDE];
+        for (int i = threadIdx.x; i < SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE; i += kBlock)
+            s_exp[i] = d_pow_exp_tab[i / SMB_POW_EXP_STRIDE];
         __syncthreads();
-        fn.tab_log = s_log;
-        fn.tab_exp = s_exp;
+        fn.tab_log = s_log + (threadIdx.x & (SMB_POW_LOG_STRIDE - 1));
+        fn.tab_exp = s_exp + (threadIdx.x & (SMB_POW_EXP_STRIDE - 1));
     }
     const uint64_t nvec = n / EPV;
     constexpr uint64_t tile_vecs = (uint64_t)kBlock * UNROLL; // launches always use kBlock threads
     const uint64_t full_tiles = nvec / tile_vecs;
     // full tiles: no bounds checks in the loop body
+    if constexpr (fn_pow_tables<Fn>::value && !HAS_B) {
+        // Compute-heavy functor on a persistent grid: the next tile's loads are issued BEFORE this
+        // tile's arithmetic (register double buffer), so HBM latency hides under ~800 issue slots of
+        // math instead of stalling the warp (ncu: long_scoreboard was the top stall without it).
+        Pack<T, VB> cur[UNROLL], nxt[UNROLL];
+        uint64_t tile = blockIdx.x;
+        if (tile < full_tiles) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+                cur[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(a) + tile * tile_vecs + threadIdx.x + u * kBlock);
+        }
 #pragma unroll 1
-    for (uint64_t tile = blockIdx.x; tile < full_tiles; tile += gridDim.x)
-        stream_tile<T, Fn, HAS_B, VB, UNROLL, false>(a, b, out, tile * tile_vecs + threadIdx.x, nvec, first, fn);
+        for (; tile < full_tiles; tile += gridDim.x) {
+            const uint64_t next = tile + gridDim.x;
+            if (next < full_tiles) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+                    nxt[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(a) + next * tile_vecs + threadIdx.x + u * kBlock);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint64_t v = tile * tile_vecs + threadIdx.x + (uint64_t)u * kBlock;
+                Pack<T, VB> r;
+                stream_vec<T, Fn, false, VB>(cur[u], cur[u], r, first + v * EPV, fn);
+                VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v, r.raw);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) cur[u].raw = nxt[u].raw;
+        }
+    } else {
+#pragma unroll 1
+        for (uint64_t tile = blockIdx.x; tile < full_tiles; tile += gridDim.x)
+            stream_tile<T, Fn, HAS_B, VB, UNROLL, false>(a, b, out, tile * tile_vecs + threadIdx.x, nvec, first, fn);
+    }
     // the ragged last tile goes to the block whose turn it would be
     if (full_tiles * tile_vecs < nvec && blockIdx.x == full_tiles % gridDim.x)
         stream_tile<T, Fn, HAS_B, VB, UNROLL, true>(a, b, out, full_tiles * tile_vecs + threadIdx.x, nvec, first, fn);

@@ -451,6 +451,28 @@ SMB_HD float rcp_seed(float x) {
 #endif
 }
 
+// Table access.  Host build: the compact tables.  Device: each entry is replicated across
+// the lanes that share a shared-memory wavefront (8 lanes for the 16-byte log entries, 16
+// for the 8-byte exp entries) and `tab_*` already points at this lane's replica, so a warp
+// reading 32 unrelated entries is bank-conflict free.  (The compact layout measured 58 %
+// conflict replays and saturated the LSU data pipe at 97 %: profiles/r1_pow_ncu.md.)
+#if defined(__CUDA_ARCH__)
+#define SMB_POW_LOG_STRIDE 8   /* entries of PowTabLog between consecutive j */
+#define SMB_POW_EXP_STRIDE 16  /* entries of PowTabExp between consecutive j */
+#else
+#define SMB_POW_LOG_STRIDE 1
+#define SMB_POW_EXP_STRIDE 1
+#endif
+SMB_HD PowTabLog pow_tab_log_at(const PowTabLog *tab, int32_t d) {
+    // j = (d >> 16) & 127, scaled to a byte offset in one shift + mask
+    const uint32_t off = ((uint32_t)d >> (16 - 4 - (SMB_POW_LOG_STRIDE == 8 ? 3 : 0))) & (127u * 16u * SMB_POW_LOG_STRIDE);
+    return *reinterpret_cast<const PowTabLog *>(reinterpret_cast<const char *>(tab) + off);
+}
+SMB_HD PowTabExp pow_tab_exp_at(const PowTabExp *tab, uint32_t k) {
+    const uint32_t off = (k << (3 + (SMB_POW_EXP_STRIDE == 16 ? 4 : 0))) & (63u * 8u * SMB_POW_EXP_STRIDE);
+    return *reinterpret_cast<const PowTabExp *>(reinterpret_cast<const char *>(tab) + off);
+}
+
 // Host-side facts about the (uniform) exponent that gate the fast core.
 SMB_HD bool pow_f32_fast_ok(const PowExpF32 &pe) {
     const uint32_t ay = f2u(pe.y) & 0x7fffffffu;
@@ -462,46 +484,59 @@ SMB_HD bool pow_f32_fast_ok(const PowExpF32 &pe) {
 // false when either element needs pow_f32 (the values written are then garbage,
 // but every table index and operation along the way is safe).  The caller
 // accumulates the flag over a whole vector and branches once.
-SMB_HD bool pow_f32_pair_fast(float x0, float x1, const PowExpF32 &pe, const PowTabLog *tab_log,
-                              const PowTabExp *tab_exp, float *r0, float *r1) {
+//
+// SMALL_Y (|y| <= 8, chosen on the host): the error terms that only matter once they
+// are multiplied by a large exponent are dropped -- the rounding error of m + c
+// (2^-25 relative in p, 2^-31 absolute in log2 x) and the renormalisation of the
+// log2 tail -- 6 of the 32 packed operations per pair.
+template<bool SMALL_Y>
+SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, uint32_t sign_reject, uint32_t odd_mask,
+                              const PowTabLog *tab_log, const PowTabExp *tab_exp, float *r0, float *r1) {
     const uint32_t u0 = f2u(x0), u1 = f2u(x1);
     const uint32_t a0 = u0 & 0x7fffffffu, a1 = u1 & 0x7fffffffu;
-    // normal finite magnitude; negative bases only with an integer exponent
-    const uint32_t neg_ok = pe.y_is_int ? 0u : 0x80000000u; // sign bits that disqualify
-    bool ok = (a0 - 0x00800000u) < 0x7f000000u && (a1 - 0x00800000u) < 0x7f000000u && ((u0 | u1) & neg_ok) == 0u;
+    // normal finite magnitude; negative bases only with an integer exponent (sign_reject = 0 then)
+    const uint32_t w0 = a0 - 0x00800000u, w1 = a1 - 0x00800000u;
+    bool ok = (w0 > w1 ? w0 : w1) < 0x7f000000u && ((u0 | u1) & sign_reject) == 0u;
     // ---- log2 |x| -------------------------------------------------------------
     const int32_t d0 = (int32_t)(a0 - 0x3f3504f3u), d1 = (int32_t)(a1 - 0x3f3504f3u);
     const f2 m = f2_make(u2f(a0 - ((uint32_t)d0 & 0xff800000u)), u2f(a1 - ((uint32_t)d1 & 0xff800000u)));
-    const PowTabLog t0 = tab_log[(d0 >> 16) & 127], t1 = tab_log[(d1 >> 16) & 127];
-    const f2 c = f2_make(t0.c, t1.c);
-    const f2 num = f2_sub(m, c);                       // exact (Sterbenz)
-    const f2 den = f2_add(m, c);
-    const f2 den_lo = f2_sub(m, f2_sub(den, c));       // den + den_lo == m + c exactly
+    const PowTabLog t0 = pow_tab_log_at(tab_log, d0), t1 = pow_tab_log_at(tab_log, d1);
+    const f2 num = f2_sub(m, f2_make(t0.c, t1.c));         // exact (Sterbenz); the only use of c
+    const f2 two = f2_splat(2.0f);
+    const f2 den = f2_fma(m, two, f2_neg(num));            // 2m - (m - c) = m + c, one rounding
     const f2 r = f2_make(rcp_seed(den.x), rcp_seed(den.y));
     const f2 p_hi = f2_mul(num, r);
     f2 res = f2_fnma(p_hi, den, num);
-    res = f2_fnma(p_hi, den_lo, res);
+    if (!SMALL_Y) {
+        // (m + c) - den, exactly: 2m - den is exact (Sterbenz) and so is the difference with num
+        const f2 den_lo = f2_sub(f2_fma(m, two, f2_neg(den)), num);
+        res = f2_fnma(p_hi, den_lo, res);
+    }
     const f2 p_lo = f2_mul(res, r);
     const f2 s = f2_mul(p_hi, p_hi);
-    const f2 q = f2_fma(s, f2_splat(0.5767093896865845f), f2_splat(0.9617967009544373f));
-    const f2 u = f2_mul(p_hi, s);
-    const f2 c0h = f2_splat(2.885390043258667f), c0l = f2_splat(3.851926067000022e-08f); // 2/ln2 = c0h + c0l
+    // log2(m/c) = C0*p + p^3*(C1 + C2 p^2): leading product exact (two floats), the rest folded
+    // into one coefficient  c0l + s*(C1 + C2 s)  (the p^3 term is < 2^-16 of the total)
+    const f2 c0h = f2_splat(2.885390043258667f);           // 2/ln2 = c0h + c0l
+    f2 qq = f2_fma(s, f2_splat(0.5767093896865845f), f2_splat(0.9617967009544373f));
+    qq = f2_fma(s, qq, f2_splat(3.851926067000022e-08f));
     const f2 lh = f2_mul(c0h, p_hi);
     f2 ll = f2_fma(c0h, p_hi, f2_neg(lh));
-    ll = f2_fma(c0l, p_hi, ll);
     ll = f2_fma(c0h, p_lo, ll);
-    ll = f2_fma(u, q, ll);
+    ll = f2_fma(p_hi, qq, ll);
     // e + L_hi is exact (integer + multiple of 2^-15, magnitude <= 150.5); scalar adds, the
     // table words are used once and packing them would cost more than it saves
     const f2 h1 = f2_make(fadd((float)(d0 >> 23), t0.l_hi), fadd((float)(d1 >> 23), t1.l_hi));
     const f2 h2 = f2_add(h1, lh);                          // fast two-sum: |h1| >= |lh| or h1 == 0
     const f2 l2 = f2_add(f2_sub(h1, h2), lh);
-    const f2 lo_raw = f2_add(f2_make(fadd(t0.l_lo, l2.x), fadd(t1.l_lo, l2.y)), ll);
-    // renormalise: L_lo alone can reach 2^-16, too coarse a tail once multiplied by a large y
-    const f2 h3 = f2_add(h2, lo_raw);
-    const f2 lo = f2_add(f2_sub(h2, h3), lo_raw);
+    f2 lo = f2_add(f2_make(fadd(t0.l_lo, l2.x), fadd(t1.l_lo, l2.y)), ll);
+    f2 h3 = h2;
+    if (!SMALL_Y) {
+        // renormalise: L_lo alone can reach 2^-16, too coarse a tail once multiplied by a large y
+        h3 = f2_add(h2, lo);
+        lo = f2_add(f2_sub(h2, h3), lo);
+    }
     // ---- t = y * log2|x| as th + tl ---------------------------------------------
-    const f2 y2 = f2_splat(pe.y);
+    const f2 y2 = f2_splat(y);
     const f2 th = f2_mul(y2, h3);
     f2 tl = f2_fma(y2, h3, f2_neg(th));
     tl = f2_fma(y2, lo, tl);
@@ -514,20 +549,24 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, const PowExpF32 &pe, const Pow
     const f2 kf = f2_sub(tk, shifter);
     f2 f = f2_fma(kf, f2_splat(-0.015625f), th);           // th - k/64, exact
     f = f2_add(f, tl);
-    const PowTabExp e0 = tab_exp[k0 & 63u], e1 = tab_exp[k1 & 63u];
+    const PowTabExp e0 = pow_tab_exp_at(tab_exp, k0), e1 = pow_tab_exp_at(tab_exp, k1);
     f2 g = f2_fma(f, f2_splat(0.05547422543168068f), f2_splat(0.24022682011127472f));
     g = f2_fma(f, g, f2_splat(0.6931471824645996f));
     const f2 w = f2_mul(f, g);                             // 2^f - 1
-    const f2 thi = f2_make(e0.t_hi, e1.t_hi);
-    const f2 v = f2_make(ffma(thi.x, w.x, e0.t_lo), ffma(thi.y, w.y, e1.t_lo));
-    const f2 z = f2_add(thi, v);                           // in [0.99, 2.01): 2^(j/64 + f)
+    // T_hi + (T_hi*w + T_lo), scalar: the table words feed straight from the LDS registers
+    const float z0 = fadd(e0.t_hi, ffma(e0.t_hi, w.x, e0.t_lo));
+    const float z1 = fadd(e1.t_hi, ffma(e1.t_hi, w.y, e1.t_lo));   // in [0.99, 2.01): 2^(j/64 + f)
     // scale by 2^n, n = k >> 6, through the exponent field (|n| <= 125 keeps the result normal):
     // (k << 17) & 0xff800000 == n << 23 (the bias 0x4b400000 << 17 vanishes mod 2^32); restore the sign
-    const uint32_t odd = pe.y_is_odd ? 0x80000000u : 0u;
-    *r0 = u2f((f2u(z.x) + ((k0 << 17) & 0xff800000u)) | (u0 & odd));
-    *r1 = u2f((f2u(z.y) + ((k1 << 17) & 0xff800000u)) | (u1 & odd));
+    *r0 = u2f((f2u(z0) + ((k0 << 17) & 0xff800000u)) | (u0 & odd_mask));
+    *r1 = u2f((f2u(z1) + ((k1 << 17) & 0xff800000u)) | (u1 & odd_mask));
     return ok;
 }
+
+// Host-side facts about the (uniform) exponent that select the variant.
+SMB_HD bool pow_f32_small_y(const PowExpF32 &pe) { return (f2u(pe.y) & 0x7fffffffu) <= 0x41000000u; } // |y| <= 8
+SMB_HD uint32_t pow_f32_sign_reject(const PowExpF32 &pe) { return pe.y_is_int ? 0u : 0x80000000u; }
+SMB_HD uint32_t pow_f32_odd_mask(const PowExpF32 &pe) { return pe.y_is_odd ? 0x80000000u : 0u; }
 
 // ============================================================== double pow ===
 // Double-double (hi + lo, |lo| <= ulp(hi)/2) helpers built on FMA.

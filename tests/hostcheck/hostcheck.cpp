@@ -18,12 +18,15 @@ static const PowTabExp kExp[SMB_POW_EXP_ENTRIES] = SMB_POW_EXP_TABLE_INIT;
 // pairs of elements, pow_f32 for whatever the core declines.  *declined counts those.
 void hc_pow_f32_fast(const float *x, float y, uint64_t n, float *out, uint64_t *declined) {
     PowExpF32 pe = classify_exp(y);
-    const bool fast = pow_f32_fast_ok(pe);
+    const bool fast = pow_f32_fast_ok(pe), small = pow_f32_small_y(pe);
+    const uint32_t rej = pow_f32_sign_reject(pe), odd = pow_f32_odd_mask(pe);
     uint64_t dec = 0;
     #pragma omp parallel for schedule(static) reduction(+:dec)
     for (int64_t i = 0; i < (int64_t)(n / 2); ++i) {
         float r0, r1;
-        if (pow_f32_pair_fast(x[2 * i], x[2 * i + 1], pe, kLog, kExp, &r0, &r1) && fast) {
+        const bool ok = small ? pow_f32_pair_fast<true>(x[2 * i], x[2 * i + 1], y, rej, odd, kLog, kExp, &r0, &r1)
+                              : pow_f32_pair_fast<false>(x[2 * i], x[2 * i + 1], y, rej, odd, kLog, kExp, &r0, &r1);
+        if (ok && fast) {
             out[2 * i] = r0; out[2 * i + 1] = r1;
         } else {
             out[2 * i] = pow_f32(x[2 * i], pe); out[2 * i + 1] = pow_f32(x[2 * i + 1], pe);

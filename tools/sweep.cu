@@ -168,19 +168,18 @@ static void run_add(const float *a, const float *b, float *out, uint64_t n) {
     }
 }
 
-template<int VB, int UNROLL>
+template<int VB, int UNROLL, bool SMALL>
 static void run_pow(const float *a, float *out, uint64_t n, float y) {
     const int caps[] = {0, 4, 8, 16};
     for (int cap : caps) {
         constexpr uint64_t per_block = 256ull * UNROLL * (VB / 4);
         uint64_t blocks = (n + per_block - 1) / per_block;
         if (cap) blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * cap);
-        using Fn = ScalarFn<OP_POW, float>;
-        Fn fn;
-        fn.pe = classify_exp(y); fn.lane_end = 0; fn.fast = pow_f32_fast_ok(fn.pe) ? 1 : 0; fn.tab_log = nullptr; fn.tab_exp = nullptr;
+        using Fn = PowF32Fn<SMALL>;
+        Fn fn = Fn::make(y, 0);
         float ms = time_ms([&] { k_stream<float, Fn, false, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, nullptr, out, n, 0, fn); });
         char p[128];
-        snprintf(p, sizeof p, "y=%.2f vb=%d unroll=%d ctas_per_sm=%d", y, VB, UNROLL, cap);
+        snprintf(p, sizeof p, "y=%.2f small_y=%d vb=%d unroll=%d ctas_per_sm=%d", y, (int)SMALL, VB, UNROLL, cap);
         report("pow_f32_general", p, 8.0 * n, ms);
     }
 }
@@ -292,11 +291,24 @@ int main(int argc, char **argv) {
         run_tma<4096, 8, true>(a, b, out, n);
     }
     if (want("pow")) {
-        run_pow<16, 1>(a, out, n, 2.5f);
-        run_pow<16, 2>(a, out, n, 2.5f);
-        run_pow<16, 4>(a, out, n, 2.5f);
-        run_pow<32, 1>(a, out, n, 2.5f);
-        run_pow<32, 2>(a, out, n, 2.5f);
+        run_pow<16, 2, true>(a, out, n, 2.5f);
+        run_pow<16, 4, true>(a, out, n, 2.5f);
+        run_pow<32, 2, true>(a, out, n, 2.5f);
+        run_pow<16, 4, false>(a, out, n, 2.5f);
+        run_pow<32, 2, false>(a, out, n, 2.5f);
+    }
+    if (want("fill")) { // write-only roofline (C4 is write-dominated)
+        const int caps[] = {0, 8, 16, 32};
+        for (int cap : caps) {
+            uint64_t blocks = (n + 1023) / 1024;
+            if (cap) blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * cap);
+            float ms = time_ms([&] { k_fill<uint32_t><<<(unsigned)blocks, 256>>>((uint32_t *)out, n, 5u); });
+            char p[64];
+            snprintf(p, sizeof p, "scalar stores ctas_per_sm=%d", cap);
+            report("fill_u32", p, 4.0 * n, ms);
+        }
+        float ms = time_ms([&] { cudaMemsetAsync(out, 0, n * 4); });
+        report("cudaMemset", "", 4.0 * n, ms);
     }
     if (want("row")) {
         { // C2: f32 {4096,4096} + {1,4096}
