@@ -138,6 +138,9 @@ def cpu_reference(elems: int, steps: int, warmup: int):
     a = orc.fill_uniform_f32(0, elems, 1, -1.0, 1.0)
     b = orc.fill_uniform_f32(0, elems, 2, -1.0, 1.0)
     x = orc.fill_uniform_f32(0, elems, 3, 0.01, 100.0)
+    if kind == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the baseline is the reference with ALL host threads
+        ref.h.smref_set_threads(os.cpu_count() or 1)
     cores = ref.threads() if kind == "reference" else (os.cpu_count() or 1)
 
     def step():
@@ -210,6 +213,7 @@ def run_smb(args):
     smb.lib().smb_set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SMB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.elems

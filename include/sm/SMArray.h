@@ -78,6 +78,7 @@ namespace sm {
             ndim = 1;
             data = storage::acquire<T>(totalSize);
             std::memcpy(data, list.begin(), totalSize * sizeof(T));
+            smb_host_written(data); // pages are on the host now: prefetch before the first kernel
         }
 
         // Rows given as arrays: shape = {rows, child shape...}; children are dense.
@@ -94,6 +95,7 @@ namespace sm {
                 std::memcpy(data + at, row.data, row.totalSize * sizeof(T));
                 at += row.totalSize;
             }
+            smb_host_written(data);
             calculateStride();
         }
 

@@ -14,6 +14,7 @@ namespace sm {
     SMArray<T> empty(Args... args) {
         std::vector<size_t> shape = {static_cast<size_t>(args)...};
         T *data = storage::acquire<T>(calculateTotalSize(shape));
+        smb_host_written(data); // the caller fills it through data / operator() on the host
         return {data, std::move(shape)};
     }
 

@@ -78,8 +78,11 @@ enum {
     SMB_OPT_POW_SPECIALISE = 0,
     /* Bytes per staging chunk of the host-operand pipeline (default 64 MiB). */
     SMB_OPT_STAGE_CHUNK_BYTES = 1,
-    /* Kernel variant override for tuning sweeps (0 = library default). */
+    /* Dense-stream kernels: cap the grid at this many CTAs per SM (0 = library default:
+     * one tile per CTA for plain streams, 8 per SM for the table-driven f32 pow). */
     SMB_OPT_CONTIG_VARIANT = 2,
+    /* Broadcast kernel: 1 = stage a small reused operand in shared memory (cp.async.bulk);
+     * 0 (default) = read it through L1/L2, which measured faster on B200. */
     SMB_OPT_BCAST_VARIANT = 3
 };
 
@@ -128,6 +131,10 @@ int smb_array_scalar(int op, int dtype, const void *a, const void *scalar,
 void *smb_alloc(size_t bytes, int kind);
 int smb_free(void *ptr);
 int smb_owns(const void *ptr);
+/* Hint: the host has (re)written a managed block wholesale (constructor memcpy, a fill loop
+ * through SMArray::data).  The next launch that reads it prefetches it to the GPU instead of
+ * demand-paging.  Never needed for correctness. */
+int smb_host_written(const void *ptr);
 int smb_pool_trim(void);
 /* stats[0]=bytes in use, [1]=bytes cached, [2]=cudaMalloc-class calls, [3]=pool hits */
 int smb_pool_stats(uint64_t stats[4]);

@@ -43,6 +43,7 @@ SYMBOLS = {
     "smb_alloc": (_vp, [ctypes.c_size_t, _i]),
     "smb_free": (_i, [_vp]),
     "smb_owns": (_i, [_vp]),
+    "smb_host_written": (_i, [_vp]),
     "smb_pool_trim": (_i, []),
     "smb_pool_stats": (_i, [_u64p]),
     "smb_fill": (_i, [_i, _vp, _vp, _u64, _vp]),

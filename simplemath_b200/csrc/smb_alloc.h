@@ -24,6 +24,11 @@ struct Block {
     size_t bytes;   // rounded (bucket) size
     int device;     // owning device (-1 for pinned host)
     int kind;       // SMB_MEM_*
+    // Managed blocks only: pages may currently live in host memory (fresh from the driver, or
+    // the owner said the host wrote them).  Launchers prefetch such a block to the GPU once and
+    // clear the flag; blocks last written by a kernel / fill stay clean.  A stale "clean" is only
+    // a performance matter -- the GPU then demand-pages what the host touched.
+    bool maybe_on_host = true;
 };
 
 class Pool {
@@ -36,6 +41,10 @@ public:
     void *alloc(size_t bytes, int kind, int device, cudaError_t *err);
     bool free(void *ptr);
     bool owns(const void *ptr, Block *out = nullptr);
+    // For a managed address: returns the containing block and whether it needed a prefetch
+    // (and clears the flag).  false when the address is not in a live pool block.
+    bool take_host_flag(const void *ptr, Block *out, bool *was_on_host);
+    void set_host_flag(const void *ptr, bool on_host);
     void trim();
     void stats(uint64_t s[4]);
 

@@ -157,6 +157,26 @@ bool Pool::owns(const void *ptr, Block *out) {
     if (out) *out = b;
     return true;
 }
+bool Pool::take_host_flag(const void *ptr, Block *out, bool *was_on_host) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = live_.upper_bound((uintptr_t)ptr);
+    if (it == live_.begin()) return false;
+    --it;
+    Block &b = it->second;
+    if ((uintptr_t)ptr >= (uintptr_t)b.base + b.bytes) return false;
+    *out = b;
+    *was_on_host = b.maybe_on_host;
+    b.maybe_on_host = false;
+    return true;
+}
+void Pool::set_host_flag(const void *ptr, bool on_host) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = live_.upper_bound((uintptr_t)ptr);
+    if (it == live_.begin()) return;
+    --it;
+    Block &b = it->second;
+    if ((uintptr_t)ptr < (uintptr_t)b.base + b.bytes) b.maybe_on_host = on_host;
+}
 void Pool::trim() {
     std::lock_guard<std::mutex> lk(mu_);
     for (auto &kv : cached_) raw_free(kv.second);
@@ -188,6 +208,11 @@ struct Scratch {
 // ------------------------------------------------------- pointer kinds ------
 enum MemType { MT_HOST = 0, MT_PINNED = 1, MT_DEVICE = 2, MT_MANAGED = 3 };
 static MemType mem_type(const void *p) {
+    // Pool blocks first: no driver call (cudaPointerGetAttributes costs microseconds per operand,
+    // which is most of the launch overhead of a small operator).
+    Block blk;
+    if (Pool::instance().owns(p, &blk))
+        return blk.kind == SMB_MEM_DEVICE ? MT_DEVICE : blk.kind == SMB_MEM_MANAGED ? MT_MANAGED : MT_PINNED;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return MT_HOST; }
     switch (at.type) {
@@ -199,9 +224,20 @@ static MemType mem_type(const void *p) {
 }
 static inline bool on_host(MemType t) { return t == MT_HOST || t == MT_PINNED; }
 
+// Managed operands: bring the pages to the GPU before the launch -- but only when they may be
+// on the host.  cudaMemPrefetchAsync costs ~50 us even for resident pages (measured: 164 us per
+// 3-operand call), so pool blocks carry a "maybe on host" flag (smb_alloc.h); foreign managed
+// memory is always prefetched.
 static void prefetch_managed(const void *p, size_t bytes, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
+    Block blk;
+    bool was_on_host = true;
+    if (Pool::instance().take_host_flag(p, &blk, &was_on_host)) {
+        if (!was_on_host) return;
+        p = blk.base;        // whole block: views of it become resident too
+        bytes = blk.bytes;
+    }
     if (cudaMemPrefetchAsync(p, bytes, dev, s) != cudaSuccess) cudaGetLastError(); // best effort
 }
 
@@ -411,14 +447,43 @@ static int launch_bcast(const DeviceCtx &c, const ElementwisePlan &p, const T *a
         const int vb = row_vector_bytes<T>(p, a, b, out, lin_base, count);
         const int ar = operand_reused(p, p.sa), br = operand_reused(p, p.sb);
         const uint64_t nvec = count / (vb / sizeof(T));
-        const unsigned grid = grid_for(nvec, kThreads, c.sm_count, 0);
+        // Shared-memory staging of a small reused operand (SMB_OPT_BCAST_VARIANT = 1): kept as an
+        // option with its measurement -- on B200 the reused operand already sits in L1/L2 and the
+        // staged form is slower (C2: 6.47 vs 7.14 TB/s; profiles/r1_sweep_summary.md), so the
+        // default reads it through the caching load path.
+        int stage = 0;
+        uint32_t stage_elems = 0;
+        size_t smem = 0;
+        if (g_opt_bcast_variant.load() == 1 && vb == 16 && !wide) {
+            const uint64_t lim = 96 * 1024 / sizeof(T);
+            if (br && p.extent_b <= lim && (!ar || p.extent_b <= p.extent_a)) { stage = 2; stage_elems = (uint32_t)p.extent_b; }
+            else if (ar && p.extent_a <= lim) { stage = 1; stage_elems = (uint32_t)p.extent_a; }
+            if (stage) smem = 16 + (size_t)stage_elems * sizeof(T);
+        }
+        // both operands reused = output much larger than the inputs (outer-product-like, C4): a
+        // persistent grid of 32 CTAs/SM measured best; otherwise one tile per CTA
+        constexpr int UNROLL = 2;
+        const int64_t cap = stage ? 16 : ((ar && br) ? 32 : 0);
+        const unsigned grid = grid_for(nvec, (uint64_t)kThreads * UNROLL, c.sm_count, cap);
         if (vb == 16) {
-            if (wide) k_row<T, Fn, 16, true><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, fn);
-            else k_row<T, Fn, 16, false><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, fn);
-            g_last_kernel = wide ? "k_row<vec16,wide>" : "k_row<vec16>";
+            if (stage == 2) {
+                SMB_CK(cudaFuncSetAttribute(k_row<T, Fn, 16, false, UNROLL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_row<T, Fn, 16, false, UNROLL, 2><<<grid, kThreads, smem, s>>>(a, b, out, t, ar, br, stage_elems, fn);
+                g_last_kernel = "k_row<vec16,stage_b>";
+            } else if (stage == 1) {
+                SMB_CK(cudaFuncSetAttribute(k_row<T, Fn, 16, false, UNROLL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_row<T, Fn, 16, false, UNROLL, 1><<<grid, kThreads, smem, s>>>(a, b, out, t, ar, br, stage_elems, fn);
+                g_last_kernel = "k_row<vec16,stage_a>";
+            } else if (wide) {
+                k_row<T, Fn, 16, true, UNROLL, 0><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, 0u, fn);
+                g_last_kernel = "k_row<vec16,wide>";
+            } else {
+                k_row<T, Fn, 16, false, UNROLL, 0><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, 0u, fn);
+                g_last_kernel = "k_row<vec16>";
+            }
         } else {
-            if (wide) k_row<T, Fn, (int)sizeof(T), true><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, fn);
-            else k_row<T, Fn, (int)sizeof(T), false><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, fn);
+            if (wide) k_row<T, Fn, (int)sizeof(T), true, UNROLL, 0><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, 0u, fn);
+            else k_row<T, Fn, (int)sizeof(T), false, UNROLL, 0><<<grid, kThreads, 0, s>>>(a, b, out, t, ar, br, 0u, fn);
             g_last_kernel = wide ? "k_row<scalar,wide>" : "k_row<scalar>";
         }
     }
@@ -733,6 +798,11 @@ void *smb_alloc(size_t bytes, int kind) {
 int smb_free(void *ptr) {
     if (!ptr) return SMB_OK;
     if (!Pool::instance().free(ptr)) return fail(SMB_ERR_INVALID, "smb_free: %p was not returned by smb_alloc", ptr);
+    return SMB_OK;
+}
+
+int smb_host_written(const void *ptr) {
+    if (ptr) Pool::instance().set_host_flag(ptr, true);
     return SMB_OK;
 }
 

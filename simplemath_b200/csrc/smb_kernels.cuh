@@ -383,47 +383,112 @@ __device__ __forceinline__ void offsets_of(const BcastTable &t, uint64_t lin, ui
     }
 }
 
-// k_row: inner strides in {0,1}.  Each thread produces EPV consecutive outputs
-// of one row (host guarantees inner length, lin_base and the row bases are
-// multiples of EPV and 16/32-byte aligned when EPV > 1).  An operand with inner
-// stride 1 is read with one vector load; with inner stride 0 with one scalar
-// load that is splat.  Operands with any zero stride are re-read by other
-// threads, so they use the default (caching) load path; pure streams use the
-// streaming hints.
-template<typename T, typename Fn, int VB, bool WIDE>
+// ---------------------------------------------------------------------------
+// mbarrier + 1-D bulk copy (TMA engine, SASS UBLKCP): used to stage a reused broadcast
+// operand in shared memory with one instruction instead of a load/store loop.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(smem)), "l"(gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// k_row: inner strides in {0,1}.  Each thread produces UNROLL vectors of EPV consecutive
+// outputs per iteration (host guarantees inner length, lin_base and the row bases are
+// multiples of EPV and 16-byte aligned when EPV > 1); all operand loads of an iteration are
+// issued before the first use.  An operand with inner stride 1 is read with one vector
+// load; with inner stride 0 with one scalar load that is splat.  Operands with any zero
+// stride are re-read by other threads, so they use the default (caching) load path; pure
+// streams use the streaming hints.
+//
+// STAGE = 1 / 2: operand a / b is small (its whole extent fits the shared-memory budget)
+// and reused -- it is staged in shared memory once per CTA (one cp.async.bulk when
+// 16-byte aligned, else a copy loop) and every later read of it is an LDS.  The grid is
+// persistent in that case so the staging is amortised.
+template<typename T, typename Fn, int VB, bool WIDE, int UNROLL, int STAGE>
 __global__ void __launch_bounds__(256) k_row(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
-                                            const __grid_constant__ BcastTable t, int a_reused, int b_reused, Fn fn) {
+                                            const __grid_constant__ BcastTable t, int a_reused, int b_reused,
+                                            uint32_t stage_elems, Fn fn) {
     constexpr int EPV = VB / (int)sizeof(T);
+    extern __shared__ __align__(16) unsigned char k_row_smem[];
+    if constexpr (STAGE != 0) {
+        T *s_op = reinterpret_cast<T *>(k_row_smem + 16);
+        uint64_t *bar = reinterpret_cast<uint64_t *>(k_row_smem);
+        const T *src = STAGE == 1 ? a : b;
+        const uint32_t bytes = stage_elems * (uint32_t)sizeof(T);
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (bytes & 15) == 0) {
+            if (threadIdx.x == 0) {
+                mbar_init(bar, 1);
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(s_op, src, bytes, bar);
+            }
+            __syncthreads();
+            mbar_wait(bar, 0);
+        } else {
+            for (uint32_t i = threadIdx.x; i < stage_elems; i += kBlock) s_op[i] = src[i];
+            __syncthreads();
+        }
+        if (STAGE == 1) a = s_op; else b = s_op;
+    }
     const uint64_t nvec = t.count / EPV; // host guarantees count % EPV == 0 when EPV > 1
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const int m = t.ndim;
     const bool ia = t.sa[m - 1] != 0, ib = t.sb[m - 1] != 0;
-    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        const uint64_t lin = t.lin_base + v * EPV;
-        uint64_t oa, ob;
-        offsets_of<WIDE>(t, lin, oa, ob);
-        Pack<T, VB> pa, pb, r;
-        if constexpr (EPV == 1) {
-            pa.e[0] = a[oa];
-            pb.e[0] = b[ob];
-        } else {
-            if (ia) pa.raw = a_reused ? VecIO<VB, false>::load(a + oa) : VecIO<VB, true>::load(a + oa);
-            else {
-                const T s = a[oa];
+    constexpr uint64_t tile = (uint64_t)kBlock * UNROLL;
+    for (uint64_t v0 = (uint64_t)blockIdx.x * tile + threadIdx.x; v0 < nvec; v0 += (uint64_t)gridDim.x * tile) {
+        Pack<T, VB> pa[UNROLL], pb[UNROLL];
 #pragma unroll
-                for (int k = 0; k < EPV; ++k) pa.e[k] = s;
-            }
-            if (ib) pb.raw = b_reused ? VecIO<VB, false>::load(b + ob) : VecIO<VB, true>::load(b + ob);
-            else {
-                const T s = b[ob];
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t v = v0 + (uint64_t)u * kBlock;
+            if (v < nvec) {
+                uint64_t oa, ob;
+                offsets_of<WIDE>(t, t.lin_base + v * EPV, oa, ob);
+                if constexpr (EPV == 1) {
+                    pa[u].e[0] = a[oa];
+                    pb[u].e[0] = b[ob];
+                } else {
+                    if (ia) {
+                        if (STAGE == 1) pa[u].raw = *reinterpret_cast<const RawVec<VB> *>(a + oa);
+                        else pa[u].raw = a_reused ? VecIO<VB, false>::load(a + oa) : VecIO<VB, true>::load(a + oa);
+                    } else {
+                        const T s = a[oa];
 #pragma unroll
-                for (int k = 0; k < EPV; ++k) pb.e[k] = s;
+                        for (int k = 0; k < EPV; ++k) pa[u].e[k] = s;
+                    }
+                    if (ib) {
+                        if (STAGE == 2) pb[u].raw = *reinterpret_cast<const RawVec<VB> *>(b + ob);
+                        else pb[u].raw = b_reused ? VecIO<VB, false>::load(b + ob) : VecIO<VB, true>::load(b + ob);
+                    } else {
+                        const T s = b[ob];
+#pragma unroll
+                        for (int k = 0; k < EPV; ++k) pb[u].e[k] = s;
+                    }
+                }
             }
         }
 #pragma unroll
-        for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa.e[k], pb.e[k], t.lane_base + v * EPV + k);
-        if constexpr (EPV == 1) out[v] = r.e[0];
-        else VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v, r.raw);
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t v = v0 + (uint64_t)u * kBlock;
+            if (v < nvec) {
+                Pack<T, VB> r;
+#pragma unroll
+                for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa[u].e[k], pb[u].e[k], t.lane_base + v * EPV + k);
+                if constexpr (EPV == 1) out[v] = r.e[0];
+                else VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v, r.raw);
+            }
+        }
     }
 }
 

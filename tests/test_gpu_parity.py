@@ -252,6 +252,27 @@ def test_staging_pipeline_many_chunks(orc):
         smb.set_option(smb.OPT_STAGE_CHUNK_BYTES, 64 << 20)
 
 
+def test_shared_memory_staged_broadcast_variant(orc):
+    """SMB_OPT_BCAST_VARIANT=1: the small reused operand is staged in shared memory
+    (cp.async.bulk when aligned, copy loop otherwise); same bits as the default path."""
+    rng = np.random.default_rng(21)
+    smb.set_option(smb.OPT_BCAST_VARIANT, 1)
+    try:
+        a = rng.standard_normal((300, 1024)).astype(np.float32)
+        row = rng.standard_normal((1, 1024)).astype(np.float32)
+        assert_same_bits(smb.binary("add", a, row), orc.binary("add", a, row), "stage b (bulk copy)")
+        assert smb.last_kernel() == "k_row<vec16,stage_b>"
+        assert_same_bits(smb.binary("sub", row, a), orc.binary("sub", row, a), "stage a")
+        assert smb.last_kernel() == "k_row<vec16,stage_a>"
+        big = rng.integers(-99, 99, size=(4, 64, 20, 4)).astype(np.int32)
+        small = rng.integers(1, 9, size=(1, 64, 1, 4)).astype(np.int32)
+        assert_same_bits(smb.binary("mul", big[2], small), orc.binary("mul", big[2], small), "4-D view, staged small operand")
+        col = rng.standard_normal((300, 1)).astype(np.float32)
+        assert_same_bits(smb.binary("mul", a, col), orc.binary("mul", a, col), "inner-broadcast operand staged")
+    finally:
+        smb.set_option(smb.OPT_BCAST_VARIANT, 0)
+
+
 # ---- device-resident operands (torch owns the memory; the C ABI gets raw addresses) ----
 def _torch():
     import torch

@@ -1,0 +1,135 @@
+"""tools/bench_configs.py -- BASELINE.json configs C1-C4 (and f64 / specialised pow),
+GPU (device-resident operands, CUDA events) beside the compiled reference on the
+host cores.  Not the headline (bench.py is); this fills the per-config table in
+profiles/ and README.md.
+
+    python tools/bench_configs.py [--reps 20] [--no-cpu] > gpurun_out/configs.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import simplemath_b200 as smb
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--no-cpu", action="store_true")
+args = ap.parse_args()
+PEAK = 6540.5
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+stream = torch.cuda.current_stream()
+sp = stream.cuda_stream
+TD = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32}
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def cpu_time(fn, reps=3):
+    fn()
+    best = 1e30
+    for _ in range(reps):
+        t = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t)
+    return best * 1e3
+
+
+def report(name, bytes_, n, ms, cpu_ms=None, note=""):
+    row = {"config": name, "elements": n, "algorithmic_bytes": bytes_, "gpu_ms": ms, "gpu_gbs": bytes_ / ms / 1e6,
+           "gpu_gelem_s": n / ms / 1e6, "frac_measured_peak": bytes_ / ms / 1e6 / PEAK, "frac_nominal_8000": bytes_ / ms / 1e6 / 8000,
+           "kernel": smb.last_kernel(), "note": note}
+    if cpu_ms is not None:
+        row.update(cpu_ms=cpu_ms, cpu_gbs=bytes_ / cpu_ms / 1e6, speedup_vs_cpu=cpu_ms / ms)
+    print(json.dumps(row), flush=True)
+
+
+ref = None
+if not args.no_cpu:
+    import oracle
+    ref = oracle.reference()
+    if ref is not None:
+        ref.h.smref_set_threads(os.cpu_count() or 1)
+
+
+def binary_case(name, op, a, b, note=""):
+    dt = smb.dtype_code(a.dtype)
+    shape, sa, sb, n = smb.broadcast(a.shape, smb.row_major_strides(a.shape), b.shape, smb.row_major_strides(b.shape))
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = torch.empty(n, dtype=TD[a.dtype.type], device="cuda")
+    # pre-marshalled arguments: the small configs are launch-latency bound, keep Python out of the loop
+    lib, u = smb.lib(), smb._u64arr
+    argv = (smb.OPS[op], dt, da.data_ptr(), u(sa), db.data_ptr(), u(sb), u(shape), len(shape), n, out.data_ptr(), sp)
+    fn = lambda: lib.smb_elementwise(*argv)
+    ms = timed(fn, args.reps)
+    bytes_ = a.itemsize * (n + a.size + b.size)
+    cpu_ms = cpu_time(lambda: ref.smarray_binary(op, a, b, want_result=False)) if ref is not None else None
+    report(name, bytes_, n, ms, cpu_ms, note)
+
+
+def scalar_case(name, op, a, v, spec=1, note=""):
+    dt = smb.dtype_code(a.dtype)
+    n = a.size
+    da = torch.from_numpy(a).cuda()
+    out = torch.empty(n, dtype=TD[a.dtype.type], device="cuda")
+    smb.set_option(smb.OPT_POW_SPECIALISE, spec)
+    import ctypes
+    val = smb._CT[dt](v)
+    lib = smb.lib()
+    argv = (smb.OPS[op], dt, da.data_ptr(), ctypes.byref(val), n, out.data_ptr(), sp)
+    fn = lambda: lib.smb_array_scalar(*argv)
+    ms = timed(fn, args.reps)
+    smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+    cpu_ms = cpu_time(lambda: ref.smarray_scalar(op, a, v, want_result=False), reps=2) if ref is not None else None
+    report(name, 2 * a.itemsize * n, n, ms, cpu_ms, note)
+
+
+rng = np.random.default_rng(1)
+# C1: benchmark_add million_check
+a = rng.uniform(-1, 1, 1_000_000).astype(np.float32)
+b = rng.uniform(-1, 1, 1_000_000).astype(np.float32)
+binary_case("C1 f32 1M contiguous a+b (million_check)", "add", a, b, "12 MB: launch-latency bound, L2 resident")
+# C2: row broadcast
+a = rng.uniform(-1, 1, (4096, 4096)).astype(np.float32)
+b = rng.uniform(-1, 1, (1, 4096)).astype(np.float32)
+binary_case("C2 f32 {4096,4096}+{1,4096}", "add", a, b, "134 MB: about the size of L2")
+a = rng.uniform(-1, 1, (65536, 4096)).astype(np.float32)
+binary_case("C2x16 f32 {65536,4096}+{1,4096}", "add", a, b, "1 GiB, not L2 resident")
+del a
+# C3: pow on 256M elements
+x = (np.add.outer(np.arange(16384, dtype=np.float32), np.arange(16384, dtype=np.float32)) + 1).ravel()  # arr(i,j)=i+j+1
+scalar_case("C3 f32 pow(arr,2.0) 256M, i+j+1 fill, specialised x*x", "pow", x, 2.0, 1)
+scalar_case("C3 f32 pow(arr,2.0) 256M, i+j+1 fill, general kernel", "pow", x, 2.0, 0)
+x = rng.uniform(0.01, 100, 1 << 28).astype(np.float32)
+scalar_case("C3 f32 pow(arr,2.5) 256M uniform(0.01,100), general kernel", "pow", x, 2.5, 0)
+scalar_case("C3 f32 pow(arr,17.5) 256M uniform, large-|y| variant", "pow", x, 17.5, 0, "many results overflow -> slow path share")
+scalar_case("C3 f32 pow(arr,9.25) 256M uniform, large-|y| variant", "pow", x, 9.25, 0)
+xd = x[: 1 << 27].astype(np.float64)
+del x
+scalar_case("C3 f64 pow(arr,2.5) 128M uniform, general kernel (FP64-pipe bound)", "pow", xd, 2.5, 0)
+scalar_case("C3 f64 pow(arr,2.0) 128M specialised", "pow", xd, 2.0, 1)
+del xd
+# C4: int32 3-D broadcast
+ia = rng.integers(-1000, 1001, size=(512, 1, 1024)).astype(np.int32)
+ib = rng.integers(1, 98, size=(1, 512, 1024)).astype(np.int32)
+binary_case("C4 i32 {512,1,1024}*{1,512,1024}", "mul", ia, ib, "write-dominated: 1 GiB out, 4 MiB in")
+binary_case("C4 i32 {512,1,1024}/{1,512,1024}", "div", ia, ib, "integer division is instruction-bound")

@@ -62,24 +62,7 @@ __global__ void __launch_bounds__(256) k_copy(const float *__restrict__ a, float
 // memory.  One thread issues cp.async.bulk global->shared for the operands
 // (completion on an mbarrier) and cp.async.bulk shared->global for results;
 // all threads do LDS.128 / FADD / STS.128 in between.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return smem_addr(p); }
 __device__ __forceinline__ void bulk_s2g(void *gmem, const void *smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gmem), "r"(smem_u32(smem)), "r"(bytes) : "memory");
 }
@@ -214,9 +197,32 @@ static void run_tma(const float *a, const float *b, float *out, uint64_t n) {
     }
 }
 
+template<typename T, int OP, int UNROLL, int STAGE>
+static void run_row_variant(const char *name, const T *a, const T *b, T *out, const ElementwisePlan &p, const BcastTable &t,
+                            double bytes) {
+    using Fn = BinaryFn<OP, T>;
+    auto reused = [&](const uint64_t *s) { for (int k = 0; k < p.ndim; ++k) if (s[k] == 0 && p.shape[k] > 1) return 1; return 0; };
+    const int ar = reused(p.sa), br = reused(p.sb);
+    const uint64_t ext = STAGE == 1 ? p.extent_a : p.extent_b;
+    const size_t smem = STAGE ? 16 + ext * sizeof(T) : 0;
+    if (smem > 200 * 1024) return;
+    if (STAGE) CK(cudaFuncSetAttribute(k_row<T, Fn, 16, false, UNROLL, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int caps[] = {0, 4, 8, 16, 32};
+    for (int cap : caps) {
+        if (STAGE && cap == 0) continue;
+        uint64_t nvec = p.n / (16 / sizeof(T));
+        uint64_t blocks = (nvec + 256 * UNROLL - 1) / (256 * UNROLL);
+        if (cap) blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * cap);
+        float ms = time_ms([&] { k_row<T, Fn, 16, false, UNROLL, STAGE><<<(unsigned)blocks, 256, smem>>>(a, b, out, t, ar, br, (uint32_t)ext, Fn{0}); });
+        char pr[128];
+        snprintf(pr, sizeof pr, "vec16 unroll=%d stage=%d ctas_per_sm=%d", UNROLL, STAGE, cap);
+        report(name, pr, bytes, ms);
+    }
+}
+
 template<typename T, int OP>
 static void run_row(const char *name, const T *a, const T *b, T *out, const uint64_t *shape, const uint64_t *sa, const uint64_t *sb,
-                    int ndim, double bytes) {
+                    int ndim, double bytes, bool try_stage_b) {
     ElementwisePlan p = make_plan(sa, sb, shape, ndim);
     BcastTable t;
     memset(&t, 0, sizeof t);
@@ -230,18 +236,12 @@ static void run_row(const char *name, const T *a, const T *b, T *out, const uint
         t.shape[k] = f.d; t.mul[k] = f.mul; t.shr[k] = f.shr;
     }
     t.lin_base = 0; t.count = p.n; t.lane_base = 0;
-    using Fn = BinaryFn<OP, T>;
-    const int caps[] = {0, 8, 16, 32};
-    for (int cap : caps) {
-        uint64_t nvec = p.n / (16 / sizeof(T));
-        uint64_t blocks = (nvec + 255) / 256;
-        if (cap) blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * cap);
-        auto reused = [&](const uint64_t *s) { for (int k = 0; k < p.ndim; ++k) if (s[k] == 0 && p.shape[k] > 1) return 1; return 0; };
-        const int ar = reused(p.sa), br = reused(p.sb);
-        float ms = time_ms([&] { k_row<T, Fn, 16, false><<<(unsigned)blocks, 256>>>(a, b, out, t, ar, br, Fn{0}); });
-        char pr[128];
-        snprintf(pr, sizeof pr, "vec16 ctas_per_sm=%d", cap);
-        report(name, pr, bytes, ms);
+    run_row_variant<T, OP, 1, 0>(name, a, b, out, p, t, bytes);
+    run_row_variant<T, OP, 2, 0>(name, a, b, out, p, t, bytes);
+    run_row_variant<T, OP, 4, 0>(name, a, b, out, p, t, bytes);
+    if (try_stage_b) {
+        run_row_variant<T, OP, 1, 2>(name, a, b, out, p, t, bytes);
+        run_row_variant<T, OP, 4, 2>(name, a, b, out, p, t, bytes);
     }
 }
 
@@ -313,19 +313,19 @@ int main(int argc, char **argv) {
     if (want("row")) {
         { // C2: f32 {4096,4096} + {1,4096}
             const uint64_t shape[2] = {4096, 4096}, sa[2] = {4096, 1}, sb[2] = {0, 1};
-            run_row<float, OP_ADD>("c2_row_add_f32", a, b, out, shape, sa, sb, 2, 4.0 * (2 * 16777216.0 + 4096));
+            run_row<float, OP_ADD>("c2_row_add_f32", a, b, out, shape, sa, sb, 2, 4.0 * (2 * 16777216.0 + 4096), true);
         }
         { // C2 scaled up to 1 GiB so it is not L2-resident: {65536,4096} + {1,4096}
             const uint64_t shape[2] = {65536, 4096}, sa[2] = {4096, 1}, sb[2] = {0, 1};
-            if (n >= (1ull << 28)) run_row<float, OP_ADD>("c2x16_row_add_f32", a, b, out, shape, sa, sb, 2, 4.0 * (2 * 268435456.0 + 4096));
+            if (n >= (1ull << 28)) run_row<float, OP_ADD>("c2x16_row_add_f32", a, b, out, shape, sa, sb, 2, 4.0 * (2 * 268435456.0 + 4096), true);
         }
         { // C4: i32 {512,1,1024} * {1,512,1024}
             const uint64_t shape[3] = {512, 512, 1024}, sa[3] = {1024, 0, 1}, sb[3] = {0, 1024, 1};
             if (n >= (1ull << 28)) {
-                run_row<int32_t, OP_MUL>("c4_row_mul_i32", (const int32_t *)a, (const int32_t *)b, (int32_t *)out, shape, sa, sb, 3, 4.0 * (268435456.0 + 2 * 524288));
+                run_row<int32_t, OP_MUL>("c4_row_mul_i32", (const int32_t *)a, (const int32_t *)b, (int32_t *)out, shape, sa, sb, 3, 4.0 * (268435456.0 + 2 * 524288), false);
                 k_fill<uint32_t><<<g_sms * 8, 256>>>((uint32_t *)b, 524288, 7u);
                 CK(cudaDeviceSynchronize());
-                run_row<int32_t, OP_DIV>("c4_row_div_i32", (const int32_t *)a, (const int32_t *)b, (int32_t *)out, shape, sa, sb, 3, 4.0 * (268435456.0 + 2 * 524288));
+                run_row<int32_t, OP_DIV>("c4_row_div_i32", (const int32_t *)a, (const int32_t *)b, (int32_t *)out, shape, sa, sb, 3, 4.0 * (268435456.0 + 2 * 524288), false);
             }
         }
     }
