@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libsmb200.so")
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW = range(5)
 F32, F64, I32 = range(3)
 MEM_DEVICE, MEM_MANAGED, MEM_PINNED = range(3)
-OPT_POW_SPECIALISE, OPT_STAGE_CHUNK_BYTES, OPT_CONTIG_VARIANT, OPT_BCAST_VARIANT = range(4)
+OPT_POW_SPECIALISE, OPT_STAGE_CHUNK_BYTES, OPT_CONTIG_VARIANT, OPT_BCAST_VARIANT, OPT_FORCE_WIDE_INDEX = range(5)
 PLAN_CONTIGUOUS, PLAN_ROW, PLAN_GENERIC = range(3)
 MAX_NDIM = 6
 

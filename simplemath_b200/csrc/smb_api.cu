@@ -45,6 +45,7 @@ static std::atomic<int64_t> g_opt_pow_specialise{1};
 static std::atomic<int64_t> g_opt_chunk_bytes{64ll << 20};
 static std::atomic<int64_t> g_opt_contig_variant{0};
 static std::atomic<int64_t> g_opt_bcast_variant{0};
+static std::atomic<int64_t> g_opt_force_wide{0};
 
 // ------------------------------------------------------ device context ------
 constexpr int kSlots = 3; // staging pipeline depth (H2D | kernel | D2H in flight)
@@ -382,7 +383,7 @@ static BcastTable make_table(const ElementwisePlan &p, uint64_t lin_base, uint64
     BcastTable t;
     memset(&t, 0, sizeof t);
     t.ndim = p.ndim;
-    bool w = lin_base + count > (1ull << 31);
+    bool w = lin_base + count > (1ull << 31) || g_opt_force_wide.load() != 0;
     for (int k = 0; k < SMB_MAX_NDIM; ++k) {
         const uint64_t d = k < p.ndim ? p.shape[k] : 1;
         if (d >= (1ull << 31)) w = true;
@@ -874,6 +875,7 @@ int smb_set_option(int key, int64_t value) {
         case SMB_OPT_STAGE_CHUNK_BYTES: g_opt_chunk_bytes = value; return SMB_OK;
         case SMB_OPT_CONTIG_VARIANT: g_opt_contig_variant = value; return SMB_OK;
         case SMB_OPT_BCAST_VARIANT: g_opt_bcast_variant = value; return SMB_OK;
+        case SMB_OPT_FORCE_WIDE_INDEX: g_opt_force_wide = value ? 1 : 0; return SMB_OK;
     }
     return fail(SMB_ERR_INVALID, "unknown option %d", key);
 }
@@ -883,6 +885,7 @@ int64_t smb_get_option(int key) {
         case SMB_OPT_STAGE_CHUNK_BYTES: return g_opt_chunk_bytes;
         case SMB_OPT_CONTIG_VARIANT: return g_opt_contig_variant;
         case SMB_OPT_BCAST_VARIANT: return g_opt_bcast_variant;
+        case SMB_OPT_FORCE_WIDE_INDEX: return g_opt_force_wide;
     }
     return -1;
 }

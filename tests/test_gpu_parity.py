@@ -273,6 +273,51 @@ def test_shared_memory_staged_broadcast_variant(orc):
         smb.set_option(smb.OPT_BCAST_VARIANT, 0)
 
 
+def test_wide_index_path_on_small_shapes(orc):
+    """The 64-bit index kernels (results beyond 2^31 elements) forced on small shapes."""
+    rng = np.random.default_rng(31)
+    smb.set_option(smb.OPT_FORCE_WIDE_INDEX, 1)
+    try:
+        for s1, s2 in SHAPES:
+            a, b = _operands(rng, np.int32, "mul", s1, s2)
+            assert_same_bits(smb.binary("mul", a, b), orc.binary("mul", a, b), f"wide {s1}x{s2} [{smb.last_kernel()}]")
+        a = rng.standard_normal((64, 256)).astype(np.float32)
+        row = rng.standard_normal((1, 256)).astype(np.float32)
+        smb.binary("add", a, row)
+        assert smb.last_kernel() == "k_row<vec16,wide>"
+        m = rng.standard_normal((37, 53)).astype(np.float64)
+        n = rng.standard_normal((53, 37)).astype(np.float64)
+        assert_same_bits(smb.binary("div", m.T, n), orc.binary("div", m.T, n), "wide generic")
+        assert smb.last_kernel() == "k_generic<wide>"
+    finally:
+        smb.set_option(smb.OPT_FORCE_WIDE_INDEX, 0)
+
+
+def test_result_beyond_2_31_elements(orc):
+    """A real > 2^31-element result: {3, 2^30} + {1, 2^30} int32 (12 GiB out), sampled windows
+    against the oracle plus a whole-array identity on the device."""
+    torch = _torch()
+    L = 1 << 30
+    a = torch.empty(3 * L, dtype=torch.int32, device="cuda")
+    b = torch.empty(L, dtype=torch.int32, device="cuda")
+    out = torch.empty(3 * L, dtype=torch.int32, device="cuda")
+    # deterministic fill: reuse the f32 generator's bit patterns as int32 data
+    smb.fill_uniform_f32_ptr(a.data_ptr(), 0, 3 * L, 11, 1.0, 2.0)
+    smb.fill_uniform_f32_ptr(b.data_ptr(), 0, L, 12, 1.0, 2.0)
+    shape, sa, sb, n = smb.broadcast((3, L), (L, 1), (1, L), (L, 1))
+    assert n == 3 * L > 2**31
+    smb.elementwise_ptr(smb.OP_ADD, smb.I32, a.data_ptr(), sa, b.data_ptr(), sb, shape, out.data_ptr())
+    assert smb.last_kernel() == "k_row<vec16,wide>"
+    for row in range(3):
+        assert bool((out[row * L:(row + 1) * L] == a[row * L:(row + 1) * L] + b).all())
+    w = 1 << 16
+    for start in (0, 2**31 - w // 2, 3 * L - w):
+        ha = orc.fill_uniform_f32(start, w, 11, 1.0, 2.0).view(np.int32)
+        hb = np.concatenate([orc.fill_uniform_f32((start + k) % L, w // 2, 12, 1.0, 2.0) for k in (0, w // 2)]).view(np.int32)
+        want = orc.elementwise("add", ha, [1], hb, [1], [w])
+        assert_same_bits(out[start:start + w].cpu().numpy(), want, f"window at {start}")
+
+
 # ---- device-resident operands (torch owns the memory; the C ABI gets raw addresses) ----
 def _torch():
     import torch
