@@ -335,9 +335,11 @@ int scalar_t<float>(const DeviceCtx &c, int op, const float *a, float v, float *
             }
             {
                 const PowExpF32 pe = classify_exp(v);
-                if (pow_f32_small_y(pe))
-                    return launch_stream<T, PowF32Fn<true>, false>(c, a, nullptr, out, n, first, PowF32Fn<true>::make(v, lane_end), s);
-                return launch_stream<T, PowF32Fn<false>, false>(c, a, nullptr, out, n, first, PowF32Fn<false>::make(v, lane_end), s);
+                const bool small = pow_f32_small_y(pe), odd = pe.y_is_odd != 0;
+#define SMB_POW_LAUNCH(S, O) launch_stream<T, PowF32Fn<S, O>, false>(c, a, nullptr, out, n, first, PowF32Fn<S, O>::make(v, lane_end), s)
+                if (small) return odd ? SMB_POW_LAUNCH(true, true) : SMB_POW_LAUNCH(true, false);
+                return odd ? SMB_POW_LAUNCH(false, true) : SMB_POW_LAUNCH(false, false);
+#undef SMB_POW_LAUNCH
             }
         }
     }

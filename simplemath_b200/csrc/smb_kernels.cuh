@@ -20,9 +20,6 @@
 namespace smb {
 
 constexpr int kBlock = 256; // threads per CTA of every kernel in this file
-#ifndef SMB_POW_MIN_BLOCKS
-#define SMB_POW_MIN_BLOCKS 1 // no register cap: 74 regs, 3 CTAs/SM measured fastest (tools/sweep, caps 3/4/5 were slower)
-#endif
 
 // ---------------------------------------------------------------------------
 // 16-byte and 32-byte global vector access with streaming cache hints.
@@ -130,20 +127,19 @@ __device__ __noinline__ float pow_f32_slow(float x, PowExpF32 pe) { return pow_f
 static __device__ const PowTabLog d_pow_log_tab[SMB_POW_LOG_ENTRIES] = SMB_POW_LOG_TABLE_INIT;
 static __device__ const PowTabExp d_pow_exp_tab[SMB_POW_EXP_ENTRIES] = SMB_POW_EXP_TABLE_INIT;
 
-template<bool SMALL_Y> struct PowF32Fn {
+template<bool SMALL_Y, bool ODD_Y> struct PowF32Fn {
     static constexpr bool PAIRWISE = true;    // stream_vec feeds two elements per call
     static constexpr bool POW_TABLES = true;  // k_stream stages the lookup tables in shared memory
     PowExpF32 pe;  // exponent classified once on the host
     uint64_t lane_end;
     int fast;              // pow_f32_fast_ok(pe)
     uint32_t sign_reject;  // 0x80000000 when negative bases must take the slow path (non-integer y)
-    uint32_t odd_mask;     // 0x80000000 when y is an odd integer (result keeps the base's sign)
     const PowTabLog *tab_log;
     const PowTabExp *tab_exp;
     __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return pow_f32_slow(a, pe); }
     // Two elements through the branch-free fast core; false = redo on the slow path.
     __device__ __forceinline__ bool pair(float a0, float a1, float &r0, float &r1) const {
-        return pow_f32_pair_fast<SMALL_Y>(a0, a1, pe.y, sign_reject, odd_mask, tab_log, tab_exp, &r0, &r1) && fast != 0;
+        return pow_f32_pair_fast<SMALL_Y, ODD_Y>(a0, a1, pe.y, sign_reject, tab_log, tab_exp, &r0, &r1) && fast != 0;
     }
     static PowF32Fn make(float y, uint64_t lane_end_) {
         PowF32Fn fn;
@@ -151,13 +147,12 @@ template<bool SMALL_Y> struct PowF32Fn {
         fn.lane_end = lane_end_;
         fn.fast = pow_f32_fast_ok(fn.pe) ? 1 : 0;
         fn.sign_reject = pow_f32_sign_reject(fn.pe);
-        fn.odd_mask = pow_f32_odd_mask(fn.pe);
         fn.tab_log = nullptr; // set per CTA from shared memory
         fn.tab_exp = nullptr;
         return fn;
     }
 };
-template<> struct ScalarFn<OP_POW, float> : PowF32Fn<false> {};
+template<> struct ScalarFn<OP_POW, float> : PowF32Fn<false, true> {};
 template<> struct ScalarFn<OP_POW, double> {
     PowExpF64 pe;
     uint64_t lane_end;
@@ -248,7 +243,7 @@ __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__
 }
 
 template<typename T, typename Fn, bool HAS_B, int VB, int UNROLL>
-__global__ void __launch_bounds__(256, fn_pow_tables<Fn>::value ? SMB_POW_MIN_BLOCKS : 1) k_stream(const T *__restrict__ a, const T *__restrict__ b,
+__global__ void __launch_bounds__(256) k_stream(const T *__restrict__ a, const T *__restrict__ b,
                                                T *__restrict__ out, uint64_t n, uint64_t first, Fn fn_in) {
     constexpr int EPV = VB / (int)sizeof(T); // elements per vector
     Fn fn = fn_in;

@@ -463,9 +463,9 @@ SMB_HD float rcp_seed(float x) {
 #define SMB_POW_LOG_STRIDE 1
 #define SMB_POW_EXP_STRIDE 1
 #endif
-SMB_HD PowTabLog pow_tab_log_at(const PowTabLog *tab, int32_t d) {
-    // j = (d >> 16) & 127, scaled to a byte offset in one shift + mask
-    const uint32_t off = ((uint32_t)d >> (16 - 4 - (SMB_POW_LOG_STRIDE == 8 ? 3 : 0))) & (127u * 16u * SMB_POW_LOG_STRIDE);
+SMB_HD PowTabLog pow_tab_log_at(const PowTabLog *tab, uint32_t a) {
+    // j = top 7 mantissa bits = (a >> 16) & 127, scaled to a byte offset in one shift + mask
+    const uint32_t off = (a >> (16 - 4 - (SMB_POW_LOG_STRIDE == 8 ? 3 : 0))) & (127u * 16u * SMB_POW_LOG_STRIDE);
     return *reinterpret_cast<const PowTabLog *>(reinterpret_cast<const char *>(tab) + off);
 }
 SMB_HD PowTabExp pow_tab_exp_at(const PowTabExp *tab, uint32_t k) {
@@ -487,20 +487,22 @@ SMB_HD bool pow_f32_fast_ok(const PowExpF32 &pe) {
 //
 // SMALL_Y (|y| <= 8, chosen on the host): the error terms that only matter once they
 // are multiplied by a large exponent are dropped -- the rounding error of m + c
-// (2^-25 relative in p, 2^-31 absolute in log2 x) and the renormalisation of the
-// log2 tail -- 6 of the 32 packed operations per pair.
-template<bool SMALL_Y>
-SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, uint32_t sign_reject, uint32_t odd_mask,
+// (2^-25 relative in p, 2^-31 absolute in log2 x), the low word of 2/ln2, the p^5
+// term and the renormalisation of the log2 tail.
+// ODD_Y: y is an odd integer, the result takes the sign of the base.
+template<bool SMALL_Y, bool ODD_Y>
+SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, uint32_t sign_reject,
                               const PowTabLog *tab_log, const PowTabExp *tab_exp, float *r0, float *r1) {
     const uint32_t u0 = f2u(x0), u1 = f2u(x1);
     const uint32_t a0 = u0 & 0x7fffffffu, a1 = u1 & 0x7fffffffu;
-    // normal finite magnitude; negative bases only with an integer exponent (sign_reject = 0 then)
-    const uint32_t w0 = a0 - 0x00800000u, w1 = a1 - 0x00800000u;
-    bool ok = (w0 > w1 ? w0 : w1) < 0x7f000000u && ((u0 | u1) & sign_reject) == 0u;
-    // ---- log2 |x| -------------------------------------------------------------
-    const int32_t d0 = (int32_t)(a0 - 0x3f3504f3u), d1 = (int32_t)(a1 - 0x3f3504f3u);
-    const f2 m = f2_make(u2f(a0 - ((uint32_t)d0 & 0xff800000u)), u2f(a1 - ((uint32_t)d1 & 0xff800000u)));
-    const PowTabLog t0 = pow_tab_log_at(tab_log, d0), t1 = pow_tab_log_at(tab_log, d1);
+    const uint32_t eb0 = a0 >> 23, eb1 = a1 >> 23;           // biased exponents
+    // normal finite magnitude (biased exponent 1..254); negative bases only with an integer
+    // exponent (sign_reject = 0 then)
+    const uint32_t w0 = eb0 - 1u, w1 = eb1 - 1u;
+    bool ok = (w0 > w1 ? w0 : w1) < 254u && ((u0 | u1) & sign_reject) == 0u;
+    // ---- log2 |x|,  |x| = 2^E * f,  f in [1, 2) ----------------------------------
+    const f2 m = f2_make(u2f((a0 & 0x007fffffu) | 0x3f800000u), u2f((a1 & 0x007fffffu) | 0x3f800000u));
+    const PowTabLog t0 = pow_tab_log_at(tab_log, a0), t1 = pow_tab_log_at(tab_log, a1);
     const f2 num = f2_sub(m, f2_make(t0.c, t1.c));         // exact (Sterbenz); the only use of c
     const f2 two = f2_splat(2.0f);
     const f2 den = f2_fma(m, two, f2_neg(num));            // 2m - (m - c) = m + c, one rounding
@@ -517,15 +519,20 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, uint32_t sign_reject,
     // log2(m/c) = C0*p + p^3*(C1 + C2 p^2): leading product exact (two floats), the rest folded
     // into one coefficient  c0l + s*(C1 + C2 s)  (the p^3 term is < 2^-16 of the total)
     const f2 c0h = f2_splat(2.885390043258667f);           // 2/ln2 = c0h + c0l
-    f2 qq = f2_fma(s, f2_splat(0.5767093896865845f), f2_splat(0.9617967009544373f));
-    qq = f2_fma(s, qq, f2_splat(3.851926067000022e-08f));
+    f2 qq;
+    if (SMALL_Y) {
+        qq = f2_mul(s, f2_splat(0.9618070721626282f));
+    } else {
+        qq = f2_fma(s, f2_splat(0.5767093896865845f), f2_splat(0.9617967009544373f));
+        qq = f2_fma(s, qq, f2_splat(3.851926067000022e-08f));
+    }
     const f2 lh = f2_mul(c0h, p_hi);
     f2 ll = f2_fma(c0h, p_hi, f2_neg(lh));
     ll = f2_fma(c0h, p_lo, ll);
     ll = f2_fma(p_hi, qq, ll);
-    // e + L_hi is exact (integer + multiple of 2^-15, magnitude <= 150.5); scalar adds, the
-    // table words are used once and packing them would cost more than it saves
-    const f2 h1 = f2_make(fadd((float)(d0 >> 23), t0.l_hi), fadd((float)(d1 >> 23), t1.l_hi));
+    // float(biased exponent) + (L_hi - 127) is exact: integer + multiple of 2^-15, magnitude
+    // <= 128.  Scalar adds -- the table words are used once, packing them costs more than it saves.
+    const f2 h1 = f2_make(fadd((float)(int32_t)eb0, t0.l_hi), fadd((float)(int32_t)eb1, t1.l_hi));
     const f2 h2 = f2_add(h1, lh);                          // fast two-sum: |h1| >= |lh| or h1 == 0
     const f2 l2 = f2_add(f2_sub(h1, h2), lh);
     f2 lo = f2_add(f2_make(fadd(t0.l_lo, l2.x), fadd(t1.l_lo, l2.y)), ll);
@@ -557,16 +564,17 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, uint32_t sign_reject,
     const float z0 = fadd(e0.t_hi, ffma(e0.t_hi, w.x, e0.t_lo));
     const float z1 = fadd(e1.t_hi, ffma(e1.t_hi, w.y, e1.t_lo));   // in [0.99, 2.01): 2^(j/64 + f)
     // scale by 2^n, n = k >> 6, through the exponent field (|n| <= 125 keeps the result normal):
-    // (k << 17) & 0xff800000 == n << 23 (the bias 0x4b400000 << 17 vanishes mod 2^32); restore the sign
-    *r0 = u2f((f2u(z0) + ((k0 << 17) & 0xff800000u)) | (u0 & odd_mask));
-    *r1 = u2f((f2u(z1) + ((k1 << 17) & 0xff800000u)) | (u1 & odd_mask));
+    // (k << 17) & 0xff800000 == n << 23 (the bias 0x4b400000 << 17 vanishes mod 2^32)
+    uint32_t b0 = f2u(z0) + ((k0 << 17) & 0xff800000u), b1 = f2u(z1) + ((k1 << 17) & 0xff800000u);
+    if (ODD_Y) { b0 |= u0 & 0x80000000u; b1 |= u1 & 0x80000000u; } // odd integer y: keep the base's sign
+    *r0 = u2f(b0);
+    *r1 = u2f(b1);
     return ok;
 }
 
 // Host-side facts about the (uniform) exponent that select the variant.
 SMB_HD bool pow_f32_small_y(const PowExpF32 &pe) { return (f2u(pe.y) & 0x7fffffffu) <= 0x41000000u; } // |y| <= 8
 SMB_HD uint32_t pow_f32_sign_reject(const PowExpF32 &pe) { return pe.y_is_int ? 0u : 0x80000000u; }
-SMB_HD uint32_t pow_f32_odd_mask(const PowExpF32 &pe) { return pe.y_is_odd ? 0x80000000u : 0u; }
 
 // ============================================================== double pow ===
 // Double-double (hi + lo, |lo| <= ulp(hi)/2) helpers built on FMA.

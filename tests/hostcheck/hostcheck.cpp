@@ -19,13 +19,17 @@ static const PowTabExp kExp[SMB_POW_EXP_ENTRIES] = SMB_POW_EXP_TABLE_INIT;
 void hc_pow_f32_fast(const float *x, float y, uint64_t n, float *out, uint64_t *declined) {
     PowExpF32 pe = classify_exp(y);
     const bool fast = pow_f32_fast_ok(pe), small = pow_f32_small_y(pe);
-    const uint32_t rej = pow_f32_sign_reject(pe), odd = pow_f32_odd_mask(pe);
+    const uint32_t rej = pow_f32_sign_reject(pe);
+    const bool odd = pe.y_is_odd != 0;
     uint64_t dec = 0;
     #pragma omp parallel for schedule(static) reduction(+:dec)
     for (int64_t i = 0; i < (int64_t)(n / 2); ++i) {
         float r0, r1;
-        const bool ok = small ? pow_f32_pair_fast<true>(x[2 * i], x[2 * i + 1], y, rej, odd, kLog, kExp, &r0, &r1)
-                              : pow_f32_pair_fast<false>(x[2 * i], x[2 * i + 1], y, rej, odd, kLog, kExp, &r0, &r1);
+        const float a = x[2 * i], b = x[2 * i + 1];
+        const bool ok = small ? (odd ? pow_f32_pair_fast<true, true>(a, b, y, rej, kLog, kExp, &r0, &r1)
+                                     : pow_f32_pair_fast<true, false>(a, b, y, rej, kLog, kExp, &r0, &r1))
+                              : (odd ? pow_f32_pair_fast<false, true>(a, b, y, rej, kLog, kExp, &r0, &r1)
+                                     : pow_f32_pair_fast<false, false>(a, b, y, rej, kLog, kExp, &r0, &r1));
         if (ok && fast) {
             out[2 * i] = r0; out[2 * i + 1] = r1;
         } else {

@@ -106,7 +106,7 @@ def test_pow_f32_fast_core_ulp(hc, orc, y):
     edges = []
     for j in range(128):
         for d in (-2, -1, 0, 1, 2):
-            edges += [0x3F3504F3 + (j << 16) + d, 0x3F3504F3 + (j << 16) + 0xFFFF + d]
+            edges += [0x3F800000 + (j << 16) + d, 0x3F800000 + (j << 16) + 0xFFFF + d]  # table-entry edges
     xe = np.array(edges, dtype=np.uint32).view(np.float32)
     xe = np.concatenate([xe * np.float32(2.0 ** k) for k in (-20, -3, -1, 0, 1, 2, 7, 30)])
     x = np.concatenate([rng.uniform(0.01, 100, 1 << 20).astype(np.float32),
