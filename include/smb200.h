@@ -82,7 +82,8 @@ enum {
      * one tile per CTA for plain streams, 8 per SM for the table-driven f32 pow). */
     SMB_OPT_CONTIG_VARIANT = 2,
     /* Broadcast kernel: 1 = stage a small reused operand in shared memory (cp.async.bulk);
-     * 0 (default) = read it through L1/L2, which measured faster on B200. */
+     * 0 (default) = read it through L1/L2, which measured faster on B200; 2 = also disable
+     * the register-tiled outer kernel (A/B comparisons). */
     SMB_OPT_BCAST_VARIANT = 3,
     /* Test hook: 1 = take the 64-bit index path (results beyond 2^31 elements) for every
      * broadcast launch, so it can be exercised on small shapes. */

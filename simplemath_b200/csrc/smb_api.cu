@@ -441,6 +441,40 @@ static int launch_bcast(const DeviceCtx &c, const ElementwisePlan &p, const T *a
     if (count == 0) return SMB_OK;
     bool wide = false;
     const BcastTable t = make_table(p, lin_base, count, lane_base, &wide);
+    // {D0,1,L} (op) {1,D1,L}: both operands broadcast along different outer dims -> register-tiled
+    // outer kernel (whole result or whole dim-0 slabs of it; vector-aligned rows)
+    if (p.kind == PLAN_ROW && p.ndim == 3 && p.sa[2] == 1 && p.sb[2] == 1 && g_opt_bcast_variant.load() != 2) {
+        const bool a0 = p.sa[1] == 0 && p.sb[0] == 0 && p.sa[0] != 0 && p.sb[1] != 0; // a varies with dim 0
+        const bool b0 = p.sb[1] == 0 && p.sa[0] == 0 && p.sb[0] != 0 && p.sa[1] != 0; // b varies with dim 0
+        const uint64_t slab = p.shape[1] * p.shape[2];
+        constexpr uint64_t epv = 16 / sizeof(T);
+        const uint64_t s0 = a0 ? p.sa[0] : p.sb[0], s1 = a0 ? p.sb[1] : p.sa[1];
+        if ((a0 || b0) && lin_base % slab == 0 && count % slab == 0 && p.shape[2] % epv == 0 && s0 % epv == 0 &&
+            s1 % epv == 0 && (uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0 && (uintptr_t)out % 16 == 0 &&
+            p.shape[0] < (1ull << 31) && p.shape[1] < (1ull << 31) && p.shape[2] < (1ull << 31)) {
+            constexpr int TI = 4, TJ = 4;
+            const uint64_t i_begin = lin_base / slab, i_count = count / slab;
+            OuterParams op;
+            op.d0 = (uint32_t)i_count;
+            op.d1 = (uint32_t)p.shape[1];
+            op.len = (uint32_t)p.shape[2];
+            op.s0 = s0;
+            op.s1 = s1;
+            op.lane_base = lane_base;
+            const T *pa = a0 ? a + i_begin * p.sa[0] : a;
+            const T *pb = a0 ? b : b + i_begin * p.sb[0];
+            const uint64_t gy = (op.d1 + TJ - 1) / TJ, gz = (op.d0 + TI - 1) / TI;
+            if (gy <= 65535 && gz <= 65535) {
+                const dim3 grid((unsigned)((op.len / epv + kThreads - 1) / kThreads), (unsigned)gy, (unsigned)gz);
+                if (a0) k_outer<T, Fn, TI, TJ, true><<<grid, kThreads, 0, s>>>(pa, pb, out, op, fn);
+                else k_outer<T, Fn, TI, TJ, false><<<grid, kThreads, 0, s>>>(pa, pb, out, op, fn);
+                g_last_kernel = "k_outer<4x4>";
+                ++g_launches;
+                SMB_CK(cudaGetLastError());
+                return SMB_OK;
+            }
+        }
+    }
     if (p.kind == PLAN_GENERIC) {
         const unsigned grid = grid_for(count, kThreads, c.sm_count, 32);
         if (wide) k_generic<T, Fn, true><<<grid, kThreads, 0, s>>>(a, b, out, t, fn);

@@ -487,6 +487,52 @@ __global__ void __launch_bounds__(256) k_row(const T *__restrict__ a, const T *_
     }
 }
 
+// k_outer: the "two operands, each broadcast along a different outer dim" pattern
+// (BASELINE config C4: {D0,1,L} (op) {1,D1,L} -> {D0,D1,L}): out[i][j][k] = x[i][k] (op) y[j][k].
+// The output is D1 (resp. D0) times larger than either operand, so the kernel is a store
+// stream fed from L2; what can be saved is L2 -> SM read traffic.  Each thread keeps TI
+// vectors of the dim-0 operand and TJ vectors of the dim-1 operand in registers and
+// produces the TI x TJ block of output vectors from them: (TI+TJ) loads per TI*TJ stores
+// instead of 2 per store (k_row).  A_ON_DIM0 says which reference operand varies with
+// dim 0, so non-commutative ops keep their operand order.
+struct OuterParams {
+    uint32_t d0, d1, len;   // (sub-)problem shape: d0 x d1 rows of `len` elements
+    uint64_t s0, s1;        // element stride of the dim-0 / dim-1 operand between its rows
+    uint64_t lane_base;     // absolute flat index of out[0] (int pow lane/scalar split)
+};
+template<typename T, typename Fn, int TI, int TJ, bool A_ON_DIM0>
+__global__ void __launch_bounds__(256) k_outer(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
+                                              const __grid_constant__ OuterParams p, Fn fn) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const uint32_t k = (blockIdx.x * kBlock + threadIdx.x) * EPV;
+    if (k >= p.len) return;
+    const uint32_t j0 = blockIdx.y * TJ, i0 = blockIdx.z * TI;
+    const T *x = A_ON_DIM0 ? a : b; // varies with dim 0
+    const T *y = A_ON_DIM0 ? b : a; // varies with dim 1
+    Pack<T, 16> xv[TI], yv[TJ];
+#pragma unroll
+    for (int ti = 0; ti < TI; ++ti)
+        if (i0 + ti < p.d0) xv[ti].raw = VecIO<16, false>::load(x + (uint64_t)(i0 + ti) * p.s0 + k);
+#pragma unroll
+    for (int tj = 0; tj < TJ; ++tj)
+        if (j0 + tj < p.d1) yv[tj].raw = VecIO<16, false>::load(y + (uint64_t)(j0 + tj) * p.s1 + k);
+#pragma unroll
+    for (int ti = 0; ti < TI; ++ti) {
+        if (i0 + ti >= p.d0) break;
+#pragma unroll
+        for (int tj = 0; tj < TJ; ++tj) {
+            if (j0 + tj >= p.d1) break;
+            const uint64_t lin = ((uint64_t)(i0 + ti) * p.d1 + (j0 + tj)) * p.len + k;
+            Pack<T, 16> r;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                r.e[e] = A_ON_DIM0 ? fn(xv[ti].e[e], yv[tj].e[e], p.lane_base + lin + e)
+                                   : fn(yv[tj].e[e], xv[ti].e[e], p.lane_base + lin + e);
+            VecIO<16, true>::store(out + lin, r.raw);
+        }
+    }
+}
+
 // k_generic: arbitrary element strides; one output element per thread per
 // iteration, coalesced stores, gathered loads.
 template<typename T, typename Fn, bool WIDE>

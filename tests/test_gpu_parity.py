@@ -273,6 +273,45 @@ def test_shared_memory_staged_broadcast_variant(orc):
         smb.set_option(smb.OPT_BCAST_VARIANT, 0)
 
 
+def test_outer_broadcast_kernel(orc):
+    """{D0,1,L} (op) {1,D1,L} (config C4's pattern) takes the register-tiled k_outer kernel:
+    both operand orders, non-commutative ops, ragged tile edges, slab-aligned shards."""
+    torch = _torch()
+    rng = np.random.default_rng(41)
+    for d0, d1, L in ((5, 7, 40), (16, 16, 1024), (3, 130, 12), (33, 2, 2052)):
+        x = rng.integers(-1000, 1001, size=(d0, 1, L)).astype(np.int32)
+        y = rng.integers(1, 98, size=(1, d1, L)).astype(np.int32)
+        for op in ("sub", "div", "mul"):
+            assert_same_bits(smb.binary(op, x, y), orc.binary(op, x, y), f"outer {op} a-on-dim0 {d0}x{d1}x{L}")
+            assert smb.last_kernel() == "k_outer<4x4>", smb.last_kernel()
+            assert_same_bits(smb.binary(op, y, x + (x == 0)), orc.binary(op, y, x + (x == 0)), f"outer {op} b-on-dim0")
+            assert smb.last_kernel() == "k_outer<4x4>"
+        xf, yf = x.astype(np.float64), y.astype(np.float64)
+        assert_same_bits(smb.binary("div", xf, yf), orc.binary("div", xf, yf), "outer f64")
+    # not vector-aligned rows -> k_row; disabled by option -> k_row; results identical
+    x = rng.integers(-9, 9, size=(6, 1, 37)).astype(np.int32)
+    y = rng.integers(1, 9, size=(1, 5, 37)).astype(np.int32)
+    assert_same_bits(smb.binary("mul", x, y), orc.binary("mul", x, y), "odd row length")
+    assert smb.last_kernel().startswith("k_row")
+    # shards: slab-aligned ranges use k_outer, others k_row
+    x = rng.standard_normal((8, 1, 64)).astype(np.float32)
+    y = rng.standard_normal((1, 6, 64)).astype(np.float32)
+    want = orc.binary("sub", x, y).ravel()
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    shape, sa, sb, n = smb.broadcast(x.shape, smb.row_major_strides(x.shape), y.shape, smb.row_major_strides(y.shape))
+    for lo, cnt, kern in ((0, n, "k_outer"), (2 * 6 * 64, 3 * 6 * 64, "k_outer"), (100, 1000, "k_row")):
+        part = torch.empty(cnt, dtype=torch.float32, device="cuda")
+        smb.elementwise_range_ptr(smb.OP_SUB, smb.F32, dx.data_ptr(), sa, dy.data_ptr(), sb, shape, lo, cnt, part.data_ptr())
+        assert smb.last_kernel().startswith(kern), (lo, cnt, smb.last_kernel())
+        assert_same_bits(part.cpu().numpy(), want[lo:lo + cnt], f"range {lo}+{cnt}")
+    smb.set_option(smb.OPT_BCAST_VARIANT, 2)
+    try:
+        assert_same_bits(smb.binary("sub", x, y), orc.binary("sub", x, y), "outer kernel disabled")
+        assert smb.last_kernel().startswith("k_row")
+    finally:
+        smb.set_option(smb.OPT_BCAST_VARIANT, 0)
+
+
 def test_wide_index_path_on_small_shapes(orc):
     """The 64-bit index kernels (results beyond 2^31 elements) forced on small shapes."""
     rng = np.random.default_rng(31)
