@@ -361,7 +361,9 @@ int scalar_t<double>(const DeviceCtx &c, int op, const double *a, double v, doub
                 if (v == 0.5) return launch_stream<T, PowSpecialFn<POWS_SQRT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
                 if (v == 1.0) return launch_stream<T, PowSpecialFn<POWS_IDENT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
             }
-            return launch_stream<T, ScalarFn<OP_POW, T>, false>(c, a, nullptr, out, n, first, {classify_exp(v), lane_end}, s);
+            if (classify_exp(v).y_is_odd)
+                return launch_stream<T, PowF64Fn<true>, false>(c, a, nullptr, out, n, first, PowF64Fn<true>::make(v, lane_end), s);
+            return launch_stream<T, PowF64Fn<false>, false>(c, a, nullptr, out, n, first, PowF64Fn<false>::make(v, lane_end), s);
         }
     }
     return fail(SMB_ERR_INVALID, "unknown op %d", op);

@@ -141,6 +141,19 @@ template<bool SMALL_Y, bool ODD_Y> struct PowF32Fn {
     __device__ __forceinline__ bool pair(float a0, float a1, float &r0, float &r1) const {
         return pow_f32_pair_fast<SMALL_Y, ODD_Y>(a0, a1, pe.y, sign_reject, tab_log, tab_exp, &r0, &r1) && fast != 0;
     }
+    // Lookup tables, L2 -> shared memory once per CTA, each entry replicated across the lanes
+    // of a wavefront (24 KB) so the per-lane lookups never conflict; see smb_math.cuh.
+    __device__ __forceinline__ void block_init() {
+        __shared__ __align__(16) PowTabLog s_log[SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE];
+        __shared__ __align__(16) PowTabExp s_exp[SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE];
+        for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE; i += kBlock)
+            s_log[i] = d_pow_log_tab[i / SMB_POW_LOG_STRIDE];
+        for (int i = threadIdx.x; i < SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE; i += kBlock)
+            s_exp[i] = d_pow_exp_tab[i / SMB_POW_EXP_STRIDE];
+        __syncthreads();
+        tab_log = s_log + (threadIdx.x & (SMB_POW_LOG_STRIDE - 1));
+        tab_exp = s_exp + (threadIdx.x & (SMB_POW_EXP_STRIDE - 1));
+    }
     static PowF32Fn make(float y, uint64_t lane_end_) {
         PowF32Fn fn;
         fn.pe = classify_exp(y);
@@ -153,16 +166,57 @@ template<bool SMALL_Y, bool ODD_Y> struct PowF32Fn {
     }
 };
 template<> struct ScalarFn<OP_POW, float> : PowF32Fn<false, true> {};
-template<> struct ScalarFn<OP_POW, double> {
+// sm::pow(arr, y) for double: table-driven fast core per element, double-double
+// reference-accuracy path (out of line) for whatever it declines.
+__device__ __noinline__ double pow_f64_slow(double x, PowExpF64 pe) { return pow_f64(x, pe); }
+
+static __device__ const PowTabLog64 d_pow64_log_tab[SMB_POW_LOG_ENTRIES] = SMB_POW64_LOG_TABLE_INIT;
+static __device__ const PowTabExp64 d_pow64_exp_tab[SMB_POW_EXP_ENTRIES] = SMB_POW64_EXP_TABLE_INIT;
+
+template<bool ODD_Y> struct PowF64Fn {
+    static constexpr bool CHECKED = true;
+    static constexpr bool POW_TABLES = true;
     PowExpF64 pe;
     uint64_t lane_end;
-    __device__ __forceinline__ double operator()(double a, double, uint64_t) const { return pow_f64(a, pe); }
+    int fast_ok;
+    uint64_t sign_reject;
+    const PowTabLog64 *tab_log;
+    const PowTabExp64 *tab_exp;
+    __device__ __forceinline__ double operator()(double a, double, uint64_t) const { return pow_f64_slow(a, pe); }
+    __device__ __forceinline__ bool fast(double a, double &r) const {
+        return pow_f64_fast<ODD_Y>(a, pe.y, sign_reject, tab_log, tab_exp, &r) && fast_ok != 0;
+    }
+    __device__ __forceinline__ void block_init() { // 40 KB: 128 x 32 B x 4 lanes + 64 x 16 B x 8 lanes
+        __shared__ __align__(16) PowTabLog64 s_log[SMB_POW_LOG_ENTRIES * SMB_POW64_LOG_STRIDE];
+        __shared__ __align__(16) PowTabExp64 s_exp[SMB_POW_EXP_ENTRIES * SMB_POW64_EXP_STRIDE];
+        for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES * SMB_POW64_LOG_STRIDE; i += kBlock)
+            s_log[i] = d_pow64_log_tab[i / SMB_POW64_LOG_STRIDE];
+        for (int i = threadIdx.x; i < SMB_POW_EXP_ENTRIES * SMB_POW64_EXP_STRIDE; i += kBlock)
+            s_exp[i] = d_pow64_exp_tab[i / SMB_POW64_EXP_STRIDE];
+        __syncthreads();
+        tab_log = s_log + (threadIdx.x & (SMB_POW64_LOG_STRIDE - 1));
+        tab_exp = s_exp + (threadIdx.x & (SMB_POW64_EXP_STRIDE - 1));
+    }
+    static PowF64Fn make(double y, uint64_t lane_end_) {
+        PowF64Fn fn;
+        fn.pe = classify_exp(y);
+        fn.lane_end = lane_end_;
+        fn.fast_ok = pow_f64_fast_ok(fn.pe) ? 1 : 0;
+        fn.sign_reject = fn.pe.y_is_int ? 0ull : 0x8000000000000000ull;
+        fn.tab_log = nullptr;
+        fn.tab_exp = nullptr;
+        return fn;
+    }
 };
+template<> struct ScalarFn<OP_POW, double> : PowF64Fn<true> {};
 
 template<typename Fn, typename = void> struct fn_pairwise : std::false_type {};
 template<typename Fn> struct fn_pairwise<Fn, std::void_t<decltype(Fn::PAIRWISE)>> : std::bool_constant<Fn::PAIRWISE> {};
 template<typename Fn, typename = void> struct fn_pow_tables : std::false_type {};
 template<typename Fn> struct fn_pow_tables<Fn, std::void_t<decltype(Fn::POW_TABLES)>> : std::bool_constant<Fn::POW_TABLES> {};
+// CHECKED functors offer `bool fast(a, r)`: a branch-free fast path that may decline.
+template<typename Fn, typename = void> struct fn_checked : std::false_type {};
+template<typename Fn> struct fn_checked<Fn, std::void_t<decltype(Fn::CHECKED)>> : std::bool_constant<Fn::CHECKED> {};
 
 // Exact special forms of sm::pow(arr, y) for y in {2, 0.5, -1, 1}: one correctly
 // rounded instruction instead of exp2(y*log2 x).  Chosen on the host
@@ -212,6 +266,14 @@ __device__ __forceinline__ void stream_vec(const Pack<T, VB> &pa, const Pack<T, 
 #pragma unroll
             for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa.e[k], pa.e[k], 0);
         }
+    } else if constexpr (fn_checked<Fn>::value && !HAS_B) {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < EPV; ++k) ok &= fn.fast(pa.e[k], r.e[k]);
+        if (!ok) {
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa.e[k], pa.e[k], 0);
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa.e[k], HAS_B ? pb.e[k] : pa.e[k], first_elem + k);
@@ -247,19 +309,7 @@ __global__ void __launch_bounds__(256) k_stream(const T *__restrict__ a, const T
                                                T *__restrict__ out, uint64_t n, uint64_t first, Fn fn_in) {
     constexpr int EPV = VB / (int)sizeof(T); // elements per vector
     Fn fn = fn_in;
-    if constexpr (fn_pow_tables<Fn>::value) {
-        // Lookup tables, L2 -> shared memory once per CTA, each entry replicated across the lanes
-        // of a wavefront (24 KB) so the per-lane lookups never conflict; see smb_math.cuh.
-        __shared__ __align__(16) PowTabLog s_log[SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE];
-        __shared__ __align__(16) PowTabExp s_exp[SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE];
-        for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE; i += kBlock)
-            s_log[i] = d_pow_log_tab[i / SMB_POW_LOG_STRIDE];
-        for (int i = threadIdx.x; i < SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE; i += kBlock)
-            s_exp[i] = d_pow_exp_tab[i / SMB_POW_EXP_STRIDE];
-        __syncthreads();
-        fn.tab_log = s_log + (threadIdx.x & (SMB_POW_LOG_STRIDE - 1));
-        fn.tab_exp = s_exp + (threadIdx.x & (SMB_POW_EXP_STRIDE - 1));
-    }
+    if constexpr (fn_pow_tables<Fn>::value) fn.block_init(); // stage the lookup tables in shared memory
     const uint64_t nvec = n / EPV;
     constexpr uint64_t tile_vecs = (uint64_t)kBlock * UNROLL; // launches always use kBlock threads
     const uint64_t full_tiles = nvec / tile_vecs;

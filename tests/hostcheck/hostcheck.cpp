@@ -49,6 +49,23 @@ void hc_pow_f64(const double *x, double y, uint64_t n, double *out) {
     #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = pow_f64(x[i], pe);
 }
+static const PowTabLog64 kLog64[SMB_POW_LOG_ENTRIES] = SMB_POW64_LOG_TABLE_INIT;
+static const PowTabExp64 kExp64[SMB_POW_EXP_ENTRIES] = SMB_POW64_EXP_TABLE_INIT;
+// The f64 kernel's own path: table-driven fast core, pow_f64 for declined elements.
+void hc_pow_f64_fast(const double *x, double y, uint64_t n, double *out, uint64_t *declined) {
+    PowExpF64 pe = classify_exp(y);
+    const bool fast = pow_f64_fast_ok(pe), odd = pe.y_is_odd != 0;
+    const uint64_t rej = pe.y_is_int ? 0ull : 0x8000000000000000ull;
+    uint64_t dec = 0;
+    #pragma omp parallel for schedule(static) reduction(+:dec)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        double r;
+        const bool ok = odd ? pow_f64_fast<true>(x[i], y, rej, kLog64, kExp64, &r) : pow_f64_fast<false>(x[i], y, rej, kLog64, kExp64, &r);
+        if (ok && fast) out[i] = r;
+        else { out[i] = pow_f64(x[i], pe); ++dec; }
+    }
+    if (declined) *declined = dec;
+}
 void hc_pow_f64_pair(const double *x, const double *y, uint64_t n, double *out) {
     #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = DevOp<OP_POW, double>::apply(x[i], y[i]);
