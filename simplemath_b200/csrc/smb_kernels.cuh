@@ -180,21 +180,29 @@ template<bool ODD_Y> struct PowF64Fn {
     uint64_t lane_end;
     int fast_ok;
     uint64_t sign_reject;
-    const PowTabLog64 *tab_log;
+    const PowTabLog64A *tab_a;
+    const PowTabLog64B *tab_b;
     const PowTabExp64 *tab_exp;
     __device__ __forceinline__ double operator()(double a, double, uint64_t) const { return pow_f64_slow(a, pe); }
     __device__ __forceinline__ bool fast(double a, double &r) const {
-        return pow_f64_fast<ODD_Y>(a, pe.y, sign_reject, tab_log, tab_exp, &r) && fast_ok != 0;
+        return pow_f64_fast<ODD_Y>(a, pe.y, sign_reject, tab_a, tab_b, tab_exp, &r) && fast_ok != 0;
     }
-    __device__ __forceinline__ void block_init() { // 40 KB: 128 x 32 B x 4 lanes + 64 x 16 B x 8 lanes
-        __shared__ __align__(16) PowTabLog64 s_log[SMB_POW_LOG_ENTRIES * SMB_POW64_LOG_STRIDE];
+    __device__ __forceinline__ void block_init() { // 40 KB, every entry replicated per wavefront lane
+        __shared__ __align__(16) PowTabLog64A s_a[SMB_POW_LOG_ENTRIES * SMB_POW64_A_STRIDE];
+        __shared__ __align__(16) PowTabLog64B s_b[SMB_POW_LOG_ENTRIES * SMB_POW64_B_STRIDE];
         __shared__ __align__(16) PowTabExp64 s_exp[SMB_POW_EXP_ENTRIES * SMB_POW64_EXP_STRIDE];
-        for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES * SMB_POW64_LOG_STRIDE; i += kBlock)
-            s_log[i] = d_pow64_log_tab[i / SMB_POW64_LOG_STRIDE];
+        for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES * SMB_POW64_A_STRIDE; i += kBlock) {
+            const PowTabLog64 e = d_pow64_log_tab[i / SMB_POW64_A_STRIDE];
+            s_a[i].c = e.c;
+            s_a[i].l_hi = e.l_hi;
+        }
+        for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES * SMB_POW64_B_STRIDE; i += kBlock)
+            s_b[i].l_lo = d_pow64_log_tab[i / SMB_POW64_B_STRIDE].l_lo;
         for (int i = threadIdx.x; i < SMB_POW_EXP_ENTRIES * SMB_POW64_EXP_STRIDE; i += kBlock)
             s_exp[i] = d_pow64_exp_tab[i / SMB_POW64_EXP_STRIDE];
         __syncthreads();
-        tab_log = s_log + (threadIdx.x & (SMB_POW64_LOG_STRIDE - 1));
+        tab_a = s_a + (threadIdx.x & (SMB_POW64_A_STRIDE - 1));
+        tab_b = s_b + (threadIdx.x & (SMB_POW64_B_STRIDE - 1));
         tab_exp = s_exp + (threadIdx.x & (SMB_POW64_EXP_STRIDE - 1));
     }
     static PowF64Fn make(double y, uint64_t lane_end_) {
@@ -203,7 +211,8 @@ template<bool ODD_Y> struct PowF64Fn {
         fn.lane_end = lane_end_;
         fn.fast_ok = pow_f64_fast_ok(fn.pe) ? 1 : 0;
         fn.sign_reject = fn.pe.y_is_int ? 0ull : 0x8000000000000000ull;
-        fn.tab_log = nullptr;
+        fn.tab_a = nullptr;
+        fn.tab_b = nullptr;
         fn.tab_exp = nullptr;
         return fn;
     }

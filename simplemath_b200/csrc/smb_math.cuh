@@ -775,13 +775,17 @@ SMB_HD double pow_f64(double x, const PowExpF64 &pe) {
 //   FMA residual steps;  2^t = 2^(k>>6) * T[k&63] * (1 + f*(E1 + ... + E7 f^6)), |f| <= 2^-7.
 // Declines (returns false) anything outside "normal magnitude, result well inside the
 // normal range"; pow_f64 handles those.  Error <= 0.52 ULP measured (bound 1 ULP).
-struct PowTabLog64 { double c, l_hi, l_lo, pad; };
+struct PowTabLog64 { double c, l_hi, l_lo, pad; };   // generated (compact) form
+struct PowTabLog64A { double c, l_hi; };             // device layout: split so that every lookup is
+struct PowTabLog64B { double l_lo; };                // one conflict-free LDS.128 / LDS.64
 struct PowTabExp64 { double t_hi, t_lo; };
 #if defined(__CUDA_ARCH__)
-#define SMB_POW64_LOG_STRIDE 4   /* 32-byte entries read as two LDS.128: 4 lanes share a wavefront */
-#define SMB_POW64_EXP_STRIDE 8   /* 16-byte entries, one LDS.128: 8 lanes per wavefront */
+#define SMB_POW64_A_STRIDE 8    /* 16-byte entries: the 8 lanes of a wavefront get their own replica */
+#define SMB_POW64_B_STRIDE 16   /*  8-byte entries: 16 lanes per wavefront */
+#define SMB_POW64_EXP_STRIDE 8
 #else
-#define SMB_POW64_LOG_STRIDE 1
+#define SMB_POW64_A_STRIDE 1
+#define SMB_POW64_B_STRIDE 1
 #define SMB_POW64_EXP_STRIDE 1
 #endif
 
@@ -792,7 +796,7 @@ SMB_HD bool pow_f64_fast_ok(const PowExpF64 &pe) {
 }
 
 template<bool ODD_Y>
-SMB_HD bool pow_f64_fast(double x, double y, uint64_t sign_reject, const PowTabLog64 *tab_log,
+SMB_HD bool pow_f64_fast(double x, double y, uint64_t sign_reject, const PowTabLog64A *tab_a, const PowTabLog64B *tab_b,
                          const PowTabExp64 *tab_exp, double *out) {
     const uint64_t u = d2u(x);
     const uint64_t a = u & 0x7fffffffffffffffull;
@@ -801,7 +805,8 @@ SMB_HD bool pow_f64_fast(double x, double y, uint64_t sign_reject, const PowTabL
     // |x| = 2^E * m, m in [1, 2)
     const double m = u2d((a & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
     const uint32_t j = (uint32_t)(a >> 45) & 127u;
-    const PowTabLog64 t = tab_log[j * SMB_POW64_LOG_STRIDE];
+    const PowTabLog64A t = tab_a[j * SMB_POW64_A_STRIDE];
+    const double t_l_lo = tab_b[j * SMB_POW64_B_STRIDE].l_lo;
     const double num = dsub(m, t.c);                       // exact
     const double den = dfma(m, 2.0, -num);                 // m + c, one rounding
     const double den_lo = dsub(dfma(m, 2.0, -den), num);   // exact error of den
@@ -824,7 +829,7 @@ SMB_HD bool pow_f64_fast(double x, double y, uint64_t sign_reject, const PowTabL
     const double h1 = dadd((double)(int32_t)eb, t.l_hi);   // exact: integer + multiple of 2^-40
     const double h2 = dadd(h1, lh);                        // fast two-sum: |h1| >= |lh| or h1 == 0
     const double l2 = dadd(dsub(h1, h2), lh);
-    const double lo_raw = dadd(dadd(t.l_lo, l2), ll);
+    const double lo_raw = dadd(dadd(t_l_lo, l2), ll);
     const double h3 = dadd(h2, lo_raw);
     const double lo = dadd(dsub(h2, h3), lo_raw);
     const double th = dmul(y, h3);

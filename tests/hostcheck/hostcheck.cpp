@@ -51,6 +51,12 @@ void hc_pow_f64(const double *x, double y, uint64_t n, double *out) {
 }
 static const PowTabLog64 kLog64[SMB_POW_LOG_ENTRIES] = SMB_POW64_LOG_TABLE_INIT;
 static const PowTabExp64 kExp64[SMB_POW_EXP_ENTRIES] = SMB_POW64_EXP_TABLE_INIT;
+static PowTabLog64A kLog64A[SMB_POW_LOG_ENTRIES];
+static PowTabLog64B kLog64B[SMB_POW_LOG_ENTRIES];
+static const bool kLog64Split = [] {
+    for (int i = 0; i < SMB_POW_LOG_ENTRIES; ++i) { kLog64A[i].c = kLog64[i].c; kLog64A[i].l_hi = kLog64[i].l_hi; kLog64B[i].l_lo = kLog64[i].l_lo; }
+    return true;
+}();
 // The f64 kernel's own path: table-driven fast core, pow_f64 for declined elements.
 void hc_pow_f64_fast(const double *x, double y, uint64_t n, double *out, uint64_t *declined) {
     PowExpF64 pe = classify_exp(y);
@@ -60,7 +66,7 @@ void hc_pow_f64_fast(const double *x, double y, uint64_t n, double *out, uint64_
     #pragma omp parallel for schedule(static) reduction(+:dec)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         double r;
-        const bool ok = odd ? pow_f64_fast<true>(x[i], y, rej, kLog64, kExp64, &r) : pow_f64_fast<false>(x[i], y, rej, kLog64, kExp64, &r);
+        const bool ok = odd ? pow_f64_fast<true>(x[i], y, rej, kLog64A, kLog64B, kExp64, &r) : pow_f64_fast<false>(x[i], y, rej, kLog64A, kLog64B, kExp64, &r);
         if (ok && fast) out[i] = r;
         else { out[i] = pow_f64(x[i], pe); ++dec; }
     }
