@@ -36,6 +36,7 @@
 #include "math/multiply.h"
 #include "math/division.h"
 #include "math/calculate.h"
+#include "math/product.h"
 
 namespace sm {
     template<typename T>
@@ -190,14 +191,9 @@ namespace sm {
             return SMArray(fresh, std::move(newShape));
         }
 
-        // Dot product (reference math/product.h): a reduction, not part of the
-        // elementwise path this build accelerates ("next" row 2);
-        // kept as plain host arithmetic over the same storage so the API compiles.
-        T operator%(SMArray &arr) const {
-            T acc{};
-            for (size_t i = 0; i < arr.totalSize; ++i) acc += data[i] * arr.data[i];
-            return acc;
-        }
+        // Dot product over the dense data (reference SMArray.h:213-215 -> math/product.h): the
+        // first row widened after the elementwise path; device reduction for float/double/int32.
+        T operator%(SMArray &arr) const { return dot_product(data, arr.data, arr.totalSize); }
 
         SMArray operator+(const SMArray &arr) const { return binary<AddOp<T> >(arr); }
         SMArray operator+(const T val) const { return withScalar<AddOp<T> >(val); }

@@ -127,6 +127,14 @@ int smb_contiguous(int op, int dtype, const void *a, const void *b, void *out,
 int smb_array_scalar(int op, int dtype, const void *a, const void *scalar,
                      uint64_t n, void *out, void *stream);
 
+/* ---- next row after the elementwise path -------------------- */
+/* Replaces dot_product<T>(a, b, n) behind SMArray::operator% -- include/math/product.h:8-224,
+ * include/SMArray.h:213-215.  Dense operands (16-byte aligned), `result` points at one host T.
+ * int32 wraps like the reference's mullo/add_epi32 (bit-exact); float/double are summed
+ * pairwise in their own type (deterministic; more accurate than the reference's sequential
+ * lane accumulators, so parity is a tolerance). */
+int smb_dot(int dtype, const void *a, const void *b, uint64_t n, void *result, void *stream);
+
 /* ---- storage: replaces `new T[n]` / `delete[]` of SMArray<T>::data ------- */
 /* include/SMArray.h:33-34,70-76,219,342-346; include/UserFunctions.h:8-40.
  * Pooled (size-class caching) so a fresh result block per operator call costs

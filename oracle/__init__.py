@@ -59,6 +59,15 @@ class _Lib:
         f("broadcast", _i, [_u64p, _u64p, _i, _u64p, _u64p, _i, _u64p, _u64p, _u64p, ctypes.POINTER(_i), _u64p])
         f("is_contiguous", _i, [_u64p, _u64p, _i])
 
+    def dot(self, a: np.ndarray, b: np.ndarray):
+        """dot_product<T> with the reference's exact association order."""
+        a, b = np.ascontiguousarray(a).ravel(), np.ascontiguousarray(b).ravel()
+        name = {np.dtype(np.float32): "dot_f32", np.dtype(np.float64): "dot_f64", np.dtype(np.int32): "dot_i32"}[a.dtype]
+        fn = getattr(self.h, self.prefix + name)
+        fn.restype = CT[NP_DTYPES[a.dtype]]
+        fn.argtypes = [_vp, _vp, _u64]
+        return a.dtype.type(fn(_ptr(a), _ptr(b), a.size))
+
     def _f(self, name, res, args):
         fn = getattr(self.h, self.prefix + name)
         fn.restype, fn.argtypes = res, args

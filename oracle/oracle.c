@@ -273,6 +273,40 @@ void orc_pow_ref_f64(const double *x, double y, uint64_t n, double *hi, double *
     }
 }
 
+/* ------------------------------------------------------------------ dot_product
+ * include/math/product.h (AVX build): int32 :26-71 -- 8 wrapping lane accumulators, lanes
+ * folded, scalar tail; float :74-118 -- 8 float lane accumulators (mul then add), low+high
+ * halves, buf[0]+buf[1]+buf[2]+buf[3], scalar tail; double :121-165 -- 4 lanes likewise.
+ * The float/double results depend on this exact association order, which is what is
+ * restated here (so the restatement can be pinned bit-for-bit against the compiled
+ * reference); the device kernel sums pairwise and is compared by tolerance. */
+int32_t orc_dot_i32(const int32_t *a, const int32_t *b, uint64_t n) {
+    uint32_t r = 0;
+    for (uint64_t i = 0; i < n; ++i) r += (uint32_t)a[i] * (uint32_t)b[i];
+    return (int32_t)r; /* wrapping addition is associative: one loop states all orders */
+}
+float orc_dot_f32(const float *a, const float *b, uint64_t n) {
+    float lane[8] = {0, 0, 0, 0, 0, 0, 0, 0}, result = 0.0f;
+    uint64_t i = 0;
+    for (; i + 7 < n; i += 8)
+        for (int l = 0; l < 8; ++l) lane[l] = lane[l] + a[i + l] * b[i + l];
+    float s[4];
+    for (int l = 0; l < 4; ++l) s[l] = lane[l] + lane[l + 4];
+    result += s[0] + s[1] + s[2] + s[3];
+    for (; i < n; ++i) result += a[i] * b[i];
+    return result;
+}
+double orc_dot_f64(const double *a, const double *b, uint64_t n) {
+    double lane[4] = {0, 0, 0, 0}, result = 0.0;
+    uint64_t i = 0;
+    for (; i + 3 < n; i += 4)
+        for (int l = 0; l < 4; ++l) lane[l] = lane[l] + a[i + l] * b[i + l];
+    double s0 = lane[0] + lane[2], s1 = lane[1] + lane[3];
+    result += s0 + s1;
+    for (; i < n; ++i) result += a[i] * b[i];
+    return result;
+}
+
 /* Counter-based input generator shared by bench.py's CPU and GPU legs
  * (SURVEY.md §8d C5): splitmix64 of the flat index -> uniform float in
  * [lo, hi).  The device kernel in simplemath_b200/csrc re-states the same

@@ -211,6 +211,11 @@ int smref_broadcast(const uint64_t *shape1, const uint64_t *strides1, int ndim1,
     }
 }
 
+// dot_product<T> (include/math/product.h), what SMArray::operator% calls.
+int32_t smref_dot_i32(const int32_t *a, const int32_t *b, uint64_t n) { return dot_product<int>(a, b, n); }
+float smref_dot_f32(const float *a, const float *b, uint64_t n) { return dot_product<float>(a, b, n); }
+double smref_dot_f64(const double *a, const double *b, uint64_t n) { return dot_product<double>(a, b, n); }
+
 int smref_is_contiguous(const uint64_t *shape, const uint64_t *stride, int ndim) {
     return is_contiguous(vec(shape, ndim), vec(stride, ndim)) ? 1 : 0;
 }

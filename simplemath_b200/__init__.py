@@ -40,6 +40,7 @@ SYMBOLS = {
     "smb_elementwise_range": (_i, [_i, _i, _vp, _u64p, _vp, _u64p, _u64p, _i, _u64, _u64, _vp, _vp]),
     "smb_contiguous": (_i, [_i, _i, _vp, _vp, _vp, _u64, _vp]),
     "smb_array_scalar": (_i, [_i, _i, _vp, _vp, _u64, _vp, _vp]),
+    "smb_dot": (_i, [_i, _vp, _vp, _u64, _vp, _vp]),
     "smb_alloc": (_vp, [ctypes.c_size_t, _i]),
     "smb_free": (_i, [_vp]),
     "smb_owns": (_i, [_vp]),
@@ -245,6 +246,23 @@ def scalar(op, a: np.ndarray, value) -> np.ndarray:
     if a.size:
         array_scalar_ptr(op, dt, a.ctypes.data, value, a.size, out.ctypes.data)
     return out
+
+
+def dot(a: np.ndarray, b: np.ndarray):
+    """SMArray::operator% (include/SMArray.h:213-215): sum(a[i]*b[i]) over the dense data."""
+    if a.dtype != b.dtype or a.size != b.size:
+        raise SmbError("dot: operands must share element type and size")
+    dt = dtype_code(a.dtype)
+    a, b = np.ascontiguousarray(a).ravel(), np.ascontiguousarray(b).ravel()
+    res = _CT[dt]()
+    _check(lib().smb_dot(dt, a.ctypes.data, b.ctypes.data, a.size, ctypes.byref(res), None))
+    return a.dtype.type(res.value)
+
+
+def dot_ptr(dtype, a_ptr, b_ptr, n, stream=0):
+    res = _CT[dtype]()
+    _check(lib().smb_dot(dtype, a_ptr, b_ptr, int(n), ctypes.byref(res), stream or None))
+    return res.value
 
 
 def pow(a: np.ndarray, y) -> np.ndarray:  # noqa: A001 - mirrors sm::pow

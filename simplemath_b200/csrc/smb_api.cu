@@ -775,6 +775,32 @@ static int elementwise_entry(int op, int dtype, const void *a, const uint64_t *s
     return SMB_OK;
 }
 
+// SMArray::operator% (reference math/product.h).  `result` is one host T.  Operands on the host
+// are staged whole; the partial / ticket / result scratch lives in one pooled device block.
+template<typename T>
+static int dot_t(DeviceCtx &c, const T *a, const T *b, uint64_t n, void *result, cudaStream_t s) {
+    using A = typename DotAcc<T>::type;
+    int dev = 0;
+    SMB_CK(cudaGetDevice(&dev));
+    constexpr int UNROLL = 4;
+    const uint64_t nvec = n / (16 / sizeof(T));
+    const unsigned grid = grid_for(nvec ? nvec : 1, (uint64_t)kThreads * UNROLL, c.sm_count, 8);
+    Scratch scratch;
+    const size_t bytes = 16 + sizeof(A) * ((size_t)grid + 1);
+    if (int rc = scratch.get(bytes, dev)) return rc;
+    unsigned int *ticket = (unsigned int *)scratch.p;
+    A *res = (A *)((char *)scratch.p + 8);
+    A *partials = (A *)((char *)scratch.p + 16);
+    SMB_CK(cudaMemsetAsync(scratch.p, 0, 16, s));
+    k_dot<T, UNROLL><<<grid, kThreads, 0, s>>>(a, b, n, partials, ticket, res);
+    ++g_launches;
+    g_last_kernel = "k_dot";
+    SMB_CK(cudaGetLastError());
+    SMB_CK(cudaMemcpyAsync(result, res, sizeof(A), cudaMemcpyDeviceToHost, s));
+    SMB_CK(cudaStreamSynchronize(s)); // a scalar result: always synchronous
+    return SMB_OK;
+}
+
 } // namespace smb
 
 using namespace smb;
@@ -820,6 +846,31 @@ int smb_array_scalar(int op, int dtype, const void *a, const void *scalar, uint6
     if (int rc = scalar_device(*c, op, dtype, a, scalar, out, n, 0, lane_end, s)) return rc;
     if (!stream) SMB_CK(cudaStreamSynchronize(s));
     return SMB_OK;
+}
+
+int smb_dot(int dtype, const void *a, const void *b, uint64_t n, void *result, void *stream) {
+    if (dtype < SMB_F32 || dtype > SMB_I32) return fail(SMB_ERR_INVALID, "unknown dtype %d", dtype);
+    if (!result) return fail(SMB_ERR_INVALID, "null result pointer");
+    DeviceCtx *c = nullptr;
+    if (int rc = current_ctx(&c)) return rc;
+    const size_t es = esize(dtype);
+    if (n == 0) { memset(result, 0, es); return SMB_OK; }
+    if (!a || !b) return fail(SMB_ERR_INVALID, "null operand pointer");
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
+    const MemType ta = mem_type(a), tb = mem_type(b);
+    int dev = 0;
+    SMB_CK(cudaGetDevice(&dev));
+    Scratch da, db;
+    if (on_host(ta)) { if (int rc = da.get(n * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(da.p, a, n * es, cudaMemcpyDefault, s)); a = da.p; }
+    else if (ta == MT_MANAGED) prefetch_managed(a, n * es, s);
+    if (on_host(tb)) { if (int rc = db.get(n * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(db.p, b, n * es, cudaMemcpyDefault, s)); b = db.p; }
+    else if (tb == MT_MANAGED) prefetch_managed(b, n * es, s);
+    if (((uintptr_t)a | (uintptr_t)b) & 15) return fail(SMB_ERR_INVALID, "smb_dot: operands must be 16-byte aligned");
+    switch (dtype) {
+        case SMB_F32: return dot_t<float>(*c, (const float *)a, (const float *)b, n, result, s);
+        case SMB_F64: return dot_t<double>(*c, (const double *)a, (const double *)b, n, result, s);
+        default: return dot_t<int32_t>(*c, (const int32_t *)a, (const int32_t *)b, n, result, s);
+    }
 }
 
 void *smb_alloc(size_t bytes, int kind) {

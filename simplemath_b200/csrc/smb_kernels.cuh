@@ -607,6 +607,101 @@ __global__ void __launch_bounds__(256) k_generic(const T *__restrict__ a, const 
 }
 
 // ---------------------------------------------------------------------------
+// k_dot: sum_i a[i]*b[i]  (SMArray::operator%, reference math/product.h:8-224) -- the first
+// "next" row after the elementwise path.  HBM-bound reduction: each thread
+// accumulates UNROLL independent vector products per iteration, then warp shuffle -> shared
+// memory -> one partial per CTA; the LAST CTA to finish (ticket counter) adds the partials in
+// index order, so the result is deterministic for a given grid and needs no float atomics.
+// int32 wraps (product.h:26-71: mullo + add_epi32), so any summation order is bit-exact;
+// float/double are summed pairwise in their own type -- closer to the exact sum than the
+// reference's 8 (4) sequential lane accumulators, so parity there is a tolerance.
+template<typename T> struct DotAcc { using type = T; };
+template<> struct DotAcc<int32_t> { using type = uint32_t; };
+
+template<typename T>
+__device__ __forceinline__ typename DotAcc<T>::type dot_mul(T x, T y) {
+    if constexpr (sizeof(T) == 8) return __dmul_rn(x, y);
+    else if constexpr (std::is_same<T, float>::value) return __fmul_rn(x, y);
+    else return (uint32_t)x * (uint32_t)y;
+}
+template<typename A> __device__ __forceinline__ A dot_add(A x, A y) {
+    if constexpr (std::is_same<A, double>::value) return __dadd_rn(x, y);
+    else if constexpr (std::is_same<A, float>::value) return __fadd_rn(x, y);
+    else return x + y;
+}
+
+template<typename T, int UNROLL>
+__global__ void __launch_bounds__(256) k_dot(const T *__restrict__ a, const T *__restrict__ b, uint64_t n,
+                                            typename DotAcc<T>::type *__restrict__ partials, unsigned int *__restrict__ ticket,
+                                            typename DotAcc<T>::type *__restrict__ result) {
+    using A = typename DotAcc<T>::type;
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const uint64_t nvec = n / EPV;
+    A acc[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) acc[u] = A(0);
+    const uint64_t stride = (uint64_t)gridDim.x * kBlock * UNROLL;
+    for (uint64_t v0 = (uint64_t)blockIdx.x * kBlock * UNROLL + threadIdx.x; v0 < nvec; v0 += stride) {
+        Pack<T, 16> pa[UNROLL], pb[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t v = v0 + (uint64_t)u * kBlock;
+            if (v < nvec) {
+                pa[u].raw = VecIO<16, true>::load(reinterpret_cast<const RawVec<16> *>(a) + v);
+                pb[u].raw = VecIO<16, true>::load(reinterpret_cast<const RawVec<16> *>(b) + v);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t v = v0 + (uint64_t)u * kBlock;
+            if (v < nvec) {
+                A s = dot_mul<T>(pa[u].e[0], pb[u].e[0]);
+#pragma unroll
+                for (int k = 1; k < EPV; ++k) s = dot_add<A>(s, dot_mul<T>(pa[u].e[k], pb[u].e[k]));
+                acc[u] = dot_add<A>(acc[u], s);
+            }
+        }
+    }
+    A sum = acc[0];
+#pragma unroll
+    for (int u = 1; u < UNROLL; ++u) sum = dot_add<A>(sum, acc[u]);
+    // scalar tail (n % EPV elements) by the first threads of block 0
+    if (blockIdx.x == 0 && threadIdx.x < n - nvec * EPV) {
+        const uint64_t i = nvec * EPV + threadIdx.x;
+        sum = dot_add<A>(sum, dot_mul<T>(a[i], b[i]));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum = dot_add<A>(sum, __shfl_down_sync(0xffffffffu, sum, off));
+    __shared__ A warp_sums[kBlock / 32];
+    __shared__ bool is_last;
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        A s = warp_sums[0];
+        for (int w = 1; w < kBlock / 32; ++w) s = dot_add<A>(s, warp_sums[w]);
+        partials[blockIdx.x] = s;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) { // fixed-order final reduction of the per-CTA partials
+        __threadfence();
+        A s = A(0);
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += kBlock) s = dot_add<A>(s, ((volatile A *)partials)[i]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s = dot_add<A>(s, __shfl_down_sync(0xffffffffu, s, off));
+        if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            A t = warp_sums[0];
+            for (int w = 1; w < kBlock / 32; ++w) t = dot_add<A>(t, warp_sums[w]);
+            *result = t;
+            *ticket = 0; // ready for the next launch on this stream
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // fill (sm::ones / sm::zeros) and the counter-based uniform generator.
 template<typename T>
 __global__ void __launch_bounds__(256) k_fill(T *__restrict__ out, uint64_t n, T v) {

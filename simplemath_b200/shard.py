@@ -43,3 +43,13 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def allreduce_scalar_sum(value, dtype=torch.float64, device=None, group=None):
+    """Sum of per-rank partial reductions (the sharded dot product: each rank reduces its flat
+    range with smb_dot, then ONE scalar all-reduce -- the first place a collective sits on a
+    path).  int32 partials wrap exactly like the single-GPU result when summed as
+    int64 and truncated by the caller."""
+    t = torch.tensor([value], dtype=dtype, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.item()

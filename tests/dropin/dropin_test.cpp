@@ -146,6 +146,20 @@ TEST(DropIn, PowSpecialValues) {
     EXPECT_EQ(pn(0), INFINITY); EXPECT_EQ(pn(5), 0.0f); EXPECT_EQ(pn(8), 0.03125f);
 }
 
+TEST(DropIn, DotProductOperator) {
+    sm::SMArray<int> a = {1, 2, 3, 4, 5, 6, 7, 8, 9};
+    sm::SMArray<int> b = {9, 8, 7, 6, 5, 4, 3, 2, 1};
+    EXPECT_EQ(a % b, 165);
+    sm::SMArray<int> big = {2147483647, 2, -3};
+    sm::SMArray<int> two = {2, 1073741824, 7};
+    EXPECT_EQ(big % two, (int) (uint32_t) (2147483647u * 2u + 2u * 1073741824u + (uint32_t) (-21)));   // wraps like mullo/add_epi32
+    auto x = sm::ones<float>(1000, 100);
+    auto y = sm::ones<float>(1000, 100) * 0.5f;
+    EXPECT_FLOAT_EQ(x % y, 50000.0f);
+    auto d = sm::ones<double>(12345) * 3.0;
+    EXPECT_DOUBLE_EQ(d % d, 9.0 * 12345);
+}
+
 TEST(DropIn, IncompatibleShapesThrowLikeTheReference) {
     sm::SMArray<float> a = {{1, 2, 3}, {4, 5, 6}};
     sm::SMArray<float> b = {{1, 2}, {3, 4}};

@@ -506,3 +506,51 @@ def test_config_c3_c5_large_pow_and_add_properties(orc):
     assert bool((out == x + y).all())
     w = orc.fill_uniform_f32(n - 4096, 4096, 3, 0.01, 100.0), orc.fill_uniform_f32(n - 4096, 4096, 4, -1.0, 1.0)
     assert_same_bits(out[n - 4096:].cpu().numpy(), orc.elementwise("add", w[0], [1], w[1], [1], [4096]), "C5 add tail window")
+
+
+# ---- dot product (SMArray::operator%) on the device --------------------
+def test_dot_int32_bit_exact(orc):
+    rng = np.random.default_rng(51)
+    for n in (1, 3, 4, 5, 1000, 100_003, 1 << 22):
+        a = rng.integers(-2**31, 2**31, n, dtype=np.int64).astype(np.int32)
+        b = rng.integers(-2**31, 2**31, n, dtype=np.int64).astype(np.int32)
+        assert smb.dot(a, b) == orc.dot(a, b), n
+    assert smb.last_kernel() == "k_dot"
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_dot_float_within_tolerance_and_no_worse_than_the_reference(orc, dtype):
+    """float/double: the device sums pairwise, the reference in 8 (4) sequential lanes; both are
+    compared with the exactly rounded sum.  Tolerance: |err| <= 8 eps * sum|a_i b_i| (a loose
+    pairwise-summation bound); in practice the device is closer than the reference."""
+    import math
+    rng = np.random.default_rng(52)
+    eps = np.finfo(dtype).eps
+    for n in (1, 7, 1000, 100_003, 1 << 22):
+        a, b = rng.standard_normal(n).astype(dtype), rng.standard_normal(n).astype(dtype)
+        prods = a.astype(np.float64) * b.astype(np.float64) if dtype == np.float32 else None
+        exact = math.fsum(prods) if dtype == np.float32 else float(np.sum(a.astype(np.longdouble) * b.astype(np.longdouble)))
+        bound = 8 * eps * float(np.sum(np.abs(a.astype(np.float64) * b.astype(np.float64)))) + 1e-300
+        got, refv = float(smb.dot(a, b)), float(orc.dot(a, b))
+        assert abs(got - exact) <= bound, (n, got, exact, bound)
+        if n >= 100_003:
+            assert abs(got - exact) <= abs(refv - exact) + bound * 1e-3, (n, got, refv, exact)
+    a = rng.standard_normal(1 << 20).astype(dtype)
+    assert smb.dot(a, a) == smb.dot(a, a)  # deterministic
+
+
+def test_dot_device_pointers_and_sharded_sum(orc):
+    torch = _torch()
+    n = 1 << 24
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    y = torch.empty(n, dtype=torch.float32, device="cuda")
+    smb.fill_uniform_f32_ptr(x.data_ptr(), 0, n, 5, -1.0, 1.0)
+    smb.fill_uniform_f32_ptr(y.data_ptr(), 0, n, 6, -1.0, 1.0)
+    full = smb.dot_ptr(smb.F32, x.data_ptr(), y.data_ptr(), n)
+    ref = float((x.double() * y.double()).sum().item())
+    assert abs(full - ref) <= 1e-6 * n ** 0.5 + 1e-3 * abs(ref)
+    parts = 0.0
+    for r in range(4):  # the multi-GPU form: per-shard partial sums + one tiny all-reduce
+        lo, hi = smb.shard_range(n, r, 4, align=4)
+        parts += smb.dot_ptr(smb.F32, x.data_ptr() + 4 * lo, y.data_ptr() + 4 * lo, hi - lo)
+    assert abs(parts - ref) <= 1e-6 * n ** 0.5 + 1e-3 * abs(ref)

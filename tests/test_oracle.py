@@ -181,3 +181,20 @@ def test_fill_uniform_is_deterministic_and_in_range(orc):
     y = orc.fill_uniform_f32(1024, 1024, 3, 0.01, 100.0)
     assert np.array_equal(x[1024:2048], y)
     assert x.min() >= 0.01 and x.max() <= 100.0 and len(np.unique(x)) > 4000
+
+
+def test_oracle_dot_product_vs_reference(orc, ref):
+    """dot_product<T> (include/math/product.h), the row widened after the elementwise path:
+    the restatement reproduces the reference's association order bit for bit."""
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    for n in (1, 3, 7, 8, 9, 15, 16, 17, 1000, 100_003):
+        for dt in (np.float32, np.float64, np.int32):
+            if dt == np.int32:
+                a = rng.integers(-2**31, 2**31, n, dtype=np.int64).astype(dt)
+                b = rng.integers(-2**31, 2**31, n, dtype=np.int64).astype(dt)
+            else:
+                a, b = rng.standard_normal(n).astype(dt), rng.standard_normal(n).astype(dt)
+            assert orc.dot(a, b).tobytes() == ref.dot(a, b).tobytes(), (n, dt)
+    assert orc.dot(np.array([1, 2, 3], np.int32), np.array([4, 5, 6], np.int32)) == 32

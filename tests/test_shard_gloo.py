@@ -32,12 +32,18 @@ def _worker(rank, world, port, n, align, q):
         full_add = shard.gather_shards(torch.from_numpy(add_loc), n, align).numpy()
         full_pow = shard.gather_shards(torch.from_numpy(pow_loc), n, align).numpy()
         worst = shard.max_over_ranks(float(rank + 1))
+        # sharded dot product: per-rank partial (oracle) + one scalar all-reduce; int32 wraps exactly
+        ia = (a_loc * 1e6).astype(np.int32)
+        ib = (b_loc * 1e6).astype(np.int32)
+        part = int(orc.dot(ia, ib)) if e > b else 0
+        total = int(shard.allreduce_scalar_sum(part, dtype=torch.int64)) & 0xFFFFFFFF
         if rank == 0:
             a = orc.fill_uniform_f32(0, n, 1, -1.0, 1.0)
             bb = orc.fill_uniform_f32(0, n, 2, -1.0, 1.0)
             ok = np.array_equal(full_add, orc.elementwise("add", a, [1], bb, [1], [n]))
             ok &= np.array_equal(full_pow, orc.array_scalar("pow", np.abs(a) + np.float32(0.01), 2.5))
             ok &= worst == float(world)
+            ok &= total == (int(orc.dot((a * 1e6).astype(np.int32), (bb * 1e6).astype(np.int32))) & 0xFFFFFFFF)
             q.put(bool(ok))
     finally:
         dist.destroy_process_group()

@@ -133,3 +133,17 @@ ia = rng.integers(-1000, 1001, size=(512, 1, 1024)).astype(np.int32)
 ib = rng.integers(1, 98, size=(1, 512, 1024)).astype(np.int32)
 binary_case("C4 i32 {512,1,1024}*{1,512,1024}", "mul", ia, ib, "write-dominated: 1 GiB out, 4 MiB in")
 binary_case("C4 i32 {512,1,1024}/{1,512,1024}", "div", ia, ib, "integer division is instruction-bound")
+
+# §8(f) row 2: dot product (SMArray::operator%), HBM-bound reduction: 2*sizeof(T) bytes per element
+for npdt, tdt, n in ((np.float32, torch.float32, 1 << 28), (np.float64, torch.float64, 1 << 27), (np.int32, torch.int32, 1 << 28)):
+    xa = (torch.rand(n, device="cuda") * 2 - 1).to(tdt) if npdt != np.int32 else torch.randint(-1000, 1000, (n,), dtype=tdt, device="cuda")
+    xb = xa.flip(0).contiguous()
+    dt = smb.dtype_code(npdt)
+    ms = timed(lambda: smb.dot_ptr(dt, xa.data_ptr(), xb.data_ptr(), n, sp), args.reps)
+    cpu_ms = None
+    if ref is not None:
+        ha, hb = xa[: 1 << 24].cpu().numpy(), xb[: 1 << 24].cpu().numpy()
+        cpu_ms = cpu_time(lambda: ref.dot(ha, hb)) * (n / (1 << 24))
+    report(f"dot {np.dtype(npdt).name} {n} elements (operator%)", 2 * np.dtype(npdt).itemsize * n, n, ms, cpu_ms,
+           "synchronous scalar result; CPU time scaled from a 2^24-element sample (single-threaded SIMD loop)")
+    del xa, xb
