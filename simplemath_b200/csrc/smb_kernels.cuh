@@ -20,6 +20,9 @@
 namespace smb {
 
 constexpr int kBlock = 256; // threads per CTA of every kernel in this file
+#ifndef SMB_POW_MIN_BLOCKS
+#define SMB_POW_MIN_BLOCKS 3 // resident CTAs per SM the f32 pow kernel is compiled for
+#endif
 
 // ---------------------------------------------------------------------------
 // 16-byte and 32-byte global vector access with streaming cache hints.
@@ -314,7 +317,7 @@ __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__
 }
 
 template<typename T, typename Fn, bool HAS_B, int VB, int UNROLL>
-__global__ void __launch_bounds__(256) k_stream(const T *__restrict__ a, const T *__restrict__ b,
+__global__ void __launch_bounds__(256, (fn_pow_tables<Fn>::value && sizeof(T) == 4) ? SMB_POW_MIN_BLOCKS : 2) k_stream(const T *__restrict__ a, const T *__restrict__ b,
                                                T *__restrict__ out, uint64_t n, uint64_t first, Fn fn_in) {
     constexpr int EPV = VB / (int)sizeof(T); // elements per vector
     Fn fn = fn_in;

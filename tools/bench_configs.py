@@ -134,6 +134,25 @@ ib = rng.integers(1, 98, size=(1, 512, 1024)).astype(np.int32)
 binary_case("C4 i32 {512,1,1024}*{1,512,1024}", "mul", ia, ib, "write-dominated: 1 GiB out, 4 MiB in")
 binary_case("C4 i32 {512,1,1024}/{1,512,1024}", "div", ia, ib, "integer division is instruction-bound")
 
+# strided operand: a.transpose() + b (generic element strides; no reference test covers it)
+def transposed_case(name, n0, n1):
+    a = torch.rand(n1 * n0, device="cuda")  # a is {n1, n0} dense; a^T has shape {n0, n1}, strides {1, n0}
+    b = torch.rand(n0 * n1, device="cuda")
+    out = torch.empty(n0 * n1, device="cuda")
+    lib, u = smb.lib(), smb._u64arr
+    argv = (smb.OP_ADD, smb.F32, a.data_ptr(), u([1, n0]), b.data_ptr(), u([n1, 1]), u([n0, n1]), 2, n0 * n1, out.data_ptr(), sp)
+    ms = timed(lambda: lib.smb_elementwise(*argv), args.reps)
+    ok = bool(torch.equal(out.view(n0, n1), a.view(n1, n0).t() + b.view(n0, n1)))
+    cpu_ms = None
+    if ref is not None:
+        ha, hb = a.cpu().numpy(), b.cpu().numpy()
+        cpu_ms = cpu_time(lambda: ref.elementwise("add", ha, [1, n0], hb, [n1, 1], [n0, n1]), reps=1)
+    report(name, 12 * n0 * n1, n0 * n1, ms, cpu_ms, f"verified={ok}")
+
+
+transposed_case("T f32 {8192,8192}^T + {8192,8192} (transposed operand)", 8192, 8192)
+transposed_case("T f32 {16384,1000}^T + {1000,16384}... shape {1000,16384}", 1000, 16384)
+
 # §8(f) row 2: dot product (SMArray::operator%), HBM-bound reduction: 2*sizeof(T) bytes per element
 for npdt, tdt, n in ((np.float32, torch.float32, 1 << 28), (np.float64, torch.float64, 1 << 27), (np.int32, torch.int32, 1 << 28)):
     xa = (torch.rand(n, device="cuda") * 2 - 1).to(tdt) if npdt != np.int32 else torch.randint(-1000, 1000, (n,), dtype=tdt, device="cuda")
