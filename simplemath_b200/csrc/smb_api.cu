@@ -254,6 +254,10 @@ static inline size_t esize(int dtype) { return dtype == SMB_F64 ? 8 : 4; }
 #define SMB_STREAM_UNROLL 4
 #endif
 constexpr int kThreads = kBlock;
+#ifndef SMB_TILE_R
+#define SMB_TILE_R 64 // k_tile: rows per tile (transposed operand's contiguous direction); halved for 8-byte types
+#define SMB_TILE_C 64 // cols per tile (result's contiguous direction)
+#endif
 
 static unsigned grid_for(uint64_t work_items, uint64_t items_per_block, int sm_count, int64_t ctas_per_sm) {
     uint64_t blocks = (work_items + items_per_block - 1) / items_per_block;
@@ -475,6 +479,53 @@ static int launch_bcast(const DeviceCtx &c, const ElementwisePlan &p, const T *a
                 SMB_CK(cudaGetLastError());
                 return SMB_OK;
             }
+        }
+    }
+    // transposed operand(s): stride 1 along an earlier dim k, a larger stride along the last dim
+    // (SMArray::transpose()) -> shared-memory tile transpose over (k, last).  Whole results only.
+    if (p.kind == PLAN_GENERIC && p.ndim >= 2 && lin_base == 0 && count == p.n && g_opt_bcast_variant.load() != 2) {
+        const int m = p.ndim;
+        auto unit_dim = [&](const uint64_t *st) { // the dim (other than the last) this operand is contiguous in
+            if (st[m - 1] <= 1) return -1;
+            for (int k = m - 2; k >= 0; --k)
+                if (st[k] == 1 && p.shape[k] > 1) return k;
+            return -2; // strided along the last dim but contiguous nowhere: not a transpose
+        };
+        const int ka = unit_dim(p.sa), kb = unit_dim(p.sb);
+        const int k = ka >= 0 ? ka : kb;
+        const bool at = ka >= 0, bt = kb >= 0;
+        uint64_t nbatch = 1, prod[SMB_MAX_NDIM];
+        prod[m - 1] = 1;
+        for (int d = m - 2; d >= 0; --d) prod[d] = prod[d + 1] * p.shape[d + 1];
+        for (int d = 0; d < m - 1; ++d) if (d != k) nbatch *= p.shape[d];
+        if (k >= 0 && ka != -2 && kb != -2 && (!at || !bt || ka == kb) && p.shape[m - 1] < (1ull << 31) &&
+            p.shape[k] < (1ull << 31) && nbatch <= 65535 && (p.shape[k] + 31) / 32 <= 65535) {
+            TileParams tp;
+            memset(&tp, 0, sizeof tp);
+            tp.rows = (uint32_t)p.shape[k];
+            tp.cols = (uint32_t)p.shape[m - 1];
+            tp.a_r = p.sa[k]; tp.a_c = p.sa[m - 1];
+            tp.b_r = p.sb[k]; tp.b_c = p.sb[m - 1];
+            tp.o_r = prod[k];
+            int nb = 0;
+            for (int d = 0; d < m - 1; ++d) {
+                if (d == k) continue;
+                const FastDiv32 f = make_fastdiv32((uint32_t)p.shape[d]);
+                tp.bshape[nb] = f.d; tp.bmul[nb] = f.mul; tp.bshr[nb] = f.shr;
+                tp.ba[nb] = p.sa[d]; tp.bb[nb] = p.sb[d]; tp.bo[nb] = prod[d];
+                ++nb;
+            }
+            tp.nbatch_dims = (uint32_t)nb;
+            tp.lane_base = lane_base;
+            constexpr int TR = sizeof(T) == 8 ? SMB_TILE_R / 2 : SMB_TILE_R, TC = SMB_TILE_C; // <= 17 KB of shared memory per tile
+            const dim3 grid((tp.cols + TC - 1) / TC, (tp.rows + TR - 1) / TR, (unsigned)nbatch);
+            if (at && bt) k_tile<T, Fn, true, true, TR, TC><<<grid, kThreads, 0, s>>>(a, b, out, tp, fn);
+            else if (at) k_tile<T, Fn, true, false, TR, TC><<<grid, kThreads, 0, s>>>(a, b, out, tp, fn);
+            else k_tile<T, Fn, false, true, TR, TC><<<grid, kThreads, 0, s>>>(a, b, out, tp, fn);
+            g_last_kernel = "k_tile<transpose>";
+            ++g_launches;
+            SMB_CK(cudaGetLastError());
+            return SMB_OK;
         }
     }
     if (p.kind == PLAN_GENERIC) {

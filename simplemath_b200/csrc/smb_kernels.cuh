@@ -595,6 +595,96 @@ __global__ void __launch_bounds__(256) k_outer(const T *__restrict__ a, const T 
     }
 }
 
+// k_tile: a TRANSPOSED operand (what SMArray::transpose() hands to element_wise_op: stride 1
+// along some earlier result dim, a large stride along the last).  Read directly, every
+// warp would touch 32 different rows for 128 useful bytes; instead each CTA moves a 32x32 tile
+// of that operand through shared memory -- global reads coalesced along the operand's own
+// contiguous direction, the transpose done on chip -- and writes the result rows coalesced.
+// The other operand is read directly (inner stride 0 or 1) or through a second tile when it
+// is transposed too.  Leading dims are batches: their offsets come from the stride table by
+// fast-divmod, once per CTA.
+struct TileParams {
+    uint32_t rows, cols;            // tile dims: rows = the dim the transposed operand is contiguous in, cols = last dim
+    uint64_t a_r, a_c, b_r, b_c;    // element strides of each operand along rows / cols
+    uint64_t o_r;                   // result stride along rows (cols are contiguous in the result)
+    uint32_t nbatch_dims;           // every other dim, enumerated by blockIdx.z
+    uint32_t bshape[SMB_MAX_NDIM], bmul[SMB_MAX_NDIM], bshr[SMB_MAX_NDIM];
+    uint64_t ba[SMB_MAX_NDIM], bb[SMB_MAX_NDIM], bo[SMB_MAX_NDIM];
+    uint64_t lane_base;
+};
+template<typename T, typename Fn, bool A_T, bool B_T, int TR, int TC, bool FULL>
+__device__ __forceinline__ void tile_body(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
+                                          const TileParams &p, const Fn &fn, uint32_t r0, uint32_t c0, uint64_t obase,
+                                          T (*ta)[TR + 1], T (*tb)[TR + 1]) {
+    static_assert(kBlock % TR == 0 && kBlock % TC == 0, "tile dims must divide the CTA size");
+    constexpr int PER = TR * TC / kBlock;  // elements per thread
+    constexpr int SSTEP = kBlock / TR;     // stage pass: thread -> (row tid % TR, col tid / TR + j * SSTEP)
+    constexpr int PSTEP = kBlock / TC;     // produce pass: thread -> (col tid % TC, row tid / TC + j * PSTEP)
+    const uint32_t slr = threadIdx.x % TR, slc = threadIdx.x / TR;
+    const uint32_t plc = threadIdx.x % TC, plr = threadIdx.x / TC;
+    // every global load of the tile is issued before the first use: the transposed operand along
+    // its own contiguous direction (stage coordinates), a direct operand at the result's coordinates
+    const T *as = a + (uint64_t)(r0 + slr) * p.a_r + (uint64_t)(c0 + slc) * p.a_c;
+    const T *ap = a + (uint64_t)(r0 + plr) * p.a_r + (uint64_t)(c0 + plc) * p.a_c;
+    const T *bs = b + (uint64_t)(r0 + slr) * p.b_r + (uint64_t)(c0 + slc) * p.b_c;
+    const T *bp = b + (uint64_t)(r0 + plr) * p.b_r + (uint64_t)(c0 + plc) * p.b_c;
+    const uint64_t a_step = A_T ? (uint64_t)SSTEP * p.a_c : (uint64_t)PSTEP * p.a_r;
+    const uint64_t b_step = B_T ? (uint64_t)SSTEP * p.b_c : (uint64_t)PSTEP * p.b_r;
+    const bool s_row_ok = FULL || r0 + slr < p.rows, p_col_ok = FULL || c0 + plc < p.cols;
+    T va[PER], vb[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const bool s_ok = FULL || (s_row_ok && c0 + slc + j * SSTEP < p.cols);
+        const bool p_ok = FULL || (p_col_ok && r0 + plr + j * PSTEP < p.rows);
+        if (A_T ? s_ok : p_ok) va[j] = __ldg((A_T ? as : ap) + (uint64_t)j * a_step);
+        if (B_T ? s_ok : p_ok) vb[j] = __ldg((B_T ? bs : bp) + (uint64_t)j * b_step);
+    }
+    if (A_T || B_T) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (A_T) ta[slc + j * SSTEP][slr] = va[j];
+            if (B_T) tb[slc + j * SSTEP][slr] = vb[j];
+        }
+        __syncthreads();
+    }
+    T *o = out + obase + (uint64_t)(r0 + plr) * p.o_r + (c0 + plc);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        if (FULL || (p_col_ok && r0 + plr + j * PSTEP < p.rows)) {
+            const T x = A_T ? ta[plc][plr + j * PSTEP] : va[j];
+            const T y = B_T ? tb[plc][plr + j * PSTEP] : vb[j];
+            const uint64_t off = (uint64_t)j * PSTEP * p.o_r;
+            o[off] = fn(x, y, p.lane_base + (uint64_t)(o + off - out));
+        }
+    }
+}
+
+template<typename T, typename Fn, bool A_T, bool B_T, int TR, int TC>
+__global__ void __launch_bounds__(256) k_tile(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
+                                             const __grid_constant__ TileParams p, Fn fn) {
+    // tile: TR rows (the transposed operand's contiguous direction) x TC cols (the result's);
+    // the +1 pad makes both the row-wise fill and the column-wise drain conflict-free
+    __shared__ T ta[A_T ? TC : 1][TR + 1], tb[B_T ? TC : 1][TR + 1];
+    const uint32_t c0 = blockIdx.x * TC, r0 = blockIdx.y * TR;
+    uint64_t oa = 0, ob = 0, obase = 0;
+    uint32_t rem = blockIdx.z;
+#pragma unroll
+    for (int k = SMB_MAX_NDIM - 1; k >= 0; --k) {
+        if (k < (int)p.nbatch_dims) {
+            const uint32_t q = k == 0 ? 0u : fastdiv(rem, p.bshape[k], p.bmul[k], p.bshr[k]);
+            const uint32_t idx = k == 0 ? rem : rem - q * p.bshape[k];
+            rem = q;
+            oa += (uint64_t)idx * p.ba[k];
+            ob += (uint64_t)idx * p.bb[k];
+            obase += (uint64_t)idx * p.bo[k];
+        }
+    }
+    if (r0 + TR <= p.rows && c0 + TC <= p.cols)
+        tile_body<T, Fn, A_T, B_T, TR, TC, true>(a + oa, b + ob, out, p, fn, r0, c0, obase, ta, tb);
+    else
+        tile_body<T, Fn, A_T, B_T, TR, TC, false>(a + oa, b + ob, out, p, fn, r0, c0, obase, ta, tb);
+}
+
 // k_generic: arbitrary element strides; one output element per thread per
 // iteration, coalesced stores, gathered loads.
 template<typename T, typename Fn, bool WIDE>

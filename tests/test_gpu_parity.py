@@ -119,7 +119,7 @@ def test_views_interior_pointers_and_transposes(orc):
     m = rng.standard_normal((37, 53)).astype(np.float32)
     n = rng.standard_normal((53, 37)).astype(np.float32)
     assert_same_bits(smb.binary("mul", m.T, n), orc.binary("mul", m.T, n), "transposed operand")
-    assert smb.last_kernel().startswith("k_generic")
+    assert smb.last_kernel().startswith("k_tile")
     w = rng.standard_normal((64, 100)).astype(np.float32)
     sl = w[:, 3:67]                                  # misaligned rows: inner stride 1, odd base offset
     assert_same_bits(smb.binary("sub", sl, sl), orc.binary("sub", sl, sl), "misaligned slice")
@@ -312,6 +312,36 @@ def test_outer_broadcast_kernel(orc):
         smb.set_option(smb.OPT_BCAST_VARIANT, 0)
 
 
+def test_transposed_operands_tile_kernel(orc):
+    """SMArray::transpose() views (stride 1 along an earlier dim): shared-memory tile transpose."""
+    rng = np.random.default_rng(61)
+    for r, c in ((37, 53), (64, 64), (1, 200), (200, 1), (129, 1025), (1000, 33)):
+        m = rng.standard_normal((c, r)).astype(np.float32)      # m.T has shape {r, c}, strides {1, r}
+        n = rng.standard_normal((r, c)).astype(np.float32)
+        for op in ("sub", "div"):
+            assert_same_bits(smb.binary(op, m.T, n), orc.binary(op, m.T, n), f"a^T {op} b {r}x{c}")
+            assert_same_bits(smb.binary(op, n, m.T), orc.binary(op, n, m.T), f"a {op} b^T {r}x{c}")
+            assert_same_bits(smb.binary(op, m.T, m.T * 2), orc.binary(op, m.T, m.T * 2), f"a^T {op} (2a)^T")
+        if r > 1 and c > 1:
+            smb.binary("add", m.T, n)
+            assert smb.last_kernel() == "k_tile<transpose>", smb.last_kernel()
+        row = rng.standard_normal((1, c)).astype(np.float32)
+        assert_same_bits(smb.binary("mul", m.T, row), orc.binary("mul", m.T, row), "a^T * row")
+        col = rng.standard_normal((r, 1)).astype(np.float32)
+        assert_same_bits(smb.binary("mul", col, m.T), orc.binary("mul", col, m.T), "col * a^T")
+    # 3-D full transpose (reversed dims) against a dense operand, int32 and f64
+    for dt in (np.int32, np.float64):
+        x = (rng.standard_normal((7, 40, 33)) * 100).astype(dt)
+        y = (rng.standard_normal((33, 40, 7)) * 100).astype(dt)
+        assert_same_bits(smb.binary("add", x.T, y), orc.binary("add", x.T, y), f"3-D reversed {np.dtype(dt).name}")
+        assert smb.last_kernel() == "k_tile<transpose>", smb.last_kernel()
+        assert_same_bits(smb.binary("sub", x.transpose(0, 2, 1), x.transpose(0, 2, 1)), orc.binary("sub", x.transpose(0, 2, 1), x.transpose(0, 2, 1)), "batched transpose")
+    # a strided slice that is not a transpose stays on the generic kernel
+    w = rng.standard_normal((64, 100)).astype(np.float32)
+    assert_same_bits(smb.binary("add", w[:, ::2], w[:, 1::2]), orc.binary("add", w[:, ::2], w[:, 1::2]), "stride-2 columns")
+    assert smb.last_kernel().startswith("k_generic")
+
+
 def test_wide_index_path_on_small_shapes(orc):
     """The 64-bit index kernels (results beyond 2^31 elements) forced on small shapes."""
     rng = np.random.default_rng(31)
@@ -326,7 +356,8 @@ def test_wide_index_path_on_small_shapes(orc):
         assert smb.last_kernel() == "k_row<vec16,wide>"
         m = rng.standard_normal((37, 53)).astype(np.float64)
         n = rng.standard_normal((53, 37)).astype(np.float64)
-        assert_same_bits(smb.binary("div", m.T, n), orc.binary("div", m.T, n), "wide generic")
+        w2 = rng.standard_normal((64, 100))
+        assert_same_bits(smb.binary("div", w2[:, ::2], w2[:, 1::2]), orc.binary("div", w2[:, ::2], w2[:, 1::2]), "wide generic")
         assert smb.last_kernel() == "k_generic<wide>"
     finally:
         smb.set_option(smb.OPT_FORCE_WIDE_INDEX, 0)
