@@ -339,10 +339,18 @@ int scalar_t<float>(const DeviceCtx &c, int op, const float *a, float v, float *
             }
             {
                 const PowExpF32 pe = classify_exp(v);
-                const bool small = pow_f32_small_y(pe), odd = pe.y_is_odd != 0;
-#define SMB_POW_LAUNCH(S, O) launch_stream<T, PowF32Fn<S, O>, false>(c, a, nullptr, out, n, first, PowF32Fn<S, O>::make(v, lane_end), s)
-                if (small) return odd ? SMB_POW_LAUNCH(true, true) : SMB_POW_LAUNCH(true, false);
-                return odd ? SMB_POW_LAUNCH(false, true) : SMB_POW_LAUNCH(false, false);
+                if (!pow_f32_fast_ok(pe)) // |y| >= 2^64, tiny, zero, inf or NaN: the reference-accuracy path alone
+                    return launch_stream<T, PowF32SlowFn, false>(c, a, nullptr, out, n, first, PowF32SlowFn::make(v, lane_end), s);
+                const bool small = pow_f32_small_y(pe), lt1 = pow_f32_y_lt_1(pe);
+                const int sign = pow_f32_sign_mode(pe);
+#define SMB_POW_LAUNCH(S, G, L) launch_stream<T, PowF32Fn<S, G, L>, false>(c, a, nullptr, out, n, first, PowF32Fn<S, G, L>::make(v, lane_end), s)
+                if (lt1) return SMB_POW_LAUNCH(true, POW_SIGN_REJECT, true); // 0 < |y| < 1 is never an integer
+                if (small) return sign == POW_SIGN_REJECT ? SMB_POW_LAUNCH(true, POW_SIGN_REJECT, false)
+                                : sign == POW_SIGN_EVEN   ? SMB_POW_LAUNCH(true, POW_SIGN_EVEN, false)
+                                                          : SMB_POW_LAUNCH(true, POW_SIGN_ODD, false);
+                return sign == POW_SIGN_REJECT ? SMB_POW_LAUNCH(false, POW_SIGN_REJECT, false)
+                     : sign == POW_SIGN_EVEN   ? SMB_POW_LAUNCH(false, POW_SIGN_EVEN, false)
+                                               : SMB_POW_LAUNCH(false, POW_SIGN_ODD, false);
 #undef SMB_POW_LAUNCH
             }
         }

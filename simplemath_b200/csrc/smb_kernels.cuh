@@ -127,48 +127,54 @@ template<> struct ScalarFn<OP_POW, int32_t> {
 // kept out of line so the hot loop stays small.
 __device__ __noinline__ float pow_f32_slow(float x, PowExpF32 pe) { return pow_f32(x, pe); }
 
-static __device__ const PowTabLog d_pow_log_tab[SMB_POW_LOG_ENTRIES] = SMB_POW_LOG_TABLE_INIT;
+static __device__ const PowTabLog d_pow_log_tab[SMB_POW_LOG_ENTRIES] = SMB_POW_LOG_TABLE_INIT;   // small-y: {invc, -log2 invc}
+static __device__ const PowTabLog d_pow_logc_tab[SMB_POW_LOG_ENTRIES] = SMB_POW_LOGC_TABLE_INIT; // large-y: {c, log2 c}
 static __device__ const PowTabExp d_pow_exp_tab[SMB_POW_EXP_ENTRIES] = SMB_POW_EXP_TABLE_INIT;
 
-template<bool SMALL_Y, bool ODD_Y> struct PowF32Fn {
+// The reference-accuracy path alone: exponents the fast core cannot take (|y| >= 2^64 or
+// y * log2 x denormal), and the scalar-access kernels.
+struct PowF32SlowFn {
+    PowExpF32 pe;
+    uint64_t lane_end;
+    __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return pow_f32_slow(a, pe); }
+    static PowF32SlowFn make(float y, uint64_t lane_end_) { return PowF32SlowFn{classify_exp(y), lane_end_}; }
+};
+template<> struct ScalarFn<OP_POW, float> : PowF32SlowFn {};
+
+// The host only launches this functor when pow_f32_fast_ok(pe); the variant (SMALL_Y, SIGN,
+// Y_LT_1) is picked from the uniform exponent, see pow_f32_pair_fast.
+template<bool SMALL_Y, int SIGN, bool Y_LT_1> struct PowF32Fn {
     static constexpr bool PAIRWISE = true;    // stream_vec feeds two elements per call
     static constexpr bool POW_TABLES = true;  // k_stream stages the lookup tables in shared memory
     PowExpF32 pe;  // exponent classified once on the host
     uint64_t lane_end;
-    int fast;              // pow_f32_fast_ok(pe)
-    uint32_t sign_reject;  // 0x80000000 when negative bases must take the slow path (non-integer y)
-    const PowTabLog *tab_log;
-    const PowTabExp *tab_exp;
+    PowLane lane;  // this thread's replica offsets into the shared-memory tables
     __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return pow_f32_slow(a, pe); }
     // Two elements through the branch-free fast core; false = redo on the slow path.
     __device__ __forceinline__ bool pair(float a0, float a1, float &r0, float &r1) const {
-        return pow_f32_pair_fast<SMALL_Y, ODD_Y>(a0, a1, pe.y, sign_reject, tab_log, tab_exp, &r0, &r1) && fast != 0;
+        return pow_f32_pair_fast<SMALL_Y, SIGN, Y_LT_1>(a0, a1, pe.y, lane, nullptr, nullptr, &r0, &r1);
     }
     // Lookup tables, L2 -> shared memory once per CTA, each entry replicated across the lanes
     // of a wavefront (24 KB) so the per-lane lookups never conflict; see smb_math.cuh.
     __device__ __forceinline__ void block_init() {
-        __shared__ __align__(16) PowTabLog s_log[SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE];
-        __shared__ __align__(16) PowTabExp s_exp[SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE];
+        const PowTabLog *src = SMALL_Y ? d_pow_log_tab : d_pow_logc_tab;
         for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE; i += kBlock)
-            s_log[i] = d_pow_log_tab[i / SMB_POW_LOG_STRIDE];
+            smb_s_pow_log[i] = src[i / SMB_POW_LOG_STRIDE];
         for (int i = threadIdx.x; i < SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE; i += kBlock)
-            s_exp[i] = d_pow_exp_tab[i / SMB_POW_EXP_STRIDE];
+            smb_s_pow_exp[i] = d_pow_exp_tab[i / SMB_POW_EXP_STRIDE];
+        // the lookups read these arrays from inline PTX (by symbol): tell the compiler they are read
+        asm volatile("" :: "l"(smb_s_pow_log), "l"(smb_s_pow_exp) : "memory");
         __syncthreads();
-        tab_log = s_log + (threadIdx.x & (SMB_POW_LOG_STRIDE - 1));
-        tab_exp = s_exp + (threadIdx.x & (SMB_POW_EXP_STRIDE - 1));
+        lane = pow_lane(threadIdx.x, lane.c);
     }
     static PowF32Fn make(float y, uint64_t lane_end_) {
         PowF32Fn fn;
         fn.pe = classify_exp(y);
         fn.lane_end = lane_end_;
-        fn.fast = pow_f32_fast_ok(fn.pe) ? 1 : 0;
-        fn.sign_reject = pow_f32_sign_reject(fn.pe);
-        fn.tab_log = nullptr; // set per CTA from shared memory
-        fn.tab_exp = nullptr;
+        fn.lane = PowLane{0, 0, pow_consts()}; // offsets set per thread in block_init; the constants ride in as kernel parameters
         return fn;
     }
 };
-template<> struct ScalarFn<OP_POW, float> : PowF32Fn<false, true> {};
 // sm::pow(arr, y) for double: table-driven fast core per element, double-double
 // reference-accuracy path (out of line) for whatever it declines.
 __device__ __noinline__ double pow_f64_slow(double x, PowExpF64 pe) { return pow_f64(x, pe); }

@@ -386,23 +386,26 @@ SMB_HD float pow_f32(float x, const PowExpF32 &pe) {
 // The double core runs on the half-rate FP64 pipe and made sm::pow compute-bound
 // at a third of the HBM rate (2.15 TB/s measured on B200).  This core keeps the
 // arithmetic on the FP32 pipe and issues it as packed fma.rn.f32x2 (SASS FFMA2,
-// new with sm_100): two elements per instruction, which is what lets ~35
-// floating-point operations per element fit under the memory roofline.
+// new with sm_100): two elements per instruction, ~30 instructions per element in
+// all, which is what fits under the memory roofline.
 //
-//   x = 2^e * m, m in [sqrt(1/2), sqrt(2)); the top 7 bits of m's offset select a
-//   table entry {c, L_hi, L_lo}, log2(c) = L_hi + L_lo, c = 1 exactly around m = 1
-//   (so x near 1 keeps full RELATIVE accuracy);
-//   p = (m-c)/(m+c), |p| <= 0.0059, as p_hi + p_lo (MUFU.RCP seed + two FMA
-//   residual steps; m-c is exact, m+c is carried with its rounding error);
-//   log2 x = (e + L_hi) + [C0*p + L_lo + p^3*(C1 + C2 p^2)]  -- e + L_hi is exact
-//   because L_hi is a multiple of 2^-15; the bracket is kept as two floats;
-//   t = y*log2 x as th + tl; k = rint(64 t): 2^t = 2^n * T[j] * 2^f, n = k >> 6,
+//   |x| = 2^E * m, m in [1, 2); the top 7 mantissa bits select {invc, L_hi, L_lo} with
+//   -log2(invc) = L_hi + L_lo and invc = k/256 an EIGHT-bit reciprocal of the entry's centre:
+//   r = fma(m, invc, -1) is then exact (|r| <= 2^-7, M*k - 2^31 fits 24 bits) -- no division,
+//   no reciprocal, no error term to carry.  invc = 1 for the first entry and 1/2 for the last
+//   two, so x near 1 keeps full RELATIVE accuracy (E + L == 0 there).
+//   log2|x| = (E + L_hi) + [C1h*r + L_lo + (C1h*r)_err + r*(C1l + r*(C2 + r*C3 ...))]
+//   -- float(biased exponent) + (L_hi - 127) is exact because L_hi is a multiple of 2^-15;
+//   the bracket is kept as two floats;
+//   t = y*log2|x| as th + tl; k = rint(64 t): 2^t = 2^n * T[j] * 2^f, n = k >> 6,
 //   j = k & 63, |f| <= 2^-7, T[j] = 2^(j/64) as T_hi + T_lo,
 //   2^f - 1 = f*(E1 + f*(E2 + f*E3)).
-// Error: <= 0.5 (final rounding) + ~0.05 ULP typical; tests bound it by 1 ULP.
+// Error: <= 0.5 (final rounding) + ~0.06 ULP; tests bound it by 1 ULP.
 // The core declines (returns false) anything that is not "normal positive
 // magnitude, result comfortably inside the normal range"; the caller then uses
-// pow_f32 above for that element.
+// pow_f32 above for that element.  There is no separate test of the INPUT: zero, denormal,
+// infinite, NaN and (for a non-integer exponent) negative bases all push the biased-exponent
+// term far enough that the one range test on t (or on log2|x| when |y| < 1) rejects them.
 struct f2 { float x, y; };
 SMB_HD f2 f2_make(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
 SMB_HD f2 f2_splat(float a) { return f2_make(a, a); }
@@ -435,42 +438,105 @@ SMB_HD f2 f2_neg(f2 a) { return f2_make(-a.x, -a.y); }
 SMB_HD f2 f2_sub(f2 a, f2 b) { return f2_add(a, f2_neg(b)); }
 SMB_HD f2 f2_fnma(f2 a, f2 b, f2 c) { return f2_fma(f2_neg(a), b, c); } // c - a*b, one rounding
 
-struct PowTabLog { float c, l_hi, l_lo, pad; };
-struct PowTabExp { float t_hi, t_lo; };
+struct PowTabLog { float c, l_hi, l_lo, pad; }; // c: the entry's centre (large-y table) or its 8-bit reciprocal (small-y table)
 
-#ifndef SMB_RCP_PERTURB
-#define SMB_RCP_PERTURB(r) (r)
-#endif
+// MUFU.RCP seed (the f64 core refines it); the host build stands in with a correctly rounded 1/x.
 SMB_HD float rcp_seed(float x) {
 #if defined(__CUDA_ARCH__)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 #else
-    return SMB_RCP_PERTURB(1.0f / x);
+    return 1.0f / x;
 #endif
 }
+struct PowTabExp { float t_hi, t_lo; };
 
-// Table access.  Host build: the compact tables.  Device: each entry is replicated across
-// the lanes that share a shared-memory wavefront (8 lanes for the 16-byte log entries, 16
-// for the 8-byte exp entries) and `tab_*` already points at this lane's replica, so a warp
-// reading 32 unrelated entries is bank-conflict free.  (The compact layout measured 58 %
-// conflict replays and saturated the LSU data pipe at 97 %: profiles/r1_pow_ncu.md.)
-#if defined(__CUDA_ARCH__)
+// Table access.  Host build: the compact tables behind `tab_*`.  Device: the tables live in
+// shared memory (smb_s_pow_log / smb_s_pow_exp below, filled per CTA by PowF32Fn::block_init) with each
+// entry replicated across the lanes that share a shared-memory wavefront (8 lanes for the
+// 16-byte log entries, 16 for the 8-byte exp entries), so a warp reading 32 unrelated entries is
+// bank-conflict free.  (The compact layout measured 58 % conflict replays and saturated the LSU
+// data pipe at 97 %: profiles/r1_pow_ncu.md.)  The lane's replica offset is OR-ed into the
+// entry offset and the array base is a compile-time shared address, so a lookup costs
+// SHF + LOP3 + LDS [R + imm].
+#if defined(__CUDACC__)
 #define SMB_POW_LOG_STRIDE 8   /* entries of PowTabLog between consecutive j */
 #define SMB_POW_EXP_STRIDE 16  /* entries of PowTabExp between consecutive j */
+} // namespace smb
+// C linkage: the lookups below name these arrays from inline PTX, so that their (compile-time)
+// shared addresses fold into the LDS immediate instead of going through a generic pointer.
+extern "C" {
+__shared__ __align__(128) smb::PowTabLog smb_s_pow_log[SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE];
+__shared__ __align__(128) smb::PowTabExp smb_s_pow_exp[SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE];
+}
+namespace smb {
 #else
 #define SMB_POW_LOG_STRIDE 1
 #define SMB_POW_EXP_STRIDE 1
 #endif
-SMB_HD PowTabLog pow_tab_log_at(const PowTabLog *tab, uint32_t a) {
-    // j = top 7 mantissa bits = (a >> 16) & 127, scaled to a byte offset in one shift + mask
-    const uint32_t off = (a >> (16 - 4 - (SMB_POW_LOG_STRIDE == 8 ? 3 : 0))) & (127u * 16u * SMB_POW_LOG_STRIDE);
-    return *reinterpret_cast<const PowTabLog *>(reinterpret_cast<const char *>(tab) + off);
+// Per-thread lookup state: this lane's replica offsets (bytes) into the two tables, zero on the
+// host.  On the device they are fetched from a small global table rather than computed from the
+// thread index: ptxas would otherwise re-derive `(tid & 7) * 16` at every use to save the
+// register, which costs a second LOP3 per lookup.
+// PowConsts: constants that ride in as kernel parameters (uniform registers) -- `one` keeps
+// `(u & 0x007fffff) | one` ONE three-input LOP3 (with both words literal ptxas emits an AND and an
+// OR), the floats feed FFMA2's scalar-splat operand without a per-vector MOV.
+struct PowConsts { uint32_t one; float k64, s_c3, e3; };
+SMB_HD PowConsts pow_consts() { PowConsts c; c.one = 0x3f800000u; c.k64 = 64.0f; c.s_c3 = SMB_POW_S_C3; c.e3 = 0.05547422543168068f; return c; }
+struct PowLane { uint32_t log_off, exp_off; PowConsts c; };
+#if defined(__CUDACC__)
+static __device__ uint2 d_pow_lane_tab[16] = {{0, 0}, {16, 8}, {32, 16}, {48, 24}, {64, 32}, {80, 40}, {96, 48}, {112, 56},
+                                              {0, 64}, {16, 72}, {32, 80}, {48, 88}, {64, 96}, {80, 104}, {96, 112}, {112, 120}};
+#endif
+SMB_HD PowLane pow_lane(uint32_t tid, PowConsts c) {
+    PowLane l;
+    l.c = c;
+#if defined(__CUDA_ARCH__)
+    const uint2 o = d_pow_lane_tab[tid & 15u];
+    l.log_off = o.x;
+    l.exp_off = o.y;
+#else
+    (void)tid;
+    l.log_off = l.exp_off = 0;
+#endif
+    return l;
 }
-SMB_HD PowTabExp pow_tab_exp_at(const PowTabExp *tab, uint32_t k) {
-    const uint32_t off = (k << (3 + (SMB_POW_EXP_STRIDE == 16 ? 4 : 0))) & (63u * 8u * SMB_POW_EXP_STRIDE);
-    return *reinterpret_cast<const PowTabExp *>(reinterpret_cast<const char *>(tab) + off);
+SMB_HD PowTabLog pow_tab_log_at(const PowTabLog *tab, uint32_t lane_off, uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    // j = top 7 mantissa bits = (u >> 16) & 127; entry j starts at byte j * 128.
+    // SHF + LOP3 + LDS [R + imm]
+    const uint32_t off = ((u >> 9) & (127u << 7)) | lane_off;
+    PowTabLog e;
+    asm("{\n\t.reg .u32 a;\n\t.reg .u64 b;\n\tmov.u64 b, smb_s_pow_log;\n\tcvt.u32.u64 a, b;\n\tadd.u32 a, a, %4;\n\t"
+        "ld.shared.v4.f32 {%0,%1,%2,%3}, [a];\n\t}" : "=f"(e.c), "=f"(e.l_hi), "=f"(e.l_lo), "=f"(e.pad) : "r"(off));
+    return e;
+#else
+    (void)lane_off;
+    return tab[(u >> 16) & 127u];
+#endif
+}
+SMB_HD PowTabExp pow_tab_exp_at(const PowTabExp *tab, uint32_t lane_off, uint32_t k) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t off = ((k << 7) & (63u << 7)) | lane_off; // entry j = k & 63 starts at byte j * 128
+    PowTabExp e;
+    asm("{\n\t.reg .u32 a;\n\t.reg .u64 b;\n\tmov.u64 b, smb_s_pow_exp;\n\tcvt.u32.u64 a, b;\n\tadd.u32 a, a, %2;\n\t"
+        "ld.shared.v2.f32 {%0,%1}, [a];\n\t}" : "=f"(e.t_hi), "=f"(e.t_lo) : "r"(off));
+    return e;
+#else
+    (void)lane_off;
+    return tab[k & 63u];
+#endif
+}
+// zbits + ((k & ~63) << 17): mask, then ONE multiply-add (ptxas would otherwise shift, mask, add)
+SMB_HD uint32_t pow_scale_bits(uint32_t k, uint32_t zbits) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 131072, %2;" : "=r"(r) : "r"(k & 0xffffffc0u), "r"(zbits));
+    return r;
+#else
+    return ((k & 0xffffffc0u) << 17) + zbits;
+#endif
 }
 
 // Host-side facts about the (uniform) exponent that gate the fast core.
@@ -485,54 +551,68 @@ SMB_HD bool pow_f32_fast_ok(const PowExpF32 &pe) {
 // but every table index and operation along the way is safe).  The caller
 // accumulates the flag over a whole vector and branches once.
 //
-// SMALL_Y (|y| <= 8, chosen on the host): the error terms that only matter once they
-// are multiplied by a large exponent are dropped -- the rounding error of m + c
-// (2^-25 relative in p, 2^-31 absolute in log2 x), the low word of 2/ln2, the p^5
-// term and the renormalisation of the log2 tail.
-// ODD_Y: y is an odd integer, the result takes the sign of the base.
-template<bool SMALL_Y, bool ODD_Y>
-SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, uint32_t sign_reject,
+// SMALL_Y (|y| <= 8, chosen on the host): the division-free r-series above on the invc table, no
+// renormalisation of the log2 tail -- what is dropped only matters once multiplied by a large
+// exponent.  Otherwise: the {c, log2 c} table and the series in p = (m-c)/(m+c), whose second
+// term is p^3 (the r-series would need r^2 in two floats there).
+// SIGN: POW_SIGN_REJECT -- y is not an integer, a negative base must reach the slow path (NaN):
+//         the sign bit is converted together with the biased exponent, which adds 256 to log2|x|;
+//       POW_SIGN_EVEN   -- even integer y, the sign of the base is dropped;
+//       POW_SIGN_ODD    -- odd integer y, the result takes the sign of the base.
+// Y_LT_1 (|y| < 1): the range test is made on log2|x| instead of t (|t| < |log2|x|| then).
+enum { POW_SIGN_REJECT = 0, POW_SIGN_EVEN = 1, POW_SIGN_ODD = 2 };
+template<bool SMALL_Y, int SIGN, bool Y_LT_1>
+SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
                               const PowTabLog *tab_log, const PowTabExp *tab_exp, float *r0, float *r1) {
-    const uint32_t u0 = f2u(x0), u1 = f2u(x1);
-    const uint32_t a0 = u0 & 0x7fffffffu, a1 = u1 & 0x7fffffffu;
-    const uint32_t eb0 = a0 >> 23, eb1 = a1 >> 23;           // biased exponents
-    // normal finite magnitude (biased exponent 1..254); negative bases only with an integer
-    // exponent (sign_reject = 0 then)
-    const uint32_t w0 = eb0 - 1u, w1 = eb1 - 1u;
-    bool ok = (w0 > w1 ? w0 : w1) < 254u && ((u0 | u1) & sign_reject) == 0u;
-    // ---- log2 |x|,  |x| = 2^E * f,  f in [1, 2) ----------------------------------
-    const f2 m = f2_make(u2f((a0 & 0x007fffffu) | 0x3f800000u), u2f((a1 & 0x007fffffu) | 0x3f800000u));
-    const PowTabLog t0 = pow_tab_log_at(tab_log, a0), t1 = pow_tab_log_at(tab_log, a1);
-    const f2 num = f2_sub(m, f2_make(t0.c, t1.c));         // exact (Sterbenz); the only use of c
-    const f2 two = f2_splat(2.0f);
-    const f2 den = f2_fma(m, two, f2_neg(num));            // 2m - (m - c) = m + c, one rounding
-    const f2 r = f2_make(rcp_seed(den.x), rcp_seed(den.y));
-    const f2 p_hi = f2_mul(num, r);
-    f2 res = f2_fnma(p_hi, den, num);
-    if (!SMALL_Y) {
-        // (m + c) - den, exactly: 2m - den is exact (Sterbenz) and so is the difference with num
-        const f2 den_lo = f2_sub(f2_fma(m, two, f2_neg(den)), num);
-        res = f2_fnma(p_hi, den_lo, res);
-    }
-    const f2 p_lo = f2_mul(res, r);
-    const f2 s = f2_mul(p_hi, p_hi);
-    // log2(m/c) = C0*p + p^3*(C1 + C2 p^2): leading product exact (two floats), the rest folded
-    // into one coefficient  c0l + s*(C1 + C2 s)  (the p^3 term is < 2^-16 of the total)
-    const f2 c0h = f2_splat(2.885390043258667f);           // 2/ln2 = c0h + c0l
-    f2 qq;
+    uint32_t u0 = f2u(x0), u1 = f2u(x1);
+    const uint32_t s0 = u0, s1 = u1;
+    if (SIGN != POW_SIGN_REJECT) { u0 &= 0x7fffffffu; u1 &= 0x7fffffffu; } // integer y: |x| from here on
+    // ---- log2 |x|,  |x| = 2^E * m,  m in [1, 2) ----------------------------------
+    const f2 m = f2_make(u2f((u0 & 0x007fffffu) | lane.c.one), u2f((u1 & 0x007fffffu) | lane.c.one));
+    const PowTabLog t0 = pow_tab_log_at(tab_log, lane.log_off, u0), t1 = pow_tab_log_at(tab_log, lane.log_off, u1);
+    f2 lh, ll; // log2(m * invc) [or log2(m / c)] as lh + ll
     if (SMALL_Y) {
-        qq = f2_mul(s, f2_splat(0.9618070721626282f));
+        // exact; .c holds invc here.  Scalar FMAs: the operands come straight from the LDS
+        // registers, packing them first would cost more moves than the packed form saves.
+        const f2 r = f2_make(ffma(m.x, t0.c, -1.0f), ffma(m.y, t1.c, -1.0f));
+        const f2 c1h = f2_splat(SMB_POW_C1H);              // 1/ln2 = c1h + c1l
+        lh = f2_mul(c1h, r);
+        ll = f2_fma(c1h, r, f2_neg(lh));                   // the rounding error of lh, exactly
+        f2 q = f2_fma(r, f2_splat(lane.c.s_c3), f2_splat(SMB_POW_S_C2));
+        q = f2_fma(r, q, f2_splat(SMB_POW_C1L));
+        ll = f2_fma(r, q, ll);
     } else {
-        qq = f2_fma(s, f2_splat(0.5767093896865845f), f2_splat(0.9617967009544373f));
+        // The r-series would need its r^2 term in two floats once y is large; the odd series in
+        // p = (m - c)/(m + c), |p| <= 0.0059, has p^3 as its second term and does not.
+        // p = p_hi + p_lo: MUFU.RCP seed + FMA residual steps; m - c is exact (Sterbenz), m + c is
+        // carried with its rounding error.
+        const f2 num = f2_sub(m, f2_make(t0.c, t1.c));
+        const f2 two = f2_splat(2.0f);
+        const f2 den = f2_fma(m, two, f2_neg(num));        // 2m - (m - c) = m + c, one rounding
+        const f2 rc = f2_make(rcp_seed(den.x), rcp_seed(den.y));
+        const f2 p_hi = f2_mul(num, rc);
+        f2 res = f2_fnma(p_hi, den, num);
+        const f2 den_lo = f2_sub(f2_fma(m, two, f2_neg(den)), num);  // (m + c) - den, exactly
+        res = f2_fnma(p_hi, den_lo, res);
+        const f2 p_lo = f2_mul(res, rc);
+        const f2 s = f2_mul(p_hi, p_hi);
+        // log2(m/c) = C0*p + p^3*(C1 + C2 p^2): leading product exact (two floats), the rest folded
+        // into one coefficient  c0l + s*(C1 + C2 s)
+        const f2 c0h = f2_splat(2.885390043258667f);       // 2/ln2 = c0h + c0l
+        f2 qq = f2_fma(s, f2_splat(0.5767093896865845f), f2_splat(0.9617967009544373f));
         qq = f2_fma(s, qq, f2_splat(3.851926067000022e-08f));
+        lh = f2_mul(c0h, p_hi);
+        ll = f2_fma(c0h, p_hi, f2_neg(lh));
+        ll = f2_fma(c0h, p_lo, ll);
+        ll = f2_fma(p_hi, qq, ll);
     }
-    const f2 lh = f2_mul(c0h, p_hi);
-    f2 ll = f2_fma(c0h, p_hi, f2_neg(lh));
-    ll = f2_fma(c0h, p_lo, ll);
-    ll = f2_fma(p_hi, qq, ll);
-    // float(biased exponent) + (L_hi - 127) is exact: integer + multiple of 2^-15, magnitude
-    // <= 128.  Scalar adds -- the table words are used once, packing them costs more than it saves.
-    const f2 h1 = f2_make(fadd((float)(int32_t)eb0, t0.l_hi), fadd((float)(int32_t)eb1, t1.l_hi));
+    // E + L_hi, exactly.  The upper half-word of x is [sign | biased exponent | j] with j the
+    // table index, so float(u >> 16) / 128 = 256 sign + biased exponent + j/128 (one I2F with a
+    // half-word selector, no shift); the table's L_hi word is L_hi - 127 - j/128, a multiple of
+    // 2^-15, so the FMA below is exact (every intermediate fits 24 bits, magnitude < 512).
+    // A rejected sign rides along as +256.  Scalar -- the table words are used once.
+    const float e0 = (float)(uint16_t)(u0 >> 16), e1 = (float)(uint16_t)(u1 >> 16);
+    const f2 h1 = f2_make(ffma(e0, 0.0078125f, t0.l_hi), ffma(e1, 0.0078125f, t1.l_hi));
     const f2 h2 = f2_add(h1, lh);                          // fast two-sum: |h1| >= |lh| or h1 == 0
     const f2 l2 = f2_add(f2_sub(h1, h2), lh);
     f2 lo = f2_add(f2_make(fadd(t0.l_lo, l2.x), fadd(t1.l_lo, l2.y)), ll);
@@ -547,26 +627,29 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, uint32_t sign_reject,
     const f2 th = f2_mul(y2, h3);
     f2 tl = f2_fma(y2, h3, f2_neg(th));
     tl = f2_fma(y2, lo, tl);
-    // results outside the comfortable normal range (incl. overflow / underflow) go to the slow path
-    ok = ok && fabsf(th.x) < 125.0f && fabsf(th.y) < 125.0f;
+    // The one validity test.  Results outside the comfortable normal range (incl. overflow and
+    // underflow) go to the slow path, and so does every input that is not a normal number: a zero
+    // or denormal has log2 <= -126 here, inf / NaN >= 128, a rejected negative base >= 129.
+    const f2 rng = Y_LT_1 ? h3 : th;
+    const bool ok = fabsf(rng.x) < 125.0f && fabsf(rng.y) < 125.0f;
     // ---- 2^t --------------------------------------------------------------------
     const f2 shifter = f2_splat(12582912.0f);              // 1.5 * 2^23
-    const f2 tk = f2_fma(th, f2_splat(64.0f), shifter);    // low mantissa bits hold k = rint(64 th)
+    const f2 tk = f2_fma(th, f2_splat(lane.c.k64), shifter);    // low mantissa bits hold k = rint(64 th)
     const uint32_t k0 = f2u(tk.x), k1 = f2u(tk.y);         // biased by 0x4b400000, a multiple of 64
     const f2 kf = f2_sub(tk, shifter);
     f2 f = f2_fma(kf, f2_splat(-0.015625f), th);           // th - k/64, exact
     f = f2_add(f, tl);
-    const PowTabExp e0 = pow_tab_exp_at(tab_exp, k0), e1 = pow_tab_exp_at(tab_exp, k1);
-    f2 g = f2_fma(f, f2_splat(0.05547422543168068f), f2_splat(0.24022682011127472f));
+    const PowTabExp x0e = pow_tab_exp_at(tab_exp, lane.exp_off, k0), x1e = pow_tab_exp_at(tab_exp, lane.exp_off, k1);
+    f2 g = f2_fma(f, f2_splat(lane.c.e3), f2_splat(0.24022682011127472f));
     g = f2_fma(f, g, f2_splat(0.6931471824645996f));
     const f2 w = f2_mul(f, g);                             // 2^f - 1
     // T_hi + (T_hi*w + T_lo), scalar: the table words feed straight from the LDS registers
-    const float z0 = fadd(e0.t_hi, ffma(e0.t_hi, w.x, e0.t_lo));
-    const float z1 = fadd(e1.t_hi, ffma(e1.t_hi, w.y, e1.t_lo));   // in [0.99, 2.01): 2^(j/64 + f)
+    const float z0 = fadd(x0e.t_hi, ffma(x0e.t_hi, w.x, x0e.t_lo));
+    const float z1 = fadd(x1e.t_hi, ffma(x1e.t_hi, w.y, x1e.t_lo));   // in [0.99, 2.01): 2^(j/64 + f)
     // scale by 2^n, n = k >> 6, through the exponent field (|n| <= 125 keeps the result normal):
-    // (k << 17) & 0xff800000 == n << 23 (the bias 0x4b400000 << 17 vanishes mod 2^32)
-    uint32_t b0 = f2u(z0) + ((k0 << 17) & 0xff800000u), b1 = f2u(z1) + ((k1 << 17) & 0xff800000u);
-    if (ODD_Y) { b0 |= u0 & 0x80000000u; b1 |= u1 & 0x80000000u; } // odd integer y: keep the base's sign
+    // (k & ~63) << 17 == n << 23 (the bias 0x4b400000 << 17 vanishes mod 2^32)
+    uint32_t b0 = pow_scale_bits(k0, f2u(z0)), b1 = pow_scale_bits(k1, f2u(z1));
+    if (SIGN == POW_SIGN_ODD) { b0 |= s0 & 0x80000000u; b1 |= s1 & 0x80000000u; } // keep the base's sign
     *r0 = u2f(b0);
     *r1 = u2f(b1);
     return ok;
@@ -574,7 +657,8 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, uint32_t sign_reject,
 
 // Host-side facts about the (uniform) exponent that select the variant.
 SMB_HD bool pow_f32_small_y(const PowExpF32 &pe) { return (f2u(pe.y) & 0x7fffffffu) <= 0x41000000u; } // |y| <= 8
-SMB_HD uint32_t pow_f32_sign_reject(const PowExpF32 &pe) { return pe.y_is_int ? 0u : 0x80000000u; }
+SMB_HD int pow_f32_sign_mode(const PowExpF32 &pe) { return !pe.y_is_int ? POW_SIGN_REJECT : pe.y_is_odd ? POW_SIGN_ODD : POW_SIGN_EVEN; }
+SMB_HD bool pow_f32_y_lt_1(const PowExpF32 &pe) { return (f2u(pe.y) & 0x7fffffffu) < 0x3f800000u; }
 
 // ============================================================== double pow ===
 // Double-double (hi + lo, |lo| <= ulp(hi)/2) helpers built on FMA.

@@ -158,7 +158,7 @@ static void run_pow(const float *a, float *out, uint64_t n, float y) {
         constexpr uint64_t per_block = 256ull * UNROLL * (VB / 4);
         uint64_t blocks = (n + per_block - 1) / per_block;
         if (cap) blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * cap);
-        using Fn = PowF32Fn<SMALL, false>;
+        using Fn = PowF32Fn<SMALL, POW_SIGN_REJECT, false>;
         Fn fn = Fn::make(y, 0);
         float ms = time_ms([&] { k_stream<float, Fn, false, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, nullptr, out, n, 0, fn); });
         char p[128];
