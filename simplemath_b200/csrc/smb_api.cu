@@ -80,6 +80,10 @@ static int current_ctx(DeviceCtx **out) {
             SMB_CK(cudaStreamCreateWithFlags(&c.main, cudaStreamNonBlocking));
             for (int i = 0; i < kSlots; ++i) SMB_CK(cudaStreamCreateWithFlags(&c.slot[i], cudaStreamNonBlocking));
             SMB_CK(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+            // ready-made shared-memory images of the f32 pow tables (one bulk copy per CTA later)
+            k_pow_image_init<<<8, kBlock, 0, c.main>>>();
+            SMB_CK(cudaGetLastError());
+            SMB_CK(cudaStreamSynchronize(c.main));
             c.ready = true;
         }
     }
@@ -254,6 +258,9 @@ static inline size_t esize(int dtype) { return dtype == SMB_F64 ? 8 : 4; }
 #define SMB_STREAM_UNROLL 4
 #endif
 constexpr int kThreads = kBlock;
+#ifndef SMB_POW_TILES_PER_CTA
+#define SMB_POW_TILES_PER_CTA 8 // f32 pow: consecutive 16 KB tiles per CTA (tools/sweep)
+#endif
 #ifndef SMB_TILE_R
 #define SMB_TILE_R 64 // k_tile: rows per tile (transposed operand's contiguous direction); halved for 8-byte types
 #define SMB_TILE_C 64 // cols per tile (result's contiguous direction)
@@ -273,9 +280,11 @@ static int launch_stream(const DeviceCtx &c, const T *a, const T *b, T *out, uin
     constexpr int VB = SMB_STREAM_VB, UNROLL = SMB_STREAM_UNROLL;
     const uintptr_t ma = (uintptr_t)a % VB, mb = HAS_B ? (uintptr_t)b % VB : ma, mo = (uintptr_t)out % VB;
     int64_t cps = g_opt_contig_variant.load();
-    // kernels that stage lookup tables in shared memory (f32 pow) amortise the 24 KB fill over a
-    // persistent grid; plain streams run one tile per CTA (tools/sweep: fastest on B200)
-    if (fn_pow_tables<Fn>::value && cps == 0) cps = 8;
+    // Plain streams run one tile per CTA (tools/sweep: fastest on B200).  Kernels that stage lookup
+    // tables in shared memory (pow) give each CTA a few consecutive tiles to amortise the fill --
+    // one bulk copy for f32, an in-kernel fill of 40 KB for f64 -- but stay many waves deep: a grid
+    // of resident CTAs measured 10-15 % slower.  For them the option counts tiles per CTA.
+    const int64_t tiles_per_cta = cps > 0 ? cps : (sizeof(T) == 4 ? SMB_POW_TILES_PER_CTA : 4 * SMB_POW_TILES_PER_CTA);
     if (ma == mb && ma == mo && ma % sizeof(T) == 0) {
         uint64_t head = ma ? (VB - ma) / sizeof(T) : 0;
         if (head > n) head = n;
@@ -286,7 +295,9 @@ static int launch_stream(const DeviceCtx &c, const T *a, const T *b, T *out, uin
         const uint64_t rest = n - head;
         if (rest) {
             constexpr uint64_t per_block = (uint64_t)kThreads * UNROLL * (VB / sizeof(T));
-            const unsigned grid = grid_for(rest, per_block, c.sm_count, cps);
+            const unsigned grid = fn_pow_tables<Fn>::value && SMB_POW_BLOCKED
+                                      ? grid_for(rest, per_block * (uint64_t)tiles_per_cta, c.sm_count, 0)
+                                      : grid_for(rest, per_block, c.sm_count, fn_pow_tables<Fn>::value && cps == 0 ? 8 : cps);
             k_stream<T, Fn, HAS_B, VB, UNROLL><<<grid, kThreads, 0, s>>>(a + head, HAS_B ? b + head : nullptr, out + head,
                                                                        rest, first + head, fn);
             ++g_launches;

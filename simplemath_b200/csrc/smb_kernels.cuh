@@ -20,6 +20,18 @@
 namespace smb {
 
 constexpr int kBlock = 256; // threads per CTA of every kernel in this file
+#ifndef SMB_POW_BLOCKED
+#define SMB_POW_BLOCKED 1 // pow loop: consecutive tiles per CTA on a many-wave grid (0: resident grid, grid-stride)
+#endif
+#ifndef SMB_POW_PINGPONG
+#define SMB_POW_PINGPONG 1 // f32/f64 pow loop: swap the two tile buffers (unroll by two) instead of copying
+#endif
+// The pow tile body is one long basic block; without a fence ptxas sinks the next tile's loads
+// to its end (no prefetch left) and holds every store until then.  A warp-level barrier is one
+// instruction it will not move memory operations across.
+#ifndef SMB_POW_SCHED_FENCE
+#define SMB_POW_SCHED_FENCE() __syncwarp()
+#endif
 #ifndef SMB_POW_MIN_BLOCKS
 #define SMB_POW_MIN_BLOCKS 3 // resident CTAs per SM the f32 pow kernel is compiled for
 #endif
@@ -45,6 +57,21 @@ template<> struct VecIO<16, true> {
                      :: "l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]) : "memory");
     }
 };
+// Same access without .nc: an ordinary (coherent) load, which ptxas will not move across a warp
+// barrier -- used to pin the pow kernel's prefetch at the top of its tile.
+__device__ __forceinline__ RawVec<16> load_stream_pinned(const RawVec<16> *p) {
+    RawVec<16> v;
+    asm volatile("ld.global.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ RawVec<32> load_stream_pinned(const RawVec<32> *p) {
+    RawVec<32> v;
+    asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
+                 : "l"(p) : "memory");
+    return v;
+}
 template<> struct VecIO<16, false> {
     static __device__ __forceinline__ RawVec<16> load(const void *p) {
         RawVec<16> v;
@@ -93,6 +120,29 @@ template<typename T, int BYTES> union Pack {
 };
 
 // ---------------------------------------------------------------------------
+// mbarrier + 1-D bulk copy (TMA engine, SASS UBLKCP): used to stage the pow lookup tables and a
+// reused broadcast operand in shared memory with one instruction instead of a load/store loop.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(smem)), "l"(gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------
 // Functors: what a launch applies to (a[i], b[i]).  `lane` tells the i32 pow
 // instantiation whether flat element i is one the reference computes in an
 // AVX2 lane (wrapping) or with scalar Op::apply (through double); see
@@ -131,6 +181,20 @@ static __device__ const PowTabLog d_pow_log_tab[SMB_POW_LOG_ENTRIES] = SMB_POW_L
 static __device__ const PowTabLog d_pow_logc_tab[SMB_POW_LOG_ENTRIES] = SMB_POW_LOGC_TABLE_INIT; // large-y: {c, log2 c}
 static __device__ const PowTabExp d_pow_exp_tab[SMB_POW_EXP_ENTRIES] = SMB_POW_EXP_TABLE_INIT;
 
+// The replicated shared-memory layout of the two f32 pow tables, kept ready-made in global memory
+// ([0] small-y, [1] large-y; 24 KB each, L2 resident) so that a CTA stages them with ONE bulk copy
+// instead of ~60 instructions per thread -- which is what lets the pow grid be many waves deep
+// (a few tiles per CTA).  Built once per device by k_pow_image_init (smb_api.cu: current_ctx).
+static __device__ __align__(128) SmbPowTabs g_pow_image[2];
+__global__ void k_pow_image_init() {
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int v = 0; v < 2; ++v) {
+        const PowTabLog *src = v == 0 ? d_pow_log_tab : d_pow_logc_tab;
+        for (int i = t0; i < SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE; i += stride) g_pow_image[v].log[i] = src[i / SMB_POW_LOG_STRIDE];
+        for (int i = t0; i < SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE; i += stride) g_pow_image[v].exp[i] = d_pow_exp_tab[i / SMB_POW_EXP_STRIDE];
+    }
+}
+
 // The reference-accuracy path alone: exponents the fast core cannot take (|y| >= 2^64 or
 // y * log2 x denormal), and the scalar-access kernels.
 struct PowF32SlowFn {
@@ -149,29 +213,39 @@ template<bool SMALL_Y, int SIGN, bool Y_LT_1> struct PowF32Fn {
     PowExpF32 pe;  // exponent classified once on the host
     uint64_t lane_end;
     PowLane lane;  // this thread's replica offsets into the shared-memory tables
+    uint64_t *tab_bar; // mbarrier the table copy completes on
     __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return pow_f32_slow(a, pe); }
+    __device__ __forceinline__ float slow(float a) const { return pow_f32(a, pe); } // inlined, see pow_tile
     // Two elements through the branch-free fast core; false = redo on the slow path.
     __device__ __forceinline__ bool pair(float a0, float a1, float &r0, float &r1) const {
         return pow_f32_pair_fast<SMALL_Y, SIGN, Y_LT_1>(a0, a1, pe.y, lane, nullptr, nullptr, &r0, &r1);
     }
     // Lookup tables, L2 -> shared memory once per CTA, each entry replicated across the lanes
     // of a wavefront (24 KB) so the per-lane lookups never conflict; see smb_math.cuh.
+    // block_init only ISSUES the copy (one cp.async.bulk of the ready-made image); block_wait is
+    // called after the CTA's first tile loads are in flight, so the two latencies overlap.
     __device__ __forceinline__ void block_init() {
-        const PowTabLog *src = SMALL_Y ? d_pow_log_tab : d_pow_logc_tab;
-        for (int i = threadIdx.x; i < SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE; i += kBlock)
-            smb_s_pow_log[i] = src[i / SMB_POW_LOG_STRIDE];
-        for (int i = threadIdx.x; i < SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE; i += kBlock)
-            smb_s_pow_exp[i] = d_pow_exp_tab[i / SMB_POW_EXP_STRIDE];
-        // the lookups read these arrays from inline PTX (by symbol): tell the compiler they are read
-        asm volatile("" :: "l"(smb_s_pow_log), "l"(smb_s_pow_exp) : "memory");
-        __syncthreads();
+        __shared__ __align__(8) uint64_t bar;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, (uint32_t)sizeof(SmbPowTabs));
+            bulk_g2s(&smb_s_pow, &g_pow_image[SMALL_Y ? 0 : 1], (uint32_t)sizeof(SmbPowTabs), &bar);
+        }
         lane = pow_lane(threadIdx.x, lane.c);
+        tab_bar = &bar;
+        __syncthreads(); // the barrier is initialised before anyone waits on it
+    }
+    __device__ __forceinline__ void block_wait() {
+        mbar_wait(tab_bar, 0);
+        // the lookups name the table from inline PTX; tie them to the wait through the lane offsets
+        asm volatile("" : "+r"(lane.log_off), "+r"(lane.exp_off) :: "memory");
     }
     static PowF32Fn make(float y, uint64_t lane_end_) {
         PowF32Fn fn;
         fn.pe = classify_exp(y);
         fn.lane_end = lane_end_;
         fn.lane = PowLane{0, 0, pow_consts()}; // offsets set per thread in block_init; the constants ride in as kernel parameters
+        fn.tab_bar = nullptr;
         return fn;
     }
 };
@@ -193,9 +267,11 @@ template<bool ODD_Y> struct PowF64Fn {
     const PowTabLog64B *tab_b;
     const PowTabExp64 *tab_exp;
     __device__ __forceinline__ double operator()(double a, double, uint64_t) const { return pow_f64_slow(a, pe); }
+    __device__ __forceinline__ double slow(double a) const { return pow_f64(a, pe); } // inlined, see pow_tile
     __device__ __forceinline__ bool fast(double a, double &r) const {
         return pow_f64_fast<ODD_Y>(a, pe.y, sign_reject, tab_a, tab_b, tab_exp, &r) && fast_ok != 0;
     }
+    __device__ __forceinline__ void block_wait() {}
     __device__ __forceinline__ void block_init() { // 40 KB, every entry replicated per wavefront lane
         __shared__ __align__(16) PowTabLog64A s_a[SMB_POW_LOG_ENTRIES * SMB_POW64_A_STRIDE];
         __shared__ __align__(16) PowTabLog64B s_b[SMB_POW_LOG_ENTRIES * SMB_POW64_B_STRIDE];
@@ -322,6 +398,48 @@ __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__
     }
 }
 
+// One tile of a table-driven pow functor: the branch-free fast core on every vector, results
+// stored under a predicate; the vectors it declined (specials, denormals, results near overflow --
+// rare) are redone afterwards on the reference-accuracy path, ONE branch per tile.  Their input
+// is re-read from memory rather than kept in registers; it has not been overwritten even when
+// out aliases a, because the declined vector's store was skipped.
+template<typename T, typename Fn, int VB, int UNROLL>
+__device__ __forceinline__ void pow_tile(const Pack<T, VB> (&in)[UNROLL], const T *__restrict__ a, T *__restrict__ out,
+                                         uint64_t v0, const Fn &fn) {
+    constexpr int EPV = VB / (int)sizeof(T);
+    bool ok[UNROLL], all = true;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        Pack<T, VB> r;
+        ok[u] = true;
+        if constexpr (fn_pairwise<Fn>::value) {
+#pragma unroll
+            for (int k = 0; k < EPV; k += 2) ok[u] &= fn.pair(in[u].e[k], in[u].e[k + 1], r.e[k], r.e[k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < EPV; ++k) ok[u] &= fn.fast(in[u].e[k], r.e[k]);
+        }
+        if (ok[u]) VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v0 + (uint64_t)u * kBlock, r.raw);
+        all &= ok[u];
+        SMB_POW_SCHED_FENCE();
+    }
+    if (!all) {
+        // ONE inlined copy of the reference-accuracy body in a rolled loop over the tile's elements:
+        // a call here would make ptxas spill everything that lives across it (the prefetched tile).
+        uint32_t bad = 0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) bad |= ok[u] ? 0u : 1u << u;
+#pragma unroll 1
+        for (int e = 0; e < UNROLL * EPV; ++e) {
+            const int u = e / EPV;
+            if ((bad >> u) & 1u) {
+                const uint64_t i = (v0 + (uint64_t)u * kBlock) * EPV + (uint64_t)(e % EPV);
+                out[i] = fn.slow(a[i]);
+            }
+        }
+    }
+}
+
 template<typename T, typename Fn, bool HAS_B, int VB, int UNROLL>
 __global__ void __launch_bounds__(256, (fn_pow_tables<Fn>::value && sizeof(T) == 4) ? SMB_POW_MIN_BLOCKS : 2) k_stream(const T *__restrict__ a, const T *__restrict__ b,
                                                T *__restrict__ out, uint64_t n, uint64_t first, Fn fn_in) {
@@ -334,33 +452,64 @@ __global__ void __launch_bounds__(256, (fn_pow_tables<Fn>::value && sizeof(T) ==
     // full tiles: no bounds checks in the loop body
     if constexpr (fn_pow_tables<Fn>::value && !HAS_B) {
         // Compute-heavy functor on a persistent grid: the next tile's loads are issued BEFORE this
-        // tile's arithmetic (register double buffer), so HBM latency hides under ~800 issue slots of
+        // tile's arithmetic (register double buffer), so HBM latency hides under ~500 issue slots of
         // math instead of stalling the warp (ncu: long_scoreboard was the top stall without it).
-        Pack<T, VB> cur[UNROLL], nxt[UNROLL];
+        // The two buffers swap roles every other tile (loop unrolled by two) -- copying one into
+        // the other cost a MOV per element.
+        Pack<T, VB> buf0[UNROLL], buf1[UNROLL];
+        const RawVec<VB> *av = reinterpret_cast<const RawVec<VB> *>(a);
+#if SMB_POW_BLOCKED
+        // CTA b owns the consecutive tiles [b * tpc, (b + 1) * tpc): the host sizes the grid so that
+        // tpc is a handful of tiles -- enough to amortise the table fill, few enough that the grid is
+        // many waves deep (a grid of resident CTAs striding over everything measured 10-15 % slower
+        // on B200 for any 1-read-1-write stream: profiles/r1_sweep_summary.md)
+        const uint64_t tpc = (full_tiles + gridDim.x - 1) / gridDim.x, tstep = 1;
+        uint64_t tile = blockIdx.x * tpc;
+        const uint64_t tiles_end = tile + tpc < full_tiles ? tile + tpc : full_tiles;
+#else
+        const uint64_t tstep = gridDim.x, tiles_end = full_tiles;
         uint64_t tile = blockIdx.x;
-        if (tile < full_tiles) {
+#endif
+        if (tile < tiles_end) {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u)
-                cur[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(a) + tile * tile_vecs + threadIdx.x + u * kBlock);
+            for (int u = 0; u < UNROLL; ++u) buf0[u].raw = load_stream_pinned(av + tile * tile_vecs + threadIdx.x + u * kBlock);
         }
+        fn.block_wait(); // the tables have landed (the copy overlapped the loads above)
+#if SMB_POW_PINGPONG
 #pragma unroll 1
-        for (; tile < full_tiles; tile += gridDim.x) {
-            const uint64_t next = tile + gridDim.x;
-            if (next < full_tiles) {
+        while (tile < tiles_end) {
+            uint64_t next = tile + tstep;
+            if (next < tiles_end) {
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
-                    nxt[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(a) + next * tile_vecs + threadIdx.x + u * kBlock);
+                for (int u = 0; u < UNROLL; ++u) buf1[u].raw = load_stream_pinned(av + next * tile_vecs + threadIdx.x + u * kBlock);
             }
+            SMB_POW_SCHED_FENCE();
+            pow_tile<T, Fn, VB, UNROLL>(buf0, a, out, tile * tile_vecs + threadIdx.x, fn);
+            tile = next;
+            if (tile >= tiles_end) break;
+            next = tile + tstep;
+            if (next < tiles_end) {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const uint64_t v = tile * tile_vecs + threadIdx.x + (uint64_t)u * kBlock;
-                Pack<T, VB> r;
-                stream_vec<T, Fn, false, VB>(cur[u], cur[u], r, first + v * EPV, fn);
-                VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v, r.raw);
+                for (int u = 0; u < UNROLL; ++u) buf0[u].raw = load_stream_pinned(av + next * tile_vecs + threadIdx.x + u * kBlock);
             }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) cur[u].raw = nxt[u].raw;
+            SMB_POW_SCHED_FENCE();
+            pow_tile<T, Fn, VB, UNROLL>(buf1, a, out, tile * tile_vecs + threadIdx.x, fn);
+            tile = next;
         }
+#else
+#pragma unroll 1
+        for (; tile < tiles_end; tile += tstep) {
+            const uint64_t next = tile + tstep;
+            if (next < tiles_end) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) buf1[u].raw = load_stream_pinned(av + next * tile_vecs + threadIdx.x + u * kBlock);
+            }
+            SMB_POW_SCHED_FENCE();
+            pow_tile<T, Fn, VB, UNROLL>(buf0, a, out, tile * tile_vecs + threadIdx.x, fn);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) buf0[u].raw = buf1[u].raw;
+        }
+#endif
     } else {
 #pragma unroll 1
         for (uint64_t tile = blockIdx.x; tile < full_tiles; tile += gridDim.x)
@@ -444,29 +593,6 @@ __device__ __forceinline__ void offsets_of(const BcastTable &t, uint64_t lin, ui
             }
         }
     }
-}
-
-// ---------------------------------------------------------------------------
-// mbarrier + 1-D bulk copy (TMA engine, SASS UBLKCP): used to stage a reused broadcast
-// operand in shared memory with one instruction instead of a load/store loop.
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(smem)), "l"(gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
 // k_row: inner strides in {0,1}.  Each thread produces UNROLL vectors of EPV consecutive

@@ -453,7 +453,7 @@ SMB_HD float rcp_seed(float x) {
 struct PowTabExp { float t_hi, t_lo; };
 
 // Table access.  Host build: the compact tables behind `tab_*`.  Device: the tables live in
-// shared memory (smb_s_pow_log / smb_s_pow_exp below, filled per CTA by PowF32Fn::block_init) with each
+// shared memory (smb_s_pow below, filled per CTA by PowF32Fn::block_init) with each
 // entry replicated across the lanes that share a shared-memory wavefront (8 lanes for the
 // 16-byte log entries, 16 for the 8-byte exp entries), so a warp reading 32 unrelated entries is
 // bank-conflict free.  (The compact layout measured 58 % conflict replays and saturated the LSU
@@ -461,14 +461,18 @@ struct PowTabExp { float t_hi, t_lo; };
 // entry offset and the array base is a compile-time shared address, so a lookup costs
 // SHF + LOP3 + LDS [R + imm].
 #if defined(__CUDACC__)
+static_assert(SMB_POW_LOG_ENTRIES * 8 * 16 == 16384, "pow_tab_exp_at hard-codes the exp table's offset");
 #define SMB_POW_LOG_STRIDE 8   /* entries of PowTabLog between consecutive j */
 #define SMB_POW_EXP_STRIDE 16  /* entries of PowTabExp between consecutive j */
 } // namespace smb
 // C linkage: the lookups below name these arrays from inline PTX, so that their (compile-time)
 // shared addresses fold into the LDS immediate instead of going through a generic pointer.
 extern "C" {
-__shared__ __align__(128) smb::PowTabLog smb_s_pow_log[SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE];
-__shared__ __align__(128) smb::PowTabExp smb_s_pow_exp[SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE];
+struct SmbPowTabs { // one object, so both tables share one base register (the exp table sits at +16384)
+    smb::PowTabLog log[SMB_POW_LOG_ENTRIES * SMB_POW_LOG_STRIDE];
+    smb::PowTabExp exp[SMB_POW_EXP_ENTRIES * SMB_POW_EXP_STRIDE];
+};
+__shared__ __align__(128) SmbPowTabs smb_s_pow;
 }
 namespace smb {
 #else
@@ -506,9 +510,13 @@ SMB_HD PowTabLog pow_tab_log_at(const PowTabLog *tab, uint32_t lane_off, uint32_
 #if defined(__CUDA_ARCH__)
     // j = top 7 mantissa bits = (u >> 16) & 127; entry j starts at byte j * 128.
     // SHF + LOP3 + LDS [R + imm]
+#ifdef SMB_POW_EXPERIMENT_LOG_BROADCAST /* tools/sweep only: every lane reads entry 0 (wrong results) */
+    const uint32_t off = (u >> 9) & 0u;
+#else
     const uint32_t off = ((u >> 9) & (127u << 7)) | lane_off;
+#endif
     PowTabLog e;
-    asm("{\n\t.reg .u32 a;\n\t.reg .u64 b;\n\tmov.u64 b, smb_s_pow_log;\n\tcvt.u32.u64 a, b;\n\tadd.u32 a, a, %4;\n\t"
+    asm("{\n\t.reg .u32 a;\n\t.reg .u64 b;\n\tmov.u64 b, smb_s_pow;\n\tcvt.u32.u64 a, b;\n\tadd.u32 a, a, %4;\n\t"
         "ld.shared.v4.f32 {%0,%1,%2,%3}, [a];\n\t}" : "=f"(e.c), "=f"(e.l_hi), "=f"(e.l_lo), "=f"(e.pad) : "r"(off));
     return e;
 #else
@@ -518,10 +526,14 @@ SMB_HD PowTabLog pow_tab_log_at(const PowTabLog *tab, uint32_t lane_off, uint32_
 }
 SMB_HD PowTabExp pow_tab_exp_at(const PowTabExp *tab, uint32_t lane_off, uint32_t k) {
 #if defined(__CUDA_ARCH__)
+#ifdef SMB_POW_EXPERIMENT_EXP_BROADCAST
+    const uint32_t off = (k << 7) & 0u;
+#else
     const uint32_t off = ((k << 7) & (63u << 7)) | lane_off; // entry j = k & 63 starts at byte j * 128
+#endif
     PowTabExp e;
-    asm("{\n\t.reg .u32 a;\n\t.reg .u64 b;\n\tmov.u64 b, smb_s_pow_exp;\n\tcvt.u32.u64 a, b;\n\tadd.u32 a, a, %2;\n\t"
-        "ld.shared.v2.f32 {%0,%1}, [a];\n\t}" : "=f"(e.t_hi), "=f"(e.t_lo) : "r"(off));
+    asm("{\n\t.reg .u32 a;\n\t.reg .u64 b;\n\tmov.u64 b, smb_s_pow;\n\tcvt.u32.u64 a, b;\n\tadd.u32 a, a, %2;\n\t"
+        "ld.shared.v2.f32 {%0,%1}, [a+16384];\n\t}" : "=f"(e.t_hi), "=f"(e.t_lo) : "r"(off));
     return e;
 #else
     (void)lane_off;

@@ -151,18 +151,44 @@ static void run_add(const float *a, const float *b, float *out, uint64_t n) {
     }
 }
 
-template<int VB, int UNROLL, bool SMALL>
-static void run_pow(const float *a, float *out, uint64_t n, float y) {
-    const int caps[] = {0, 4, 8, 16};
-    for (int cap : caps) {
+// The pow kernel's loop (persistent grid, register double buffer, pinned prefetch) with the
+// arithmetic removed: what its memory access pattern alone sustains.
+struct PowLoopOnlyFn {
+    static constexpr bool PAIRWISE = true;
+    static constexpr bool POW_TABLES = true;
+    uint64_t lane_end;
+    __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return a; }
+    __device__ __forceinline__ float slow(float a) const { return a; }
+    __device__ __forceinline__ bool pair(float a0, float a1, float &r0, float &r1) const { r0 = a0 + 1.0f; r1 = a1 + 1.0f; return true; }
+    __device__ __forceinline__ void block_init() {}
+    __device__ __forceinline__ void block_wait() {}
+};
+template<int VB, int UNROLL>
+static void run_pow_loop_only(const float *a, float *out, uint64_t n) {
+    const int caps[] = {1, 2, 4, 8, 16, 32, 64, 128};
+    for (int cap : caps) { // cap = tiles per CTA (SMB_POW_BLOCKED)
         constexpr uint64_t per_block = 256ull * UNROLL * (VB / 4);
         uint64_t blocks = (n + per_block - 1) / per_block;
-        if (cap) blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * cap);
+        blocks = (blocks + cap - 1) / cap;
+        float ms = time_ms([&] { k_stream<float, PowLoopOnlyFn, false, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, nullptr, out, n, 0, PowLoopOnlyFn{0}); });
+        char p[128];
+        snprintf(p, sizeof p, "vb=%d unroll=%d tiles_per_cta=%d", VB, UNROLL, cap);
+        report("pow_loop_only", p, 8.0 * n, ms);
+    }
+}
+
+template<int VB, int UNROLL, bool SMALL>
+static void run_pow(const float *a, float *out, uint64_t n, float y) {
+    const int caps[] = {1, 2, 4, 8, 16, 32, 64, 128};
+    for (int cap : caps) { // cap = tiles per CTA (SMB_POW_BLOCKED)
+        constexpr uint64_t per_block = 256ull * UNROLL * (VB / 4);
+        uint64_t blocks = (n + per_block - 1) / per_block;
+        blocks = (blocks + cap - 1) / cap;
         using Fn = PowF32Fn<SMALL, POW_SIGN_REJECT, false>;
         Fn fn = Fn::make(y, 0);
         float ms = time_ms([&] { k_stream<float, Fn, false, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, nullptr, out, n, 0, fn); });
         char p[128];
-        snprintf(p, sizeof p, "y=%.2f small_y=%d vb=%d unroll=%d ctas_per_sm=%d", y, (int)SMALL, VB, UNROLL, cap);
+        snprintf(p, sizeof p, "y=%.2f small_y=%d vb=%d unroll=%d tiles_per_cta=%d", y, (int)SMALL, VB, UNROLL, cap);
         report("pow_f32_general", p, 8.0 * n, ms);
     }
 }
@@ -290,12 +316,18 @@ int main(int argc, char **argv) {
         run_tma<4096, 4, true>(a, b, out, n);
         run_tma<4096, 8, true>(a, b, out, n);
     }
+    if (want("loop")) {
+        run_pow_loop_only<16, 4>(a, out, n);
+        run_pow_loop_only<16, 2>(a, out, n);
+        run_pow_loop_only<16, 8>(a, out, n);
+    }
     if (want("pow")) {
+        k_pow_image_init<<<8, 256>>>();
+        CK(cudaDeviceSynchronize());
         run_pow<16, 2, true>(a, out, n, 2.5f);
         run_pow<16, 4, true>(a, out, n, 2.5f);
         run_pow<32, 2, true>(a, out, n, 2.5f);
-        run_pow<16, 4, false>(a, out, n, 2.5f);
-        run_pow<32, 2, false>(a, out, n, 2.5f);
+        run_pow<16, 4, false>(a, out, n, 9.25f);
     }
     if (want("fill")) { // write-only roofline (C4 is write-dominated)
         const int caps[] = {0, 8, 16, 32};
