@@ -689,6 +689,36 @@ __global__ void __launch_bounds__(256) k_row(const T *__restrict__ a, const T *_
 // produces the TI x TJ block of output vectors from them: (TI+TJ) loads per TI*TJ stores
 // instead of 2 per store (k_row).  A_ON_DIM0 says which reference operand varies with
 // dim 0, so non-commutative ops keep their operand order.
+// int32 a / b with the divisor's reciprocal precomputed in double and nudged up by 2^-50:
+//   r = (1 / b) * (1 + 2^-50);  q = trunc(double(a) * r)
+// Exact for every pair the reference defines (b != 0, not INT_MIN / -1): a true quotient that is
+// not an integer is at least 1/|b| away from one, and the error of a*r is below 2^-18/|b|; a true
+// quotient k that IS an integer comes out as k (1 + 2^-50 +- 2^-51.4) (r within an ulp of 1/b,
+// one more half-ulp for the product), strictly beyond k by
+// less than 2^-18, so truncation returns k.  Truncation itself avoids the (slow) F2I.F64:
+// trunc(v) = rint(v - 0.5 sign(v)) for such v, fused into the product, and rint is the low word of
+// (w + 1.5 * 2^52).  Per quotient: one LOP3 (the signed half), one DFMA, one DADD -- instead of
+// the ~25-instruction software s32 division; worth it when a divisor is reused (k_outer).
+__device__ __forceinline__ double idiv_recip(int32_t b) {
+    // 1/b to within an ulp: MUFU.RCP64H seed (20 bits) and two Newton steps; b is a non-zero
+    // integer, so none of __drcp_rn's special-case handling (and its branches) is needed.
+    const double d = (double)b;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = __fma_rn(r, __fma_rn(-d, r, 1.0), r);
+    r = __fma_rn(r, __fma_rn(-d, r, 1.0), r);
+    return __dmul_rn(r, 1.0 + 0x1p-50);
+}
+// high word of -0.5 * sign(r): XOR-ed with the dividend's sign bit it becomes -0.5 * sign(a / b)
+__device__ __forceinline__ uint32_t idiv_half_hi(double r) { return ((uint32_t)__double2hiint(r) & 0x80000000u) ^ 0xbfe00000u; }
+__device__ __forceinline__ int32_t idiv_by_recip(int32_t a, double a_as_double, double r, uint32_t half_hi) {
+    const double half = __hiloint2double((int)(((uint32_t)a & 0x80000000u) ^ half_hi), 0);
+    const double w = __fma_rn(a_as_double, r, half);
+    return __double2loint(__dadd_rn(w, 6755399441055744.0));
+}
+template<typename T, typename Fn> struct is_int_div : std::false_type {};
+template<> struct is_int_div<int32_t, BinaryFn<OP_DIV, int32_t>> : std::true_type {};
+
 struct OuterParams {
     uint32_t d0, d1, len;   // (sub-)problem shape: d0 x d1 rows of `len` elements
     uint64_t s0, s1;        // element stride of the dim-0 / dim-1 operand between its rows
@@ -710,19 +740,56 @@ __global__ void __launch_bounds__(256) k_outer(const T *__restrict__ a, const T 
 #pragma unroll
     for (int tj = 0; tj < TJ; ++tj)
         if (j0 + tj < p.d1) yv[tj].raw = VecIO<16, false>::load(y + (uint64_t)(j0 + tj) * p.s1 + k);
+    if constexpr (is_int_div<T, Fn>::value) {
+        // every divisor is used TI (TJ) times: one reciprocal each, then a multiply per quotient
+        constexpr int ND = A_ON_DIM0 ? TJ : TI;
+        double rc[ND][EPV];
+        uint32_t hh[ND][EPV];
 #pragma unroll
-    for (int ti = 0; ti < TI; ++ti) {
-        if (i0 + ti >= p.d0) break;
+        for (int t = 0; t < ND; ++t) {
+            if ((A_ON_DIM0 ? j0 : i0) + t < (A_ON_DIM0 ? p.d1 : p.d0)) {
 #pragma unroll
-        for (int tj = 0; tj < TJ; ++tj) {
-            if (j0 + tj >= p.d1) break;
-            const uint64_t lin = ((uint64_t)(i0 + ti) * p.d1 + (j0 + tj)) * p.len + k;
-            Pack<T, 16> r;
+                for (int e = 0; e < EPV; ++e) {
+                    rc[t][e] = idiv_recip(A_ON_DIM0 ? yv[t].e[e] : xv[t].e[e]);
+                    hh[t][e] = idiv_half_hi(rc[t][e]);
+                }
+            }
+        }
+        // outer loop over the dividend's vectors: each dividend is converted to double once too
+        constexpr int NN = A_ON_DIM0 ? TI : TJ;
 #pragma unroll
-            for (int e = 0; e < EPV; ++e)
-                r.e[e] = A_ON_DIM0 ? fn(xv[ti].e[e], yv[tj].e[e], p.lane_base + lin + e)
-                                   : fn(yv[tj].e[e], xv[ti].e[e], p.lane_base + lin + e);
-            VecIO<16, true>::store(out + lin, r.raw);
+        for (int tn = 0; tn < NN; ++tn) {
+            if ((A_ON_DIM0 ? i0 : j0) + tn >= (A_ON_DIM0 ? p.d0 : p.d1)) break;
+            double num[EPV];
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) num[e] = (double)(A_ON_DIM0 ? xv[tn].e[e] : yv[tn].e[e]);
+#pragma unroll
+            for (int td = 0; td < ND; ++td) {
+                if ((A_ON_DIM0 ? j0 : i0) + td >= (A_ON_DIM0 ? p.d1 : p.d0)) break;
+                const uint32_t i = i0 + (A_ON_DIM0 ? tn : td), j = j0 + (A_ON_DIM0 ? td : tn);
+                const uint64_t lin = ((uint64_t)i * p.d1 + j) * p.len + k;
+                Pack<T, 16> r;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    r.e[e] = idiv_by_recip(A_ON_DIM0 ? xv[tn].e[e] : yv[tn].e[e], num[e], rc[td][e], hh[td][e]);
+                VecIO<16, true>::store(out + lin, r.raw);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti) {
+            if (i0 + ti >= p.d0) break;
+#pragma unroll
+            for (int tj = 0; tj < TJ; ++tj) {
+                if (j0 + tj >= p.d1) break;
+                const uint64_t lin = ((uint64_t)(i0 + ti) * p.d1 + (j0 + tj)) * p.len + k;
+                Pack<T, 16> r;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    r.e[e] = A_ON_DIM0 ? fn(xv[ti].e[e], yv[tj].e[e], p.lane_base + lin + e)
+                                       : fn(yv[tj].e[e], xv[ti].e[e], p.lane_base + lin + e);
+                VecIO<16, true>::store(out + lin, r.raw);
+            }
         }
     }
 }

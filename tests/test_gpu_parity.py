@@ -312,6 +312,31 @@ def test_outer_broadcast_kernel(orc):
         smb.set_option(smb.OPT_BCAST_VARIANT, 0)
 
 
+def test_outer_int_division_by_reciprocal_full_range(orc):
+    """k_outer divides int32 by a precomputed double reciprocal (one multiply per quotient):
+    bit-exact with C truncating division over the full operand range, exact multiples, +-1
+    around multiples and the extreme values (b != 0, not INT_MIN / -1: undefined in the reference)."""
+    rng = np.random.default_rng(43)
+    L = 1024
+    edge = np.array([-2**31, -2**31 + 1, 2**31 - 1, 2**31 - 2, -1, 1, 2, -2, 3, -3, 7, 65535, 65536, -65536, 46341, -46341], np.int64)
+    cases = []
+    a = rng.integers(-2**31, 2**31, size=(16, 1, L)); b = rng.integers(-2**31, 2**31, size=(1, 12, L)); cases.append((a, b))
+    b = rng.integers(-2**16, 2**16, size=(1, 12, L)); k = rng.integers(-2**15, 2**15, size=(16, 1, L)); cases.append((k * b[:, :1, :], b))
+    b = rng.integers(-1000, 1000, size=(1, 8, L)); k = rng.integers(-2**20, 2**20, size=(8, 1, L)); cases.append((k * b[:, :1, :] + rng.integers(-1, 2, size=(8, 1, L)), b))
+    cases.append((np.resize(edge, (16, 1, L)), np.resize(np.roll(np.repeat(edge, 16), 3), (1, 16, L))))
+    for a, b in cases:
+        a = np.clip(a, -2**31 + 1, 2**31 - 1).astype(np.int32)   # keeps INT_MIN / -1 out
+        b = np.where(b == 0, 3, np.clip(b, -2**31, 2**31 - 1)).astype(np.int32)
+        assert_same_bits(smb.binary("div", a, b), orc.binary("div", a, b), "outer div, divisor on dim 1")
+        assert smb.last_kernel() == "k_outer<4x4>", smb.last_kernel()
+        bt = np.ascontiguousarray(b.transpose(1, 0, 2)); at = np.ascontiguousarray(a.transpose(1, 0, 2))
+        assert_same_bits(smb.binary("div", at, bt), orc.binary("div", at, bt), "outer div, divisor on dim 0")
+        assert smb.last_kernel() == "k_outer<4x4>", smb.last_kernel()
+    amin = np.full((4, 1, L), -2**31, np.int32)
+    bb = rng.integers(2, 2**31, size=(1, 4, L)).astype(np.int32)
+    assert_same_bits(smb.binary("div", amin, bb), orc.binary("div", amin, bb), "INT_MIN / b")
+
+
 def test_transposed_operands_tile_kernel(orc):
     """SMArray::transpose() views (stride 1 along an earlier dim): shared-memory tile transpose."""
     rng = np.random.default_rng(61)
