@@ -135,6 +135,35 @@ int smb_array_scalar(int op, int dtype, const void *a, const void *scalar,
  * lane accumulators, so parity is a tolerance). */
 int smb_dot(int dtype, const void *a, const void *b, uint64_t n, void *result, void *stream);
 
+/* Op-chain fusion: a left-deep chain of the same Op structs evaluated in
+ * ONE pass,
+ *     acc = leaf_0;  acc = acc (op_i) leaf_i   [or leaf_i (op_i) acc when swap_i]   i = 1 .. nsteps-1
+ * instead of one full temporary per operator (the reference materialises a fresh result in every
+ * SMArray operator, include/SMArray.h:217-305, and in sm::pow, include/UserFunctions.h:42-48).
+ * Each leaf is an array broadcast against the result shape (its stride table as sm::broadcast()
+ * returns it, 0 on broadcast dims) or a scalar constant.  Every intermediate is rounded to T
+ * exactly as the separate operators would round it (no contraction), so + - * / chains are
+ * bit-identical to the unfused sequence; SMB_OP_POW needs a constant leaf as exponent (array ^
+ * scalar, the only pow the reference exposes) and uses the reference-accuracy path (int32: the
+ * lane / scalar-tail split of array_scalar_op on the dense intermediate).
+ * Leaves must be device-accessible (device, managed or pinned memory).  At most SMB_CHAIN_MAX
+ * steps. */
+#define SMB_CHAIN_MAX 8
+typedef struct smb_chain_step {
+    int32_t op;                    /* SMB_OP_*; ignored for step 0                           */
+    int32_t swap;                  /* 1: acc = leaf (op) acc                                  */
+    const void *data;              /* array leaf, or NULL for the constant `value`           */
+    uint64_t stride[SMB_MAX_NDIM]; /* element strides against the result shape (array leaf)  */
+    union { float f32; double f64; int32_t i32; } value;
+} smb_chain_step;
+int smb_chain(int dtype, const smb_chain_step *steps, int nsteps,
+              const uint64_t *shape, int ndim, uint64_t n, void *out, void *stream);
+/* The flat output range [lin_begin, lin_begin + lin_count) only (multi-GPU shards); out[0] is
+ * flat element lin_begin. */
+int smb_chain_range(int dtype, const smb_chain_step *steps, int nsteps,
+                    const uint64_t *shape, int ndim, uint64_t lin_begin, uint64_t lin_count,
+                    void *out, void *stream);
+
 /* ---- storage: replaces `new T[n]` / `delete[]` of SMArray<T>::data ------- */
 /* include/SMArray.h:33-34,70-76,219,342-346; include/UserFunctions.h:8-40.
  * Pooled (size-class caching) so a fresh result block per operator call costs

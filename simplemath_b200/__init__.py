@@ -27,11 +27,22 @@ MEM_DEVICE, MEM_MANAGED, MEM_PINNED = range(3)
 OPT_POW_SPECIALISE, OPT_STAGE_CHUNK_BYTES, OPT_CONTIG_VARIANT, OPT_BCAST_VARIANT, OPT_FORCE_WIDE_INDEX = range(5)
 PLAN_CONTIGUOUS, PLAN_ROW, PLAN_GENERIC = range(3)
 MAX_NDIM = 6
+CHAIN_MAX = 8
 
 OPS = {"add": OP_ADD, "sub": OP_SUB, "mul": OP_MUL, "div": OP_DIV, "pow": OP_POW}
 _NP_DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32}
 _CT = {F32: ctypes.c_float, F64: ctypes.c_double, I32: ctypes.c_int32}
 ELEM_SIZE = {F32: 4, F64: 8, I32: 4}
+
+class _ChainValue(ctypes.Union):
+    _fields_ = [("f32", ctypes.c_float), ("f64", ctypes.c_double), ("i32", ctypes.c_int32)]
+
+
+class ChainStep(ctypes.Structure):
+    """smb_chain_step of include/smb200.h."""
+    _fields_ = [("op", ctypes.c_int32), ("swap", ctypes.c_int32), ("data", ctypes.c_void_p),
+                ("stride", ctypes.c_uint64 * MAX_NDIM), ("value", _ChainValue)]
+
 
 # every symbol include/smb200.h declares, with its ctypes signature
 _u64, _vp, _i, _u64p = ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64)
@@ -41,6 +52,8 @@ SYMBOLS = {
     "smb_contiguous": (_i, [_i, _i, _vp, _vp, _vp, _u64, _vp]),
     "smb_array_scalar": (_i, [_i, _i, _vp, _vp, _u64, _vp, _vp]),
     "smb_dot": (_i, [_i, _vp, _vp, _u64, _vp, _vp]),
+    "smb_chain": (_i, [_i, ctypes.POINTER(ChainStep), _i, _u64p, _i, _u64, _vp, _vp]),
+    "smb_chain_range": (_i, [_i, ctypes.POINTER(ChainStep), _i, _u64p, _i, _u64, _u64, _vp, _vp]),
     "smb_alloc": (_vp, [ctypes.c_size_t, _i]),
     "smb_free": (_i, [_vp]),
     "smb_owns": (_i, [_vp]),
@@ -263,6 +276,71 @@ def dot_ptr(dtype, a_ptr, b_ptr, n, stream=0):
     res = _CT[dtype]()
     _check(lib().smb_dot(dtype, a_ptr, b_ptr, int(n), ctypes.byref(res), stream or None))
     return res.value
+
+
+def chain_steps(dtype: int, leaves, shape):
+    """Build the smb_chain_step array.  `leaves` = [(op, swap, leaf)], leaf = (ptr, strides) for an
+    array broadcast against `shape` (strides already 0 on broadcast dims) or a Python scalar."""
+    arr = (ChainStep * len(leaves))()
+    for st, (op, swap, leaf) in zip(arr, leaves):
+        st.op = OPS.get(op, op) if op is not None else 0
+        st.swap = 1 if swap else 0
+        if isinstance(leaf, tuple):
+            st.data = leaf[0]
+            for k, v in enumerate(leaf[1]):
+                st.stride[k] = int(v)
+        else:
+            st.data = None
+            if dtype == F32:
+                st.value.f32 = leaf
+            elif dtype == F64:
+                st.value.f64 = leaf
+            else:
+                st.value.i32 = int(leaf)
+    return arr
+
+
+def chain_ptr(dtype, leaves, shape, out_ptr, stream=0, lin_range=None):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    arr = chain_steps(dtype, leaves, shape)
+    if lin_range is None:
+        _check(lib().smb_chain(dtype, arr, len(leaves), _u64arr(shape), len(shape), n, out_ptr, stream or None))
+    else:
+        _check(lib().smb_chain_range(dtype, arr, len(leaves), _u64arr(shape), len(shape), int(lin_range[0]),
+                                     int(lin_range[1]), out_ptr, stream or None))
+
+
+def chain(first: np.ndarray, *steps) -> np.ndarray:
+    """Fused left-deep chain on numpy operands: chain(a, ("add", b), ("mul", 2.0), ("rsub", c), ("pow", 2.5)).
+    A leading "r" swaps the operands of that step (leaf (op) acc).  Leaves broadcast NumPy-style
+    against each other exactly as a sequence of SMArray operators would."""
+    dt = dtype_code(first.dtype)
+    arrays = [first] + [leaf for _, leaf in steps if isinstance(leaf, np.ndarray)]
+    shape = list(np.broadcast_shapes(*[x.shape for x in arrays]))
+    if len(shape) > MAX_NDIM:
+        raise SmbError(f"rank {len(shape)} > MAX_NDIM {MAX_NDIM}")
+
+    def leaf_of(x):
+        if not isinstance(x, np.ndarray):
+            return x
+        if x.dtype != first.dtype:
+            raise SmbError("operands must share one element type")
+        pad = len(shape) - x.ndim
+        st = [0] * pad + _elem_strides(x)
+        dims = [1] * pad + list(x.shape)
+        st = [0 if d == 1 and r > 1 else s for d, r, s in zip(dims, shape, st)]
+        return (x.ctypes.data, st)
+
+    leaves = [(None, False, leaf_of(first))]
+    for op, leaf in steps:
+        swap = op.startswith("r") and op[1:] in OPS
+        leaves.append((op[1:] if swap else op, swap, leaf_of(leaf)))
+    out = np.empty(shape, dtype=first.dtype)
+    if out.size:
+        chain_ptr(dt, leaves, shape, out.ctypes.data)
+    return out
 
 
 def pow(a: np.ndarray, y) -> np.ndarray:  # noqa: A001 - mirrors sm::pow

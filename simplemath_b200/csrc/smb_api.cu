@@ -876,6 +876,115 @@ static int dot_t(DeviceCtx &c, const T *a, const T *b, uint64_t n, void *result,
 using namespace smb;
 
 // =============================================================== C ABI =====
+// ---- op-chain fusion ---------------------------------
+template<typename T>
+static int chain_launch(const DeviceCtx &c, const ChainPlan &p, const smb_chain_step *steps, const void *const *data,
+                        uint64_t lin_begin, uint64_t lin_count, uint64_t lane_end, T *out, cudaStream_t s) {
+    ChainTable t;
+    memset(&t, 0, sizeof t);
+    t.ndim = p.ndim;
+    t.nsteps = p.nleaf;
+    const bool wide = p.n > 0x7fffffffull || g_opt_force_wide.load() != 0;
+    for (int k = 0; k < SMB_MAX_NDIM; ++k) {
+        t.shape64[k] = p.shape[k];
+        if (!wide) {
+            const FastDiv32 f = make_fastdiv32((uint32_t)p.shape[k]);
+            t.shape[k] = f.d; t.mul[k] = f.mul; t.shr[k] = f.shr;
+        }
+    }
+    constexpr int EPVV = 16 / (int)sizeof(T);
+    bool vec = p.inner_unit_or_zero && p.shape[p.ndim - 1] % EPVV == 0 && lin_begin % EPVV == 0 && lin_count % EPVV == 0 &&
+               (uintptr_t)out % 16 == 0;
+    for (int i = 0; i < p.nleaf; ++i) {
+        t.data[i] = data[i];
+        t.op[i] = (uint8_t)steps[i].op;
+        t.swap[i] = (uint8_t)(steps[i].swap != 0);
+        for (int k = 0; k < SMB_MAX_NDIM; ++k) t.stride[i][k] = p.stride[i][k];
+        if (!data[i]) {
+            if (sizeof(T) == 8) memcpy(&t.cbits[i], &steps[i].value.f64, 8);
+            else { uint32_t w; memcpy(&w, &steps[i].value.f32, 4); t.cbits[i] = w; } // f32 and i32 share the low word
+        } else if (p.stride[i][p.ndim - 1] == 1) {
+            if ((uintptr_t)data[i] % 16 != 0) vec = false;
+            for (int k = 0; k + 1 < p.ndim; ++k) if (p.stride[i][k] % EPVV != 0) vec = false;
+        }
+    }
+    t.lin_base = lin_begin;
+    t.count = lin_count;
+    t.lane_end = lane_end;
+    const uint64_t items = vec ? lin_count / EPVV : lin_count;
+    const unsigned grid = grid_for(items, kThreads, c.sm_count, 0);
+    if (vec) {
+        if (wide) k_chain<T, EPVV, true><<<grid, kThreads, 0, s>>>(out, t);
+        else k_chain<T, EPVV, false><<<grid, kThreads, 0, s>>>(out, t);
+        g_last_kernel = wide ? "k_chain<vec16,wide>" : "k_chain<vec16>";
+    } else {
+        if (wide) k_chain<T, 1, true><<<grid, kThreads, 0, s>>>(out, t);
+        else k_chain<T, 1, false><<<grid, kThreads, 0, s>>>(out, t);
+        g_last_kernel = wide ? "k_chain<scalar,wide>" : "k_chain<scalar>";
+    }
+    ++g_launches;
+    SMB_CK(cudaGetLastError());
+    return SMB_OK;
+}
+
+static int chain_entry(int dtype, const smb_chain_step *steps, int nsteps, const uint64_t *shape, int ndim,
+                       uint64_t lin_begin, uint64_t lin_count, bool whole, void *out, void *stream) {
+    if (dtype < SMB_F32 || dtype > SMB_I32) return fail(SMB_ERR_INVALID, "unknown dtype %d (float, double, int32 only)", dtype);
+    if (!steps || nsteps < 1 || nsteps > SMB_CHAIN_MAX) return fail(SMB_ERR_INVALID, "chain of %d steps (1..%d)", nsteps, SMB_CHAIN_MAX);
+    if (ndim < 1 || ndim > SMB_MAX_NDIM || !shape) return fail(SMB_ERR_INVALID, "rank %d outside 1..%d", ndim, SMB_MAX_NDIM);
+    const uint64_t *strides[SMB_CHAIN_MAX];
+    for (int i = 0; i < nsteps; ++i) {
+        strides[i] = steps[i].data ? steps[i].stride : nullptr;
+        if (i == 0) continue;
+        if (steps[i].op < SMB_OP_ADD || steps[i].op > SMB_OP_POW) return fail(SMB_ERR_INVALID, "step %d: unknown op %d", i, steps[i].op);
+        if (steps[i].op == SMB_OP_POW && (steps[i].data || steps[i].swap))
+            return fail(SMB_ERR_INVALID, "step %d: pow in a chain takes a constant exponent on the right (array ^ scalar)", i);
+    }
+    DeviceCtx *c = nullptr;
+    if (int rc = current_ctx(&c)) return rc;
+    const ChainPlan p = make_chain_plan(strides, nsteps, shape, ndim);
+    if (whole) { lin_begin = 0; lin_count = p.n; }
+    if (lin_begin > p.n || lin_count > p.n - lin_begin) return fail(SMB_ERR_INVALID, "flat range outside the result");
+    if (lin_count == 0) return SMB_OK;
+    if (!out) return fail(SMB_ERR_INVALID, "null result pointer");
+    const size_t es = esize(dtype);
+    int dev = 0;
+    SMB_CK(cudaGetDevice(&dev));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
+    // host leaves / result are staged whole through pooled scratch (no overlap: the fused path is
+    // meant for resident arrays); managed blocks are prefetched like everywhere else
+    Scratch scratch[SMB_CHAIN_MAX], dout;
+    const void *data[SMB_CHAIN_MAX];
+    for (int i = 0; i < nsteps; ++i) {
+        data[i] = steps[i].data;
+        if (!data[i]) continue;
+        const MemType mt = mem_type(data[i]);
+        if (on_host(mt)) {
+            if (stream) return fail(SMB_ERR_INVALID, "smb_chain: host operands need the synchronous form (stream == NULL)");
+            if (int rc = scratch[i].get(p.extent[i] * es, dev)) return rc;
+            SMB_CK(cudaMemcpyAsync(scratch[i].p, data[i], p.extent[i] * es, cudaMemcpyDefault, s));
+            data[i] = scratch[i].p;
+        } else if (mt == MT_MANAGED) prefetch_managed(data[i], p.extent[i] * es, s);
+    }
+    void *po = out;
+    const MemType to = mem_type(out);
+    if (on_host(to)) {
+        if (stream) return fail(SMB_ERR_INVALID, "smb_chain: a host result needs the synchronous form (stream == NULL)");
+        if (int rc = dout.get(lin_count * es, dev)) return rc;
+        po = dout.p;
+    } else if (to == MT_MANAGED) prefetch_managed(out, lin_count * es, s);
+    const uint64_t lane_end = dtype == SMB_I32 ? scalar_lane_end(dtype, p.n) : 0; // array_scalar_op on the dense intermediate
+    int rc;
+    switch (dtype) {
+        case SMB_F32: rc = chain_launch<float>(*c, p, steps, data, lin_begin, lin_count, lane_end, (float *)po, s); break;
+        case SMB_F64: rc = chain_launch<double>(*c, p, steps, data, lin_begin, lin_count, lane_end, (double *)po, s); break;
+        default: rc = chain_launch<int32_t>(*c, p, steps, data, lin_begin, lin_count, lane_end, (int32_t *)po, s); break;
+    }
+    if (rc) return rc;
+    if (on_host(to)) SMB_CK(cudaMemcpyAsync(out, po, lin_count * es, cudaMemcpyDefault, s));
+    if (!stream) SMB_CK(cudaStreamSynchronize(s));
+    return SMB_OK;
+}
 extern "C" {
 
 int smb_elementwise(int op, int dtype, const void *a, const uint64_t *stride_a, const void *b, const uint64_t *stride_b,
@@ -941,6 +1050,20 @@ int smb_dot(int dtype, const void *a, const void *b, uint64_t n, void *result, v
         case SMB_F64: return dot_t<double>(*c, (const double *)a, (const double *)b, n, result, s);
         default: return dot_t<int32_t>(*c, (const int32_t *)a, (const int32_t *)b, n, result, s);
     }
+}
+
+int smb_chain(int dtype, const smb_chain_step *steps, int nsteps, const uint64_t *shape, int ndim, uint64_t n, void *out,
+              void *stream) {
+    if (shape && ndim >= 1 && ndim <= SMB_MAX_NDIM) {
+        uint64_t prod = 1;
+        for (int k = 0; k < ndim; ++k) prod *= shape[k];
+        if (prod != n) return fail(SMB_ERR_INVALID, "n = %llu is not the product of the shape (%llu)", (unsigned long long)n, (unsigned long long)prod);
+    }
+    return chain_entry(dtype, steps, nsteps, shape, ndim, 0, 0, true, out, stream);
+}
+int smb_chain_range(int dtype, const smb_chain_step *steps, int nsteps, const uint64_t *shape, int ndim, uint64_t lin_begin,
+                    uint64_t lin_count, void *out, void *stream) {
+    return chain_entry(dtype, steps, nsteps, shape, ndim, lin_begin, lin_count, false, out, stream);
 }
 
 void *smb_alloc(size_t bytes, int kind) {

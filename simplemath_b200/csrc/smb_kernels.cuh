@@ -884,6 +884,123 @@ __global__ void __launch_bounds__(256) k_tile(const T *__restrict__ a, const T *
         tile_body<T, Fn, A_T, B_T, TR, TC, false>(a + oa, b + ob, out, p, fn, r0, c0, obase, ta, tb);
 }
 
+// ---------------------------------------------------------------------------
+// k_chain: a left-deep chain of Op structs in one pass (smb_chain),
+//     acc = leaf_0;  acc = acc (op_i) leaf_i   [leaf_i (op_i) acc when swap_i]
+// Every leaf is an array broadcast against the result (stride table, 0 on broadcast dims) or a
+// constant.  EPV elements per thread along the inner dim: an inner-stride-1 leaf is one vector
+// load, an inner-stride-0 leaf one scalar load splat (EPV == 1: any strides).  All leaves are
+// loaded before the first operator is applied (the loop over steps is fully unrolled with
+// uniform guards, so the leaf values sit in registers); each intermediate is rounded to T by the
+// same DevOp bodies the single operators use, so the result is bit-identical to the unfused
+// sequence.  HBM-bound: (array leaves + 1) * sizeof(T) bytes per element instead of
+// 3 * sizeof(T) per operator.
+struct ChainTable {
+    int ndim, nsteps;
+    uint32_t shape[SMB_MAX_NDIM], mul[SMB_MAX_NDIM], shr[SMB_MAX_NDIM];
+    uint64_t shape64[SMB_MAX_NDIM];
+    uint64_t stride[kChainMax][SMB_MAX_NDIM];
+    const void *data[kChainMax];   // nullptr: constant leaf
+    uint64_t cbits[kChainMax];     // the constant, as T, in the low bytes
+    uint8_t op[kChainMax], swap[kChainMax];
+    uint64_t lin_base, count;      // flat output range of this launch
+    uint64_t lane_end;             // int32 pow: flat indices below it use AVX2-lane semantics
+};
+template<typename T> __device__ __forceinline__ T chain_const(uint64_t bits) {
+    if constexpr (sizeof(T) == 8) return __longlong_as_double((long long)bits);
+    else if constexpr (std::is_same<T, float>::value) return __uint_as_float((uint32_t)bits);
+    else return (T)(uint32_t)bits;
+}
+template<typename T> __device__ __forceinline__ T chain_apply(int op, T a, T b, bool lane) {
+    switch (op) {
+        case OP_ADD: return DevOp<OP_ADD, T>::apply(a, b);
+        case OP_SUB: return DevOp<OP_SUB, T>::apply(a, b);
+        case OP_MUL: return DevOp<OP_MUL, T>::apply(a, b);
+        case OP_DIV: return DevOp<OP_DIV, T>::apply(a, b);
+        default:
+            if constexpr (std::is_same<T, int32_t>::value) return lane ? powi_lane(a, b) : powi_scalar(a, b);
+            else return DevOp<OP_POW, T>::apply(a, b);
+    }
+}
+template<typename T, int EPV, bool WIDE>
+__global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid_constant__ ChainTable t) {
+    const uint64_t nvec = t.count / EPV; // host guarantees count % EPV == 0
+    for (uint64_t v = (uint64_t)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * kBlock) {
+        const uint64_t lin = t.lin_base + v * EPV;
+        // flat index -> per-dim indices, innermost first
+        uint64_t idx[SMB_MAX_NDIM];
+        if (WIDE) {
+            uint64_t rem = lin;
+#pragma unroll
+            for (int k = SMB_MAX_NDIM - 1; k >= 0; --k) {
+                if (k < t.ndim) {
+                    if (k == 0) idx[k] = rem;
+                    else { const uint64_t q = rem / t.shape64[k]; idx[k] = rem - q * t.shape64[k]; rem = q; }
+                }
+            }
+        } else {
+            uint32_t rem = (uint32_t)lin;
+#pragma unroll
+            for (int k = SMB_MAX_NDIM - 1; k >= 0; --k) {
+                if (k < t.ndim) {
+                    if (k == 0) idx[k] = rem;
+                    else { const uint32_t q = fastdiv(rem, t.shape[k], t.mul[k], t.shr[k]); idx[k] = rem - q * t.shape[k]; rem = q; }
+                }
+            }
+        }
+        // every leaf first (independent loads in flight together)
+        T leaf[kChainMax][EPV];
+#pragma unroll
+        for (int s = 0; s < kChainMax; ++s) {
+            if (s < t.nsteps) {
+                const T *base = static_cast<const T *>(t.data[s]);
+                if (base == nullptr) {
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) leaf[s][e] = chain_const<T>(t.cbits[s]);
+                } else {
+                    uint64_t off = 0;
+#pragma unroll
+                    for (int k = 0; k < SMB_MAX_NDIM; ++k)
+                        if (k < t.ndim) off += idx[k] * t.stride[s][k];
+                    if (EPV > 1 && t.stride[s][t.ndim - 1] == 1) {
+                        Pack<T, 16> pk; // EPV * sizeof(T) == 16
+                        pk.raw = VecIO<16, false>::load(base + off);
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) leaf[s][e] = pk.e[e];
+                    } else {
+                        const T x = __ldg(base + off);
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) leaf[s][e] = x;
+                    }
+                }
+            }
+        }
+        T acc[EPV];
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[e] = leaf[0][e];
+#pragma unroll
+        for (int s = 1; s < kChainMax; ++s) {
+            if (s < t.nsteps) {
+                const int op = t.op[s];
+                const bool sw = t.swap[s] != 0;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    const bool lane = lin + e < t.lane_end;
+                    acc[e] = sw ? chain_apply<T>(op, leaf[s][e], acc[e], lane) : chain_apply<T>(op, acc[e], leaf[s][e], lane);
+                }
+            }
+        }
+        if (EPV > 1) {
+            Pack<T, 16> r;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) r.e[e] = acc[e];
+            VecIO<16, true>::store(out + v * EPV, r.raw);
+        } else {
+            out[v] = acc[0];
+        }
+    }
+}
+
 // k_generic: arbitrary element strides; one output element per thread per
 // iteration, coalesced stores, gathered loads.
 template<typename T, typename Fn, bool WIDE>

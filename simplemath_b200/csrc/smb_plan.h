@@ -96,4 +96,56 @@ inline ElementwisePlan make_plan(const uint64_t *stride_a, const uint64_t *strid
     return p;
 }
 
+// ---- op chains (smb_chain): the same coalescing over up to kChainMax leaves ----
+constexpr int kChainMax = 8;
+struct ChainPlan {
+    int ndim;
+    int nleaf;
+    uint64_t shape[SMB_MAX_NDIM];
+    uint64_t stride[kChainMax][SMB_MAX_NDIM]; // all zero for a constant leaf
+    uint64_t extent[kChainMax];               // elements spanned by each array leaf
+    uint64_t n;
+    bool inner_unit_or_zero;                  // every leaf has inner stride 0 or 1
+};
+// strides[i] == nullptr marks a constant leaf.
+inline ChainPlan make_chain_plan(const uint64_t *const *strides, int nleaf, const uint64_t *shape, int ndim) {
+    ChainPlan p;
+    p.nleaf = nleaf;
+    uint64_t n = 1;
+    for (int k = 0; k < ndim; ++k) n *= shape[k];
+    p.n = n;
+    int m = 0;
+    auto st = [&](int i, int k) -> uint64_t { return strides[i] ? strides[i][k] : 0; };
+    for (int k = 0; k < ndim; ++k) {
+        if (shape[k] == 1) continue;
+        bool merge = m > 0;
+        for (int i = 0; merge && i < nleaf; ++i) merge = p.stride[i][m - 1] == shape[k] * st(i, k);
+        if (merge) {
+            p.shape[m - 1] *= shape[k];
+            for (int i = 0; i < nleaf; ++i) p.stride[i][m - 1] = st(i, k);
+        } else {
+            p.shape[m] = shape[k];
+            for (int i = 0; i < nleaf; ++i) p.stride[i][m] = st(i, k);
+            ++m;
+        }
+    }
+    if (m == 0) {
+        p.shape[0] = n ? 1 : 0;
+        for (int i = 0; i < nleaf; ++i) p.stride[i][0] = strides[i] ? 1 : 0;
+        m = 1;
+    }
+    p.ndim = m;
+    for (int k = m; k < SMB_MAX_NDIM; ++k) {
+        p.shape[k] = 1;
+        for (int i = 0; i < nleaf; ++i) p.stride[i][k] = 0;
+    }
+    p.inner_unit_or_zero = true;
+    for (int i = 0; i < nleaf; ++i) {
+        p.extent[i] = n ? 1 : 0;
+        if (n) for (int k = 0; k < m; ++k) p.extent[i] += (p.shape[k] - 1) * p.stride[i][k];
+        if (p.stride[i][m - 1] > 1) p.inner_unit_or_zero = false;
+    }
+    return p;
+}
+
 } // namespace smb

@@ -1,0 +1,194 @@
+"""smb_chain: op-chain fusion.  The fused result must be what the
+reference's separate operators produce one after another -- each SMArray operator
+(include/SMArray.h:217-305) materialises a rounded intermediate, so the oracle is the chain of
+oracle operators on the same inputs: bit-exact for + - * / (float, double, int32 wrap), the
+array_scalar_op lane / scalar-tail split for int32 pow, the stated ULP bound for float pow."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+import simplemath_b200 as smb
+from conftest import assert_same_bits
+
+
+def oracle_chain(orc, first, steps):
+    """The unfused sequence on the CPU oracle.  Returns the last intermediate too (for pow ULPs)."""
+    acc, prev = np.ascontiguousarray(first), None
+    for op, leaf in steps:
+        swap = op.startswith("r") and op[1:] in smb.OPS
+        op = op[1:] if swap else op
+        prev = acc
+        if isinstance(leaf, np.ndarray):
+            acc = orc.binary(op, leaf, acc) if swap else orc.binary(op, acc, leaf)
+        elif swap:
+            acc = orc.binary(op, np.full((1,) * acc.ndim, leaf, acc.dtype), acc)
+        else:
+            acc = orc.array_scalar(op, acc, leaf)
+    return acc, prev
+
+
+# ---------------------------------------------------------------- no GPU needed
+def test_chain_argument_checks_need_no_device():
+    lib = smb.lib()
+    shape = smb._u64arr([4])
+    steps = smb.chain_steps(smb.F32, [(None, False, 1.0), ("add", False, 2.0)], [4])
+    out = np.zeros(4, np.float32)
+    assert lib.smb_chain(smb.F32, steps, 0, shape, 1, 4, out.ctypes.data, None) == 1          # no steps
+    assert lib.smb_chain(smb.F32, steps, 9, shape, 1, 4, out.ctypes.data, None) == 1          # too many
+    assert lib.smb_chain(7, steps, 2, shape, 1, 4, out.ctypes.data, None) == 1                # dtype
+    assert lib.smb_chain(smb.F32, steps, 2, shape, 1, 5, out.ctypes.data, None) == 1          # n != prod(shape)
+    bad = smb.chain_steps(smb.F32, [(None, False, 1.0), ("pow", False, (out.ctypes.data, [1]))], [4])
+    assert lib.smb_chain(smb.F32, bad, 2, shape, 1, 4, out.ctypes.data, None) == 1            # array exponent
+    assert b"constant exponent" in lib.smb_last_error()
+    if smb.device_count() == 0:   # valid arguments: fails loudly without a GPU, never computes on the CPU
+        assert lib.smb_chain(smb.F32, steps, 2, shape, 1, 4, out.ctypes.data, None) == 2
+        assert b"no CPU fallback" in lib.smb_last_error()
+
+
+def test_chain_step_struct_matches_header():
+    hdr = open(smb.HERE + "/../include/smb200.h").read()
+    assert "#define SMB_CHAIN_MAX 8" in hdr and smb.CHAIN_MAX == 8
+    assert ctypes.sizeof(smb.ChainStep) == 4 + 4 + 8 + 8 * smb.MAX_NDIM + 8
+
+
+# ------------------------------------------------------------------------- GPU
+pytestmark_gpu = pytest.mark.gpu
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32])
+def test_chain_bit_exact_against_unfused_oracle_sequence(orc, dt):
+    rng = np.random.default_rng(71)
+
+    def rnd(shape):
+        if dt == np.int32:
+            return rng.integers(-2**31, 2**31, size=shape).astype(np.int32)
+        return (rng.standard_normal(shape) * 100).astype(dt)
+
+    def nz(shape):  # divisors
+        if dt == np.int32:
+            return rng.integers(1, 1000, size=shape).astype(np.int32) * rng.choice(np.array([-1, 1], np.int32), size=shape)
+        return (rng.uniform(0.5, 3, size=shape) * rng.choice([-1, 1], size=shape)).astype(dt)
+
+    c3 = 3 if dt == np.int32 else 2.5
+    a, b, c, d = rnd((64, 256)), rnd((64, 256)), nz((64, 256)), rnd((64, 256))
+    cases = [
+        (a, [("add", b)]),
+        (a, [("add", b), ("mul", c)]),
+        (a, [("add", b), ("mul", c), ("sub", d)]),
+        (a, [("sub", b), ("div", c), ("add", c3), ("rsub", d), ("mul", a)]),
+        (a, [("mul", c3), ("radd", b), ("rdiv", c3)] if dt != np.int32 else [("mul", c3), ("radd", b), ("div", c)]),
+        # broadcast leaves: a row, a column, a rank-1 row, constants in between
+        (a, [("add", b[:1]), ("mul", c[:, :1]), ("sub", d[0]), ("add", c3)]),
+        (a[:, :1], [("add", b[:1]), ("mul", c)]),                       # the first leaf is the broadcast one
+        (rnd((8, 1, 32)), [("mul", rnd((1, 16, 32))), ("add", rnd((8, 16, 1))), ("sub", rnd((32,)))]),  # 3-D
+        (rnd((5, 3, 2, 4, 2, 8)), [("add", rnd((5, 1, 2, 1, 2, 8))), ("mul", rnd((1, 3, 1, 4, 1, 1)))]),  # rank 6
+        (rnd((1000,)), [("add", rnd((1000,))), ("mul", rnd((1000,))), ("sub", rnd((1000,))), ("add", rnd((1000,))),
+                        ("mul", rnd((1000,))), ("sub", rnd((1000,))), ("add", rnd((1000,)))]),           # 8 leaves
+        (rnd((7, 13)), [("add", rnd((7, 13))), ("mul", rnd((13,)))]),   # odd inner length -> scalar variant
+        (a.T, [("add", b.T), ("mul", c.T)]),                            # transposed leaves -> scalar variant
+        (a[:, 1:65], [("add", b[:, 3:67]), ("sub", d[:, :64])]),        # misaligned interior pointers
+    ]
+    for first, steps in cases:
+        want, _ = oracle_chain(orc, first, steps)
+        got = smb.chain(first, *steps)
+        assert got.shape == want.shape
+        assert_same_bits(got, want, f"{np.dtype(dt).name} chain {[s[0] for s in steps]} {first.shape}")
+    smb.chain(a, ("add", b), ("mul", c))
+    assert smb.last_kernel() == "k_chain<vec16>"
+    smb.chain(a.T, ("add", b.T))
+    assert smb.last_kernel() == "k_chain<scalar>"
+
+
+@pytest.mark.gpu
+def test_chain_int_pow_lane_and_tail_semantics(orc):
+    rng = np.random.default_rng(72)
+    for n in (5, 8, 1003, 4096):
+        a = rng.integers(-6, 7, size=n).astype(np.int32)
+        b = rng.integers(-3, 4, size=n).astype(np.int32)
+        for e in (3, 2, 20, -2, 0, 31):
+            steps = [("add", b), ("pow", e), ("sub", 1)]
+            want, _ = oracle_chain(orc, a, steps)
+            assert_same_bits(smb.chain(a, *steps), want, f"int pow chain n={n} e={e}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt,bound", [(np.float32, 1.0), (np.float64, 1.0)])
+def test_chain_float_pow_within_ulp_bound(orc, dt, bound):
+    rng = np.random.default_rng(73)
+    a = rng.uniform(0.01, 50, size=(128, 512)).astype(dt)
+    b = rng.uniform(0.01, 50, size=(1, 512)).astype(dt)
+    for y in (2.0, 2.5, -0.75, 7.0):
+        steps = [("add", b), ("pow", y)]
+        _, base = oracle_chain(orc, a, steps)          # base = a + b, bit-exact
+        got = smb.chain(a, *steps)
+        assert_same_bits(smb.chain(a, ("add", b)), base, "pow base")
+        if dt == np.float32:
+            err = oracle.ulp_error_f32(got.ravel(), orc.pow_ref_f32(base.ravel(), float(np.float32(y))))
+        else:
+            hi, lo = orc.pow_ref_f64(base.ravel(), y)
+            err = oracle.ulp_error_f64(got.ravel(), hi, lo)
+        assert err.max() <= bound, (y, err.max())
+        # and a step after the pow consumes the rounded power
+        got2 = smb.chain(a, ("add", b), ("pow", y), ("mul", a))
+        assert_same_bits(got2, orc.binary("mul", got, a), "step after pow")
+
+
+@pytest.mark.gpu
+def test_chain_wide_index_ranges_and_device_pointers(orc):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(74)
+    a = rng.standard_normal((33, 40)).astype(np.float32)
+    b = rng.standard_normal((1, 40)).astype(np.float32)
+    c = rng.standard_normal((33, 1)).astype(np.float32)
+    steps = [("mul", b), ("add", c), ("sub", 0.5)]
+    want, _ = oracle_chain(orc, a, steps)
+    smb.set_option(smb.OPT_FORCE_WIDE_INDEX, 1)
+    try:
+        assert_same_bits(smb.chain(a, *steps), want, "wide index")
+        assert smb.last_kernel() == "k_chain<vec16,wide>"
+    finally:
+        smb.set_option(smb.OPT_FORCE_WIDE_INDEX, 0)
+    # device-resident leaves, flat sub-ranges (the multi-GPU shard unit), asynchronous on a stream
+    ta, tb, tc = (torch.from_numpy(x).cuda() for x in (a, b, c))
+    n = a.size
+    leaves = [(None, False, (ta.data_ptr(), [40, 1])), ("mul", False, (tb.data_ptr(), [0, 1])),
+              ("add", False, (tc.data_ptr(), [1, 0])), ("sub", False, 0.5)]
+    sp = torch.cuda.current_stream().cuda_stream
+    for lo, cnt in ((0, n), (40, 400), (4, 1316), (13, 77)):
+        out = torch.zeros(cnt, dtype=torch.float32, device="cuda")
+        smb.chain_ptr(smb.F32, leaves, [33, 40], out.data_ptr(), stream=sp, lin_range=(lo, cnt))
+        torch.cuda.synchronize()
+        assert_same_bits(out.cpu().numpy(), want.ravel()[lo:lo + cnt], f"range {lo}+{cnt}")
+    l0 = smb.launch_count()
+    out = torch.zeros(n, dtype=torch.float32, device="cuda")
+    smb.chain_ptr(smb.F32, leaves, [33, 40], out.data_ptr(), stream=sp)
+    torch.cuda.synchronize()
+    assert smb.launch_count() == l0 + 1      # ONE kernel for the whole chain
+
+
+@pytest.mark.gpu
+def test_chain_full_size_properties():
+    """At a size the oracle would not finish quickly: (x + y) - y == x wherever the sum is exact,
+    and fused == the library's own unfused operators, bit for bit."""
+    torch = pytest.importorskip("torch")
+    n = 1 << 26
+    sp = torch.cuda.current_stream().cuda_stream
+    x = torch.randint(-2**20, 2**20, (n,), device="cuda").to(torch.float32)
+    y = torch.randint(-2**20, 2**20, (n,), device="cuda").to(torch.float32)
+    z = torch.rand(n, device="cuda") + 0.5
+    out, t1, t2 = (torch.empty(n, dtype=torch.float32, device="cuda") for _ in range(3))
+    leaves = [(None, False, (x.data_ptr(), [1])), ("add", False, (y.data_ptr(), [1])), ("sub", False, (y.data_ptr(), [1]))]
+    smb.chain_ptr(smb.F32, leaves, [n], out.data_ptr(), stream=sp)
+    torch.cuda.synchronize()
+    assert torch.equal(out, x)
+    leaves = [(None, False, (x.data_ptr(), [1])), ("add", False, (y.data_ptr(), [1])), ("div", False, (z.data_ptr(), [1])),
+              ("mul", False, 3.0)]
+    smb.chain_ptr(smb.F32, leaves, [n], out.data_ptr(), stream=sp)
+    smb.contiguous_ptr(smb.OP_ADD, smb.F32, x.data_ptr(), y.data_ptr(), t1.data_ptr(), n, sp)
+    smb.contiguous_ptr(smb.OP_DIV, smb.F32, t1.data_ptr(), z.data_ptr(), t2.data_ptr(), n, sp)
+    smb.array_scalar_ptr(smb.OP_MUL, smb.F32, t2.data_ptr(), 3.0, n, t1.data_ptr(), sp)
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int32), t1.view(torch.int32))
