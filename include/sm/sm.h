@@ -4,3 +4,4 @@
 #pragma once
 #include "SMArray.h"
 #include "UserFunctions.h"
+#include "Lazy.h" // opt-in op-chain fusion (not in the reference)
