@@ -897,8 +897,8 @@ static int chain_launch(const DeviceCtx &c, const ChainPlan &p, const smb_chain_
                (uintptr_t)out % 16 == 0;
     for (int i = 0; i < p.nleaf; ++i) {
         t.data[i] = data[i];
-        t.op[i] = (uint8_t)steps[i].op;
-        t.swap[i] = (uint8_t)(steps[i].swap != 0);
+        // leaf (op) acc: only - and / care which side the leaf is on
+        t.op[i] = (uint8_t)(steps[i].swap && steps[i].op == SMB_OP_SUB ? CH_RSUB : steps[i].swap && steps[i].op == SMB_OP_DIV ? CH_RDIV : steps[i].op);
         for (int k = 0; k < SMB_MAX_NDIM; ++k) t.stride[i][k] = p.stride[i][k];
         if (!data[i]) {
             if (sizeof(T) == 8) memcpy(&t.cbits[i], &steps[i].value.f64, 8);
@@ -912,16 +912,50 @@ static int chain_launch(const DeviceCtx &c, const ChainPlan &p, const smb_chain_
     t.count = lin_count;
     t.lane_end = lane_end;
     const uint64_t items = vec ? lin_count / EPVV : lin_count;
-    const unsigned grid = grid_for(items, kThreads, c.sm_count, 0);
-    if (vec) {
-        if (wide) k_chain<T, EPVV, true><<<grid, kThreads, 0, s>>>(out, t);
-        else k_chain<T, EPVV, false><<<grid, kThreads, 0, s>>>(out, t);
+    // f32 pow steps with an exponent the table-driven core takes: stage its tables (vector variant)
+    bool powfast = false;
+    t.pow_consts = pow_consts();
+    t.pow_small = 1;
+    if constexpr (std::is_same<T, float>::value) {
+        for (int i = 1; i < p.nleaf && vec; ++i) {
+            if (steps[i].op != SMB_OP_POW) continue;
+            const PowExpF32 pe = classify_exp(steps[i].value.f32);
+            if (!pow_f32_fast_ok(pe)) continue;
+            t.pow_fast[i] = 1;
+            t.pow_abs_mask[i] = pe.y_is_int ? 0x7fffffffu : 0xffffffffu;
+            t.pow_sign_or[i] = pe.y_is_odd ? 0x80000000u : 0u;
+            if (!pow_f32_small_y(pe)) t.pow_small = 0;
+            powfast = true;
+        }
+    }
+    t.tiles_per_cta = powfast ? 8 : 1; // amortise the 24 KB table copy, stay many waves deep
+    // compiled-in chain capacity / vectors per thread: short chains keep more loads in flight
+#define SMB_CHAIN_LAUNCH(E, W, NS, U, PF)                                                                         \
+    k_chain<T, E, W, NS, U, PF><<<grid_for(items, (uint64_t)kThreads * U * t.tiles_per_cta, c.sm_count, 0), kThreads, 0, s>>>(out, t)
+#define SMB_CHAIN_BY_LEN(E, W, PF)                                                                \
+    do {                                                                                          \
+        if (p.nleaf <= 3 && PF) SMB_CHAIN_LAUNCH(E, W, 3, 2, PF); /* pow: fewer registers, more CTAs */ \
+        else if (p.nleaf <= 3) SMB_CHAIN_LAUNCH(E, W, 3, 4, PF);                                  \
+        else if (p.nleaf <= 5) SMB_CHAIN_LAUNCH(E, W, 5, 2, PF);                                  \
+        else SMB_CHAIN_LAUNCH(E, W, 8, 1, PF);                                                    \
+    } while (0)
+    if (vec && powfast) {
+        if constexpr (std::is_same<T, float>::value) {
+            if (wide) SMB_CHAIN_BY_LEN(EPVV, true, true);
+            else SMB_CHAIN_BY_LEN(EPVV, false, true);
+        }
+        g_last_kernel = wide ? "k_chain<vec16,wide,pow>" : "k_chain<vec16,pow>";
+    } else if (vec) {
+        if (wide) SMB_CHAIN_BY_LEN(EPVV, true, false);
+        else SMB_CHAIN_BY_LEN(EPVV, false, false);
         g_last_kernel = wide ? "k_chain<vec16,wide>" : "k_chain<vec16>";
     } else {
-        if (wide) k_chain<T, 1, true><<<grid, kThreads, 0, s>>>(out, t);
-        else k_chain<T, 1, false><<<grid, kThreads, 0, s>>>(out, t);
+        if (wide) SMB_CHAIN_BY_LEN(1, true, false);
+        else SMB_CHAIN_BY_LEN(1, false, false);
         g_last_kernel = wide ? "k_chain<scalar,wide>" : "k_chain<scalar>";
     }
+#undef SMB_CHAIN_BY_LEN
+#undef SMB_CHAIN_LAUNCH
     ++g_launches;
     SMB_CK(cudaGetLastError());
     return SMB_OK;

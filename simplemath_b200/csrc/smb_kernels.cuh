@@ -890,7 +890,7 @@ __global__ void __launch_bounds__(256) k_tile(const T *__restrict__ a, const T *
 // Every leaf is an array broadcast against the result (stride table, 0 on broadcast dims) or a
 // constant.  EPV elements per thread along the inner dim: an inner-stride-1 leaf is one vector
 // load, an inner-stride-0 leaf one scalar load splat (EPV == 1: any strides).  All leaves are
-// loaded before the first operator is applied (the loop over steps is fully unrolled with
+// loaded before the first operator is applied (the loops over steps are fully unrolled with
 // uniform guards, so the leaf values sit in registers); each intermediate is rounded to T by the
 // same DevOp bodies the single operators use, so the result is bit-identical to the unfused
 // sequence.  HBM-bound: (array leaves + 1) * sizeof(T) bytes per element instead of
@@ -902,30 +902,64 @@ struct ChainTable {
     uint64_t stride[kChainMax][SMB_MAX_NDIM];
     const void *data[kChainMax];   // nullptr: constant leaf
     uint64_t cbits[kChainMax];     // the constant, as T, in the low bytes
-    uint8_t op[kChainMax], swap[kChainMax];
+    uint8_t op[kChainMax];         // CH_* step codes (the mirrored forms fold the swap flag in)
     uint64_t lin_base, count;      // flat output range of this launch
     uint64_t lane_end;             // int32 pow: flat indices below it use AVX2-lane semantics
+    uint32_t tiles_per_cta;        // consecutive tiles per CTA (1; a few when the pow tables are staged)
+    // f32 pow steps the table-driven core may take (POWFAST kernels): per step the two sign masks of
+    // pow_f32_pair_fast<.., POW_SIGN_RUNTIME, ..>; pow_fast[s] == 0 keeps the reference-accuracy path
+    uint8_t pow_fast[kChainMax];
+    uint32_t pow_small;            // 1: the small-y table image and core (every fast step has |y| <= 8)
+    uint32_t pow_abs_mask[kChainMax], pow_sign_or[kChainMax];
+    PowConsts pow_consts;
 };
 template<typename T> __device__ __forceinline__ T chain_const(uint64_t bits) {
     if constexpr (sizeof(T) == 8) return __longlong_as_double((long long)bits);
     else if constexpr (std::is_same<T, float>::value) return __uint_as_float((uint32_t)bits);
     else return (T)(uint32_t)bits;
 }
-template<typename T> __device__ __forceinline__ T chain_apply(int op, T a, T b, bool lane) {
-    switch (op) {
-        case OP_ADD: return DevOp<OP_ADD, T>::apply(a, b);
-        case OP_SUB: return DevOp<OP_SUB, T>::apply(a, b);
-        case OP_MUL: return DevOp<OP_MUL, T>::apply(a, b);
-        case OP_DIV: return DevOp<OP_DIV, T>::apply(a, b);
-        default:
-            if constexpr (std::is_same<T, int32_t>::value) return lane ? powi_lane(a, b) : powi_scalar(a, b);
-            else return DevOp<OP_POW, T>::apply(a, b);
-    }
+// pow inside a chain is the reference-accuracy path, out of line: inlined at every step it would
+// multiply the kernel's code size by the chain length for a case most chains do not contain.
+template<typename T> __device__ __noinline__ T chain_pow(T a, T b, bool lane) {
+    if constexpr (std::is_same<T, int32_t>::value) return lane ? powi_lane(a, b) : powi_scalar(a, b);
+    else return DevOp<OP_POW, T>::apply(a, b);
 }
-template<typename T, int EPV, bool WIDE>
+// step codes: the four ops, the two non-commutative ones mirrored (leaf on the left), pow
+enum { CH_ADD = 0, CH_SUB = 1, CH_MUL = 2, CH_DIV = 3, CH_POW = 4, CH_RSUB = 5, CH_RDIV = 6 };
+// NS: compiled-in capacity of the chain (leaf registers); UNROLL: vectors per thread, all of whose
+// leaf loads are issued before the first operator (UNROLL * NS independent loads in flight per
+// thread -- a single vector per thread left HBM half idle).  One tile of 256 * UNROLL vectors per CTA.
+// POWFAST (float, EPV == 4): the large-y pow tables are staged per CTA (one bulk copy, overlapped
+// with the first tile's loads) and a pow step goes through the FFMA2 core, two elements per call,
+// the reference-accuracy path only for the vectors it declines -- sm::pow(a + b, e) in one pass.
+template<typename T, int EPV, bool WIDE, int NS, int UNROLL, bool POWFAST>
 __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid_constant__ ChainTable t) {
     const uint64_t nvec = t.count / EPV; // host guarantees count % EPV == 0
-    for (uint64_t v = (uint64_t)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * kBlock) {
+    [[maybe_unused]] PowLane lane;
+    [[maybe_unused]] __shared__ __align__(8) uint64_t tab_bar;
+    if constexpr (POWFAST) {
+        if (threadIdx.x == 0) {
+            mbar_init(&tab_bar, 1);
+            mbar_expect_tx(&tab_bar, (uint32_t)sizeof(SmbPowTabs));
+            bulk_g2s(&smb_s_pow, &g_pow_image[t.pow_small ? 0 : 1], (uint32_t)sizeof(SmbPowTabs), &tab_bar);
+        }
+        lane = pow_lane(threadIdx.x, t.pow_consts);
+        __syncthreads();
+    }
+    const uint64_t ntiles = (nvec + kBlock * UNROLL - 1) / (kBlock * UNROLL);
+    // plain chains: exactly one tile per CTA (the loop below folds away); POWFAST: a few consecutive ones
+    const uint32_t tpc = POWFAST ? t.tiles_per_cta : 1u;
+    uint64_t tile = (uint64_t)blockIdx.x * tpc;
+    if (tile >= ntiles) return;
+    const uint64_t tile_end = POWFAST ? (tile + tpc < ntiles ? tile + tpc : ntiles) : tile + 1;
+#pragma unroll 1
+    for (bool first_tile = true; tile < tile_end; ++tile, first_tile = false) {
+    const uint64_t v0 = tile * (kBlock * UNROLL) + threadIdx.x;
+    T leaf[UNROLL][NS][EPV];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const uint64_t v = v0 + (uint64_t)u * kBlock;
+        if (v >= nvec) continue; // (its registers stay undefined; nothing of it is stored)
         const uint64_t lin = t.lin_base + v * EPV;
         // flat index -> per-dim indices, innermost first
         uint64_t idx[SMB_MAX_NDIM];
@@ -948,15 +982,13 @@ __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid
                 }
             }
         }
-        // every leaf first (independent loads in flight together)
-        T leaf[kChainMax][EPV];
 #pragma unroll
-        for (int s = 0; s < kChainMax; ++s) {
+        for (int s = 0; s < NS; ++s) {
             if (s < t.nsteps) {
                 const T *base = static_cast<const T *>(t.data[s]);
                 if (base == nullptr) {
 #pragma unroll
-                    for (int e = 0; e < EPV; ++e) leaf[s][e] = chain_const<T>(t.cbits[s]);
+                    for (int e = 0; e < EPV; ++e) leaf[u][s][e] = chain_const<T>(t.cbits[s]);
                 } else {
                     uint64_t off = 0;
 #pragma unroll
@@ -966,39 +998,101 @@ __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid
                         Pack<T, 16> pk; // EPV * sizeof(T) == 16
                         pk.raw = VecIO<16, false>::load(base + off);
 #pragma unroll
-                        for (int e = 0; e < EPV; ++e) leaf[s][e] = pk.e[e];
+                        for (int e = 0; e < EPV; ++e) leaf[u][s][e] = pk.e[e];
                     } else {
                         const T x = __ldg(base + off);
 #pragma unroll
-                        for (int e = 0; e < EPV; ++e) leaf[s][e] = x;
+                        for (int e = 0; e < EPV; ++e) leaf[u][s][e] = x;
                     }
                 }
             }
         }
-        T acc[EPV];
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) acc[e] = leaf[0][e];
-#pragma unroll
-        for (int s = 1; s < kChainMax; ++s) {
-            if (s < t.nsteps) {
-                const int op = t.op[s];
-                const bool sw = t.swap[s] != 0;
-#pragma unroll
-                for (int e = 0; e < EPV; ++e) {
-                    const bool lane = lin + e < t.lane_end;
-                    acc[e] = sw ? chain_apply<T>(op, leaf[s][e], acc[e], lane) : chain_apply<T>(op, acc[e], leaf[s][e], lane);
-                }
-            }
-        }
-        if (EPV > 1) {
-            Pack<T, 16> r;
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) r.e[e] = acc[e];
-            VecIO<16, true>::store(out + v * EPV, r.raw);
-        } else {
-            out[v] = acc[0];
+    }
+    if constexpr (POWFAST) {
+        if (first_tile) {
+            mbar_wait(&tab_bar, 0); // the tables have landed
+            asm volatile("" : "+r"(lane.log_off), "+r"(lane.exp_off) :: "memory"); // ties the lookups to the wait
         }
     }
+    // the operators: ONE uniform switch per step, straight-line code over every element the thread
+    // holds inside each case (a switch per element made the kernel branch-bound)
+    T acc[UNROLL][EPV];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[u][e] = leaf[u][0][e];
+#define SMB_CHAIN_CASE(CODE, EXPR)                                                       \
+    case CODE:                                                                           \
+        _Pragma("unroll") for (int u = 0; u < UNROLL; ++u)                               \
+            _Pragma("unroll") for (int e = 0; e < EPV; ++e) {                            \
+                const T x = acc[u][e], y = leaf[u][s][e];                                \
+                acc[u][e] = EXPR;                                                        \
+            }                                                                            \
+        break;
+#pragma unroll
+    for (int s = 1; s < NS; ++s) {
+        if (s < t.nsteps) {
+            switch (t.op[s]) {
+                SMB_CHAIN_CASE(CH_ADD, (DevOp<OP_ADD, T>::apply(x, y)))
+                SMB_CHAIN_CASE(CH_SUB, (DevOp<OP_SUB, T>::apply(x, y)))
+                SMB_CHAIN_CASE(CH_MUL, (DevOp<OP_MUL, T>::apply(x, y)))
+                SMB_CHAIN_CASE(CH_DIV, (DevOp<OP_DIV, T>::apply(x, y)))
+                SMB_CHAIN_CASE(CH_RSUB, (DevOp<OP_SUB, T>::apply(y, x)))
+                SMB_CHAIN_CASE(CH_RDIV, (DevOp<OP_DIV, T>::apply(y, x)))
+                default: // CH_POW
+#pragma unroll
+                    for (int u = 0; u < UNROLL; ++u) {
+                        const uint64_t lin = t.lin_base + (v0 + (uint64_t)u * kBlock) * EPV;
+                        bool done = false;
+                        if constexpr (POWFAST) {
+                            if (t.pow_fast[s]) {
+                                float r[EPV];
+                                bool ok = true;
+                                if (t.pow_small) { // every fast pow step of this chain has |y| <= 8: the r-series core
+#pragma unroll
+                                    for (int e = 0; e < EPV; e += 2)
+                                        ok &= pow_f32_pair_fast<true, POW_SIGN_RUNTIME, false>(
+                                            acc[u][e], acc[u][e + 1], leaf[u][s][0], lane, nullptr, nullptr, &r[e], &r[e + 1],
+                                            t.pow_abs_mask[s], t.pow_sign_or[s]);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < EPV; e += 2)
+                                        ok &= pow_f32_pair_fast<false, POW_SIGN_RUNTIME, false>(
+                                            acc[u][e], acc[u][e + 1], leaf[u][s][0], lane, nullptr, nullptr, &r[e], &r[e + 1],
+                                            t.pow_abs_mask[s], t.pow_sign_or[s]);
+                                }
+                                if (ok) {
+#pragma unroll
+                                    for (int e = 0; e < EPV; ++e) acc[u][e] = r[e];
+                                    done = true;
+                                }
+                            }
+                        }
+                        if (!done) {
+#pragma unroll
+                            for (int e = 0; e < EPV; ++e) acc[u][e] = chain_pow<T>(acc[u][e], leaf[u][s][e], lin + e < t.lane_end);
+                        }
+                    }
+                    break;
+            }
+        }
+    }
+#undef SMB_CHAIN_CASE
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const uint64_t v = v0 + (uint64_t)u * kBlock;
+        if (v < nvec) {
+            if (EPV > 1) {
+                Pack<T, 16> r;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) r.e[e] = acc[u][e];
+                VecIO<16, true>::store(out + v * EPV, r.raw);
+            } else {
+                out[v] = acc[u][0];
+            }
+        }
+    }
+    } // tiles
 }
 
 // k_generic: arbitrary element strides; one output element per thread per

@@ -572,13 +572,18 @@ SMB_HD bool pow_f32_fast_ok(const PowExpF32 &pe) {
 //       POW_SIGN_EVEN   -- even integer y, the sign of the base is dropped;
 //       POW_SIGN_ODD    -- odd integer y, the result takes the sign of the base.
 // Y_LT_1 (|y| < 1): the range test is made on log2|x| instead of t (|t| < |log2|x|| then).
-enum { POW_SIGN_REJECT = 0, POW_SIGN_EVEN = 1, POW_SIGN_ODD = 2 };
+//       POW_SIGN_RUNTIME -- the exponent is not known when the kernel is compiled (op chains): the
+//         two masks say what to do (abs_mask 0x7fffffff for an integer y, sign_or 0x80000000 for an
+//         odd one), and the range test is made on both t and log2|x|.
+enum { POW_SIGN_REJECT = 0, POW_SIGN_EVEN = 1, POW_SIGN_ODD = 2, POW_SIGN_RUNTIME = 3 };
 template<bool SMALL_Y, int SIGN, bool Y_LT_1>
 SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
-                              const PowTabLog *tab_log, const PowTabExp *tab_exp, float *r0, float *r1) {
+                              const PowTabLog *tab_log, const PowTabExp *tab_exp, float *r0, float *r1,
+                              uint32_t abs_mask = 0xffffffffu, uint32_t sign_or = 0u) {
     uint32_t u0 = f2u(x0), u1 = f2u(x1);
     const uint32_t s0 = u0, s1 = u1;
-    if (SIGN != POW_SIGN_REJECT) { u0 &= 0x7fffffffu; u1 &= 0x7fffffffu; } // integer y: |x| from here on
+    if (SIGN == POW_SIGN_RUNTIME) { u0 &= abs_mask; u1 &= abs_mask; }
+    else if (SIGN != POW_SIGN_REJECT) { u0 &= 0x7fffffffu; u1 &= 0x7fffffffu; } // integer y: |x| from here on
     // ---- log2 |x|,  |x| = 2^E * m,  m in [1, 2) ----------------------------------
     const f2 m = f2_make(u2f((u0 & 0x007fffffu) | lane.c.one), u2f((u1 & 0x007fffffu) | lane.c.one));
     const PowTabLog t0 = pow_tab_log_at(tab_log, lane.log_off, u0), t1 = pow_tab_log_at(tab_log, lane.log_off, u1);
@@ -643,7 +648,8 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
     // underflow) go to the slow path, and so does every input that is not a normal number: a zero
     // or denormal has log2 <= -126 here, inf / NaN >= 128, a rejected negative base >= 129.
     const f2 rng = Y_LT_1 ? h3 : th;
-    const bool ok = fabsf(rng.x) < 125.0f && fabsf(rng.y) < 125.0f;
+    bool ok = fabsf(rng.x) < 125.0f && fabsf(rng.y) < 125.0f;
+    if (SIGN == POW_SIGN_RUNTIME) ok = ok && fabsf(h3.x) < 125.0f && fabsf(h3.y) < 125.0f; // |y| unknown: both
     // ---- 2^t --------------------------------------------------------------------
     const f2 shifter = f2_splat(12582912.0f);              // 1.5 * 2^23
     const f2 tk = f2_fma(th, f2_splat(lane.c.k64), shifter);    // low mantissa bits hold k = rint(64 th)
@@ -662,6 +668,7 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
     // (k & ~63) << 17 == n << 23 (the bias 0x4b400000 << 17 vanishes mod 2^32)
     uint32_t b0 = pow_scale_bits(k0, f2u(z0)), b1 = pow_scale_bits(k1, f2u(z1));
     if (SIGN == POW_SIGN_ODD) { b0 |= s0 & 0x80000000u; b1 |= s1 & 0x80000000u; } // keep the base's sign
+    if (SIGN == POW_SIGN_RUNTIME) { b0 |= s0 & sign_or; b1 |= s1 & sign_or; }
     *r0 = u2f(b0);
     *r1 = u2f(b1);
     return ok;

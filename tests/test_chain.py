@@ -120,10 +120,12 @@ def test_chain_float_pow_within_ulp_bound(orc, dt, bound):
     rng = np.random.default_rng(73)
     a = rng.uniform(0.01, 50, size=(128, 512)).astype(dt)
     b = rng.uniform(0.01, 50, size=(1, 512)).astype(dt)
-    for y in (2.0, 2.5, -0.75, 7.0):
+    for y in (2.0, 2.5, -0.75, 7.0, 11.5, -30.0):
         steps = [("add", b), ("pow", y)]
         _, base = oracle_chain(orc, a, steps)          # base = a + b, bit-exact
         got = smb.chain(a, *steps)
+        if dt == np.float32:
+            assert smb.last_kernel() == "k_chain<vec16,pow>", smb.last_kernel()   # the table-driven core, staged tables
         assert_same_bits(smb.chain(a, ("add", b)), base, "pow base")
         if dt == np.float32:
             err = oracle.ulp_error_f32(got.ravel(), orc.pow_ref_f32(base.ravel(), float(np.float32(y))))
@@ -134,6 +136,20 @@ def test_chain_float_pow_within_ulp_bound(orc, dt, bound):
         # and a step after the pow consumes the rounded power
         got2 = smb.chain(a, ("add", b), ("pow", y), ("mul", a))
         assert_same_bits(got2, orc.binary("mul", got, a), "step after pow")
+    # negative bases: integer exponents keep / drop the sign, non-integer ones give NaN; specials fall back
+    x = np.concatenate([rng.uniform(-50, 50, 4090), [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-42]]).astype(dt)
+    z = np.zeros_like(x)
+    for y in (3.0, 4.0, -3.0, 2.5, 0.5):
+        got = smb.chain(x, ("add", z), ("pow", y))
+        if dt == np.float32:
+            ref = orc.pow_ref_f32(orc.binary("add", x, z), float(np.float32(y)))   # (-0) + 0 is +0
+            with np.errstate(all="ignore"):
+                want = ref.astype(np.float32)
+            fin = np.isfinite(want) & (want != 0)
+            assert np.array_equal(np.isnan(got), np.isnan(want)), y
+            assert np.array_equal(got[~fin & ~np.isnan(want)], want[~fin & ~np.isnan(want)]), y
+            assert np.array_equal(np.signbit(got[~np.isnan(want)]), np.signbit(want[~np.isnan(want)])), y
+            assert oracle.ulp_error_f32(got[fin], ref[fin]).max() <= bound, y
 
 
 @pytest.mark.gpu

@@ -166,3 +166,52 @@ for npdt, tdt, n in ((np.float32, torch.float32, 1 << 28), (np.float64, torch.fl
     report(f"dot {np.dtype(npdt).name} {n} elements (operator%)", 2 * np.dtype(npdt).itemsize * n, n, ms, cpu_ms,
            "synchronous scalar result; CPU time scaled from a 2^24-element sample (single-threaded SIMD loop)")
     del xa, xb
+
+# §8(f) row 1: op-chain fusion.  One pass (smb_chain) beside the same work as separate operators
+# through this library (each materialising its temporary, as the reference's operators do).
+def chain_case(name, n, leaves_fn, unfused_fn, arrays_in, note=""):
+    ms = timed(leaves_fn, args.reps)
+    kern = smb.last_kernel()
+    ms_unfused = timed(unfused_fn, args.reps)
+    bytes_ = 4 * n * (arrays_in + 1)
+    row = {"config": name, "elements": n, "algorithmic_bytes": bytes_, "gpu_ms": ms, "gpu_gbs": bytes_ / ms / 1e6,
+           "gpu_gelem_s": n / ms / 1e6, "frac_measured_peak": bytes_ / ms / 1e6 / PEAK, "frac_nominal_8000": bytes_ / ms / 1e6 / 8000,
+           "kernel": kern, "unfused_ms": ms_unfused, "fusion_speedup": ms_unfused / ms, "note": note}
+    print(json.dumps(row), flush=True)
+
+
+n = 1 << 28
+fa, fb, fc, fd = (torch.rand(n, device="cuda") + 0.5 for _ in range(4))
+frow = torch.rand(16384, device="cuda")
+fo, ft1, ft2 = (torch.empty(n, device="cuda") for _ in range(3))
+P = lambda t: t.data_ptr()
+L = lambda op, t, st=(1,): (op, False, (P(t), list(st)))
+steps3 = smb.chain_steps(smb.F32, [L(None, fa), L("add", fb), L("mul", fc)], [n])
+chain_case("F1 f32 (a+b)*c, 2^28 elements, fused", n,
+           lambda: smb.lib().smb_chain(smb.F32, steps3, 3, smb._u64arr([n]), 1, n, P(fo), sp),
+           lambda: (smb.contiguous_ptr(smb.OP_ADD, smb.F32, P(fa), P(fb), P(ft1), n, sp),
+                    smb.contiguous_ptr(smb.OP_MUL, smb.F32, P(ft1), P(fc), P(fo), n, sp)), 3,
+           "unfused = 2 operators, 24 B/elem of traffic; fused 16 B/elem")
+steps5 = smb.chain_steps(smb.F32, [L(None, fa), L("add", fb), L("mul", fc), L("sub", fd), ("div", False, 3.0)], [n])
+chain_case("F2 f32 ((a+b)*c-d)/3, 2^28 elements, fused", n,
+           lambda: smb.lib().smb_chain(smb.F32, steps5, 5, smb._u64arr([n]), 1, n, P(fo), sp),
+           lambda: (smb.contiguous_ptr(smb.OP_ADD, smb.F32, P(fa), P(fb), P(ft1), n, sp),
+                    smb.contiguous_ptr(smb.OP_MUL, smb.F32, P(ft1), P(fc), P(ft2), n, sp),
+                    smb.contiguous_ptr(smb.OP_SUB, smb.F32, P(ft2), P(fd), P(ft1), n, sp),
+                    smb.array_scalar_ptr(smb.OP_DIV, smb.F32, P(ft1), 3.0, n, P(fo), sp)), 4,
+           "unfused = 4 operators, 44 B/elem; fused 20 B/elem")
+sh = [16384, 16384]
+stepsb = smb.chain_steps(smb.F32, [(None, False, (P(fa), [16384, 1])), ("mul", False, (P(frow), [0, 1])), ("add", False, (P(fb), [16384, 1]))], sh)
+chain_case("F3 f32 a*row+b, {16384,16384} with a {1,16384} row, fused", n,
+           lambda: smb.lib().smb_chain(smb.F32, stepsb, 3, smb._u64arr(sh), 2, n, P(fo), sp),
+           lambda: (smb.elementwise_ptr(smb.OP_MUL, smb.F32, P(fa), [16384, 1], P(frow), [0, 1], sh, P(ft1), sp),
+                    smb.contiguous_ptr(smb.OP_ADD, smb.F32, P(ft1), P(fb), P(fo), n, sp)), 2,
+           "broadcast leaf inside the chain")
+smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+stepsp = smb.chain_steps(smb.F32, [L(None, fa), L("add", fb), ("pow", False, 2.5)], [n])
+chain_case("F4 f32 pow(a+b, 2.5), 2^28 elements, fused", n,
+           lambda: smb.lib().smb_chain(smb.F32, stepsp, 3, smb._u64arr([n]), 1, n, P(fo), sp),
+           lambda: (smb.contiguous_ptr(smb.OP_ADD, smb.F32, P(fa), P(fb), P(ft1), n, sp),
+                    smb.array_scalar_ptr(smb.OP_POW, smb.F32, P(ft1), 2.5, n, P(fo), sp)), 2,
+           "sm::pow(a+b, e) in one pass")
+smb.set_option(smb.OPT_POW_SPECIALISE, 1)
