@@ -928,13 +928,13 @@ static int chain_launch(const DeviceCtx &c, const ChainPlan &p, const smb_chain_
             powfast = true;
         }
     }
-    t.tiles_per_cta = powfast ? 8 : 1; // amortise the 24 KB table copy, stay many waves deep
+    t.tiles_per_cta = powfast ? 32 : 1; // amortise the 24 KB table copy, stay many waves deep
     // compiled-in chain capacity / vectors per thread: short chains keep more loads in flight
 #define SMB_CHAIN_LAUNCH(E, W, NS, U, PF)                                                                         \
     k_chain<T, E, W, NS, U, PF><<<grid_for(items, (uint64_t)kThreads * U * t.tiles_per_cta, c.sm_count, 0), kThreads, 0, s>>>(out, t)
 #define SMB_CHAIN_BY_LEN(E, W, PF)                                                                \
     do {                                                                                          \
-        if (p.nleaf <= 3 && PF) SMB_CHAIN_LAUNCH(E, W, 3, 2, PF); /* pow: fewer registers, more CTAs */ \
+        if (p.nleaf <= 3 && PF) SMB_CHAIN_LAUNCH(E, W, 3, 1, PF); /* pow: fewer registers, more CTAs */ \
         else if (p.nleaf <= 3) SMB_CHAIN_LAUNCH(E, W, 3, 4, PF);                                  \
         else if (p.nleaf <= 5) SMB_CHAIN_LAUNCH(E, W, 5, 2, PF);                                  \
         else SMB_CHAIN_LAUNCH(E, W, 8, 1, PF);                                                    \

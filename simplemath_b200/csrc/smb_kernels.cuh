@@ -929,33 +929,11 @@ enum { CH_ADD = 0, CH_SUB = 1, CH_MUL = 2, CH_DIV = 3, CH_POW = 4, CH_RSUB = 5, 
 // NS: compiled-in capacity of the chain (leaf registers); UNROLL: vectors per thread, all of whose
 // leaf loads are issued before the first operator (UNROLL * NS independent loads in flight per
 // thread -- a single vector per thread left HBM half idle).  One tile of 256 * UNROLL vectors per CTA.
-// POWFAST (float, EPV == 4): the large-y pow tables are staged per CTA (one bulk copy, overlapped
-// with the first tile's loads) and a pow step goes through the FFMA2 core, two elements per call,
-// the reference-accuracy path only for the vectors it declines -- sm::pow(a + b, e) in one pass.
-template<typename T, int EPV, bool WIDE, int NS, int UNROLL, bool POWFAST>
-__global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid_constant__ ChainTable t) {
-    const uint64_t nvec = t.count / EPV; // host guarantees count % EPV == 0
-    [[maybe_unused]] PowLane lane;
-    [[maybe_unused]] __shared__ __align__(8) uint64_t tab_bar;
-    if constexpr (POWFAST) {
-        if (threadIdx.x == 0) {
-            mbar_init(&tab_bar, 1);
-            mbar_expect_tx(&tab_bar, (uint32_t)sizeof(SmbPowTabs));
-            bulk_g2s(&smb_s_pow, &g_pow_image[t.pow_small ? 0 : 1], (uint32_t)sizeof(SmbPowTabs), &tab_bar);
-        }
-        lane = pow_lane(threadIdx.x, t.pow_consts);
-        __syncthreads();
-    }
-    const uint64_t ntiles = (nvec + kBlock * UNROLL - 1) / (kBlock * UNROLL);
-    // plain chains: exactly one tile per CTA (the loop below folds away); POWFAST: a few consecutive ones
-    const uint32_t tpc = POWFAST ? t.tiles_per_cta : 1u;
-    uint64_t tile = (uint64_t)blockIdx.x * tpc;
-    if (tile >= ntiles) return;
-    const uint64_t tile_end = POWFAST ? (tile + tpc < ntiles ? tile + tpc : ntiles) : tile + 1;
-#pragma unroll 1
-    for (bool first_tile = true; tile < tile_end; ++tile, first_tile = false) {
+// One tile (256 * UNROLL vectors) of leaf loads.  PIN: ordinary (coherent) loads, which ptxas keeps
+// on their side of a warp barrier -- the prefetch of the POWFAST loop must stay ahead of the math.
+template<typename T, int EPV, bool WIDE, int NS, int UNROLL, bool PIN>
+__device__ __forceinline__ void chain_load(const ChainTable &t, uint64_t tile, uint64_t nvec, T (&leaf)[UNROLL][NS][EPV]) {
     const uint64_t v0 = tile * (kBlock * UNROLL) + threadIdx.x;
-    T leaf[UNROLL][NS][EPV];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         const uint64_t v = v0 + (uint64_t)u * kBlock;
@@ -996,7 +974,8 @@ __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid
                         if (k < t.ndim) off += idx[k] * t.stride[s][k];
                     if (EPV > 1 && t.stride[s][t.ndim - 1] == 1) {
                         Pack<T, 16> pk; // EPV * sizeof(T) == 16
-                        pk.raw = VecIO<16, false>::load(base + off);
+                        if (PIN) pk.raw = load_stream_pinned(reinterpret_cast<const RawVec<16> *>(base + off));
+                        else pk.raw = VecIO<16, false>::load(base + off);
 #pragma unroll
                         for (int e = 0; e < EPV; ++e) leaf[u][s][e] = pk.e[e];
                     } else {
@@ -1008,14 +987,15 @@ __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid
             }
         }
     }
-    if constexpr (POWFAST) {
-        if (first_tile) {
-            mbar_wait(&tab_bar, 0); // the tables have landed
-            asm volatile("" : "+r"(lane.log_off), "+r"(lane.exp_off) :: "memory"); // ties the lookups to the wait
-        }
-    }
-    // the operators: ONE uniform switch per step, straight-line code over every element the thread
-    // holds inside each case (a switch per element made the kernel branch-bound)
+}
+
+// The operators of one tile and its stores: ONE uniform switch per step, straight-line code over
+// every element the thread holds inside each case (a switch per element made the kernel
+// branch-bound).
+template<typename T, int EPV, int NS, int UNROLL, bool POWFAST>
+__device__ __forceinline__ void chain_compute(const ChainTable &t, uint64_t tile, uint64_t nvec, const T (&leaf)[UNROLL][NS][EPV],
+                                              T *__restrict__ out, [[maybe_unused]] const PowLane &lane) {
+    const uint64_t v0 = tile * (kBlock * UNROLL) + threadIdx.x;
     T acc[UNROLL][EPV];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
@@ -1092,7 +1072,49 @@ __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid
             }
         }
     }
-    } // tiles
+}
+
+// POWFAST (float, EPV == 4): the pow tables are staged per CTA (one bulk copy, overlapped with the
+// first tile's loads) and a pow step goes through the FFMA2 core, two elements per call, the
+// reference-accuracy path only for the vectors it declines -- sm::pow(a + b, e) in one pass.  Such a
+// CTA runs several consecutive tiles to amortise the copy; plain chains run one tile per CTA.
+template<typename T, int EPV, bool WIDE, int NS, int UNROLL, bool POWFAST>
+__global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid_constant__ ChainTable t) {
+    const uint64_t nvec = t.count / EPV; // host guarantees count % EPV == 0
+    const uint64_t ntiles = (nvec + kBlock * UNROLL - 1) / (kBlock * UNROLL);
+    if constexpr (!POWFAST) {
+        const uint64_t tile = blockIdx.x;
+        if (tile >= ntiles) return;
+        T leaf[UNROLL][NS][EPV];
+        chain_load<T, EPV, WIDE, NS, UNROLL, false>(t, tile, nvec, leaf);
+        chain_compute<T, EPV, NS, UNROLL, false>(t, tile, nvec, leaf, out, PowLane{});
+    } else {
+        __shared__ __align__(8) uint64_t tab_bar;
+        if (threadIdx.x == 0) {
+            mbar_init(&tab_bar, 1);
+            mbar_expect_tx(&tab_bar, (uint32_t)sizeof(SmbPowTabs));
+            bulk_g2s(&smb_s_pow, &g_pow_image[t.pow_small ? 0 : 1], (uint32_t)sizeof(SmbPowTabs), &tab_bar);
+        }
+        PowLane lane = pow_lane(threadIdx.x, t.pow_consts);
+        __syncthreads(); // the barrier is initialised before anyone waits on it
+        uint64_t tile = (uint64_t)blockIdx.x * t.tiles_per_cta;
+        const uint64_t tile_end = tile + t.tiles_per_cta < ntiles ? tile + t.tiles_per_cta : ntiles;
+        if (tile >= tile_end) return;
+        // No register prefetch here: with the leaf buffers doubled the kernel drops to two CTAs per
+        // SM and measured slower; occupancy (one vector per thread, four CTAs) hides the loads instead.
+        bool first = true;
+#pragma unroll 1
+        for (; tile < tile_end; ++tile) {
+            T leaf[UNROLL][NS][EPV];
+            chain_load<T, EPV, WIDE, NS, UNROLL, false>(t, tile, nvec, leaf);
+            if (first) {
+                mbar_wait(&tab_bar, 0); // the tables have landed (the copy overlapped the loads above)
+                asm volatile("" : "+r"(lane.log_off), "+r"(lane.exp_off) :: "memory"); // ties the lookups to the wait
+                first = false;
+            }
+            chain_compute<T, EPV, NS, UNROLL, true>(t, tile, nvec, leaf, out, lane);
+        }
+    }
 }
 
 // k_generic: arbitrary element strides; one output element per thread per
