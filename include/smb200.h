@@ -78,8 +78,9 @@ enum {
     SMB_OPT_POW_SPECIALISE = 0,
     /* Bytes per staging chunk of the host-operand pipeline (default 64 MiB). */
     SMB_OPT_STAGE_CHUNK_BYTES = 1,
-    /* Dense-stream kernels: cap the grid at this many CTAs per SM (0 = library default:
-     * one tile per CTA for plain streams, 8 per SM for the table-driven f32 pow). */
+    /* Dense-stream kernels: cap the grid at this many CTAs per SM (0 = library default: one tile
+     * per CTA).  For the table-driven pow kernels the value counts consecutive TILES PER CTA
+     * instead (0 = default: 8 for f32, 32 for f64). */
     SMB_OPT_CONTIG_VARIANT = 2,
     /* Broadcast kernel: 1 = stage a small reused operand in shared memory (cp.async.bulk);
      * 0 (default) = read it through L1/L2, which measured faster on B200; 2 = also disable
