@@ -159,13 +159,17 @@ namespace sm {
             return view;
         }
 
-        // Host-side data movement, outside the accelerated path.  np.repeat
-        // semantics (each element repeated in place along the flattened array /
-        // along `axis`); the reference's 1-D loop (SMArray.h:138-160) writes
-        // newData[i + j] and leaves most of its result uninitialised.
+        // np.repeat semantics (each element repeated in place along the flattened array / along
+        // `axis`); the reference's 1-D loop (SMArray.h:138-160) writes newData[i + j] and leaves most
+        // of its result uninitialised.  Runs on the device: the result is
+        // the input broadcast along an inserted stride-0 dim, materialised by a one-leaf smb_chain
+        // (the reference's serial host loop would also pull the managed pages back to the host).
         SMArray repeat(int numberOfRepeats) const {
             assert(numberOfRepeats > 1);
             const size_t reps = static_cast<size_t>(numberOfRepeats);
+            if constexpr (requires { smb::DTypeTag<T>::value; }) {
+                if (isDense()) return broadcastCopy({totalSize, reps}, {1, 0}, {totalSize * reps});
+            }
             T *fresh = storage::acquire<T>(totalSize * reps);
             for (size_t i = 0; i < totalSize; ++i)
                 for (size_t j = 0; j < reps; ++j) fresh[i * reps + j] = data[i];
@@ -178,6 +182,14 @@ namespace sm {
             const size_t reps = static_cast<size_t>(numberOfRepeats);
             std::vector<size_t> newShape = _shape;
             newShape[axis] *= reps;
+            if constexpr (requires { smb::DTypeTag<T>::value; }) {
+                if (ndim < MAX_NDIM) { // {.., shape[axis], reps, ..} with stride 0 on the inserted dim; views welcome
+                    std::vector<size_t> shape = _shape, strides = _strides;
+                    shape.insert(shape.begin() + axis + 1, reps);
+                    strides.insert(strides.begin() + axis + 1, 0);
+                    return broadcastCopy(std::move(shape), std::move(strides), std::move(newShape));
+                }
+            }
             size_t inner = 1;
             for (size_t k = axis + 1; k < ndim; ++k) inner *= _shape[k];
             const size_t outer = totalSize / (inner * _shape[axis]);
@@ -250,6 +262,24 @@ namespace sm {
         }
 
         bool isDense() const { return is_contiguous(_shape, _strides); }
+
+        // Dense copy of this array's data seen through (shape, strides) -- stride 0 repeats -- made on
+        // the device by a one-leaf chain; the result gets `resultShape` (same element count).
+        SMArray broadcastCopy(std::vector<size_t> shape, std::vector<size_t> strides, std::vector<size_t> resultShape) const {
+            const size_t n = calculateTotalSize(shape);
+            smb_chain_step leaf{};
+            leaf.data = data;
+            for (size_t k = 0; k < shape.size(); ++k) leaf.stride[k] = strides[k];
+            T *fresh = storage::acquire<T>(n);
+            try {
+                smb::check(smb_chain(smb::DTypeTag<T>::value, &leaf, 1, smb::u64(shape), static_cast<int>(shape.size()), n, fresh,
+                                     nullptr));
+            } catch (...) {
+                storage::release(fresh);
+                throw;
+            }
+            return SMArray(fresh, std::move(resultShape));
+        }
 
         // SMArray (op) SMArray: broadcast -> fresh dense result -> element_wise_op
         // (reference SMArray.h:217-225 and siblings).

@@ -191,6 +191,29 @@ TEST(DropIn, LazyChainsAreBitIdenticalToTheEagerOperators) {
     for (size_t i = 0; i < R * C; ++i) ASSERT_EQ(longc.data[i], le.data[i]);
 }
 
+TEST(DropIn, RepeatRunsOnTheDeviceWithNumpySemantics) {
+    sm::SMArray<int> v = {1, 2, 3};
+    const uint64_t l0 = smb_launch_count();
+    auto r = v.repeat(3);
+    EXPECT_EQ(smb_launch_count(), l0 + 1);                       // one device kernel, no host loop
+    const int want[] = {1, 1, 1, 2, 2, 2, 3, 3, 3};
+    ASSERT_EQ(r.totalSize, 9u);
+    for (int i = 0; i < 9; ++i) EXPECT_EQ(r.data[i], want[i]);
+    sm::SMArray<float> m = {{1, 2, 3}, {4, 5, 6}};
+    auto r0 = m.repeat(2, 0), r1 = m.repeat(2, 1);
+    std::vector<size_t> s0 = {4, 3}, s1 = {2, 6};
+    EXPECT_EQ(r0.shape(), s0); EXPECT_EQ(r1.shape(), s1);
+    const float w0[] = {1, 2, 3, 1, 2, 3, 4, 5, 6, 4, 5, 6}, w1[] = {1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6};
+    for (int i = 0; i < 12; ++i) { EXPECT_EQ(r0.data[i], w0[i]); EXPECT_EQ(r1.data[i], w1[i]); }
+    auto t = m.transpose().repeat(2, 1);                         // a view as input: {3,2} -> {3,4}
+    const float wt[] = {1, 1, 4, 4, 2, 2, 5, 5, 3, 3, 6, 6};
+    for (int i = 0; i < 12; ++i) EXPECT_EQ(t.data[i], wt[i]);
+    auto big = sm::ones<double>(1000, 257);
+    big(3, 5) = 7.0;
+    auto rb = big.repeat(3, 1);
+    EXPECT_EQ(rb(3, 15), 7.0); EXPECT_EQ(rb(3, 16), 7.0); EXPECT_EQ(rb(3, 17), 7.0); EXPECT_EQ(rb(3, 18), 1.0); EXPECT_EQ(rb(999, 770), 1.0);
+}
+
 TEST(DropIn, LazyPowJoinsTheChain) {
     auto a = sm::empty<float>(64, 64), b = sm::ones<float>(1, 64);
     for (size_t i = 0; i < 64 * 64; ++i) a.data[i] = 0.01f + 0.013f * float(i);

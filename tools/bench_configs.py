@@ -134,6 +134,13 @@ ib = rng.integers(1, 98, size=(1, 512, 1024)).astype(np.int32)
 binary_case("C4 i32 {512,1,1024}*{1,512,1024}", "mul", ia, ib, "write-dominated: 1 GiB out, 4 MiB in")
 binary_case("C4 i32 {512,1,1024}/{1,512,1024}", "div", ia, ib, "integer division is instruction-bound")
 
+# dense int32 division (no operand reuse: 12 B/elem), and by a scalar (8 B/elem)
+ia = rng.integers(-2**31, 2**31, size=1 << 28, dtype=np.int64).astype(np.int32)
+ib = rng.integers(1, 1 << 20, size=1 << 28).astype(np.int32)
+binary_case("I1 i32 contiguous a/b, 2^28 elements", "div", ia, ib)
+scalar_case("I2 i32 a/7, 2^28 elements", "div", ia, 7)
+del ia, ib
+
 # strided operand: a.transpose() + b (generic element strides; no reference test covers it)
 def transposed_case(name, n0, n1):
     a = torch.rand(n1 * n0, device="cuda")  # a is {n1, n0} dense; a^T has shape {n0, n1}, strides {1, n0}
