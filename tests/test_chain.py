@@ -53,7 +53,48 @@ def test_chain_step_struct_matches_header():
     assert ctypes.sizeof(smb.ChainStep) == 4 + 4 + 8 + 8 * smb.MAX_NDIM + 8
 
 
+def load_golden_chains():
+    """tests/golden/golden_chain_v1.npz: chains evaluated operator by operator on the UNMODIFIED
+    reference (oracle/make_golden_chain.py).  Yields (first, steps, out); a "fix" entry replaces the
+    accumulator before a `leaf / acc` step (the generator made it a safe divisor), so such a chain
+    is checked in two pieces."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_chain_v1.npz"))
+    i = 0
+    while f"k{i:03d}_first" in z:
+        p = f"k{i:03d}_"
+        ops = [str(o) for o in z[p + "ops"]]
+        first, steps = z[p + "first"], []
+        for s, op in enumerate(ops):
+            if p + f"fix{s}" in z:            # restart from the injected intermediate
+                first, steps = z[p + f"fix{s}"], []
+            leaf = z[p + f"leaf{s}"]
+            steps.append((op, leaf if leaf.ndim else leaf.item()))
+        yield i, first, steps, z[p + "out"]
+        i += 1
+
+
+def test_golden_chain_fixtures_agree_with_the_oracle(orc):
+    """The oracle's operator-by-operator chain reproduces the reference's (pins oracle_chain below)."""
+    n = 0
+    for i, first, steps, out in load_golden_chains():
+        want, _ = oracle_chain(orc, first, steps)
+        assert_same_bits(np.asarray(want).reshape(out.shape), out, f"golden chain {i}")
+        n += 1
+    assert n == 38
+
+
 # ------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_chain_matches_reference_golden_fixtures():
+    """Fused smb_chain against outputs of the unmodified reference's separate operators, bit for bit."""
+    n = 0
+    for i, first, steps, out in load_golden_chains():
+        assert_same_bits(smb.chain(first, *steps).reshape(out.shape), out, f"golden chain {i}: {[s[0] for s in steps]}")
+        n += 1
+    assert n == 38
+
+
 pytestmark_gpu = pytest.mark.gpu
 
 
