@@ -7,7 +7,8 @@ Workload "C5": float32, n = 2^30 elements (4 GiB per array), contiguous:
                                      general exp2(y*log2 x) kernel) }
 sharded across the N GPUs by flat output index range (rank g owns
 shard_range(n, g, N)); no collective on the data path.  Total work is fixed as N
-grows -> "scaling": "strong".
+grows -> "scaling": "strong" (the default: BASELINE config C5 shards 4 GiB arrays);
+--scaling weak keeps 2^30 elements per GPU instead.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]       this repo's CUDA path
     python bench.py --impl reference ...                      the reference's own CPU
@@ -50,6 +51,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="smb200", choices=["smb200", "reference"])
     ap.add_argument("--elems", type=int, default=N_TOTAL, help="total elements (default 2^30 = config C5)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE config C5): --elems is the TOTAL, sharded over the ranks; "
+                         "weak: --elems per GPU, the job grows with N")
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
+                    help="2 (default): the step's two independent operators go to two streams; 1: one stream")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -216,7 +222,7 @@ def run_smb(args):
         os.environ["NCCL_DEBUG"] = os.environ.get("SMB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    n = args.elems
+    n = args.elems * (world if args.scaling == "weak" else 1)
     lo, hi = smb.shard_range(n, rank, world, align=4096)
     m = hi - lo  # this rank's shard
     stream = torch.cuda.current_stream()
@@ -232,9 +238,16 @@ def run_smb(args):
     smb.fill_uniform_f32_ptr(x.data_ptr(), lo, m, 3, 0.01, 100.0, sp)
     smb.set_option(smb.OPT_POW_SPECIALISE, 0)  # headline = the general pow kernel
 
+    # The step's two operators are independent (a+b -> out, pow(x) -> pw): with --streams 2 (default)
+    # they are enqueued on two streams, so one kernel's last wave overlaps the other's first --
+    # ~15 us per launch that only shows once the shards get small (N = 8).  Each stream keeps its own
+    # operator in order from step to step; the timed region joins both.
+    stream2 = torch.cuda.Stream(device=dev) if args.streams == 2 else stream
+    sp2 = stream2.cuda_stream
+
     def step():
         smb.contiguous_ptr(smb.OP_ADD, smb.F32, a.data_ptr(), b.data_ptr(), out.data_ptr(), m, sp)
-        smb.array_scalar_ptr(smb.OP_POW, smb.F32, x.data_ptr(), POW_Y, m, pw.data_ptr(), sp)
+        smb.array_scalar_ptr(smb.OP_POW, smb.F32, x.data_ptr(), POW_Y, m, pw.data_ptr(), sp2)
 
     def barrier():
         if world > 1:
@@ -244,11 +257,17 @@ def run_smb(args):
     def timed(fn, reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        if stream2 is not stream:
+            stream2.wait_event(e0)          # the second stream starts inside the timed region ...
         for _ in range(reps):
             fn()
+        if stream2 is not stream:
+            j = torch.cuda.Event()
+            j.record(stream2)
+            stream.wait_event(j)            # ... and the closing event waits for it
         e1.record(stream)
         e1.synchronize()
-        return e0.elapsed_time(e1)  # ms, on the launching stream
+        return e0.elapsed_time(e1)  # ms, on the launching stream(s)
 
     def max_ranks(ms):
         if world == 1:
@@ -399,11 +418,12 @@ def run_smb(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "C5: f32 contiguous add (a+b) + pow(x, 2.5) on 2^30-element (4 GiB) arrays, sharded by "
-                                   "flat output index range", "elements": n, "elements_per_gpu": m, "pow_exponent": POW_Y,
+                                   "flat output index range" + (" (weak: 2^30 elements PER GPU)" if args.scaling == "weak" else ""), "elements": n, "elements_per_gpu": m, "pow_exponent": POW_Y,
                        "pow_kernel": "general exp2(y*log2 x), specialisation off", "parallelism": f"flat-range shards x{world}",
+                       "streams": args.streams,
                        "l2": f"inputs larger than L2 ({m * 4 >> 20} MiB per array per GPU vs 126 MiB L2)",
                        "inputs": "splitmix64 counter generator of the flat index, produced in HBM"},
             "elements_per_s": n / (ms_step * 1e-3),
