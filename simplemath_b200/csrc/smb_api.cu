@@ -384,9 +384,14 @@ int scalar_t<double>(const DeviceCtx &c, int op, const double *a, double v, doub
                 if (v == 0.5) return launch_stream<T, PowSpecialFn<POWS_SQRT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
                 if (v == 1.0) return launch_stream<T, PowSpecialFn<POWS_IDENT, T>, false>(c, a, nullptr, out, n, first, {lane_end}, s);
             }
-            if (classify_exp(v).y_is_odd)
-                return launch_stream<T, PowF64Fn<true>, false>(c, a, nullptr, out, n, first, PowF64Fn<true>::make(v, lane_end), s);
-            return launch_stream<T, PowF64Fn<false>, false>(c, a, nullptr, out, n, first, PowF64Fn<false>::make(v, lane_end), s);
+            {
+                const PowExpF64 pe = classify_exp(v);
+                const bool small = pow_f64_small_y(pe), odd = pe.y_is_odd != 0;
+#define SMB_POW64_LAUNCH(S, O) launch_stream<T, PowF64Fn<S, O>, false>(c, a, nullptr, out, n, first, PowF64Fn<S, O>::make(v, lane_end), s)
+                if (small) return odd ? SMB_POW64_LAUNCH(true, true) : SMB_POW64_LAUNCH(true, false);
+                return odd ? SMB_POW64_LAUNCH(false, true) : SMB_POW64_LAUNCH(false, false);
+#undef SMB_POW64_LAUNCH
+            }
         }
     }
     return fail(SMB_ERR_INVALID, "unknown op %d", op);

@@ -256,7 +256,7 @@ __device__ __noinline__ double pow_f64_slow(double x, PowExpF64 pe) { return pow
 static __device__ const PowTabLog64 d_pow64_log_tab[SMB_POW_LOG_ENTRIES] = SMB_POW64_LOG_TABLE_INIT;
 static __device__ const PowTabExp64 d_pow64_exp_tab[SMB_POW_EXP_ENTRIES] = SMB_POW64_EXP_TABLE_INIT;
 
-template<bool ODD_Y> struct PowF64Fn {
+template<bool SMALL_Y, bool ODD_Y> struct PowF64Fn {
     static constexpr bool CHECKED = true;
     static constexpr bool POW_TABLES = true;
     PowExpF64 pe;
@@ -269,7 +269,7 @@ template<bool ODD_Y> struct PowF64Fn {
     __device__ __forceinline__ double operator()(double a, double, uint64_t) const { return pow_f64_slow(a, pe); }
     __device__ __forceinline__ double slow(double a) const { return pow_f64(a, pe); } // inlined, see pow_tile
     __device__ __forceinline__ bool fast(double a, double &r) const {
-        return pow_f64_fast<ODD_Y>(a, pe.y, sign_reject, tab_a, tab_b, tab_exp, &r) && fast_ok != 0;
+        return pow_f64_fast<SMALL_Y, ODD_Y>(a, pe.y, sign_reject, tab_a, tab_b, tab_exp, &r) && fast_ok != 0;
     }
     __device__ __forceinline__ void block_wait() {}
     __device__ __forceinline__ void block_init() { // 40 KB, every entry replicated per wavefront lane
@@ -302,7 +302,7 @@ template<bool ODD_Y> struct PowF64Fn {
         return fn;
     }
 };
-template<> struct ScalarFn<OP_POW, double> : PowF64Fn<true> {};
+template<> struct ScalarFn<OP_POW, double> : PowF64Fn<false, true> {};
 
 template<typename Fn, typename = void> struct fn_pairwise : std::false_type {};
 template<typename Fn> struct fn_pairwise<Fn, std::void_t<decltype(Fn::PAIRWISE)>> : std::bool_constant<Fn::PAIRWISE> {};

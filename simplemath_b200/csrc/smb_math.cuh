@@ -892,13 +892,17 @@ struct PowTabExp64 { double t_hi, t_lo; };
 #define SMB_POW64_EXP_STRIDE 1
 #endif
 
+SMB_HD bool pow_f64_small_y(const PowExpF64 &pe) { return (d2u(pe.y) & 0x7fffffffffffffffull) <= 0x4020000000000000ull; } // |y| <= 8
 SMB_HD bool pow_f64_fast_ok(const PowExpF64 &pe) {
     const uint64_t ay = d2u(pe.y) & 0x7fffffffffffffffull;
     // finite, non-zero, 2^-400 < |y| < 2^400: y*log2 x can neither overflow nor go denormal
     return pe.y_class == 0 && ay < 0x58f0000000000000ull && ay > 0x26f0000000000000ull;
 }
 
-template<bool ODD_Y>
+// SMALL_Y (|y| <= 8, chosen on the host): the rounding error of m + c (2^-53 relative in p, below
+// 2^-59.9 absolute in log2 x) and the renormalisation of the log2 tail are dropped -- they only matter
+// once multiplied by a large exponent.
+template<bool SMALL_Y, bool ODD_Y>
 SMB_HD bool pow_f64_fast(double x, double y, uint64_t sign_reject, const PowTabLog64A *tab_a, const PowTabLog64B *tab_b,
                          const PowTabExp64 *tab_exp, double *out) {
     const uint64_t u = d2u(x);
@@ -912,12 +916,14 @@ SMB_HD bool pow_f64_fast(double x, double y, uint64_t sign_reject, const PowTabL
     const double t_l_lo = tab_b[j * SMB_POW64_B_STRIDE].l_lo;
     const double num = dsub(m, t.c);                       // exact
     const double den = dfma(m, 2.0, -num);                 // m + c, one rounding
-    const double den_lo = dsub(dfma(m, 2.0, -den), num);   // exact error of den
     double r = (double)rcp_seed((float)den);
     r = dfma(r, dfma(-den, r, 1.0), r);                    // one Newton step: 2^-44
     const double p_hi = dmul(num, r);
     double res = dfma(-p_hi, den, num);
-    res = dfma(-p_hi, den_lo, res);
+    if (!SMALL_Y) {
+        const double den_lo = dsub(dfma(m, 2.0, -den), num);   // exact error of den
+        res = dfma(-p_hi, den_lo, res);
+    }
     const double p_lo = dmul(res, r);
     const double s = dmul(p_hi, p_hi);
     double q = dfma(s, 0.3205988979753252, 0.4121985831111324);
@@ -933,8 +939,11 @@ SMB_HD bool pow_f64_fast(double x, double y, uint64_t sign_reject, const PowTabL
     const double h2 = dadd(h1, lh);                        // fast two-sum: |h1| >= |lh| or h1 == 0
     const double l2 = dadd(dsub(h1, h2), lh);
     const double lo_raw = dadd(dadd(t_l_lo, l2), ll);
-    const double h3 = dadd(h2, lo_raw);
-    const double lo = dadd(dsub(h2, h3), lo_raw);
+    double h3 = h2, lo = lo_raw;
+    if (!SMALL_Y) { // renormalise: the tail alone can reach 2^-41, too coarse once multiplied by a large y
+        h3 = dadd(h2, lo_raw);
+        lo = dadd(dsub(h2, h3), lo_raw);
+    }
     const double th = dmul(y, h3);
     double tl = dfma(y, h3, -th);
     tl = dfma(y, lo, tl);

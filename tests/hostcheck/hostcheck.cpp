@@ -71,13 +71,14 @@ static const bool kLog64Split = [] {
 // The f64 kernel's own path: table-driven fast core, pow_f64 for declined elements.
 void hc_pow_f64_fast(const double *x, double y, uint64_t n, double *out, uint64_t *declined) {
     PowExpF64 pe = classify_exp(y);
-    const bool fast = pow_f64_fast_ok(pe), odd = pe.y_is_odd != 0;
+    const bool fast = pow_f64_fast_ok(pe), odd = pe.y_is_odd != 0, small = pow_f64_small_y(pe);
     const uint64_t rej = pe.y_is_int ? 0ull : 0x8000000000000000ull;
     uint64_t dec = 0;
     #pragma omp parallel for schedule(static) reduction(+:dec)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         double r;
-        const bool ok = odd ? pow_f64_fast<true>(x[i], y, rej, kLog64A, kLog64B, kExp64, &r) : pow_f64_fast<false>(x[i], y, rej, kLog64A, kLog64B, kExp64, &r);
+        const bool ok = small ? (odd ? pow_f64_fast<true, true>(x[i], y, rej, kLog64A, kLog64B, kExp64, &r) : pow_f64_fast<true, false>(x[i], y, rej, kLog64A, kLog64B, kExp64, &r))
+                              : (odd ? pow_f64_fast<false, true>(x[i], y, rej, kLog64A, kLog64B, kExp64, &r) : pow_f64_fast<false, false>(x[i], y, rej, kLog64A, kLog64B, kExp64, &r));
         if (ok && fast) out[i] = r;
         else { out[i] = pow_f64(x[i], pe); ++dec; }
     }
