@@ -19,7 +19,7 @@ from typing import Sequence
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsmb200.so")
+LIB_PATH = os.environ.get("SMB200_LIB") or os.path.join(HERE, "libsmb200.so")  # SMB200_LIB: a variant build (tools/ A/B runs)
 
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW = range(5)
 F32, F64, I32 = range(3)

@@ -32,6 +32,9 @@ constexpr int kBlock = 256; // threads per CTA of every kernel in this file
 #ifndef SMB_POW_SCHED_FENCE
 #define SMB_POW_SCHED_FENCE() __syncwarp()
 #endif
+#ifndef SMB_POW64_MIN_BLOCKS
+#define SMB_POW64_MIN_BLOCKS 3 // resident CTAs per SM the f64 pow kernel is compiled for
+#endif
 #ifndef SMB_POW_MIN_BLOCKS
 #define SMB_POW_MIN_BLOCKS 3 // resident CTAs per SM the f32 pow kernel is compiled for
 #endif
@@ -441,7 +444,7 @@ __device__ __forceinline__ void pow_tile(const Pack<T, VB> (&in)[UNROLL], const 
 }
 
 template<typename T, typename Fn, bool HAS_B, int VB, int UNROLL>
-__global__ void __launch_bounds__(256, (fn_pow_tables<Fn>::value && sizeof(T) == 4) ? SMB_POW_MIN_BLOCKS : 2) k_stream(const T *__restrict__ a, const T *__restrict__ b,
+__global__ void __launch_bounds__(256, fn_pow_tables<Fn>::value ? (sizeof(T) == 4 ? SMB_POW_MIN_BLOCKS : SMB_POW64_MIN_BLOCKS) : 2) k_stream(const T *__restrict__ a, const T *__restrict__ b,
                                                T *__restrict__ out, uint64_t n, uint64_t first, Fn fn_in) {
     constexpr int EPV = VB / (int)sizeof(T); // elements per vector
     Fn fn = fn_in;
