@@ -352,16 +352,18 @@ int scalar_t<float>(const DeviceCtx &c, int op, const float *a, float v, float *
                 const PowExpF32 pe = classify_exp(v);
                 if (!pow_f32_fast_ok(pe)) // |y| >= 2^64, tiny, zero, inf or NaN: the reference-accuracy path alone
                     return launch_stream<T, PowF32SlowFn, false>(c, a, nullptr, out, n, first, PowF32SlowFn::make(v, lane_end), s);
-                const bool small = pow_f32_small_y(pe), lt1 = pow_f32_y_lt_1(pe);
-                const int sign = pow_f32_sign_mode(pe);
+                const bool lt1 = pow_f32_y_lt_1(pe);
+                const int tier = pow_f32_tier(pe), sign = pow_f32_sign_mode(pe);
 #define SMB_POW_LAUNCH(S, G, L) launch_stream<T, PowF32Fn<S, G, L>, false>(c, a, nullptr, out, n, first, PowF32Fn<S, G, L>::make(v, lane_end), s)
-                if (lt1) return SMB_POW_LAUNCH(true, POW_SIGN_REJECT, true); // 0 < |y| < 1 is never an integer
-                if (small) return sign == POW_SIGN_REJECT ? SMB_POW_LAUNCH(true, POW_SIGN_REJECT, false)
-                                : sign == POW_SIGN_EVEN   ? SMB_POW_LAUNCH(true, POW_SIGN_EVEN, false)
-                                                          : SMB_POW_LAUNCH(true, POW_SIGN_ODD, false);
-                return sign == POW_SIGN_REJECT ? SMB_POW_LAUNCH(false, POW_SIGN_REJECT, false)
-                     : sign == POW_SIGN_EVEN   ? SMB_POW_LAUNCH(false, POW_SIGN_EVEN, false)
-                                               : SMB_POW_LAUNCH(false, POW_SIGN_ODD, false);
+#define SMB_POW_BY_SIGN(S)                                                            \
+    (sign == POW_SIGN_REJECT ? SMB_POW_LAUNCH(S, POW_SIGN_REJECT, false)              \
+     : sign == POW_SIGN_EVEN ? SMB_POW_LAUNCH(S, POW_SIGN_EVEN, false)                \
+                             : SMB_POW_LAUNCH(S, POW_SIGN_ODD, false))
+                if (lt1) return SMB_POW_LAUNCH(POW_TIER_SMALL, POW_SIGN_REJECT, true); // 0 < |y| < 1 is never an integer
+                if (tier == POW_TIER_SMALL) return SMB_POW_BY_SIGN(POW_TIER_SMALL);
+                if (tier == POW_TIER_MEDIUM) return SMB_POW_BY_SIGN(POW_TIER_MEDIUM);
+                return SMB_POW_BY_SIGN(POW_TIER_LARGE);
+#undef SMB_POW_BY_SIGN
 #undef SMB_POW_LAUNCH
             }
         }
@@ -929,7 +931,7 @@ static int chain_launch(const DeviceCtx &c, const ChainPlan &p, const smb_chain_
             t.pow_fast[i] = 1;
             t.pow_abs_mask[i] = pe.y_is_int ? 0x7fffffffu : 0xffffffffu;
             t.pow_sign_or[i] = pe.y_is_odd ? 0x80000000u : 0u;
-            if (!pow_f32_small_y(pe)) t.pow_small = 0;
+            if (pow_f32_tier(pe) == POW_TIER_LARGE) t.pow_small = 0;
             powfast = true;
         }
     }

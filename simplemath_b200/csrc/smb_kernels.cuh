@@ -208,9 +208,9 @@ struct PowF32SlowFn {
 };
 template<> struct ScalarFn<OP_POW, float> : PowF32SlowFn {};
 
-// The host only launches this functor when pow_f32_fast_ok(pe); the variant (SMALL_Y, SIGN,
+// The host only launches this functor when pow_f32_fast_ok(pe); the variant (TIER, SIGN,
 // Y_LT_1) is picked from the uniform exponent, see pow_f32_pair_fast.
-template<bool SMALL_Y, int SIGN, bool Y_LT_1> struct PowF32Fn {
+template<int TIER, int SIGN, bool Y_LT_1> struct PowF32Fn {
     static constexpr bool PAIRWISE = true;    // stream_vec feeds two elements per call
     static constexpr bool POW_TABLES = true;  // k_stream stages the lookup tables in shared memory
     PowExpF32 pe;  // exponent classified once on the host
@@ -221,7 +221,7 @@ template<bool SMALL_Y, int SIGN, bool Y_LT_1> struct PowF32Fn {
     __device__ __forceinline__ float slow(float a) const { return pow_f32(a, pe); } // inlined, see pow_tile
     // Two elements through the branch-free fast core; false = redo on the slow path.
     __device__ __forceinline__ bool pair(float a0, float a1, float &r0, float &r1) const {
-        return pow_f32_pair_fast<SMALL_Y, SIGN, Y_LT_1>(a0, a1, pe.y, lane, nullptr, nullptr, &r0, &r1);
+        return pow_f32_pair_fast<TIER, SIGN, Y_LT_1>(a0, a1, pe.y, lane, nullptr, nullptr, &r0, &r1);
     }
     // Lookup tables, L2 -> shared memory once per CTA, each entry replicated across the lanes
     // of a wavefront (24 KB) so the per-lane lookups never conflict; see smb_math.cuh.
@@ -232,7 +232,7 @@ template<bool SMALL_Y, int SIGN, bool Y_LT_1> struct PowF32Fn {
         if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
             mbar_expect_tx(&bar, (uint32_t)sizeof(SmbPowTabs));
-            bulk_g2s(&smb_s_pow, &g_pow_image[SMALL_Y ? 0 : 1], (uint32_t)sizeof(SmbPowTabs), &bar);
+            bulk_g2s(&smb_s_pow, &g_pow_image[TIER != POW_TIER_LARGE ? 0 : 1], (uint32_t)sizeof(SmbPowTabs), &bar);
         }
         lane = pow_lane(threadIdx.x, lane.c);
         tab_bar = &bar;
@@ -912,7 +912,7 @@ struct ChainTable {
     // f32 pow steps the table-driven core may take (POWFAST kernels): per step the two sign masks of
     // pow_f32_pair_fast<.., POW_SIGN_RUNTIME, ..>; pow_fast[s] == 0 keeps the reference-accuracy path
     uint8_t pow_fast[kChainMax];
-    uint32_t pow_small;            // 1: the small-y table image and core (every fast step has |y| <= 8)
+    uint32_t pow_small;            // 1: the invc table image and the r-series core (every fast step has |y| <= 256)
     uint32_t pow_abs_mask[kChainMax], pow_sign_or[kChainMax];
     PowConsts pow_consts;
 };
@@ -1031,16 +1031,16 @@ __device__ __forceinline__ void chain_compute(const ChainTable &t, uint64_t tile
                             if (t.pow_fast[s]) {
                                 float r[EPV];
                                 bool ok = true;
-                                if (t.pow_small) { // every fast pow step of this chain has |y| <= 8: the r-series core
+                                if (t.pow_small) { // every fast pow step of this chain has |y| <= 256: the r-series core
 #pragma unroll
                                     for (int e = 0; e < EPV; e += 2)
-                                        ok &= pow_f32_pair_fast<true, POW_SIGN_RUNTIME, false>(
+                                        ok &= pow_f32_pair_fast<POW_TIER_MEDIUM, POW_SIGN_RUNTIME, false>(
                                             acc[u][e], acc[u][e + 1], leaf[u][s][0], lane, nullptr, nullptr, &r[e], &r[e + 1],
                                             t.pow_abs_mask[s], t.pow_sign_or[s]);
                                 } else {
 #pragma unroll
                                     for (int e = 0; e < EPV; e += 2)
-                                        ok &= pow_f32_pair_fast<false, POW_SIGN_RUNTIME, false>(
+                                        ok &= pow_f32_pair_fast<POW_TIER_LARGE, POW_SIGN_RUNTIME, false>(
                                             acc[u][e], acc[u][e + 1], leaf[u][s][0], lane, nullptr, nullptr, &r[e], &r[e + 1],
                                             t.pow_abs_mask[s], t.pow_sign_or[s]);
                                 }

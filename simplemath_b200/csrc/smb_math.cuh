@@ -563,10 +563,15 @@ SMB_HD bool pow_f32_fast_ok(const PowExpF32 &pe) {
 // but every table index and operation along the way is safe).  The caller
 // accumulates the flag over a whole vector and branches once.
 //
-// SMALL_Y (|y| <= 8, chosen on the host): the division-free r-series above on the invc table, no
-// renormalisation of the log2 tail -- what is dropped only matters once multiplied by a large
-// exponent.  Otherwise: the {c, log2 c} table and the series in p = (m-c)/(m+c), whose second
-// term is p^3 (the r-series would need r^2 in two floats there).
+// TIER (chosen on the host from the uniform exponent):
+//   POW_TIER_SMALL  (|y| <= 8): the division-free r-series above on the invc table, degree-3 fit, no
+//                   renormalisation of the log2 tail -- what is dropped only matters once multiplied
+//                   by a large exponent;
+//   POW_TIER_MEDIUM (|y| <= 256): the same with a degree-5 fit.  The r^2 term is carried in one
+//                   float (an error of 2^-38.6 * y in t) and the un-renormalised tail y * lo stays
+//                   below 2^-7, inside the exp2 polynomial's range: <= 0.53 ULP measured;
+//   POW_TIER_LARGE: the {c, log2 c} table and the series in p = (m-c)/(m+c), whose second term is
+//                   p^3 (the r-series would need r^2 in two floats), tail renormalised.
 // SIGN: POW_SIGN_REJECT -- y is not an integer, a negative base must reach the slow path (NaN):
 //         the sign bit is converted together with the biased exponent, which adds 256 to log2|x|;
 //       POW_SIGN_EVEN   -- even integer y, the sign of the base is dropped;
@@ -576,7 +581,8 @@ SMB_HD bool pow_f32_fast_ok(const PowExpF32 &pe) {
 //         two masks say what to do (abs_mask 0x7fffffff for an integer y, sign_or 0x80000000 for an
 //         odd one), and the range test is made on both t and log2|x|.
 enum { POW_SIGN_REJECT = 0, POW_SIGN_EVEN = 1, POW_SIGN_ODD = 2, POW_SIGN_RUNTIME = 3 };
-template<bool SMALL_Y, int SIGN, bool Y_LT_1>
+enum { POW_TIER_LARGE = 0, POW_TIER_SMALL = 1, POW_TIER_MEDIUM = 2 };
+template<int TIER, int SIGN, bool Y_LT_1>
 SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
                               const PowTabLog *tab_log, const PowTabExp *tab_exp, float *r0, float *r1,
                               uint32_t abs_mask = 0xffffffffu, uint32_t sign_or = 0u) {
@@ -588,14 +594,21 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
     const f2 m = f2_make(u2f((u0 & 0x007fffffu) | lane.c.one), u2f((u1 & 0x007fffffu) | lane.c.one));
     const PowTabLog t0 = pow_tab_log_at(tab_log, lane.log_off, u0), t1 = pow_tab_log_at(tab_log, lane.log_off, u1);
     f2 lh, ll; // log2(m * invc) [or log2(m / c)] as lh + ll
-    if (SMALL_Y) {
+    if (TIER != POW_TIER_LARGE) {
         // exact; .c holds invc here.  Scalar FMAs: the operands come straight from the LDS
         // registers, packing them first would cost more moves than the packed form saves.
         const f2 r = f2_make(ffma(m.x, t0.c, -1.0f), ffma(m.y, t1.c, -1.0f));
         const f2 c1h = f2_splat(SMB_POW_C1H);              // 1/ln2 = c1h + c1l
         lh = f2_mul(c1h, r);
         ll = f2_fma(c1h, r, f2_neg(lh));                   // the rounding error of lh, exactly
-        f2 q = f2_fma(r, f2_splat(lane.c.s_c3), f2_splat(SMB_POW_S_C2));
+        f2 q;
+        if (TIER == POW_TIER_SMALL) {
+            q = f2_fma(r, f2_splat(lane.c.s_c3), f2_splat(SMB_POW_S_C2));
+        } else { // two more terms: fit error 6e-13 instead of 7e-10
+            q = f2_fma(r, f2_splat(SMB_POW_L_C5), f2_splat(SMB_POW_L_C4));
+            q = f2_fma(r, q, f2_splat(SMB_POW_L_C3));
+            q = f2_fma(r, q, f2_splat(SMB_POW_L_C2));
+        }
         q = f2_fma(r, q, f2_splat(SMB_POW_C1L));
         ll = f2_fma(r, q, ll);
     } else {
@@ -634,7 +647,7 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
     const f2 l2 = f2_add(f2_sub(h1, h2), lh);
     f2 lo = f2_add(f2_make(fadd(t0.l_lo, l2.x), fadd(t1.l_lo, l2.y)), ll);
     f2 h3 = h2;
-    if (!SMALL_Y) {
+    if (TIER == POW_TIER_LARGE) {
         // renormalise: L_lo alone can reach 2^-16, too coarse a tail once multiplied by a large y
         h3 = f2_add(h2, lo);
         lo = f2_add(f2_sub(h2, h3), lo);
@@ -676,6 +689,10 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
 
 // Host-side facts about the (uniform) exponent that select the variant.
 SMB_HD bool pow_f32_small_y(const PowExpF32 &pe) { return (f2u(pe.y) & 0x7fffffffu) <= 0x41000000u; } // |y| <= 8
+SMB_HD int pow_f32_tier(const PowExpF32 &pe) {
+    const uint32_t ay = f2u(pe.y) & 0x7fffffffu;
+    return ay <= 0x41000000u ? POW_TIER_SMALL : ay <= 0x43800000u ? POW_TIER_MEDIUM : POW_TIER_LARGE; // 8, 256
+}
 SMB_HD int pow_f32_sign_mode(const PowExpF32 &pe) { return !pe.y_is_int ? POW_SIGN_REJECT : pe.y_is_odd ? POW_SIGN_ODD : POW_SIGN_EVEN; }
 SMB_HD bool pow_f32_y_lt_1(const PowExpF32 &pe) { return (f2u(pe.y) & 0x7fffffffu) < 0x3f800000u; }
 

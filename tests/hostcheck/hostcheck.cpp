@@ -18,11 +18,11 @@ static const PowTabExp kExp[SMB_POW_EXP_ENTRIES] = SMB_POW_EXP_TABLE_INIT;
 // The fast (table-driven, packed) core exactly as ScalarFn<OP_POW,float>::pair uses it:
 // pairs of elements, pow_f32 for whatever the core declines.  *declined counts those.
 } // extern "C"
-template<bool S, int SG, bool LT1>
+template<int S, int SG, bool LT1>
 static bool hc_pair(float a, float b, float y, float *r0, float *r1) {
-    return pow_f32_pair_fast<S, SG, LT1>(a, b, y, pow_lane(0, pow_consts()), S ? kLog : kLogC, kExp, r0, r1);
+    return pow_f32_pair_fast<S, SG, LT1>(a, b, y, pow_lane(0, pow_consts()), S != POW_TIER_LARGE ? kLog : kLogC, kExp, r0, r1);
 }
-template<bool S, bool LT1>
+template<int S, bool LT1>
 static bool hc_pair_sign(int sg, float a, float b, float y, float *r0, float *r1) {
     return sg == POW_SIGN_REJECT ? hc_pair<S, POW_SIGN_REJECT, LT1>(a, b, y, r0, r1)
          : sg == POW_SIGN_EVEN   ? hc_pair<S, POW_SIGN_EVEN, LT1>(a, b, y, r0, r1)
@@ -31,16 +31,18 @@ static bool hc_pair_sign(int sg, float a, float b, float y, float *r0, float *r1
 extern "C" {
 void hc_pow_f32_fast(const float *x, float y, uint64_t n, float *out, uint64_t *declined) {
     PowExpF32 pe = classify_exp(y);
-    const bool fast = pow_f32_fast_ok(pe), small = pow_f32_small_y(pe), lt1 = pow_f32_y_lt_1(pe);
+    const bool fast = pow_f32_fast_ok(pe), lt1 = pow_f32_y_lt_1(pe);
+    const int tier = pow_f32_tier(pe);
     const int sg = pow_f32_sign_mode(pe);
     uint64_t dec = 0;
     #pragma omp parallel for schedule(static) reduction(+:dec)
     for (int64_t i = 0; i < (int64_t)(n / 2); ++i) {
         float r0, r1;
         const float a = x[2 * i], b = x[2 * i + 1];
-        const bool ok = lt1 ? hc_pair_sign<true, true>(sg, a, b, y, &r0, &r1)
-                      : small ? hc_pair_sign<true, false>(sg, a, b, y, &r0, &r1)
-                              : hc_pair_sign<false, false>(sg, a, b, y, &r0, &r1);
+        const bool ok = lt1 ? hc_pair_sign<POW_TIER_SMALL, true>(sg, a, b, y, &r0, &r1)
+                      : tier == POW_TIER_SMALL ? hc_pair_sign<POW_TIER_SMALL, false>(sg, a, b, y, &r0, &r1)
+                      : tier == POW_TIER_MEDIUM ? hc_pair_sign<POW_TIER_MEDIUM, false>(sg, a, b, y, &r0, &r1)
+                                                : hc_pair_sign<POW_TIER_LARGE, false>(sg, a, b, y, &r0, &r1);
         if (ok && fast) {
             out[2 * i] = r0; out[2 * i + 1] = r1;
         } else {

@@ -154,11 +154,12 @@ def test_int_pow_lane_and_tail_semantics(orc):
             assert_same_bits(smb.pow(a, e), orc.array_scalar("pow", a, e), f"i32 pow e={e} n={n}")
 
 
-@pytest.mark.parametrize("y", [2.0, 2.5, 0.5, -1.0, 3.0, -2.5, 1 / 3, 17.0, 100.5, -77.7, 1e-3, 0.1])
+@pytest.mark.parametrize("y", [2.0, 2.5, 0.5, -1.0, 3.0, -2.5, 1 / 3, 17.0, 100.5, -77.7, 1e-3, 0.1, 9.25, 255.0, -256.0, 256.5, 1000.0])
 def test_pow_f32_ulp_general_kernel(orc, y):
     rng = np.random.default_rng(int(abs(y) * 1000) % 2**31)
     x = np.concatenate([rng.uniform(0.01, 100, 1 << 21).astype(np.float32),
-                        rng.integers(1, 0x7f800000, 1 << 21, dtype=np.uint32).view(np.float32)])
+                        rng.integers(1, 0x7f800000, 1 << 21, dtype=np.uint32).view(np.float32),
+                        (1 + rng.uniform(-2e-2, 2e-2, 1 << 20)).astype(np.float32)])   # keeps large |y| on the fast core
     smb.set_option(smb.OPT_POW_SPECIALISE, 0)
     try:
         got = smb.pow(x, y)

@@ -98,7 +98,8 @@ def test_pow_f32_ulp_all_magnitudes(hc, orc, y):
     assert err.max() <= F32_POW_ULP_BOUND, (y, err.max(), x[err.argmax()])
 
 
-@pytest.mark.parametrize("y", [2.0, 2.5, 0.5, -1.0, 3.0, -2.5, 1 / 3, 17.0, 1e-3, 0.1, -0.0625, 31.0, 8.0, -7.99, 8.000001, 5.0])
+@pytest.mark.parametrize("y", [2.0, 2.5, 0.5, -1.0, 3.0, -2.5, 1 / 3, 17.0, 1e-3, 0.1, -0.0625, 31.0, 8.0, -7.99, 8.000001, 5.0,
+                               9.25, 100.5, -255.0, 256.0, 256.0001, -300.0])
 def test_pow_f32_fast_core_ulp(hc, orc, y):
     """The table-driven FFMA2 core (what the GPU kernel runs for ordinary data):
     uniform values, every magnitude, signed bases, and all 128 table-entry edges."""

@@ -121,8 +121,11 @@ scalar_case("C3 f32 pow(arr,2.0) 256M, i+j+1 fill, specialised x*x", "pow", x, 2
 scalar_case("C3 f32 pow(arr,2.0) 256M, i+j+1 fill, general kernel", "pow", x, 2.0, 0)
 x = rng.uniform(0.01, 100, 1 << 28).astype(np.float32)
 scalar_case("C3 f32 pow(arr,2.5) 256M uniform(0.01,100), general kernel", "pow", x, 2.5, 0)
-scalar_case("C3 f32 pow(arr,17.5) 256M uniform, large-|y| variant", "pow", x, 17.5, 0, "many results overflow -> slow path share")
-scalar_case("C3 f32 pow(arr,9.25) 256M uniform, large-|y| variant", "pow", x, 9.25, 0)
+scalar_case("C3 f32 pow(arr,17.5) 256M uniform, medium-|y| tier (8 < |y| <= 256)", "pow", x, 17.5, 0, "many results overflow -> slow path share")
+scalar_case("C3 f32 pow(arr,9.25) 256M uniform, medium-|y| tier", "pow", x, 9.25, 0)
+x1 = (1 + rng.uniform(-2e-2, 2e-2, 1 << 28)).astype(np.float32)
+scalar_case("C3 f32 pow(arr,1000.5) 256M in [0.98,1.02], large-|y| tier (p-series)", "pow", x1, 1000.5, 0)
+del x1
 xd = x[: 1 << 27].astype(np.float64)
 del x
 scalar_case("C3 f64 pow(arr,2.5) 128M uniform, general kernel (FP64-pipe bound)", "pow", xd, 2.5, 0)

@@ -184,7 +184,7 @@ static void run_pow(const float *a, float *out, uint64_t n, float y) {
         constexpr uint64_t per_block = 256ull * UNROLL * (VB / 4);
         uint64_t blocks = (n + per_block - 1) / per_block;
         blocks = (blocks + cap - 1) / cap;
-        using Fn = PowF32Fn<SMALL, POW_SIGN_REJECT, false>;
+        using Fn = PowF32Fn<SMALL ? POW_TIER_SMALL : POW_TIER_LARGE, POW_SIGN_REJECT, false>;
         Fn fn = Fn::make(y, 0);
         float ms = time_ms([&] { k_stream<float, Fn, false, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, nullptr, out, n, 0, fn); });
         char p[128];
