@@ -937,30 +937,36 @@ static int chain_launch(const DeviceCtx &c, const ChainPlan &p, const smb_chain_
     }
     t.tiles_per_cta = powfast ? 32 : 1; // amortise the 24 KB table copy, stay many waves deep
     // compiled-in chain capacity / vectors per thread: short chains keep more loads in flight
-#define SMB_CHAIN_LAUNCH(E, W, NS, U, PF)                                                                         \
-    k_chain<T, E, W, NS, U, PF><<<grid_for(items, (uint64_t)kThreads * U * t.tiles_per_cta, c.sm_count, 0), kThreads, 0, s>>>(out, t)
-#define SMB_CHAIN_BY_LEN(E, W, PF)                                                                \
+#define SMB_CHAIN_LAUNCH(E, W, NS, U, PF, ND)                                                                     \
+    k_chain<T, E, W, NS, U, PF, ND><<<grid_for(items, (uint64_t)kThreads * U * t.tiles_per_cta, c.sm_count, 0), kThreads, 0, s>>>(out, t)
+#define SMB_CHAIN_BY_LEN(E, W, PF, ND)                                                            \
     do {                                                                                          \
-        if (p.nleaf <= 3 && PF) SMB_CHAIN_LAUNCH(E, W, 3, 1, PF); /* pow: fewer registers, more CTAs */ \
-        else if (p.nleaf <= 3) SMB_CHAIN_LAUNCH(E, W, 3, 4, PF);                                  \
-        else if (p.nleaf <= 5) SMB_CHAIN_LAUNCH(E, W, 5, 2, PF);                                  \
-        else SMB_CHAIN_LAUNCH(E, W, 8, 1, PF);                                                    \
+        if (p.nleaf <= 3 && PF) SMB_CHAIN_LAUNCH(E, W, 3, 1, PF, ND); /* pow: fewer registers, more CTAs */ \
+        else if (p.nleaf <= 3) SMB_CHAIN_LAUNCH(E, W, 3, 4, PF, ND);                              \
+        else if (p.nleaf <= 5) SMB_CHAIN_LAUNCH(E, W, 5, 2, PF, ND);                              \
+        else SMB_CHAIN_LAUNCH(E, W, 8, 1, PF, ND);                                                \
+    } while (0)
+    // rank 1 needs no division (one 64-bit index); rank 2 and the general case come in 32- / 64-bit index forms
+#define SMB_CHAIN_BY_RANK(E, PF)                                                                  \
+    do {                                                                                          \
+        if (p.ndim == 1) SMB_CHAIN_BY_LEN(E, true, PF, 1);                                        \
+        else if (p.ndim == 2 && wide) SMB_CHAIN_BY_LEN(E, true, PF, 2);                           \
+        else if (p.ndim == 2) SMB_CHAIN_BY_LEN(E, false, PF, 2);                                  \
+        else if (wide) SMB_CHAIN_BY_LEN(E, true, PF, 0);                                          \
+        else SMB_CHAIN_BY_LEN(E, false, PF, 0);                                                   \
     } while (0)
     if (vec && powfast) {
-        if constexpr (std::is_same<T, float>::value) {
-            if (wide) SMB_CHAIN_BY_LEN(EPVV, true, true);
-            else SMB_CHAIN_BY_LEN(EPVV, false, true);
-        }
+        if constexpr (std::is_same<T, float>::value) SMB_CHAIN_BY_RANK(EPVV, true);
         g_last_kernel = wide ? "k_chain<vec16,wide,pow>" : "k_chain<vec16,pow>";
     } else if (vec) {
-        if (wide) SMB_CHAIN_BY_LEN(EPVV, true, false);
-        else SMB_CHAIN_BY_LEN(EPVV, false, false);
+        SMB_CHAIN_BY_RANK(EPVV, false);
         g_last_kernel = wide ? "k_chain<vec16,wide>" : "k_chain<vec16>";
     } else {
-        if (wide) SMB_CHAIN_BY_LEN(1, true, false);
-        else SMB_CHAIN_BY_LEN(1, false, false);
+        if (wide) SMB_CHAIN_BY_LEN(1, true, false, 0);
+        else SMB_CHAIN_BY_LEN(1, false, false, 0);
         g_last_kernel = wide ? "k_chain<scalar,wide>" : "k_chain<scalar>";
     }
+#undef SMB_CHAIN_BY_RANK
 #undef SMB_CHAIN_BY_LEN
 #undef SMB_CHAIN_LAUNCH
     ++g_launches;

@@ -932,10 +932,15 @@ enum { CH_ADD = 0, CH_SUB = 1, CH_MUL = 2, CH_DIV = 3, CH_POW = 4, CH_RSUB = 5, 
 // NS: compiled-in capacity of the chain (leaf registers); UNROLL: vectors per thread, all of whose
 // leaf loads are issued before the first operator (UNROLL * NS independent loads in flight per
 // thread -- a single vector per thread left HBM half idle).  One tile of 256 * UNROLL vectors per CTA.
-// One tile (256 * UNROLL vectors) of leaf loads.  PIN: ordinary (coherent) loads, which ptxas keeps
-// on their side of a warp barrier -- the prefetch of the POWFAST loop must stay ahead of the math.
-template<typename T, int EPV, bool WIDE, int NS, int UNROLL, bool PIN>
+// One tile (256 * UNROLL vectors) of leaf loads.  NDIM: the coalesced rank when it is 1 or 2 (the
+// index and offset loops are then straight-line code on constant-bank operands -- with the rank a
+// run-time value the guarded 6-dim loops were 58 instructions per element, most of them IMAD / MOV /
+// ISETP / BRA), 0: any rank, guarded loops.
+template<typename T, int EPV, bool WIDE, int NS, int UNROLL, int NDIM>
 __device__ __forceinline__ void chain_load(const ChainTable &t, uint64_t tile, uint64_t nvec, T (&leaf)[UNROLL][NS][EPV]) {
+    using Idx = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
+    constexpr int KMAX = NDIM ? NDIM : SMB_MAX_NDIM;
+    const int ndim = NDIM ? NDIM : t.ndim;
     const uint64_t v0 = tile * (kBlock * UNROLL) + threadIdx.x;
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -943,24 +948,14 @@ __device__ __forceinline__ void chain_load(const ChainTable &t, uint64_t tile, u
         if (v >= nvec) continue; // (its registers stay undefined; nothing of it is stored)
         const uint64_t lin = t.lin_base + v * EPV;
         // flat index -> per-dim indices, innermost first
-        uint64_t idx[SMB_MAX_NDIM];
-        if (WIDE) {
-            uint64_t rem = lin;
+        Idx idx[KMAX];
+        Idx rem = (Idx)lin;
 #pragma unroll
-            for (int k = SMB_MAX_NDIM - 1; k >= 0; --k) {
-                if (k < t.ndim) {
-                    if (k == 0) idx[k] = rem;
-                    else { const uint64_t q = rem / t.shape64[k]; idx[k] = rem - q * t.shape64[k]; rem = q; }
-                }
-            }
-        } else {
-            uint32_t rem = (uint32_t)lin;
-#pragma unroll
-            for (int k = SMB_MAX_NDIM - 1; k >= 0; --k) {
-                if (k < t.ndim) {
-                    if (k == 0) idx[k] = rem;
-                    else { const uint32_t q = fastdiv(rem, t.shape[k], t.mul[k], t.shr[k]); idx[k] = rem - q * t.shape[k]; rem = q; }
-                }
+        for (int k = KMAX - 1; k >= 0; --k) {
+            if (k < ndim) {
+                if (k == 0) idx[k] = rem;
+                else if (WIDE) { const uint64_t q = rem / t.shape64[k]; idx[k] = (Idx)(rem - q * t.shape64[k]); rem = (Idx)q; }
+                else { const uint32_t q = fastdiv((uint32_t)rem, t.shape[k], t.mul[k], t.shr[k]); idx[k] = (Idx)((uint32_t)rem - q * t.shape[k]); rem = (Idx)q; }
             }
         }
 #pragma unroll
@@ -973,12 +968,11 @@ __device__ __forceinline__ void chain_load(const ChainTable &t, uint64_t tile, u
                 } else {
                     uint64_t off = 0;
 #pragma unroll
-                    for (int k = 0; k < SMB_MAX_NDIM; ++k)
-                        if (k < t.ndim) off += idx[k] * t.stride[s][k];
-                    if (EPV > 1 && t.stride[s][t.ndim - 1] == 1) {
+                    for (int k = 0; k < KMAX; ++k)
+                        if (k < ndim) off += (uint64_t)idx[k] * t.stride[s][k];
+                    if (EPV > 1 && t.stride[s][ndim - 1] == 1) {
                         Pack<T, 16> pk; // EPV * sizeof(T) == 16
-                        if (PIN) pk.raw = load_stream_pinned(reinterpret_cast<const RawVec<16> *>(base + off));
-                        else pk.raw = VecIO<16, false>::load(base + off);
+                        pk.raw = VecIO<16, false>::load(base + off);
 #pragma unroll
                         for (int e = 0; e < EPV; ++e) leaf[u][s][e] = pk.e[e];
                     } else {
@@ -1081,7 +1075,7 @@ __device__ __forceinline__ void chain_compute(const ChainTable &t, uint64_t tile
 // first tile's loads) and a pow step goes through the FFMA2 core, two elements per call, the
 // reference-accuracy path only for the vectors it declines -- sm::pow(a + b, e) in one pass.  Such a
 // CTA runs several consecutive tiles to amortise the copy; plain chains run one tile per CTA.
-template<typename T, int EPV, bool WIDE, int NS, int UNROLL, bool POWFAST>
+template<typename T, int EPV, bool WIDE, int NS, int UNROLL, bool POWFAST, int NDIM>
 __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid_constant__ ChainTable t) {
     const uint64_t nvec = t.count / EPV; // host guarantees count % EPV == 0
     const uint64_t ntiles = (nvec + kBlock * UNROLL - 1) / (kBlock * UNROLL);
@@ -1089,7 +1083,7 @@ __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid
         const uint64_t tile = blockIdx.x;
         if (tile >= ntiles) return;
         T leaf[UNROLL][NS][EPV];
-        chain_load<T, EPV, WIDE, NS, UNROLL, false>(t, tile, nvec, leaf);
+        chain_load<T, EPV, WIDE, NS, UNROLL, NDIM>(t, tile, nvec, leaf);
         chain_compute<T, EPV, NS, UNROLL, false>(t, tile, nvec, leaf, out, PowLane{});
     } else {
         __shared__ __align__(8) uint64_t tab_bar;
@@ -1109,7 +1103,7 @@ __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid
 #pragma unroll 1
         for (; tile < tile_end; ++tile) {
             T leaf[UNROLL][NS][EPV];
-            chain_load<T, EPV, WIDE, NS, UNROLL, false>(t, tile, nvec, leaf);
+            chain_load<T, EPV, WIDE, NS, UNROLL, NDIM>(t, tile, nvec, leaf);
             if (first) {
                 mbar_wait(&tab_bar, 0); // the tables have landed (the copy overlapped the loads above)
                 asm volatile("" : "+r"(lane.log_off), "+r"(lane.exp_off) :: "memory"); // ties the lookups to the wait
