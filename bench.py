@@ -335,6 +335,22 @@ def run_smb(args):
     extras["pow_y2_general_gbs_per_gpu"] = pow_y(2.0, 0)
     extras["pow_y2_specialised_gbs_per_gpu"] = pow_y(2.0, 1)
 
+    # ---- op-chain fusion: (a + b) * x in ONE pass vs the two operators
+    def P(t):
+        return t.data_ptr()
+    chain = smb.chain_steps(smb.F32, [(None, False, (P(a), [1])), ("add", False, (P(b), [1])), ("mul", False, (P(x), [1]))], [m])
+    shp = smb._u64arr([m])
+    fused = lambda: smb._check(smb.lib().smb_chain(smb.F32, chain, 3, shp, 1, m, P(pw), sp))
+    unfused = lambda: (smb.contiguous_ptr(smb.OP_ADD, smb.F32, P(a), P(b), P(out), m, sp),
+                       smb.contiguous_ptr(smb.OP_MUL, smb.F32, P(out), P(x), P(pw), m, sp))
+    fused(); unfused()
+    barrier()
+    ms_f = max_ranks(timed(fused, reps)) / reps
+    barrier()
+    ms_u = max_ranks(timed(unfused, reps)) / reps
+    extras["chain_add_mul_fused_gbs_per_gpu"] = 16.0 * m / (ms_f * 1e-3) / 1e9     # 3 leaves + result
+    extras["chain_add_mul_speedup_vs_two_operators"] = ms_u / ms_f
+
     step()  # leave out / pw holding the step's results for verification
     torch.cuda.synchronize()
     # ---- verification (outside every timed region): windows vs the oracle on rank 0,

@@ -510,11 +510,7 @@ SMB_HD PowTabLog pow_tab_log_at(const PowTabLog *tab, uint32_t lane_off, uint32_
 #if defined(__CUDA_ARCH__)
     // j = top 7 mantissa bits = (u >> 16) & 127; entry j starts at byte j * 128.
     // SHF + LOP3 + LDS [R + imm]
-#ifdef SMB_POW_EXPERIMENT_LOG_BROADCAST /* tools/sweep only: every lane reads entry 0 (wrong results) */
-    const uint32_t off = (u >> 9) & 0u;
-#else
     const uint32_t off = ((u >> 9) & (127u << 7)) | lane_off;
-#endif
     PowTabLog e;
     asm("{\n\t.reg .u32 a;\n\t.reg .u64 b;\n\tmov.u64 b, smb_s_pow;\n\tcvt.u32.u64 a, b;\n\tadd.u32 a, a, %4;\n\t"
         "ld.shared.v4.f32 {%0,%1,%2,%3}, [a];\n\t}" : "=f"(e.c), "=f"(e.l_hi), "=f"(e.l_lo), "=f"(e.pad) : "r"(off));
@@ -526,11 +522,7 @@ SMB_HD PowTabLog pow_tab_log_at(const PowTabLog *tab, uint32_t lane_off, uint32_
 }
 SMB_HD PowTabExp pow_tab_exp_at(const PowTabExp *tab, uint32_t lane_off, uint32_t k) {
 #if defined(__CUDA_ARCH__)
-#ifdef SMB_POW_EXPERIMENT_EXP_BROADCAST
-    const uint32_t off = (k << 7) & 0u;
-#else
     const uint32_t off = ((k << 7) & (63u << 7)) | lane_off; // entry j = k & 63 starts at byte j * 128
-#endif
     PowTabExp e;
     asm("{\n\t.reg .u32 a;\n\t.reg .u64 b;\n\tmov.u64 b, smb_s_pow;\n\tcvt.u32.u64 a, b;\n\tadd.u32 a, a, %2;\n\t"
         "ld.shared.v2.f32 {%0,%1}, [a+16384];\n\t}" : "=f"(e.t_hi), "=f"(e.t_lo) : "r"(off));
