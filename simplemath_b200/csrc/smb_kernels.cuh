@@ -1096,7 +1096,10 @@ __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid
         __syncthreads(); // the barrier is initialised before anyone waits on it
         uint64_t tile = (uint64_t)blockIdx.x * t.tiles_per_cta;
         const uint64_t tile_end = tile + t.tiles_per_cta < ntiles ? tile + t.tiles_per_cta : ntiles;
-        if (tile >= tile_end) return;
+        if (tile >= tile_end) { // (the host never launches such a CTA) still let the bulk copy into our shared memory land
+            mbar_wait(&tab_bar, 0);
+            return;
+        }
         // No register prefetch here: with the leaf buffers doubled the kernel drops to two CTAs per
         // SM and measured slower; occupancy (one vector per thread, four CTAs) hides the loads instead.
         bool first = true;

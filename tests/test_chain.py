@@ -249,3 +249,77 @@ def test_chain_full_size_properties():
     smb.array_scalar_ptr(smb.OP_MUL, smb.F32, t2.data_ptr(), 3.0, n, t1.data_ptr(), sp)
     torch.cuda.synchronize()
     assert torch.equal(out.view(torch.int32), t1.view(torch.int32))
+
+
+@pytest.mark.gpu
+def test_chain_randomised_shapes_ranks_and_leaf_kinds(orc):
+    """Seeded fuzz over everything the planner and the rank-specialised kernels branch on: result rank
+    1..6, per-leaf broadcast patterns (any subset of dims of size 1, lower rank), sliced / transposed views,
+    constants, swapped operands, chain lengths 1..8, the three dtypes, 32- and 64-bit index forms."""
+    rng = np.random.default_rng(20261020)
+    ops_all = ["add", "sub", "mul", "div", "rsub", "rdiv"]
+    kernels = set()
+    for case in range(160):
+        dt = [np.float32, np.float64, np.int32][case % 3]
+        rank = int(rng.integers(1, 7))
+        shape = [int(rng.choice([1, 2, 3, 4, 5, 8, 12, 16])) for _ in range(rank)]
+        if rng.random() < 0.5:
+            shape[-1] = int(rng.choice([4, 8, 16, 32, 64]))      # often a vectorisable inner dim
+
+        def leaf_array(divisor):
+            keep = [d if rng.random() < 0.7 else 1 for d in shape]
+            drop = int(rng.integers(0, rank))                     # lower rank: leading dims missing
+            lshape = keep[drop:] if rng.random() < 0.3 and drop < rank else keep
+            kind = rng.random()
+            full = [max(2 * d, 2) if kind < 0.25 else d for d in lshape]
+            if dt == np.int32:
+                base = rng.integers(1, 50, size=full) if divisor else rng.integers(-2**31, 2**31, size=full, dtype=np.int64)
+                base = (base * (rng.choice([-1, 1], size=full) if divisor else 1)).astype(np.int32)
+            else:
+                base = (rng.uniform(0.5, 2, size=full) * rng.choice([-1, 1], size=full)).astype(dt) if divisor \
+                    else (rng.standard_normal(full) * 100).astype(dt)
+            if kind < 0.25:                                        # an interior slice of a larger block
+                sl = tuple(slice(1, 1 + d) if f > d else slice(None) for d, f in zip(lshape, full))
+                return base[sl]
+            if kind < 0.4 and len(lshape) >= 2:                    # a transposed view of the right shape
+                return np.ascontiguousarray(base.swapaxes(-1, -2)).swapaxes(-1, -2)
+            return base
+
+        first = leaf_array(False)
+        steps = []
+        for _ in range(int(rng.integers(0, 8))):
+            op = str(rng.choice(ops_all))
+            if rng.random() < 0.25 and not op.startswith("r"):
+                c = int(rng.integers(1, 9)) if dt == np.int32 else float(rng.uniform(0.5, 4))
+                steps.append((op, c))
+            else:
+                steps.append((op, leaf_array(divisor=op == "div")))
+        # `leaf / acc` needs acc != 0 (and != -1 for INT_MIN): make the chain safe by construction
+        safe = []
+        for op, leaf in steps:
+            if op == "rdiv":
+                safe.append(("mul", 0 if dt == np.int32 else 0.0))
+                safe.append(("add", 3 if dt == np.int32 else 1.5))
+                if len(safe) + 1 > smb.CHAIN_MAX - 1:
+                    break
+            safe.append((op, leaf))
+            if len(safe) >= smb.CHAIN_MAX - 1:
+                break
+        steps = safe[: smb.CHAIN_MAX - 1]
+        try:
+            want, _ = oracle_chain(orc, first, steps)
+        except RuntimeError:
+            continue                                               # incompatible shapes: both sides refuse
+        if np.asarray(want).ndim > smb.MAX_NDIM:
+            continue
+        wide = case % 5 == 0
+        if wide:
+            smb.set_option(smb.OPT_FORCE_WIDE_INDEX, 1)
+        try:
+            got = smb.chain(first, *steps)
+        finally:
+            if wide:
+                smb.set_option(smb.OPT_FORCE_WIDE_INDEX, 0)
+        kernels.add(smb.last_kernel())
+        assert_same_bits(got, np.asarray(want).reshape(got.shape), f"fuzz case {case}: {np.dtype(dt).name} {shape} {[s[0] for s in steps]}")
+    assert {"k_chain<vec16>", "k_chain<scalar>", "k_chain<vec16,wide>", "k_chain<scalar,wide>"} <= kernels, kernels
