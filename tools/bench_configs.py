@@ -83,6 +83,18 @@ def binary_case(name, op, a, b, note=""):
     ms = timed(fn, args.reps)
     bytes_ = a.itemsize * (n + a.size + b.size)
     cpu_ms = cpu_time(lambda: ref.smarray_binary(op, a, b, want_result=False)) if ref is not None else None
+    if bytes_ < (256 << 20):
+        # launch-bound sizes: the same launches captured in a CUDA graph (no host gaps between them)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                gsp = torch.cuda.current_stream().cuda_stream
+                for _ in range(args.reps):
+                    lib.smb_elementwise(*argv[:-1], gsp)
+            gms = timed(g.replay, 3) / args.reps
+            note += f"; CUDA-graph replay of {args.reps} launches: {gms:.4f} ms each = {bytes_ / gms / 1e6:.0f} GB/s"
+        except Exception as e:  # capture is an extra, never the measurement
+            note += f"; graph capture unavailable: {type(e).__name__}"
     report(name, bytes_, n, ms, cpu_ms, note)
 
 
