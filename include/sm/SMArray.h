@@ -300,8 +300,8 @@ namespace sm {
         // SMArray (op) scalar (reference SMArray.h:226-237 and siblings): dense
         // arrays take array_scalar_op over data[0..totalSize).  The reference
         // does the same for views and then reads the wrong elements (it ignores
-        // strides, calculate.h:137-169); here a non-dense view broadcasts the
-        // scalar as a stride-0 operand instead, so its result is the view's.
+        // strides, calculate.h:137-169); here a non-dense view goes through a
+        // two-step smb_chain (the view, then the constant), so its result is the view's.
         template<typename Operation>
         SMArray withScalar(const T val) const {
             T *result = storage::acquire<T>(totalSize);
@@ -309,16 +309,17 @@ namespace sm {
                 if (isDense()) {
                     array_scalar_op<T, Operation>(data, val, totalSize, result);
                 } else {
-                    T *cell = storage::acquire<T>(1);
-                    *cell = val;
-                    const std::vector<size_t> zeros(ndim, 0);
-                    try {
-                        element_wise_op<T, Operation>(data, _strides, cell, zeros, totalSize, result, _shape);
-                    } catch (...) {
-                        storage::release(cell);
-                        throw;
-                    }
-                    storage::release(cell);
+                    // a strided view: one two-step chain (view leaf, then the constant) -- no temporary
+                    smb_chain_step steps[2] = {};
+                    steps[0].data = data;
+                    for (size_t k = 0; k < ndim; ++k) steps[0].stride[k] = _strides[k];
+                    steps[1].op = smb::OpTag<Operation>::value;
+                    if constexpr (std::is_same_v<T, float>) steps[1].value.f32 = val;
+                    else if constexpr (std::is_same_v<T, double>) steps[1].value.f64 = val;
+                    else steps[1].value.i32 = val;
+                    if (ndim > MAX_NDIM) throw std::runtime_error("smb200: rank exceeds MAX_NDIM");
+                    smb::check(smb_chain(smb::DTypeTag<T>::value, steps, 2, smb::u64(_shape), static_cast<int>(ndim), totalSize,
+                                         result, nullptr));
                 }
             } catch (...) {
                 storage::release(result);
