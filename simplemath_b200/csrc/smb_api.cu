@@ -861,7 +861,9 @@ static int dot_t(DeviceCtx &c, const T *a, const T *b, uint64_t n, void *result,
     SMB_CK(cudaGetDevice(&dev));
     constexpr int UNROLL = 4;
     const uint64_t nvec = n / (16 / sizeof(T));
-    const unsigned grid = grid_for(nvec ? nvec : 1, (uint64_t)kThreads * UNROLL, c.sm_count, 8);
+    // many waves of short-lived CTAs (8 grid-stride iterations each): the hardware scheduler evens out the SMs,
+    // which a resident grid with a static split cannot (the slowest SM would set the time)
+    const unsigned grid = grid_for(nvec ? nvec : 1, (uint64_t)kThreads * UNROLL * 8, c.sm_count, 0);
     Scratch scratch;
     const size_t bytes = 16 + sizeof(A) * ((size_t)grid + 1);
     if (int rc = scratch.get(bytes, dev)) return rc;
