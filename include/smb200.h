@@ -212,6 +212,13 @@ int smb_plan_elementwise(const uint64_t *stride_a, const uint64_t *stride_b,
                          int *out_ndim, uint64_t *out_shape,
                          uint64_t *out_stride_a, uint64_t *out_stride_b);
 
+/* The same for an smb_chain call: coalesces the result shape across all leaves (data == NULL marks a
+ * constant).  Writes the coalesced rank / shape and, leaf after leaf, SMB_MAX_NDIM strides each
+ * into out_strides[nsteps * SMB_MAX_NDIM].  Returns 1 when every leaf has inner stride 0 or 1 (the
+ * vector kernels), 0 otherwise, or a negative error. */
+int smb_plan_chain(const smb_chain_step *steps, int nsteps, const uint64_t *shape, int ndim,
+                   int *out_ndim, uint64_t *out_shape, uint64_t *out_strides);
+
 /* ---- bench / test support -------------------------------------------------- */
 /* Counter-based generator: out[i] = lo + (hi-lo) * U(seed, first+i), the same
  * arithmetic as oracle/oracle.c:orc_fill_uniform_f32, so inputs larger than

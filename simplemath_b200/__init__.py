@@ -73,6 +73,7 @@ SYMBOLS = {
     "smb_last_error": (ctypes.c_char_p, []),
     "smb_version": (ctypes.c_char_p, []),
     "smb_plan_elementwise": (_i, [_u64p, _u64p, _u64p, _i, _i, ctypes.POINTER(_i), _u64p, _u64p, _u64p]),
+    "smb_plan_chain": (_i, [ctypes.POINTER(ChainStep), _i, _u64p, _i, ctypes.POINTER(_i), _u64p, _u64p]),
     "smb_fill_uniform_f32": (_i, [_vp, _u64, _u64, _u64, ctypes.c_float, ctypes.c_float, _vp]),
 }
 
@@ -298,6 +299,18 @@ def chain_steps(dtype: int, leaves, shape):
             else:
                 st.value.i32 = int(leaf)
     return arr
+
+
+def plan_chain(dtype, leaves, shape):
+    """Host planner of smb_chain only (no GPU): (vectorisable, coalesced shape, per-leaf coalesced strides)."""
+    arr = chain_steps(dtype, leaves, shape)
+    ond = ctypes.c_int(0)
+    osh, ost = _u64arr([0] * MAX_NDIM), _u64arr([0] * (MAX_NDIM * len(leaves)))
+    rc = lib().smb_plan_chain(arr, len(leaves), _u64arr(shape), len(shape), ctypes.byref(ond), osh, ost)
+    if rc < 0:
+        raise SmbError(f"smb_plan_chain failed ({rc})")
+    m = ond.value
+    return bool(rc), list(osh[:m]), [list(ost[i * MAX_NDIM:i * MAX_NDIM + m]) for i in range(len(leaves))]
 
 
 def chain_ptr(dtype, leaves, shape, out_ptr, stream=0, lin_range=None):

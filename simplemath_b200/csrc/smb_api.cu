@@ -1226,6 +1226,21 @@ const char *smb_last_kernel(void) { return g_last_kernel; }
 const char *smb_last_error(void) { return g_err.c_str(); }
 const char *smb_version(void) { return "smb200 0.1 (sm_100a)"; }
 
+int smb_plan_chain(const smb_chain_step *steps, int nsteps, const uint64_t *shape, int ndim, int *out_ndim,
+                   uint64_t *out_shape, uint64_t *out_strides) {
+    if (!steps || nsteps < 1 || nsteps > SMB_CHAIN_MAX || ndim < 1 || ndim > SMB_MAX_NDIM || !shape) return -SMB_ERR_INVALID;
+    const uint64_t *strides[SMB_CHAIN_MAX];
+    for (int i = 0; i < nsteps; ++i) strides[i] = steps[i].data ? steps[i].stride : nullptr;
+    const ChainPlan p = make_chain_plan(strides, nsteps, shape, ndim);
+    if (out_ndim) *out_ndim = p.ndim;
+    for (int k = 0; k < p.ndim; ++k)
+        if (out_shape) out_shape[k] = p.shape[k];
+    if (out_strides)
+        for (int i = 0; i < nsteps; ++i)
+            for (int k = 0; k < SMB_MAX_NDIM; ++k) out_strides[i * SMB_MAX_NDIM + k] = p.stride[i][k];
+    return p.inner_unit_or_zero ? 1 : 0;
+}
+
 int smb_plan_elementwise(const uint64_t *stride_a, const uint64_t *stride_b, const uint64_t *shape, int ndim, int elem_size,
                          int *out_ndim, uint64_t *out_shape, uint64_t *out_stride_a, uint64_t *out_stride_b) {
     (void)elem_size;

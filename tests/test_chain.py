@@ -53,6 +53,49 @@ def test_chain_step_struct_matches_header():
     assert ctypes.sizeof(smb.ChainStep) == 4 + 4 + 8 + 8 * smb.MAX_NDIM + 8
 
 
+def test_chain_planner_coalescing_keeps_every_offset():
+    """smb_plan_chain (host only): dims merged across ALL leaves; the offset of every flat index of every
+    leaf is unchanged, constants coalesce with anything, and the known configs collapse as expected."""
+    rng = np.random.default_rng(5)
+
+    def offsets(shape, strides):
+        idx = np.indices(shape).reshape(len(shape), -1)
+        return (idx * np.array(strides, dtype=np.int64)[:, None]).sum(0)
+
+    for _ in range(200):
+        nd = int(rng.integers(1, 7))
+        shape = [int(x) for x in rng.integers(1, 5, size=nd)]
+        leaves, tables = [], []
+        for s in range(int(rng.integers(1, 9))):
+            if s and rng.random() < 0.25:
+                leaves.append(("add", False, 1.0))
+                tables.append(None)
+                continue
+            dims = [d if rng.random() < 0.7 else 1 for d in shape]
+            st = smb.row_major_strides(dims)
+            if rng.random() < 0.3:
+                st = [x * 2 for x in st]                         # a view with padded parent strides
+            st = [0 if d == 1 and r > 1 else x for d, r, x in zip(dims, shape, st)]
+            leaves.append((None if s == 0 else "add", False, (4096, st)))
+            tables.append(st)
+        if tables[0] is None:
+            continue
+        vec, pshape, pstrides = smb.plan_chain(smb.F32, leaves, shape)
+        assert int(np.prod(pshape)) == int(np.prod(shape))
+        for st, pst in zip(tables, pstrides):
+            if st is None:
+                assert all(x == 0 for x in pst)
+            else:
+                assert np.array_equal(offsets(shape, st), offsets(pshape, pst))
+        assert vec == all(pst[-1] <= 1 for pst in pstrides)
+    # a dense 3-leaf chain of rank 4 is one dim; config C2 as a chain stays 2-D; C4's pattern 3-D
+    dense = smb.row_major_strides([4, 5, 6, 8])
+    assert smb.plan_chain(smb.F32, [(None, False, (4096, dense)), ("add", False, (4096, dense)), ("mul", False, 2.0)], [4, 5, 6, 8])[1] == [960]
+    assert smb.plan_chain(smb.F32, [(None, False, (4096, [4096, 1])), ("add", False, (4096, [0, 1]))], [4096, 4096])[1] == [4096, 4096]
+    vec, sh, st = smb.plan_chain(smb.I32, [(None, False, (4096, [1024, 0, 1])), ("mul", False, (4096, [0, 1024, 1]))], [512, 512, 1024])
+    assert vec and sh == [512, 512, 1024] and st == [[1024, 0, 1], [0, 1024, 1]]
+
+
 def load_golden_chains():
     """tests/golden/golden_chain_v1.npz: chains evaluated operator by operator on the UNMODIFIED
     reference (oracle/make_golden_chain.py).  Yields (first, steps, out); a "fix" entry replaces the
