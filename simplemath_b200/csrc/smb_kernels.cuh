@@ -20,6 +20,12 @@
 namespace smb {
 
 constexpr int kBlock = 256; // threads per CTA of every kernel in this file
+#ifndef SMB_STREAM_LOAD_HINT
+#define SMB_STREAM_LOAD_HINT true // dense streams: L1::no_allocate loads (false: default caching loads)
+#endif
+#ifndef SMB_STREAM_STORE_HINT
+#define SMB_STREAM_STORE_HINT true
+#endif
 #ifndef SMB_POW_BLOCKED
 #define SMB_POW_BLOCKED 1 // pow loop: consecutive tiles per CTA on a many-wave grid (0: resident grid, grid-stride)
 #endif
@@ -386,8 +392,8 @@ __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__
     for (int u = 0; u < UNROLL; ++u) {
         const uint64_t v = v0 + (uint64_t)u * kBlock;
         if (!GUARD || v < nvec) {
-            pa[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(a) + v);
-            if (HAS_B) pb[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(b) + v);
+            pa[u].raw = VecIO<VB, SMB_STREAM_LOAD_HINT>::load(reinterpret_cast<const RawVec<VB> *>(a) + v);
+            if (HAS_B) pb[u].raw = VecIO<VB, SMB_STREAM_LOAD_HINT>::load(reinterpret_cast<const RawVec<VB> *>(b) + v);
         }
     }
 #pragma unroll
@@ -396,7 +402,7 @@ __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__
         if (!GUARD || v < nvec) {
             Pack<T, VB> r;
             stream_vec<T, Fn, HAS_B, VB>(pa[u], pb[u], r, first + v * EPV, fn);
-            VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v, r.raw);
+            VecIO<VB, SMB_STREAM_STORE_HINT>::store(reinterpret_cast<RawVec<VB> *>(out) + v, r.raw);
         }
     }
 }
