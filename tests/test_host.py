@@ -3,6 +3,8 @@ symbol include/smb200.h declares, the planner (dimension coalescing / kernel
 choice), the Python mirror of sm::broadcast, the shard splitter, and the
 no-CPU-fallback guarantee."""
 import ctypes
+import subprocess
+import sys
 import os
 import re
 
@@ -149,3 +151,14 @@ def test_shard_range_partitions(n, world, align):
     assert prev == n
     sizes = [smb.shard_range(n, r, world, align) for r in range(world)]
     assert max(e - b for b, e in sizes) - min(e - b for b, e in sizes) <= 2 * align
+
+
+def test_pow_tables_header_is_what_the_generator_writes(tmp_path):
+    """simplemath_b200/csrc/smb_pow_tables.h is generated (tools/gen_pow_tables.py, mpmath at 200 bits): the
+    committed header must be exactly what the committed generator produces -- tables, fitted coefficients,
+    and the exactness / two-sum assertions the generator makes along the way."""
+    pytest.importorskip("mpmath")
+    out = tmp_path / "smb_pow_tables.h"
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_pow_tables.py"), str(out)], check=True, capture_output=True)
+    committed = open(os.path.join(ROOT, "simplemath_b200", "csrc", "smb_pow_tables.h")).read()
+    assert out.read_text() == committed

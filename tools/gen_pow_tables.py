@@ -1,7 +1,7 @@
 """Generate simplemath_b200/csrc/smb_pow_tables.h: the two small lookup tables of
 the f32 pow kernel (see smb_math.cuh, "table-driven f32 pow core").
 
-    python tools/gen_pow_tables.py
+    python tools/gen_pow_tables.py [output path]
 
 f32 LOG table, 128 entries indexed by the top 7 mantissa bits of |x| = 2^E * m, m in [1, 2):
     invc   k/256, an 8-bit reciprocal of the entry's centre.  With only 8 significant bits
@@ -169,4 +169,7 @@ def main():
 
 
 if __name__ == "__main__":
+    import sys
+    if len(sys.argv) > 1:
+        OUT = sys.argv[1]   # regenerate somewhere else (tests compare it with the committed header)
     main()
