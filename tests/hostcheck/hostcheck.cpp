@@ -53,6 +53,25 @@ void hc_pow_f32_fast(const float *x, float y, uint64_t n, float *out, uint64_t *
     if (n & 1) out[n - 1] = pow_f32(x[n - 1], pe);
     if (declined) *declined = dec;
 }
+// The core as op chains run it (k_chain POWFAST): sign handling and range test decided at run time
+// (POW_SIGN_RUNTIME), tier MEDIUM for |y| <= 256 and LARGE beyond; pow_f32 for whatever it declines.
+void hc_pow_f32_fast_runtime(const float *x, float y, uint64_t n, float *out, uint64_t *declined) {
+    PowExpF32 pe = classify_exp(y);
+    const bool fast = pow_f32_fast_ok(pe), large = pow_f32_tier(pe) == POW_TIER_LARGE;
+    const uint32_t abs_mask = pe.y_is_int ? 0x7fffffffu : 0xffffffffu, sign_or = pe.y_is_odd ? 0x80000000u : 0u;
+    uint64_t dec = 0;
+    #pragma omp parallel for schedule(static) reduction(+:dec)
+    for (int64_t i = 0; i < (int64_t)(n / 2); ++i) {
+        float r0, r1;
+        const float a = x[2 * i], b = x[2 * i + 1];
+        const bool ok = large ? pow_f32_pair_fast<POW_TIER_LARGE, POW_SIGN_RUNTIME, false>(a, b, y, pow_lane(0, pow_consts()), kLogC, kExp, &r0, &r1, abs_mask, sign_or)
+                              : pow_f32_pair_fast<POW_TIER_MEDIUM, POW_SIGN_RUNTIME, false>(a, b, y, pow_lane(0, pow_consts()), kLog, kExp, &r0, &r1, abs_mask, sign_or);
+        if (ok && fast) { out[2 * i] = r0; out[2 * i + 1] = r1; }
+        else { out[2 * i] = pow_f32(a, pe); out[2 * i + 1] = pow_f32(b, pe); dec += 2; }
+    }
+    if (n & 1) out[n - 1] = pow_f32(x[n - 1], pe);
+    if (declined) *declined = dec;
+}
 void hc_pow_f32_pair(const float *x, const float *y, uint64_t n, float *out) {
     #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = DevOp<OP_POW, float>::apply(x[i], y[i]);

@@ -123,6 +123,31 @@ def test_pow_f32_fast_core_ulp(hc, orc, y):
         assert d2 == 0.0
 
 
+@pytest.mark.parametrize("y", [2.0, 2.5, 0.5, -1.0, 3.0, -3.0, 4.0, 1 / 3, 0.01, 17.0, -77.0, 255.5, 300.0, 1001.0])
+def test_pow_f32_fast_core_runtime_sign_variant_ulp(hc, orc, y):
+    """The variant op chains use (k_chain): sign masks and the double range test are run-time values.
+    Signed bases: odd exponents keep the sign, even ones drop it, non-integer ones decline to NaN."""
+    rng = np.random.default_rng(int(abs(y) * 313) % 2**31)
+    lim = min(120.0 / abs(y), 20.0)
+    x = np.concatenate([np.exp2(rng.uniform(-lim, lim, 1 << 20)), -np.exp2(rng.uniform(-lim, lim, 1 << 18)),
+                        1 + rng.uniform(-2e-2, 2e-2, 1 << 18),
+                        [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-42, -1e-42, 3e38, 1.0, -1.0]]).astype(np.float32)
+    x = np.resize(x, x.size // 2 * 2)
+    out = np.empty_like(x)
+    dec = ctypes.c_uint64(0)
+    hc.hc_pow_f32_fast_runtime(_p(x), ctypes.c_float(y), ctypes.c_uint64(x.size), _p(out), ctypes.byref(dec))
+    ref = orc.pow_ref_f32(x, float(np.float32(y)))
+    with np.errstate(all="ignore"):
+        want = ref.astype(np.float32)
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(out), nan)
+    fin = np.isfinite(want) & (want != 0) & ~nan
+    assert oracle.ulp_error_f32(out[fin], ref[fin]).max() <= F32_POW_ULP_BOUND, y
+    rest = ~fin & ~nan
+    assert np.array_equal(out[rest], want[rest]) and np.array_equal(np.signbit(out[rest]), np.signbit(want[rest]))
+    assert dec.value < 0.2 * x.size      # ordinary data stays on the fast core (negative bases decline when y is not an integer)
+
+
 def test_pow_f32_fast_core_near_one_huge_exponents(hc, orc):
     rng = np.random.default_rng(16)
     x = (1 + rng.uniform(-2e-2, 2e-2, 1 << 20)).astype(np.float32)
