@@ -20,9 +20,13 @@
  *     include/SMArray.h:397-437).  Host operands are staged through HBM by the
  *     library (chunked, copy/compute overlapped).
  *   - stream == NULL: the call is synchronous -- the result is complete when it
- *     returns, like the reference.  stream != NULL: the
- *     work is enqueued on that stream (device / managed / pinned memory only)
- *     and the caller synchronises.
+ *     returns, like the reference -- unless SMB_OPT_ASYNC is
+ *     set.  stream != NULL: the work is enqueued on that stream (device / managed
+ *     memory) and the caller synchronises.  A call with HOST operands (pinned
+ *     included) is always synchronous: its copies start after the work already
+ *     enqueued on `stream`, and the result is in host memory on return.
+ *   - smb_free requires that no work the CALLER enqueued on its own streams still
+ *     uses the block (work on the library's private stream is ordered by the pool).
  *   - Return value 0 on success, non-zero on error; smb_last_error() then
  *     returns a thread-local message.  The C++ wrappers rethrow it as
  *     std::runtime_error, the reference's error convention (include/SMUtils.h:77).
@@ -88,7 +92,27 @@ enum {
     SMB_OPT_BCAST_VARIANT = 3,
     /* Test hook: 1 = take the 64-bit index path (results beyond 2^31 elements) for every
      * broadcast launch, so it can be exercised on small shapes. */
-    SMB_OPT_FORCE_WIDE_INDEX = 4
+    SMB_OPT_FORCE_WIDE_INDEX = 4,
+    /* 1: calls with stream == NULL enqueue on the library's private stream and return without waiting
+     * (the asynchronous result hand-off of SURVEY.md §8f rank 4); results are complete after
+     * smb_sync() / smb_wait_pending().  0 (default): the reference's contract, complete on return.
+     * Calls with host (non-pinned or pinned) operands and smb_dot stay synchronous in either mode.
+     * Setting it back to 0 waits for everything pending. */
+    SMB_OPT_ASYNC = 5,
+    /* 1 (default): back-to-back kernels on one stream use programmatic dependent launch -- the next
+     * grid's CTAs become resident while the previous grid drains (and overlap it outright on the
+     * private stream when the host sees no data hazard); 0: plain stream order. */
+    SMB_OPT_PDL = 6,
+    /* Device set (smb_set_devices): results smaller than this many bytes stay on one device
+     * (default 32 MiB). */
+    SMB_OPT_SHARD_MIN_BYTES = 7,
+    /* Device set: an operand several devices read (a broadcast row, an outer-product factor) is
+     * copied to each device per call when it is at most this large (default 64 MiB); a larger shared
+     * operand makes the operator run on one device. */
+    SMB_OPT_REPLICATE_MAX_BYTES = 8,
+    /* Pool high-water mark: when more than this many freed bytes sit cached, smb_free returns the
+     * largest blocks to the driver (default 64 GiB; negative: never). */
+    SMB_OPT_POOL_MAX_CACHED_BYTES = 9
 };
 
 /* ---- the hot path ------------------------------------------------------- */
@@ -130,7 +154,8 @@ int smb_array_scalar(int op, int dtype, const void *a, const void *scalar,
 
 /* ---- next row after the elementwise path -------------------- */
 /* Replaces dot_product<T>(a, b, n) behind SMArray::operator% -- include/math/product.h:8-224,
- * include/SMArray.h:213-215.  Dense operands (16-byte aligned), `result` points at one host T.
+ * include/SMArray.h:213-215.  Dense operands at ANY element-aligned address (views pass interior
+ * pointers; the reference reads them with loadu), `result` points at one host T.
  * int32 wraps like the reference's mullo/add_epi32 (bit-exact); float/double are summed
  * pairwise in their own type (deterministic; more accurate than the reference's sequential
  * lane accumulators, so parity is a tolerance). */
@@ -192,7 +217,25 @@ int smb_prefetch(const void *ptr, size_t bytes, int device, void *stream);
 int smb_device_count(void);
 int smb_set_device(int device);
 int smb_get_device(void);
+/* Waits for everything the library has enqueued on every device (and for the current device). */
 int smb_sync(void);
+/* SMB_OPT_ASYNC: waits only if asynchronous work is pending (one atomic load otherwise) -- what the
+ * C++ headers call before the host dereferences SMArray<T>::data. */
+int smb_wait_pending(void);
+/* Multi-GPU behind the operator API (BASELINE north_star: "large arrays are partitioned
+ * across the 8 GPUs of one box by splitting the broadcast output's flat index range; broadcast
+ * operands are replicated").  After smb_set_devices({d0..dG-1}) every stream == NULL operator whose
+ * operands and result are MANAGED blocks (the drop-in SMArray storage) and whose result is at least
+ * SMB_OPT_SHARD_MIN_BYTES is spread over those devices from the calling thread: device g computes
+ * flat range g of the result on its own stream, reading its ranges of the contiguous operands in
+ * place (pages prefetched to it once, then remembered) and a private copy of shared operands.  The
+ * caller still writes `a + b` and nothing else (reference include/SMArray.h:217-225).  count <= 1
+ * restores single-device behaviour.  The environment variable SMB_DEVICES ("all", "0-7", "0,2")
+ * presets the set for unmodified programs.  Device blocks (SMB_MEM_DEVICE) are computed where they
+ * live; host operands go through the staging pipeline of the current device. */
+int smb_set_devices(const int *devices, int count);
+/* Writes up to `capacity` device indices of the active set; returns its size (1 = single device). */
+int smb_get_devices(int *devices, int capacity);
 int smb_set_option(int key, int64_t value);
 int64_t smb_get_option(int key);
 /* Kernels launched by this library in this process so far. */
@@ -218,6 +261,16 @@ int smb_plan_elementwise(const uint64_t *stride_a, const uint64_t *stride_b,
  * vector kernels), 0 otherwise, or a negative error. */
 int smb_plan_chain(const smb_chain_step *steps, int nsteps, const uint64_t *shape, int ndim,
                    int *out_ndim, uint64_t *out_shape, uint64_t *out_strides);
+
+/* The multi-GPU planner alone (smb_set_devices acts on it): where the flat result range of an
+ * smb_elementwise call is cut for `ndev` devices (out_bounds[ndev + 1]), which element range
+ * [lo, hi) of each operand device g reads (out_range_x[2 g], [2 g + 1]) and how each operand reaches
+ * the devices (out_modes: 0 in place -- the ranges are disjoint --, 1 replicated per device, 2 shared
+ * and larger than SMB_OPT_REPLICATE_MAX_BYTES).  Returns 1 when the call would be sharded, 0 when it
+ * would run on one device, or a negative error. */
+int smb_plan_shards(const uint64_t *stride_a, const uint64_t *stride_b, const uint64_t *shape, int ndim,
+                    int elem_size, int ndev, uint64_t *out_bounds, uint64_t *out_range_a,
+                    uint64_t *out_range_b, int *out_modes);
 
 /* ---- bench / test support -------------------------------------------------- */
 /* Counter-based generator: out[i] = lo + (hi-lo) * U(seed, first+i), the same

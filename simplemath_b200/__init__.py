@@ -24,7 +24,8 @@ LIB_PATH = os.environ.get("SMB200_LIB") or os.path.join(HERE, "libsmb200.so")  #
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW = range(5)
 F32, F64, I32 = range(3)
 MEM_DEVICE, MEM_MANAGED, MEM_PINNED = range(3)
-OPT_POW_SPECIALISE, OPT_STAGE_CHUNK_BYTES, OPT_CONTIG_VARIANT, OPT_BCAST_VARIANT, OPT_FORCE_WIDE_INDEX = range(5)
+(OPT_POW_SPECIALISE, OPT_STAGE_CHUNK_BYTES, OPT_CONTIG_VARIANT, OPT_BCAST_VARIANT, OPT_FORCE_WIDE_INDEX, OPT_ASYNC, OPT_PDL,
+ OPT_SHARD_MIN_BYTES, OPT_REPLICATE_MAX_BYTES, OPT_POOL_MAX_CACHED_BYTES) = range(10)
 PLAN_CONTIGUOUS, PLAN_ROW, PLAN_GENERIC = range(3)
 MAX_NDIM = 6
 CHAIN_MAX = 8
@@ -66,6 +67,9 @@ SYMBOLS = {
     "smb_set_device": (_i, [_i]),
     "smb_get_device": (_i, []),
     "smb_sync": (_i, []),
+    "smb_wait_pending": (_i, []),
+    "smb_set_devices": (_i, [ctypes.POINTER(_i), _i]),
+    "smb_get_devices": (_i, [ctypes.POINTER(_i), _i]),
     "smb_set_option": (_i, [_i, ctypes.c_int64]),
     "smb_get_option": (ctypes.c_int64, [_i]),
     "smb_launch_count": (_u64, []),
@@ -74,6 +78,7 @@ SYMBOLS = {
     "smb_version": (ctypes.c_char_p, []),
     "smb_plan_elementwise": (_i, [_u64p, _u64p, _u64p, _i, _i, ctypes.POINTER(_i), _u64p, _u64p, _u64p]),
     "smb_plan_chain": (_i, [ctypes.POINTER(ChainStep), _i, _u64p, _i, ctypes.POINTER(_i), _u64p, _u64p]),
+    "smb_plan_shards": (_i, [_u64p, _u64p, _u64p, _i, _i, _i, _u64p, _u64p, _u64p, ctypes.POINTER(_i)]),
     "smb_fill_uniform_f32": (_i, [_vp, _u64, _u64, _u64, ctypes.c_float, ctypes.c_float, _vp]),
 }
 
@@ -166,6 +171,19 @@ def plan(stride_a, stride_b, shape, elem_size=4):
     return kind, list(osh[:m]), list(osa[:m]), list(osb[:m])
 
 
+def plan_shards(stride_a, stride_b, shape, ndev, elem_size=4):
+    """Multi-GPU planner only (no GPU): (sharded?, bounds[ndev+1], ranges_a, ranges_b, (mode_a, mode_b)) for an
+    smb_elementwise call spread over ndev devices; modes: 0 in place, 1 replicated, 2 refused."""
+    nd = len(shape)
+    bounds, ra, rb = _u64arr([0] * (ndev + 1)), _u64arr([0] * (2 * ndev)), _u64arr([0] * (2 * ndev))
+    modes = (ctypes.c_int * 2)()
+    rc = lib().smb_plan_shards(_u64arr(stride_a), _u64arr(stride_b), _u64arr(shape), nd, elem_size, ndev, bounds, ra, rb, modes)
+    if rc < 0:
+        raise SmbError(f"smb_plan_shards failed ({rc})")
+    pairs = lambda v: [(int(v[2 * g]), int(v[2 * g + 1])) for g in range(ndev)]
+    return bool(rc), [int(x) for x in bounds], pairs(ra), pairs(rb), (modes[0], modes[1])
+
+
 # --------------------------------------------------------------------------
 # Raw-pointer entry points (what the C++ headers call).
 def elementwise_ptr(op, dtype, a_ptr, stride_a, b_ptr, stride_b, shape, out_ptr, stream=0):
@@ -212,6 +230,19 @@ def sync() -> None:
 
 def device_count() -> int:
     return int(lib().smb_device_count())
+
+
+def set_devices(devices: Sequence[int]) -> None:
+    """smb_set_devices: spread every following operator on managed arrays over these GPUs
+    (flat-range shards, broadcast operands replicated); [] or one entry = single device."""
+    arr = (ctypes.c_int * max(len(devices), 1))(*devices)
+    _check(lib().smb_set_devices(arr, len(devices)))
+
+
+def get_devices() -> list[int]:
+    arr = (ctypes.c_int * 64)()
+    n = lib().smb_get_devices(arr, 64)
+    return list(arr[:n])
 
 
 # --------------------------------------------------------------------------

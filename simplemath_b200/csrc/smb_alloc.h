@@ -24,11 +24,13 @@ struct Block {
     size_t bytes;   // rounded (bucket) size
     int device;     // owning device (-1 for pinned host)
     int kind;       // SMB_MEM_*
-    // Managed blocks only: pages may currently live in host memory (fresh from the driver, or
-    // the owner said the host wrote them).  Launchers prefetch such a block to the GPU once and
-    // clear the flag; blocks last written by a kernel / fill stay clean.  A stale "clean" is only
-    // a performance matter -- the GPU then demand-pages what the host touched.
-    bool maybe_on_host = true;
+    // Managed blocks only: where the launchers last PUT the pages -- 0: unknown / maybe in host memory
+    // (fresh from the driver, or the owner said the host wrote them); otherwise a signature of the
+    // placement (one device, or the byte ranges a device set shares the block by).  A launcher that
+    // needs placement P prefetches only when the recorded one differs, then records P; blocks last
+    // written by a kernel / fill stay where they are.  A stale record is only a performance matter --
+    // the GPU then demand-pages what moved.
+    uint64_t placement = 0;
 };
 
 class Pool {
@@ -41,10 +43,12 @@ public:
     void *alloc(size_t bytes, int kind, int device, cudaError_t *err);
     bool free(void *ptr);
     bool owns(const void *ptr, Block *out = nullptr);
-    // For a managed address: returns the containing block and whether it needed a prefetch
-    // (and clears the flag).  false when the address is not in a live pool block.
-    bool take_host_flag(const void *ptr, Block *out, bool *was_on_host);
-    void set_host_flag(const void *ptr, bool on_host);
+    // For a managed address: returns the containing block and whether its recorded placement
+    // already was `want` (and records `want`).  false when the address is not in a live pool block.
+    bool take_placement(const void *ptr, uint64_t want, Block *out, bool *matched);
+    void clear_placement(const void *ptr);
+    // Give cached blocks back to the driver until at most `keep_bytes` stay cached (largest first).
+    void trim_to(uint64_t keep_bytes);
     void trim();
     void stats(uint64_t s[4]);
 

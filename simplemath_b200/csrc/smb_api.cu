@@ -6,13 +6,18 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <mutex>
+#include <utility>
 #include <string>
+#include <vector>
 #include <algorithm>
 
 #include "../../include/smb200.h"
 #include "smb_alloc.h"
 #include "smb_kernels.cuh"
 #include "smb_plan.h"
+#include "smb_shard.h"
 
 namespace smb {
 
@@ -46,49 +51,179 @@ static std::atomic<int64_t> g_opt_chunk_bytes{64ll << 20};
 static std::atomic<int64_t> g_opt_contig_variant{0};
 static std::atomic<int64_t> g_opt_bcast_variant{0};
 static std::atomic<int64_t> g_opt_force_wide{0};
+static std::atomic<int64_t> g_opt_pool_max_cached{64ll << 30}; // cached (free) pool bytes beyond which smb_free trims
 
 // ------------------------------------------------------ device context ------
-constexpr int kSlots = 3; // staging pipeline depth (H2D | kernel | D2H in flight)
+constexpr int kSlots = 3;       // staging pipeline depth (H2D | kernel | D2H in flight)
+constexpr int kMaxDevices = 64;
+// Accesses of the launches enqueued on a stream since its last fully serialised launch: what a new
+// launch must not touch if it is to overlap them (programmatic dependent launch, see pdl_mode()).
+struct Span { uintptr_t lo, hi; };
+struct StreamTrack {
+    static constexpr int kCap = 24;
+    Span reads[kCap], writes[kCap];
+    int nr = 0, nw = 0;
+    void reset() { nr = nw = 0; }
+};
 struct DeviceCtx {
-    bool ready = false;
+    std::atomic<bool> ready{false};
+    int device = -1;
     int sm_count = 0;
     cudaStream_t main = nullptr;
     cudaStream_t slot[kSlots] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev = nullptr;
+    cudaEvent_t ev_user = nullptr; // orders the library's private streams after the caller's stream
+    cudaEvent_t ev_done = nullptr; // async mode, several devices: end of this device's part of the last operator
+    bool dirty = false;            // async mode: work enqueued on `main` since the last synchronisation
+    StreamTrack track;             // of `main`
 };
-static DeviceCtx g_ctx[64];
+static DeviceCtx g_ctx[kMaxDevices];
 static std::mutex g_ctx_mu;
 
-// There is no CPU fallback: every compute entry point goes through here and
-// fails loudly when no CUDA device is usable.
-static int current_ctx(DeviceCtx **out) {
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count <= 0) {
+static void destroy_ctx_handles(DeviceCtx &c) {
+    if (c.main) cudaStreamDestroy(c.main);
+    for (int i = 0; i < kSlots; ++i) if (c.slot[i]) cudaStreamDestroy(c.slot[i]);
+    if (c.ev) cudaEventDestroy(c.ev);
+    if (c.ev_user) cudaEventDestroy(c.ev_user);
+    if (c.ev_done) cudaEventDestroy(c.ev_done);
+    c.main = nullptr;
+    for (int i = 0; i < kSlots; ++i) c.slot[i] = nullptr;
+    c.ev = c.ev_user = c.ev_done = nullptr;
+    cudaGetLastError();
+}
+static int init_ctx(DeviceCtx &c, int dev) { // g_ctx_mu held, `dev` current
+    c.device = dev;
+    SMB_CK(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    SMB_CK(cudaStreamCreateWithFlags(&c.main, cudaStreamNonBlocking));
+    for (int i = 0; i < kSlots; ++i) SMB_CK(cudaStreamCreateWithFlags(&c.slot[i], cudaStreamNonBlocking));
+    SMB_CK(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+    SMB_CK(cudaEventCreateWithFlags(&c.ev_user, cudaEventDisableTiming));
+    SMB_CK(cudaEventCreateWithFlags(&c.ev_done, cudaEventDisableTiming));
+    // ready-made shared-memory images of the f32 pow tables (one bulk copy per CTA later); a
+    // __device__ global has one instance per device, so every device builds its own
+    k_pow_image_init<<<8, kBlock, 0, c.main>>>();
+    SMB_CK(cudaGetLastError());
+    SMB_CK(cudaStreamSynchronize(c.main));
+    return SMB_OK;
+}
+
+static int device_count_checked(int *count) {
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess || *count <= 0) {
         cudaGetLastError();
         return fail(SMB_ERR_NO_DEVICE, "no CUDA device available (%s); libsmb200 has no CPU fallback",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
-    int dev = 0;
-    SMB_CK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return fail(SMB_ERR_INVALID, "device index %d out of range", dev);
+    return SMB_OK;
+}
+
+// The context of device `dev` (streams, events, pow table image), created on first use.  Leaves
+// `dev` the CURRENT device when it had to initialise; callers that hop between devices restore.
+static int ctx_of(int dev, DeviceCtx **out) {
+    if (dev < 0 || dev >= kMaxDevices) return fail(SMB_ERR_INVALID, "device index %d out of range", dev);
     DeviceCtx &c = g_ctx[dev];
-    if (!c.ready) {
+    if (!c.ready.load(std::memory_order_acquire)) {
         std::lock_guard<std::mutex> lk(g_ctx_mu);
-        if (!c.ready) {
-            SMB_CK(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
-            SMB_CK(cudaStreamCreateWithFlags(&c.main, cudaStreamNonBlocking));
-            for (int i = 0; i < kSlots; ++i) SMB_CK(cudaStreamCreateWithFlags(&c.slot[i], cudaStreamNonBlocking));
-            SMB_CK(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
-            // ready-made shared-memory images of the f32 pow tables (one bulk copy per CTA later)
-            k_pow_image_init<<<8, kBlock, 0, c.main>>>();
-            SMB_CK(cudaGetLastError());
-            SMB_CK(cudaStreamSynchronize(c.main));
-            c.ready = true;
+        if (!c.ready.load(std::memory_order_relaxed)) {
+            SMB_CK(cudaSetDevice(dev));
+            if (int rc = init_ctx(c, dev)) { destroy_ctx_handles(c); return rc; } // nothing half-made survives a failed init
+            c.ready.store(true, std::memory_order_release);
         }
     }
     *out = &c;
     return SMB_OK;
+}
+
+// There is no CPU fallback: every compute entry point goes through here and
+// fails loudly when no CUDA device is usable.
+static void devices_from_env_once();
+static int current_ctx(DeviceCtx **out) {
+    int count = 0;
+    if (int rc = device_count_checked(&count)) return rc;
+    devices_from_env_once();
+    int dev = 0;
+    SMB_CK(cudaGetDevice(&dev));
+    return ctx_of(dev, out);
+}
+
+// Scoped "make `dev` current", restoring the caller's device (the sharded launchers hop).
+struct DeviceScope {
+    int saved = -1;
+    DeviceScope() { if (cudaGetDevice(&saved) != cudaSuccess) { cudaGetLastError(); saved = -1; } }
+    int set(int dev) { SMB_CK(cudaSetDevice(dev)); return SMB_OK; }
+    ~DeviceScope() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
+// ------------------------------------------------------- the device set -----
+// smb_set_devices: the devices an operator on MANAGED arrays is spread over (the
+// broadcast output's flat index range is split, contiguous operands are split by the same ranges,
+// broadcast operands are replicated).  Empty / one entry = the calling thread's current device,
+// exactly the single-GPU behaviour.  SMB_DEVICES ("all", "0-7", "0,2,5") presets it for programs
+// that only know the reference's operator API.
+static std::mutex g_set_mu;
+static std::vector<int> g_devices;
+static std::atomic<int> g_ndevices{0};
+static std::once_flag g_env_once;
+
+static int set_devices_locked(const int *devs, int n) {
+    int count = 0;
+    if (int rc = device_count_checked(&count)) return rc;
+    if (n < 0 || n > kMaxDevices || (n > 0 && !devs)) return fail(SMB_ERR_INVALID, "smb_set_devices: bad device list");
+    for (int i = 0; i < n; ++i) {
+        if (devs[i] < 0 || devs[i] >= count) return fail(SMB_ERR_INVALID, "smb_set_devices: device %d of %d does not exist", devs[i], count);
+        for (int j = 0; j < i; ++j) if (devs[j] == devs[i]) return fail(SMB_ERR_INVALID, "smb_set_devices: device %d listed twice", devs[i]);
+    }
+    DeviceScope scope;
+    for (int i = 0; i < n; ++i) { // contexts up front; peer access so a device may read a neighbour's pages in place
+        DeviceCtx *c = nullptr;
+        if (int rc = ctx_of(devs[i], &c)) return rc;
+        if (n > 1) {
+            SMB_CK(cudaSetDevice(devs[i]));
+            for (int j = 0; j < n; ++j) {
+                if (i == j) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) == cudaSuccess && can) {
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); // best effort
+                    else cudaGetLastError();
+                }
+            }
+        }
+    }
+    g_devices.assign(devs, devs + n);
+    g_ndevices.store(n);
+    return SMB_OK;
+}
+static void devices_from_env_once() {
+    std::call_once(g_env_once, [] {
+        const char *e = getenv("SMB_DEVICES");
+        if (!e || !*e) return;
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return; }
+        std::vector<int> list;
+        if (!strcmp(e, "all")) { for (int i = 0; i < count; ++i) list.push_back(i); }
+        else {
+            const char *p = e;
+            while (*p) {
+                char *end = nullptr;
+                long lo = strtol(p, &end, 10), hi = lo;
+                if (end == p) break;
+                p = end;
+                if (*p == '-') { hi = strtol(p + 1, &end, 10); if (end == p + 1) break; p = end; }
+                for (long d = lo; d <= hi && d < count; ++d) list.push_back((int)d);
+                if (*p == ',') ++p;
+            }
+        }
+        std::lock_guard<std::mutex> lk(g_set_mu);
+        if (g_devices.empty() && !list.empty() && set_devices_locked(list.data(), (int)list.size()) != SMB_OK)
+            fprintf(stderr, "smb200: SMB_DEVICES=%s ignored: %s\n", e, g_err.c_str());
+    });
+}
+static std::vector<int> active_devices() {
+    if (g_ndevices.load() <= 1) return {};
+    std::lock_guard<std::mutex> lk(g_set_mu);
+    return g_devices;
 }
 
 // ------------------------------------------------------------------ pool ----
@@ -162,7 +297,7 @@ bool Pool::owns(const void *ptr, Block *out) {
     if (out) *out = b;
     return true;
 }
-bool Pool::take_host_flag(const void *ptr, Block *out, bool *was_on_host) {
+bool Pool::take_placement(const void *ptr, uint64_t want, Block *out, bool *matched) {
     std::lock_guard<std::mutex> lk(mu_);
     auto it = live_.upper_bound((uintptr_t)ptr);
     if (it == live_.begin()) return false;
@@ -170,17 +305,33 @@ bool Pool::take_host_flag(const void *ptr, Block *out, bool *was_on_host) {
     Block &b = it->second;
     if ((uintptr_t)ptr >= (uintptr_t)b.base + b.bytes) return false;
     *out = b;
-    *was_on_host = b.maybe_on_host;
-    b.maybe_on_host = false;
+    *matched = b.placement == want;
+    b.placement = want;
     return true;
 }
-void Pool::set_host_flag(const void *ptr, bool on_host) {
+void Pool::clear_placement(const void *ptr) {
     std::lock_guard<std::mutex> lk(mu_);
     auto it = live_.upper_bound((uintptr_t)ptr);
     if (it == live_.begin()) return;
     --it;
     Block &b = it->second;
-    if ((uintptr_t)ptr < (uintptr_t)b.base + b.bytes) b.maybe_on_host = on_host;
+    if ((uintptr_t)ptr < (uintptr_t)b.base + b.bytes) b.placement = 0;
+}
+void Pool::trim_to(uint64_t keep_bytes) {
+    std::lock_guard<std::mutex> lk(mu_);
+    while (cached_bytes_ > keep_bytes && !free_.empty()) {
+        auto big = free_.end();
+        for (auto it = free_.begin(); it != free_.end(); ++it)
+            if (!it->second.empty() && (big == free_.end() || it->first.bytes > big->first.bytes)) big = it;
+        if (big == free_.end()) break;
+        void *p = big->second.back();
+        big->second.pop_back();
+        if (big->second.empty()) free_.erase(big);
+        auto c = cached_.find((uintptr_t)p);
+        cached_bytes_ -= c->second.bytes;
+        raw_free(c->second);
+        cached_.erase(c);
+    }
 }
 void Pool::trim() {
     std::lock_guard<std::mutex> lk(mu_);
@@ -200,13 +351,29 @@ void Pool::stats(uint64_t s[4]) {
 // Scoped device scratch block from the pool.
 struct Scratch {
     void *p = nullptr;
+    Scratch() = default;
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
     ~Scratch() { if (p) Pool::instance().free(p); }
-    int get(size_t bytes, int device) {
+    int get(size_t bytes, int device, int kind = SMB_MEM_DEVICE) {
         cudaError_t e;
-        p = Pool::instance().alloc(bytes, SMB_MEM_DEVICE, device, &e);
+        p = Pool::instance().alloc(bytes, kind, device, &e);
         if (!p) return fail(e == cudaErrorMemoryAllocation ? SMB_ERR_OOM : SMB_ERR_CUDA, "scratch alloc of %zu bytes: %s",
                             bytes, cudaGetErrorString(e));
         return SMB_OK;
+    }
+};
+
+// Declared AFTER the Scratch blocks of a staged call (so it runs before their destructors): whatever
+// way the call leaves -- an SMB_CK early return included -- the streams that may still be reading or
+// writing those blocks are drained before the blocks go back to the pool.
+struct DrainGuard {
+    cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n = 0;
+    void add(cudaStream_t st) { if (n < 4) s[n++] = st; }
+    ~DrainGuard() {
+        for (int i = 0; i < n; ++i)
+            if (cudaStreamSynchronize(s[i]) != cudaSuccess) cudaGetLastError();
     }
 };
 
@@ -230,20 +397,89 @@ static MemType mem_type(const void *p) {
 static inline bool on_host(MemType t) { return t == MT_HOST || t == MT_PINNED; }
 
 // Managed operands: bring the pages to the GPU before the launch -- but only when they may be
-// on the host.  cudaMemPrefetchAsync costs ~50 us even for resident pages (measured: 164 us per
-// 3-operand call), so pool blocks carry a "maybe on host" flag (smb_alloc.h); foreign managed
-// memory is always prefetched.
-static void prefetch_managed(const void *p, size_t bytes, cudaStream_t s) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+// elsewhere.  cudaMemPrefetchAsync costs ~50 us even for resident pages (measured: 164 us per
+// 3-operand call), so pool blocks record where the launchers last put them (smb_alloc.h); foreign
+// managed memory is always prefetched.
+static inline uint64_t mix64(uint64_t h, uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); return h; }
+static inline uint64_t placement_single(int dev) { return 0x5100000000000000ull | (uint64_t)(dev + 1); }
+static void prefetch_managed(const void *p, size_t bytes, int dev, cudaStream_t s) {
     Block blk;
-    bool was_on_host = true;
-    if (Pool::instance().take_host_flag(p, &blk, &was_on_host)) {
-        if (!was_on_host) return;
+    bool matched = false;
+    if (Pool::instance().take_placement(p, placement_single(dev), &blk, &matched)) {
+        if (matched) return;
         p = blk.base;        // whole block: views of it become resident too
         bytes = blk.bytes;
     }
     if (cudaMemPrefetchAsync(p, bytes, dev, s) != cudaSuccess) cudaGetLastError(); // best effort
+}
+
+// ------------------------------------------- programmatic dependent launch --
+// Back-to-back launches on one stream normally pay a launch gap plus a ramp: the next grid's first
+// CTA is scheduled only after the previous grid's last CTA has retired and its memory is flushed
+// (~15 us of a 250 us kernel at the 8-GPU shard size).  With the programmatic-stream-serialisation
+// launch attribute the next grid's CTAs become resident as soon as every CTA of the previous grid
+// has STARTED (each calls griddepcontrol.launch_dependents first thing) and fill SM slots as the
+// previous grid's tail drains.  What they may do there depends on the data:
+//   * a launch that touches nothing the launches before it (since the stream's last serialised
+//     point) write, and writes nothing they read, runs right away and executes
+//     griddepcontrol.wait only at its END -- so that ITS completion still implies theirs;
+//   * any other launch executes griddepcontrol.wait first (the wait returns once the previous grid
+//     has completed and flushed): it only saves the scheduling ramp.
+// The host knows every operand range of its own launches, so it decides; SMB_OPT_PDL = 0 turns the
+// attribute off (plain stream order).
+static std::atomic<int64_t> g_opt_pdl{1};
+// The overlapping form is used on the library's PRIVATE stream only (stream == NULL calls): there
+// every kernel is ours.  On a caller's stream the previous kernel may be anyone's (and may itself
+// trigger early), so launches there always wait first.
+static std::mutex g_launch_mu; // decision + launch are one unit per stream; launches are cheap, one lock serves all
+
+struct PdlDecision { bool attr; uint32_t flags; };
+static inline bool spans_overlap(const Span &x, const Span &y) { return x.lo < y.hi && y.lo < x.hi; }
+static PdlDecision pdl_decide(StreamTrack &t, const Span *reads, int nr, const Span &write) {
+    if (!g_opt_pdl.load(std::memory_order_relaxed)) { t.reset(); return {false, kPdlWaitFirst}; }
+    bool conflict = t.nr + nr > StreamTrack::kCap || t.nw + 1 > StreamTrack::kCap;
+    for (int i = 0; i < t.nw && !conflict; ++i) {
+        if (spans_overlap(t.writes[i], write)) conflict = true;
+        for (int j = 0; j < nr && !conflict; ++j) if (spans_overlap(t.writes[i], reads[j])) conflict = true;
+    }
+    for (int i = 0; i < t.nr && !conflict; ++i) if (spans_overlap(t.reads[i], write)) conflict = true;
+    if (conflict) t.reset(); // this launch waits first: when its work starts, everything before it is done
+    for (int j = 0; j < nr; ++j) if (reads[j].hi > reads[j].lo) t.reads[t.nr++] = reads[j];
+    t.writes[t.nw++] = write;
+    return {true, conflict ? kPdlWaitFirst : 0u};
+}
+// A launch of ours that does not take part (no griddepcontrol in the kernel): plain stream order --
+// it starts after everything before it has completed, and nothing starts before it has.
+static inline void pdl_barrier(StreamTrack &t) { t.reset(); }
+
+struct LaunchLock {
+    std::unique_lock<std::mutex> lk;
+    StreamTrack *t; // nullptr: a caller's stream
+    LaunchLock(DeviceCtx &c, cudaStream_t s) : lk(g_launch_mu), t(s == c.main ? &c.track : nullptr) {}
+    PdlDecision decide(const Span *reads, int nr, const Span &write) {
+        if (t) return pdl_decide(*t, reads, nr, write);
+        return {g_opt_pdl.load(std::memory_order_relaxed) != 0, kPdlWaitFirst};
+    }
+    void barrier() { if (t) pdl_barrier(*t); }
+};
+
+template<typename... KArgs, typename... Args>
+static cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t s, bool pdl_attr,
+                             Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    if (pdl_attr) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
 // ----------------------------------------------------------- launchers ------
@@ -273,18 +509,31 @@ static unsigned grid_for(uint64_t work_items, uint64_t items_per_block, int sm_c
     return (unsigned)std::min<uint64_t>(blocks, 0x7fffffffull);
 }
 
+static inline Span span_of(const void *p, uint64_t bytes) { return Span{(uintptr_t)p, (uintptr_t)p + bytes}; }
+
+// Consecutive tiles per CTA of the table-driven pow kernels.  Enough to amortise the table fill (one
+// bulk copy for f32, an in-kernel fill of 40 KB for f64) and the first tile's unhidden load latency,
+// few enough that the grid stays MANY waves deep: a grid of resident CTAs measured 10-15 % slower,
+// and at the 8-GPU shard size (2^27 elements) the library default of 8 left only 9 waves, whose last
+// one costs 5 % -- so the count shrinks with the array (>= 24 waves of `resident` CTAs).
+static int64_t pow_tiles_per_cta(uint64_t full_tiles, int sm_count, int resident_per_sm, int64_t dflt) {
+    const int64_t cps = g_opt_contig_variant.load();
+    if (cps > 0) return cps;
+    const uint64_t per_wave = (uint64_t)sm_count * (uint64_t)resident_per_sm;
+    const uint64_t fit = full_tiles / (per_wave * 24);
+    return (int64_t)std::max<uint64_t>(2, std::min<uint64_t>((uint64_t)dflt, fit));
+}
+
 template<typename T, typename Fn, bool HAS_B>
-static int launch_stream(const DeviceCtx &c, const T *a, const T *b, T *out, uint64_t n, uint64_t first, Fn fn,
+static int launch_stream(DeviceCtx &c, const T *a, const T *b, T *out, uint64_t n, uint64_t first, Fn fn,
                          cudaStream_t s) {
     if (n == 0) return SMB_OK;
     constexpr int VB = SMB_STREAM_VB, UNROLL = SMB_STREAM_UNROLL;
     const uintptr_t ma = (uintptr_t)a % VB, mb = HAS_B ? (uintptr_t)b % VB : ma, mo = (uintptr_t)out % VB;
-    int64_t cps = g_opt_contig_variant.load();
-    // Plain streams run one tile per CTA (tools/sweep: fastest on B200).  Kernels that stage lookup
-    // tables in shared memory (pow) give each CTA a few consecutive tiles to amortise the fill --
-    // one bulk copy for f32, an in-kernel fill of 40 KB for f64 -- but stay many waves deep: a grid
-    // of resident CTAs measured 10-15 % slower.  For them the option counts tiles per CTA.
-    const int64_t tiles_per_cta = cps > 0 ? cps : (sizeof(T) == 4 ? SMB_POW_TILES_PER_CTA : 4 * SMB_POW_TILES_PER_CTA);
+    const int64_t cps = g_opt_contig_variant.load();
+    const Span reads[2] = {span_of(a, n * sizeof(T)), span_of(HAS_B ? b : a, n * sizeof(T))};
+    const Span write = span_of(out, n * sizeof(T));
+    LaunchLock ll(c, s);
     if (ma == mb && ma == mo && ma % sizeof(T) == 0) {
         uint64_t head = ma ? (VB - ma) / sizeof(T) : 0;
         if (head > n) head = n;
@@ -295,11 +544,20 @@ static int launch_stream(const DeviceCtx &c, const T *a, const T *b, T *out, uin
         const uint64_t rest = n - head;
         if (rest) {
             constexpr uint64_t per_block = (uint64_t)kThreads * UNROLL * (VB / sizeof(T));
-            const unsigned grid = fn_pow_tables<Fn>::value && SMB_POW_BLOCKED
-                                      ? grid_for(rest, per_block * (uint64_t)tiles_per_cta, c.sm_count, 0)
-                                      : grid_for(rest, per_block, c.sm_count, fn_pow_tables<Fn>::value && cps == 0 ? 8 : cps);
-            k_stream<T, Fn, HAS_B, VB, UNROLL><<<grid, kThreads, 0, s>>>(a + head, HAS_B ? b + head : nullptr, out + head,
-                                                                       rest, first + head, fn);
+            // Plain streams run one tile per CTA (tools/sweep: fastest on B200); the pow kernels a few
+            // consecutive tiles per CTA (pow_tiles_per_cta).  SMB_OPT_CONTIG_VARIANT overrides either.
+            unsigned grid;
+            if (fn_pow_tables<Fn>::value && SMB_POW_BLOCKED) {
+                const int resident = sizeof(T) == 4 ? SMB_POW_MIN_BLOCKS : SMB_POW64_MIN_BLOCKS;
+                const int64_t tpc = pow_tiles_per_cta(rest / per_block, c.sm_count, resident,
+                                                      sizeof(T) == 4 ? SMB_POW_TILES_PER_CTA : 4 * SMB_POW_TILES_PER_CTA);
+                grid = grid_for(rest, per_block * (uint64_t)tpc, c.sm_count, 0);
+            } else {
+                grid = grid_for(rest, per_block, c.sm_count, fn_pow_tables<Fn>::value && cps == 0 ? 8 : cps);
+            }
+            const PdlDecision d = ll.decide(reads, HAS_B ? 2 : 1, write);
+            SMB_CK(launch_ex(k_stream<T, Fn, HAS_B, VB, UNROLL>, dim3(grid), kThreads, 0, s, d.attr, a + head,
+                             HAS_B ? b + head : (const T *)nullptr, out + head, rest, first + head, fn, d.flags));
             ++g_launches;
             g_last_kernel = HAS_B ? "k_stream<binary>" : "k_stream<scalar>";
         }
@@ -314,7 +572,7 @@ static int launch_stream(const DeviceCtx &c, const T *a, const T *b, T *out, uin
 }
 
 template<typename T>
-static int contiguous_t(const DeviceCtx &c, int op, const T *a, const T *b, T *out, uint64_t n, uint64_t first,
+static int contiguous_t(DeviceCtx &c, int op, const T *a, const T *b, T *out, uint64_t n, uint64_t first,
                         uint64_t lane_end, cudaStream_t s) {
     switch (op) {
         case SMB_OP_ADD: return launch_stream<T, BinaryFn<OP_ADD, T>, true>(c, a, b, out, n, first, {lane_end}, s);
@@ -329,11 +587,11 @@ static int contiguous_t(const DeviceCtx &c, int op, const T *a, const T *b, T *o
 // array (op) scalar.  `first` is the absolute flat index of a[0] (staging
 // chunks), lane_end the absolute end of the reference's SIMD region.
 template<typename T>
-static int scalar_t(const DeviceCtx &c, int op, const T *a, T v, T *out, uint64_t n, uint64_t first, uint64_t lane_end,
+static int scalar_t(DeviceCtx &c, int op, const T *a, T v, T *out, uint64_t n, uint64_t first, uint64_t lane_end,
                     cudaStream_t s);
 
 template<>
-int scalar_t<float>(const DeviceCtx &c, int op, const float *a, float v, float *out, uint64_t n, uint64_t first,
+int scalar_t<float>(DeviceCtx &c, int op, const float *a, float v, float *out, uint64_t n, uint64_t first,
                     uint64_t lane_end, cudaStream_t s) {
     using T = float;
     switch (op) {
@@ -371,7 +629,7 @@ int scalar_t<float>(const DeviceCtx &c, int op, const float *a, float v, float *
     return fail(SMB_ERR_INVALID, "unknown op %d", op);
 }
 template<>
-int scalar_t<double>(const DeviceCtx &c, int op, const double *a, double v, double *out, uint64_t n, uint64_t first,
+int scalar_t<double>(DeviceCtx &c, int op, const double *a, double v, double *out, uint64_t n, uint64_t first,
                      uint64_t lane_end, cudaStream_t s) {
     using T = double;
     switch (op) {
@@ -399,7 +657,7 @@ int scalar_t<double>(const DeviceCtx &c, int op, const double *a, double v, doub
     return fail(SMB_ERR_INVALID, "unknown op %d", op);
 }
 template<>
-int scalar_t<int32_t>(const DeviceCtx &c, int op, const int32_t *a, int32_t v, int32_t *out, uint64_t n, uint64_t first,
+int scalar_t<int32_t>(DeviceCtx &c, int op, const int32_t *a, int32_t v, int32_t *out, uint64_t n, uint64_t first,
                       uint64_t lane_end, cudaStream_t s) {
     using T = int32_t;
     switch (op) {
@@ -468,7 +726,7 @@ static int row_vector_bytes(const ElementwisePlan &p, const T *a, const T *b, co
 }
 
 template<typename T, typename Fn>
-static int launch_bcast(const DeviceCtx &c, const ElementwisePlan &p, const T *a, const T *b, T *out, uint64_t lin_base,
+static int launch_bcast(DeviceCtx &c, const ElementwisePlan &p, const T *a, const T *b, T *out, uint64_t lin_base,
                         uint64_t count, uint64_t lane_base, Fn fn, cudaStream_t s) {
     if (count == 0) return SMB_OK;
     bool wide = false;
@@ -609,7 +867,7 @@ static int launch_bcast(const DeviceCtx &c, const ElementwisePlan &p, const T *a
 }
 
 template<typename T>
-static int bcast_t(const DeviceCtx &c, int op, const ElementwisePlan &p, const T *a, const T *b, T *out, uint64_t lin_base,
+static int bcast_t(DeviceCtx &c, int op, const ElementwisePlan &p, const T *a, const T *b, T *out, uint64_t lin_base,
                    uint64_t count, uint64_t lane_base, uint64_t lane_end, cudaStream_t s) {
     switch (op) {
         case SMB_OP_ADD: return launch_bcast<T, BinaryFn<OP_ADD, T>>(c, p, a, b, out, lin_base, count, lane_base, {lane_end}, s);
@@ -624,7 +882,7 @@ static int bcast_t(const DeviceCtx &c, int op, const ElementwisePlan &p, const T
 // One elementwise launch on DEVICE-ACCESSIBLE operands.  `a`/`b` address the
 // operands of plan `p`; the launch produces flat elements
 // [lin_base, lin_base+count) of the plan's result into out[0..count).
-static int elementwise_device(const DeviceCtx &c, int op, int dtype, const ElementwisePlan &p, const void *a, const void *b,
+static int elementwise_device(DeviceCtx &c, int op, int dtype, const ElementwisePlan &p, const void *a, const void *b,
                               void *out, uint64_t lin_base, uint64_t count, uint64_t lane_base, uint64_t lane_end,
                               cudaStream_t s) {
     if (p.kind == PLAN_CONTIGUOUS) {
@@ -643,7 +901,7 @@ static int elementwise_device(const DeviceCtx &c, int op, int dtype, const Eleme
     return fail(SMB_ERR_INVALID, "unknown dtype %d", dtype);
 }
 
-static int scalar_device(const DeviceCtx &c, int op, int dtype, const void *a, const void *scalar, void *out, uint64_t n,
+static int scalar_device(DeviceCtx &c, int op, int dtype, const void *a, const void *scalar, void *out, uint64_t n,
                          uint64_t first, uint64_t lane_end, cudaStream_t s) {
     switch (dtype) {
         case SMB_F32: return scalar_t<float>(c, op, (const float *)a, *(const float *)scalar, (float *)out, n, first, lane_end, s);
@@ -681,6 +939,91 @@ static bool reference_takes_contiguous_path(const uint64_t *sa, const uint64_t *
     return true;
 }
 
+// ------------------------------------------------------- asynchronous mode ---
+// SMB_OPT_ASYNC = 1 (opt-in; sm::async_scope in the C++ headers): a call with stream == NULL enqueues
+// on the device's private stream and RETURNS -- the result hand-off of SURVEY.md §8f rank 4.  The
+// reference's contract (results complete on return) is what costs 15 us per call
+// around a 2 us kernel at the launch-bound sizes (benchmark/add.cpp:21-29).  Results are complete
+// after smb_sync() / smb_wait_pending(); the C++ headers call the latter before any host access.
+// Order is kept by the stream: every async call of a device goes to the same private stream, and a
+// pool block that is freed and handed out again is reused on that stream.  With several devices, an
+// operator's part on device d also waits for what the OTHER devices still have in flight, unless it
+// is the same partition of pure streams as the operator before it (every device then touches only
+// its own ranges).
+static std::atomic<int64_t> g_opt_async{0};
+static std::atomic<bool> g_pending{false};
+static std::mutex g_async_mu;
+static uint64_t g_dirty_mask = 0;  // devices with un-synchronised async work (g_async_mu)
+static uint64_t g_last_sig = 0;    // partition signature of the last async operator, 0: none / not a pure partition
+
+static inline bool async_mode(const void *stream) { return !stream && g_opt_async.load(std::memory_order_relaxed) != 0; }
+
+// Before enqueueing an operator's part on each device of `devs`: cross-device order (see above).
+// Events are recorded lazily, here, on the devices someone has to wait for -- the common case (one
+// device) never records or waits.
+static int async_order(const int *devs, int n, uint64_t sig) {
+    std::lock_guard<std::mutex> lk(g_async_mu);
+    if (sig != 0 && sig == g_last_sig) return SMB_OK;
+    g_last_sig = sig;
+    uint64_t recorded = 0;
+    for (int i = 0; i < n; ++i) {
+        const uint64_t others = g_dirty_mask & ~(1ull << devs[i]);
+        for (int e = 0; others >> e; ++e) {
+            if (!((others >> e) & 1ull)) continue;
+            if (!((recorded >> e) & 1ull)) { SMB_CK(cudaEventRecord(g_ctx[e].ev_done, g_ctx[e].main)); recorded |= 1ull << e; }
+            SMB_CK(cudaStreamWaitEvent(g_ctx[devs[i]].main, g_ctx[e].ev_done, 0));
+        }
+    }
+    return SMB_OK;
+}
+// After enqueueing: these devices now have work in flight.
+static int async_mark(const int *devs, int n) {
+    std::lock_guard<std::mutex> lk(g_async_mu);
+    for (int i = 0; i < n; ++i) {
+        g_ctx[devs[i]].dirty = true;
+        g_dirty_mask |= 1ull << devs[i];
+    }
+    g_pending.store(true, std::memory_order_release);
+    return SMB_OK;
+}
+// End of a stream == NULL call on one device: the reference's synchronous contract, or the hand-off.
+static int finish_call(DeviceCtx &c, cudaStream_t s, const void *user_stream) {
+    if (user_stream) return SMB_OK;
+    if (async_mode(user_stream)) return async_mark(&c.device, 1);
+    SMB_CK(cudaStreamSynchronize(s));
+    return SMB_OK;
+}
+// Start of a stream == NULL call on ONE device in async mode: wait for other devices' pending work.
+static int begin_call(DeviceCtx &c, const void *user_stream) {
+    if (!async_mode(user_stream)) return SMB_OK;
+    return async_order(&c.device, 1, 0);
+}
+static int sync_all() {
+    {
+        std::lock_guard<std::mutex> lk(g_async_mu);
+        for (int d = 0; d < kMaxDevices; ++d) {
+            DeviceCtx &c = g_ctx[d];
+            if (!c.ready.load(std::memory_order_acquire)) continue;
+            SMB_CK(cudaStreamSynchronize(c.main));
+            c.dirty = false;
+        }
+        g_dirty_mask = 0;
+        g_last_sig = 0;
+        g_pending.store(false, std::memory_order_release);
+    }
+    return SMB_OK;
+}
+
+// The library's private copy / compute streams of a STAGED (host-operand) call start after the
+// work already enqueued on the caller's stream -- or, in async mode, on the private main stream --
+// so pinned inputs an earlier async operation produces are complete before the first H2D copy.
+static int order_slots_after(DeviceCtx &c, cudaStream_t after, int nslots) {
+    if (!after) return SMB_OK;
+    SMB_CK(cudaEventRecord(c.ev_user, after));
+    for (int i = 0; i < nslots; ++i) SMB_CK(cudaStreamWaitEvent(c.slot[i], c.ev_user, 0));
+    return SMB_OK;
+}
+
 // --------------------------------------------------- host-operand staging ---
 // Operands in host memory are streamed through HBM in slabs along the leading
 // coalesced dim: slab i uses slot i % kSlots (own stream + scratch), so the H2D
@@ -688,10 +1031,9 @@ static bool reference_takes_contiguous_path(const uint64_t *sa, const uint64_t *
 // An operand that does not vary along the leading dim (stride 0 there) is
 // uploaded once.  Device/managed operands are used in place.
 static int elementwise_staged(DeviceCtx &c, int op, int dtype, const ElementwisePlan &p, const void *a, MemType ta,
-                              const void *b, MemType tb, void *out, MemType to, uint64_t lane_end) {
+                              const void *b, MemType tb, void *out, MemType to, uint64_t lane_end, cudaStream_t after) {
     const size_t es = esize(dtype);
-    int dev = 0;
-    SMB_CK(cudaGetDevice(&dev));
+    const int dev = c.device;
     const uint64_t rows = p.shape[0];
     const uint64_t inner = p.n / rows; // result elements per leading index
     const bool a_var = p.ndim > 1 ? p.sa[0] != 0 : p.sa[0] != 0;
@@ -711,6 +1053,10 @@ static int elementwise_staged(DeviceCtx &c, int op, int dtype, const Elementwise
 
     // invariant operands: upload once on slot 0, everyone else waits on the event
     Scratch inv_a, inv_b;
+    Scratch sa_[kSlots], sb_[kSlots], so_[kSlots];
+    DrainGuard drain; // after the scratch blocks: drained before they are released, on every way out
+    for (int i = 0; i < kSlots; ++i) drain.add(c.slot[i]);
+    if (int rc = order_slots_after(c, after, kSlots)) return rc;
     const void *da_inv = a, *db_inv = b;
     bool need_ev = false;
     if (on_host(ta) && !a_var) {
@@ -731,7 +1077,6 @@ static int elementwise_staged(DeviceCtx &c, int op, int dtype, const Elementwise
     }
     const uint64_t slab_ea = a_var ? (chunk_rows - 1) * p.sa[0] + ea1 : 0;
     const uint64_t slab_eb = b_var ? (chunk_rows - 1) * p.sb[0] + eb1 : 0;
-    Scratch sa_[kSlots], sb_[kSlots], so_[kSlots];
     for (int i = 0; i < nslots; ++i) {
         if (on_host(ta) && a_var) if (int rc = sa_[i].get(slab_ea * es, dev)) return rc;
         if (on_host(tb) && b_var) if (int rc = sb_[i].get(slab_eb * es, dev)) return rc;
@@ -764,21 +1109,22 @@ static int elementwise_staged(DeviceCtx &c, int op, int dtype, const Elementwise
         if (on_host(to))
             SMB_CK(cudaMemcpyAsync((char *)out + r0 * inner * es, po, sub.n * es, cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < nslots; ++i) SMB_CK(cudaStreamSynchronize(c.slot[i]));
-    if (need_ev && nslots == 0) SMB_CK(cudaStreamSynchronize(c.slot[0]));
+    for (int i = 0; i < kSlots; ++i) SMB_CK(cudaStreamSynchronize(c.slot[i]));
     return SMB_OK;
 }
 
 static int scalar_staged(DeviceCtx &c, int op, int dtype, const void *a, MemType ta, const void *scalar, void *out,
-                         MemType to, uint64_t n, uint64_t lane_end) {
+                         MemType to, uint64_t n, uint64_t lane_end, cudaStream_t after) {
     const size_t es = esize(dtype);
-    int dev = 0;
-    SMB_CK(cudaGetDevice(&dev));
+    const int dev = c.device;
     const uint64_t chunk_bytes = (uint64_t)std::max<int64_t>(g_opt_chunk_bytes.load(), 1 << 16);
     const uint64_t chunk = std::min<uint64_t>(n, std::max<uint64_t>(1, chunk_bytes / es));
     const uint64_t nchunks = (n + chunk - 1) / chunk;
     const int nslots = (int)std::min<uint64_t>(kSlots, nchunks);
     Scratch sa_[kSlots], so_[kSlots];
+    DrainGuard drain;
+    for (int i = 0; i < kSlots; ++i) drain.add(c.slot[i]);
+    if (int rc = order_slots_after(c, after, kSlots)) return rc;
     for (int i = 0; i < nslots; ++i) {
         if (on_host(ta)) if (int rc = sa_[i].get(chunk * es, dev)) return rc;
         if (on_host(to)) if (int rc = so_[i].get(chunk * es, dev)) return rc;
@@ -806,6 +1152,156 @@ static int check_args(int op, int dtype) {
     return SMB_OK;
 }
 
+// ------------------------------------------------- one operator, G devices ---
+// (the arithmetic is in smb_shard.h.)  One host thread walks the device set: on
+// device g it makes the operands of flat range g available on that device's private stream --
+// an in-place operand by prefetching the range's pages there (skipped when the block's placement
+// record says they already are), a replicated operand by one copy into pooled scratch of that device
+// -- and launches the same kernels a single GPU would, restricted to the range.  Nothing is
+// exchanged between devices.  The caller either waits for all streams (the reference's synchronous
+// contract) or, in async mode, leaves.
+static std::atomic<int64_t> g_opt_shard_min_bytes{32ll << 20};   // results below this stay on one device
+static std::atomic<int64_t> g_opt_replicate_max_bytes{64ll << 20};
+
+struct ShardOperand {
+    const void *base = nullptr;  // the operand as the caller passed it
+    OperandShards plan;
+    bool need_prefetch = false;  // in place: the block's recorded placement is not this partition
+};
+static uint64_t placement_sharded(const std::vector<int> &devs, const void *base, const OperandShards &o) {
+    uint64_t h = 0xA5ull;
+    for (size_t i = 0; i < devs.size(); ++i) {
+        h = mix64(h, (uint64_t)devs[i]);
+        h = mix64(h, o.r[i].lo);
+        h = mix64(h, o.r[i].hi);
+    }
+    h = mix64(h, (uint64_t)(uintptr_t)base & 0x1fffffull); // same block, different view offset = different pages
+    return h | 0x8000000000000000ull;
+}
+// Decide how every operand reaches the devices; false: some operand is both shared between devices
+// and too large to copy per call -- the caller runs the operator on one device instead.
+static bool shard_operands(const std::vector<int> &devs, const ShardSplit &split, const uint64_t *shape, int ndim,
+                           const void *const *bases, const uint64_t *const *strides, int nops, size_t es, ShardOperand *ops) {
+    const uint64_t rmax = (uint64_t)std::max<int64_t>(0, g_opt_replicate_max_bytes.load());
+    for (int o = 0; o < nops; ++o) {
+        ops[o].base = bases[o];
+        if (!bases[o]) continue; // a constant
+        ops[o].plan = plan_operand(shape, strides[o], ndim, split, es, rmax);
+        if (ops[o].plan.mode == SHARD_REFUSE) return false;
+    }
+    for (int o = 0; o < nops; ++o) {
+        if (!bases[o] || ops[o].plan.mode != SHARD_IN_PLACE) continue;
+        Block blk;
+        bool matched = false;
+        ops[o].need_prefetch = !(Pool::instance().take_placement(bases[o], placement_sharded(devs, bases[o], ops[o].plan), &blk, &matched) && matched);
+    }
+    return true;
+}
+// Operand `op` for device index g (the current device), on stream s: returns the base pointer the
+// kernels of that device use (the caller's pointer, or a rebased scratch copy).
+static int shard_operand_on_device(const ShardOperand &op, int g, int dev, size_t es, cudaStream_t s, Scratch &scratch,
+                                   const void **use) {
+    *use = op.base;
+    if (!op.base) return SMB_OK;
+    const ElemRange r = op.plan.r[g];
+    if (r.hi == r.lo) return SMB_OK;
+    const char *src = (const char *)op.base + r.lo * es;
+    const size_t bytes = (r.hi - r.lo) * es;
+    if (op.plan.mode == SHARD_IN_PLACE) {
+        if (op.need_prefetch && cudaMemPrefetchAsync(src, bytes, dev, s) != cudaSuccess) cudaGetLastError(); // best effort
+        return SMB_OK;
+    }
+    // replica: same 16-byte phase as the original so the vector kernels still qualify; the kernels
+    // index from the operand's element 0, so the base is moved back by the range's offset
+    const size_t pad = (uintptr_t)src & 15;
+    if (int rc = scratch.get(bytes + 16, dev)) return rc;
+    char *dst = (char *)scratch.p + pad;
+    SMB_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+    *use = dst - r.lo * es;
+    return SMB_OK;
+}
+
+// Runs `launch(ctx, g, lo, count, operand bases..., stream)` for every non-empty range of the split.
+template<typename Launch>
+static int run_sharded(const std::vector<int> &devs, const ShardSplit &split, ShardOperand *ops, int nops,
+                       const ShardOperand &result, size_t es, bool async, Launch &&launch) {
+    const int G = (int)devs.size();
+    std::vector<Scratch> scratch((size_t)G * (size_t)std::max(nops, 1));
+    DeviceScope scope;
+    bool pure = true; // every operand in place: each device touches only its own ranges
+    for (int o = 0; o < nops; ++o) if (ops[o].base && ops[o].plan.mode != SHARD_IN_PLACE) pure = false;
+    if (async) {
+        uint64_t sig = 0;
+        if (pure) { sig = 0x51ull; for (int g = 0; g <= G; ++g) sig = mix64(sig, split.bounds[g]); for (int d : devs) sig = mix64(sig, (uint64_t)d); sig |= 1; }
+        if (int rc = async_order(devs.data(), G, sig)) return rc;
+    }
+    int rc = SMB_OK;
+    int launched = 0;
+    for (int g = 0; g < G && rc == SMB_OK; ++g) {
+        const uint64_t lo = split.bounds[g], cnt = split.bounds[g + 1] - lo;
+        if (cnt == 0) continue;
+        DeviceCtx *c = nullptr;
+        if ((rc = scope.set(devs[g])) != SMB_OK) break;
+        if ((rc = ctx_of(devs[g], &c)) != SMB_OK) break;
+        const void *use[SMB_CHAIN_MAX + 2];
+        for (int o = 0; o < nops && rc == SMB_OK; ++o)
+            rc = shard_operand_on_device(ops[o], g, devs[g], es, c->main, scratch[(size_t)g * nops + o], &use[o]);
+        if (rc != SMB_OK) break;
+        if (result.base && result.need_prefetch) {
+            const ElemRange r = result.plan.r[g];
+            if (cudaMemPrefetchAsync((const char *)result.base + r.lo * es, (r.hi - r.lo) * es, devs[g], c->main) != cudaSuccess) cudaGetLastError();
+        }
+        rc = launch(*c, g, lo, cnt, use, c->main);
+        ++launched;
+    }
+    if (async && rc == SMB_OK) return async_mark(devs.data(), G);
+    // synchronous contract -- and on an error, drain what was enqueued before the scratch goes back
+    for (int g = 0; g < G; ++g) {
+        if (!g_ctx[devs[g]].ready.load(std::memory_order_acquire)) continue;
+        const cudaError_t e = cudaStreamSynchronize(g_ctx[devs[g]].main);
+        if (e != cudaSuccess && rc == SMB_OK) { cudaGetLastError(); rc = fail(SMB_ERR_CUDA, "device %d: %s", devs[g], cudaGetErrorString(e)); }
+    }
+    (void)launched;
+    return rc;
+}
+
+// Whether an operator on these pointers is spread over the device set: only MANAGED arrays are (they
+// are the drop-in SMArray storage and have one address every device can use); device blocks live on
+// one GPU and are computed there, host operands go through the staging pipeline.
+static bool want_sharding(std::vector<int> &devs, uint64_t result_bytes, const void *stream, bool whole) {
+    if (stream || !whole || g_ndevices.load(std::memory_order_relaxed) <= 1) return false;
+    if ((int64_t)result_bytes < g_opt_shard_min_bytes.load()) return false;
+    devs = active_devices();
+    return devs.size() > 1 && devs.size() <= (size_t)kMaxShards;
+}
+
+static int elementwise_sharded(const std::vector<int> &devs, int op, int dtype, const ElementwisePlan &p, const void *a,
+                               const void *b, void *out, uint64_t lane_end, bool *done) {
+    const size_t es = esize(dtype);
+    const int G = (int)devs.size();
+    const uint64_t rows = p.ndim >= 2 ? p.shape[0] : p.n, inner = p.ndim >= 2 ? p.n / p.shape[0] : 1;
+    const ShardSplit split = split_flat(p.n, rows, inner, p.ndim, G, es);
+    const void *bases[2] = {a, b};
+    const uint64_t *strides[2] = {p.sa, p.sb};
+    ShardOperand ops[2], res;
+    *done = false;
+    if (!shard_operands(devs, split, p.shape, p.ndim, bases, strides, 2, es, ops)) return SMB_OK;
+    // the result: dense, range g is exactly [bounds[g], bounds[g + 1])
+    res.base = out;
+    res.plan.mode = SHARD_IN_PLACE;
+    for (int g = 0; g < G; ++g) res.plan.r[g] = ElemRange{split.bounds[g], split.bounds[g + 1]};
+    {
+        Block blk;
+        bool matched = false;
+        res.need_prefetch = !(Pool::instance().take_placement(out, placement_sharded(devs, out, res.plan), &blk, &matched) && matched);
+    }
+    *done = true;
+    return run_sharded(devs, split, ops, 2, res, es, async_mode(nullptr),
+                       [&](DeviceCtx &c, int, uint64_t lo, uint64_t cnt, const void *const *use, cudaStream_t s) {
+                           return elementwise_device(c, op, dtype, p, use[0], use[1], (char *)out + lo * es, lo, cnt, lo, lane_end, s);
+                       });
+}
+
 static int elementwise_entry(int op, int dtype, const void *a, const uint64_t *stride_a, const void *b,
                              const uint64_t *stride_b, const uint64_t *shape, int ndim, uint64_t lin_begin,
                              uint64_t lin_count, bool whole, void *out, void *stream) {
@@ -825,14 +1321,19 @@ static int elementwise_entry(int op, int dtype, const void *a, const uint64_t *s
     const MemType ta = mem_type(a), tb = mem_type(b), to = mem_type(out);
     const size_t es = esize(dtype);
     if (on_host(ta) || on_host(tb) || on_host(to)) {
+        // Host operands: always synchronous (the result is in host memory on return); the copies are
+        // ordered after what is already enqueued on `stream` (or on the private stream in async mode).
+        cudaStream_t after = stream ? (cudaStream_t)stream : (c->dirty ? c->main : nullptr);
         if (lin_begin != 0 || lin_count != p.n) {
             // partial range with host operands: stage the touched operands whole
-            int dev = 0;
-            SMB_CK(cudaGetDevice(&dev));
+            const int dev = c->device;
             Scratch da, db, dout;
+            DrainGuard drain;
+            drain.add(c->slot[0]);
             const void *pa = a, *pb = b;
             void *po = out;
-            cudaStream_t s = c->main;
+            cudaStream_t s = c->slot[0];
+            if (int rc = order_slots_after(*c, after, 1)) return rc;
             if (on_host(ta)) { if (int rc = da.get(p.extent_a * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(da.p, a, p.extent_a * es, cudaMemcpyHostToDevice, s)); pa = da.p; }
             if (on_host(tb)) { if (int rc = db.get(p.extent_b * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(db.p, b, p.extent_b * es, cudaMemcpyHostToDevice, s)); pb = db.p; }
             if (on_host(to)) { if (int rc = dout.get(lin_count * es, dev)) return rc; po = dout.p; }
@@ -841,43 +1342,69 @@ static int elementwise_entry(int op, int dtype, const void *a, const uint64_t *s
             SMB_CK(cudaStreamSynchronize(s));
             return SMB_OK;
         }
-        return elementwise_staged(*c, op, dtype, p, a, ta, b, tb, out, to, lane_end);
+        return elementwise_staged(*c, op, dtype, p, a, ta, b, tb, out, to, lane_end, after);
+    }
+    std::vector<int> devs;
+    if (ta == MT_MANAGED && tb == MT_MANAGED && to == MT_MANAGED && want_sharding(devs, lin_count * es, stream, lin_begin == 0 && lin_count == p.n)) {
+        bool done = false;
+        const int rc = elementwise_sharded(devs, op, dtype, p, a, b, out, lane_end, &done);
+        if (rc || done) return rc;
     }
     cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
-    if (ta == MT_MANAGED) prefetch_managed(a, p.extent_a * es, s);
-    if (tb == MT_MANAGED) prefetch_managed(b, p.extent_b * es, s);
-    if (to == MT_MANAGED) prefetch_managed(out, lin_count * es, s);
+    if (int rc = begin_call(*c, stream)) return rc;
+    if (ta == MT_MANAGED) prefetch_managed(a, p.extent_a * es, c->device, s);
+    if (tb == MT_MANAGED) prefetch_managed(b, p.extent_b * es, c->device, s);
+    if (to == MT_MANAGED) prefetch_managed(out, lin_count * es, c->device, s);
     if (int rc = elementwise_device(*c, op, dtype, p, a, b, out, lin_begin, lin_count, lin_begin, lane_end, s)) return rc;
-    if (!stream) SMB_CK(cudaStreamSynchronize(s));
-    return SMB_OK;
+    return finish_call(*c, s, stream);
 }
 
-// SMArray::operator% (reference math/product.h).  `result` is one host T.  Operands on the host
-// are staged whole; the partial / ticket / result scratch lives in one pooled device block.
+// SMArray::operator% (reference math/product.h).  Enqueues the reduction of a[0..n) . b[0..n) on s;
+// the scalar lands in *result_dev (a device or pinned address).  The partial / ticket scratch lives
+// in one pooled device block the caller keeps until the stream has drained.
 template<typename T>
-static int dot_t(DeviceCtx &c, const T *a, const T *b, uint64_t n, void *result, cudaStream_t s) {
+static int dot_enqueue(DeviceCtx &c, const T *a, const T *b, uint64_t n, Scratch &scratch, void *result_pinned, cudaStream_t s) {
     using A = typename DotAcc<T>::type;
-    int dev = 0;
-    SMB_CK(cudaGetDevice(&dev));
     constexpr int UNROLL = 4;
-    const uint64_t nvec = n / (16 / sizeof(T));
+    constexpr int EPVV = 16 / (int)sizeof(T);
+    // Views hand over interior pointers (SMArray.h:208 passes `data` straight through; the reference reads them
+    // with loadu, product.h:26-71).  Same 16-byte phase: peel a scalar head up to the first common vector
+    // boundary, like launch_stream; different phases: the element-wise (coalesced scalar load) variant.
+    const uintptr_t ma = (uintptr_t)a % 16, mb = (uintptr_t)b % 16;
+    const bool vec = ma == mb && ma % sizeof(T) == 0;
+    const uint64_t head = vec && ma ? std::min<uint64_t>(n, (16 - ma) / sizeof(T)) : 0;
+    const uint64_t nvec = vec ? (n - head) / EPVV : n;
     // many waves of short-lived CTAs (8 grid-stride iterations each): the hardware scheduler evens out the SMs,
     // which a resident grid with a static split cannot (the slowest SM would set the time)
     const unsigned grid = grid_for(nvec ? nvec : 1, (uint64_t)kThreads * UNROLL * 8, c.sm_count, 0);
-    Scratch scratch;
     const size_t bytes = 16 + sizeof(A) * ((size_t)grid + 1);
-    if (int rc = scratch.get(bytes, dev)) return rc;
+    if (int rc = scratch.get(bytes, c.device)) return rc;
     unsigned int *ticket = (unsigned int *)scratch.p;
     A *res = (A *)((char *)scratch.p + 8);
     A *partials = (A *)((char *)scratch.p + 16);
     SMB_CK(cudaMemsetAsync(scratch.p, 0, 16, s));
-    k_dot<T, UNROLL><<<grid, kThreads, 0, s>>>(a, b, n, partials, ticket, res);
+    if (vec) k_dot<T, UNROLL, EPVV><<<grid, kThreads, 0, s>>>(a, b, n, head, partials, ticket, res);
+    else k_dot<T, UNROLL, 1><<<grid, kThreads, 0, s>>>(a, b, n, 0, partials, ticket, res);
     ++g_launches;
-    g_last_kernel = "k_dot";
+    g_last_kernel = vec ? "k_dot" : "k_dot<unaligned>";
     SMB_CK(cudaGetLastError());
-    SMB_CK(cudaMemcpyAsync(result, res, sizeof(A), cudaMemcpyDeviceToHost, s));
-    SMB_CK(cudaStreamSynchronize(s)); // a scalar result: always synchronous
+    SMB_CK(cudaMemcpyAsync(result_pinned, res, sizeof(A), cudaMemcpyDeviceToHost, s));
     return SMB_OK;
+}
+static int dot_enqueue_dtype(DeviceCtx &c, int dtype, const void *a, const void *b, uint64_t n, Scratch &scratch, void *result_pinned,
+                             cudaStream_t s) {
+    switch (dtype) {
+        case SMB_F32: return dot_enqueue<float>(c, (const float *)a, (const float *)b, n, scratch, result_pinned, s);
+        case SMB_F64: return dot_enqueue<double>(c, (const double *)a, (const double *)b, n, scratch, result_pinned, s);
+        default: return dot_enqueue<int32_t>(c, (const int32_t *)a, (const int32_t *)b, n, scratch, result_pinned, s);
+    }
+}
+// Adds the per-device partial results in device order, in T (int32 wraps like the reference's lanes).
+static void dot_combine(int dtype, const void *partials, int count, size_t slot_bytes, void *result) {
+    const char *p = (const char *)partials;
+    if (dtype == SMB_F32) { float s = 0; for (int i = 0; i < count; ++i) s += *(const float *)(p + i * slot_bytes); *(float *)result = s; }
+    else if (dtype == SMB_F64) { double s = 0; for (int i = 0; i < count; ++i) s += *(const double *)(p + i * slot_bytes); *(double *)result = s; }
+    else { uint32_t s = 0; for (int i = 0; i < count; ++i) s += *(const uint32_t *)(p + i * slot_bytes); *(uint32_t *)result = s; }
 }
 
 } // namespace smb
@@ -887,7 +1414,7 @@ using namespace smb;
 // =============================================================== C ABI =====
 // ---- op-chain fusion ---------------------------------
 template<typename T>
-static int chain_launch(const DeviceCtx &c, const ChainPlan &p, const smb_chain_step *steps, const void *const *data,
+static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *steps, const void *const *data,
                         uint64_t lin_begin, uint64_t lin_count, uint64_t lane_end, T *out, cudaStream_t s) {
     ChainTable t;
     memset(&t, 0, sizeof t);
@@ -976,6 +1503,15 @@ static int chain_launch(const DeviceCtx &c, const ChainPlan &p, const smb_chain_
     return SMB_OK;
 }
 
+static int chain_dispatch(DeviceCtx &c, int dtype, const ChainPlan &p, const smb_chain_step *steps, const void *const *data,
+                          uint64_t lin_begin, uint64_t lin_count, uint64_t lane_end, void *po, cudaStream_t s) {
+    switch (dtype) {
+        case SMB_F32: return chain_launch<float>(c, p, steps, data, lin_begin, lin_count, lane_end, (float *)po, s);
+        case SMB_F64: return chain_launch<double>(c, p, steps, data, lin_begin, lin_count, lane_end, (double *)po, s);
+        default: return chain_launch<int32_t>(c, p, steps, data, lin_begin, lin_count, lane_end, (int32_t *)po, s);
+    }
+}
+
 static int chain_entry(int dtype, const smb_chain_step *steps, int nsteps, const uint64_t *shape, int ndim,
                        uint64_t lin_begin, uint64_t lin_count, bool whole, void *out, void *stream) {
     if (dtype < SMB_F32 || dtype > SMB_I32) return fail(SMB_ERR_INVALID, "unknown dtype %d (float, double, int32 only)", dtype);
@@ -991,48 +1527,114 @@ static int chain_entry(int dtype, const smb_chain_step *steps, int nsteps, const
     }
     DeviceCtx *c = nullptr;
     if (int rc = current_ctx(&c)) return rc;
+    const size_t es = esize(dtype);
+    const int dev = c->device;
+    // int32 pow has two semantics in the reference (AVX2 lanes wrap, the scalar tail goes through double),
+    // applied by POSITION in the array sm::pow sees: array_scalar_op over the DENSE intermediate,
+    // lane_end = its size rounded down to 8 (calculate.h:139-140).  The fused kernel derives the position
+    // from the result's flat index, which is that array's only when the accumulator already has the
+    // result's shape at the pow step.  When leaves AFTER the pow step broadcast the result further
+    // (sm::pow(lazy(a{1,N}), e) + B{M,N}), the prefix up to the pow is evaluated first, as its own chain
+    // of its own (smaller) shape, and joins the rest as a leaf -- bit-identical to the unfused sequence.
+    if (dtype == SMB_I32 && whole) {
+        for (int sidx = nsteps - 1; sidx >= 1; --sidx) {
+            if (steps[sidx].op != SMB_OP_POW) continue;
+            uint64_t pshape[SMB_MAX_NDIM], pn = 1, rn = 1;
+            bool any_array = false;
+            for (int k = 0; k < ndim; ++k) {
+                bool varies = false;
+                for (int i = 0; i < sidx; ++i) if (steps[i].data) { any_array = true; if (steps[i].stride[k] != 0) varies = true; }
+                pshape[k] = varies || shape[k] == 1 ? shape[k] : 1;
+                pn *= pshape[k];
+                rn *= shape[k];
+            }
+            if (!any_array || pn == rn) continue;
+            if (stream) return fail(SMB_ERR_INVALID, "smb_chain: an int32 pow step on a broadcast intermediate needs the synchronous form");
+            // prefix [0, sidx]: strides of its leaves restricted to the dims it spans
+            smb_chain_step prefix[SMB_CHAIN_MAX], rest[SMB_CHAIN_MAX];
+            for (int i = 0; i <= sidx; ++i) {
+                prefix[i] = steps[i];
+                for (int k = 0; k < ndim; ++k) if (pshape[k] == 1) prefix[i].stride[k] = 0;
+            }
+            Scratch mid;
+            if (int rc = mid.get(pn * es, dev)) return rc;
+            if (int rc = chain_entry(dtype, prefix, sidx + 1, pshape, ndim, 0, 0, true, mid.p, nullptr)) return rc;
+            if (g_opt_async.load()) SMB_CK(cudaStreamSynchronize(c->main)); // `mid` is released when this call returns
+            rest[0] = smb_chain_step{};
+            rest[0].data = mid.p;
+            uint64_t acc = 1;
+            for (int k = ndim - 1; k >= 0; --k) { rest[0].stride[k] = pshape[k] == 1 ? 0 : acc; acc *= pshape[k]; }
+            int nrest = 1;
+            for (int i = sidx + 1; i < nsteps; ++i) rest[nrest++] = steps[i];
+            const int rc = chain_entry(dtype, rest, nrest, shape, ndim, 0, 0, true, out, nullptr);
+            if (rc == SMB_OK && g_opt_async.load()) SMB_CK(cudaStreamSynchronize(c->main));
+            return rc;
+        }
+    }
     const ChainPlan p = make_chain_plan(strides, nsteps, shape, ndim);
     if (whole) { lin_begin = 0; lin_count = p.n; }
     if (lin_begin > p.n || lin_count > p.n - lin_begin) return fail(SMB_ERR_INVALID, "flat range outside the result");
     if (lin_count == 0) return SMB_OK;
     if (!out) return fail(SMB_ERR_INVALID, "null result pointer");
-    const size_t es = esize(dtype);
-    int dev = 0;
-    SMB_CK(cudaGetDevice(&dev));
+    const uint64_t lane_end = dtype == SMB_I32 ? scalar_lane_end(dtype, p.n) : 0; // array_scalar_op on the dense intermediate
     cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
+    // classify the operands once
+    MemType mt[SMB_CHAIN_MAX], to = mem_type(out);
+    bool all_managed = to == MT_MANAGED, any_host = on_host(to);
+    for (int i = 0; i < nsteps; ++i) {
+        if (!steps[i].data) continue;
+        mt[i] = mem_type(steps[i].data);
+        if (mt[i] != MT_MANAGED) all_managed = false;
+        if (on_host(mt[i])) any_host = true;
+    }
+    if (any_host && stream) return fail(SMB_ERR_INVALID, "smb_chain: host operands / results need the synchronous form (stream == NULL)");
+    std::vector<int> devs;
+    if (all_managed && want_sharding(devs, lin_count * es, stream, lin_begin == 0 && lin_count == p.n)) {
+        const int G = (int)devs.size();
+        const uint64_t rows = p.ndim >= 2 ? p.shape[0] : p.n, inner = p.ndim >= 2 ? p.n / p.shape[0] : 1;
+        const ShardSplit split = split_flat(p.n, rows, inner, p.ndim, G, es);
+        const void *bases[SMB_CHAIN_MAX];
+        const uint64_t *cstr[SMB_CHAIN_MAX];
+        for (int i = 0; i < nsteps; ++i) { bases[i] = steps[i].data; cstr[i] = p.stride[i]; }
+        ShardOperand ops[SMB_CHAIN_MAX], res;
+        if (shard_operands(devs, split, p.shape, p.ndim, bases, cstr, nsteps, es, ops)) {
+            res.base = out;
+            res.plan.mode = SHARD_IN_PLACE;
+            for (int g = 0; g < G; ++g) res.plan.r[g] = ElemRange{split.bounds[g], split.bounds[g + 1]};
+            Block blk;
+            bool matched = false;
+            res.need_prefetch = !(Pool::instance().take_placement(out, placement_sharded(devs, out, res.plan), &blk, &matched) && matched);
+            return run_sharded(devs, split, ops, nsteps, res, es, async_mode(nullptr),
+                               [&](DeviceCtx &cg, int, uint64_t lo, uint64_t cnt, const void *const *use, cudaStream_t sg) {
+                                   return chain_dispatch(cg, dtype, p, steps, use, lo, cnt, lane_end, (char *)out + lo * es, sg);
+                               });
+        }
+    }
+    if (int rc = begin_call(*c, stream)) return rc;
     // host leaves / result are staged whole through pooled scratch (no overlap: the fused path is
     // meant for resident arrays); managed blocks are prefetched like everywhere else
     Scratch scratch[SMB_CHAIN_MAX], dout;
+    DrainGuard drain; // after the scratch blocks: an early return drains the stream before they are released
+    if (any_host) drain.add(s);
     const void *data[SMB_CHAIN_MAX];
     for (int i = 0; i < nsteps; ++i) {
         data[i] = steps[i].data;
         if (!data[i]) continue;
-        const MemType mt = mem_type(data[i]);
-        if (on_host(mt)) {
-            if (stream) return fail(SMB_ERR_INVALID, "smb_chain: host operands need the synchronous form (stream == NULL)");
+        if (on_host(mt[i])) {
             if (int rc = scratch[i].get(p.extent[i] * es, dev)) return rc;
             SMB_CK(cudaMemcpyAsync(scratch[i].p, data[i], p.extent[i] * es, cudaMemcpyDefault, s));
             data[i] = scratch[i].p;
-        } else if (mt == MT_MANAGED) prefetch_managed(data[i], p.extent[i] * es, s);
+        } else if (mt[i] == MT_MANAGED) prefetch_managed(data[i], p.extent[i] * es, dev, s);
     }
     void *po = out;
-    const MemType to = mem_type(out);
     if (on_host(to)) {
-        if (stream) return fail(SMB_ERR_INVALID, "smb_chain: a host result needs the synchronous form (stream == NULL)");
         if (int rc = dout.get(lin_count * es, dev)) return rc;
         po = dout.p;
-    } else if (to == MT_MANAGED) prefetch_managed(out, lin_count * es, s);
-    const uint64_t lane_end = dtype == SMB_I32 ? scalar_lane_end(dtype, p.n) : 0; // array_scalar_op on the dense intermediate
-    int rc;
-    switch (dtype) {
-        case SMB_F32: rc = chain_launch<float>(*c, p, steps, data, lin_begin, lin_count, lane_end, (float *)po, s); break;
-        case SMB_F64: rc = chain_launch<double>(*c, p, steps, data, lin_begin, lin_count, lane_end, (double *)po, s); break;
-        default: rc = chain_launch<int32_t>(*c, p, steps, data, lin_begin, lin_count, lane_end, (int32_t *)po, s); break;
-    }
-    if (rc) return rc;
+    } else if (to == MT_MANAGED) prefetch_managed(out, lin_count * es, dev, s);
+    if (int rc = chain_dispatch(*c, dtype, p, steps, data, lin_begin, lin_count, lane_end, po, s)) return rc;
     if (on_host(to)) SMB_CK(cudaMemcpyAsync(out, po, lin_count * es, cudaMemcpyDefault, s));
-    if (!stream) SMB_CK(cudaStreamSynchronize(s));
-    return SMB_OK;
+    if (any_host) { SMB_CK(cudaStreamSynchronize(s)); return SMB_OK; } // scratch in use: synchronous whatever the mode
+    return finish_call(*c, s, stream);
 }
 extern "C" {
 
@@ -1067,13 +1669,30 @@ int smb_array_scalar(int op, int dtype, const void *a, const void *scalar, uint6
     const uint64_t lane_end = scalar_lane_end(dtype, n);
     const MemType ta = mem_type(a), to = mem_type(out);
     const size_t es = esize(dtype);
-    if (on_host(ta) || on_host(to)) return scalar_staged(*c, op, dtype, a, ta, scalar, out, to, n, lane_end);
+    if (on_host(ta) || on_host(to))
+        return scalar_staged(*c, op, dtype, a, ta, scalar, out, to, n, lane_end, stream ? (cudaStream_t)stream : (c->dirty ? c->main : nullptr));
+    std::vector<int> devs;
+    if (ta == MT_MANAGED && to == MT_MANAGED && want_sharding(devs, n * es, stream, true)) {
+        const int G = (int)devs.size();
+        const ShardSplit split = split_flat(n, n, 1, 1, G, es);
+        const uint64_t shape1[1] = {n}, unit[1] = {1};
+        const void *bases[2] = {a, out};
+        const uint64_t *strides[2] = {unit, unit};
+        ShardOperand ops[2];
+        if (shard_operands(devs, split, shape1, 1, bases, strides, 2, es, ops)) {
+            const ShardOperand res = ops[1];
+            return run_sharded(devs, split, ops, 1, res, es, async_mode(nullptr),
+                               [&](DeviceCtx &cg, int, uint64_t lo, uint64_t cnt, const void *const *use, cudaStream_t s) {
+                                   return scalar_device(cg, op, dtype, (const char *)use[0] + lo * es, scalar, (char *)out + lo * es, cnt, lo, lane_end, s);
+                               });
+        }
+    }
     cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
-    if (ta == MT_MANAGED) prefetch_managed(a, n * es, s);
-    if (to == MT_MANAGED) prefetch_managed(out, n * es, s);
+    if (int rc = begin_call(*c, stream)) return rc;
+    if (ta == MT_MANAGED) prefetch_managed(a, n * es, c->device, s);
+    if (to == MT_MANAGED) prefetch_managed(out, n * es, c->device, s);
     if (int rc = scalar_device(*c, op, dtype, a, scalar, out, n, 0, lane_end, s)) return rc;
-    if (!stream) SMB_CK(cudaStreamSynchronize(s));
-    return SMB_OK;
+    return finish_call(*c, s, stream);
 }
 
 int smb_dot(int dtype, const void *a, const void *b, uint64_t n, void *result, void *stream) {
@@ -1084,21 +1703,50 @@ int smb_dot(int dtype, const void *a, const void *b, uint64_t n, void *result, v
     const size_t es = esize(dtype);
     if (n == 0) { memset(result, 0, es); return SMB_OK; }
     if (!a || !b) return fail(SMB_ERR_INVALID, "null operand pointer");
-    cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
     const MemType ta = mem_type(a), tb = mem_type(b);
-    int dev = 0;
-    SMB_CK(cudaGetDevice(&dev));
-    Scratch da, db;
-    if (on_host(ta)) { if (int rc = da.get(n * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(da.p, a, n * es, cudaMemcpyDefault, s)); a = da.p; }
-    else if (ta == MT_MANAGED) prefetch_managed(a, n * es, s);
-    if (on_host(tb)) { if (int rc = db.get(n * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(db.p, b, n * es, cudaMemcpyDefault, s)); b = db.p; }
-    else if (tb == MT_MANAGED) prefetch_managed(b, n * es, s);
-    if (((uintptr_t)a | (uintptr_t)b) & 15) return fail(SMB_ERR_INVALID, "smb_dot: operands must be 16-byte aligned");
-    switch (dtype) {
-        case SMB_F32: return dot_t<float>(*c, (const float *)a, (const float *)b, n, result, s);
-        case SMB_F64: return dot_t<double>(*c, (const double *)a, (const double *)b, n, result, s);
-        default: return dot_t<int32_t>(*c, (const int32_t *)a, (const int32_t *)b, n, result, s);
+    constexpr size_t kSlot = 16; // one partial result per device, in pinned memory
+    Scratch pinned;
+    if (int rc = pinned.get(kSlot * kMaxShards, -1, SMB_MEM_PINNED)) return rc;
+    std::vector<int> devs;
+    if (ta == MT_MANAGED && tb == MT_MANAGED && want_sharding(devs, 2 * n * es, stream, true)) {
+        // Sharded reduction: device g reduces its flat range, the host adds the G partials in device
+        // order (the one place a combine step sits on a path; across PROCESSES
+        // bench.py does the same with one NCCL all-reduce of a scalar).
+        const int G = (int)devs.size();
+        const ShardSplit split = split_flat(n, n, 1, 1, G, es);
+        const uint64_t shape1[1] = {n}, unit[1] = {1};
+        const void *bases[2] = {a, b};
+        const uint64_t *strides[2] = {unit, unit};
+        ShardOperand ops[2], none;
+        if (shard_operands(devs, split, shape1, 1, bases, strides, 2, es, ops)) {
+            std::vector<Scratch> partial_scratch((size_t)G);
+            int parts = 0;
+            // a scalar result: always synchronous (async = false), every device's stream is drained before the sum
+            const int rc = run_sharded(devs, split, ops, 2, none, es, false,
+                                       [&](DeviceCtx &cg, int g, uint64_t lo, uint64_t cnt, const void *const *use, cudaStream_t s) {
+                                           ++parts;
+                                           return dot_enqueue_dtype(cg, dtype, (const char *)use[0] + lo * es, (const char *)use[1] + lo * es, cnt,
+                                                                    partial_scratch[(size_t)g], (char *)pinned.p + kSlot * (size_t)(parts - 1), s);
+                                       });
+            if (rc) return rc;
+            dot_combine(dtype, pinned.p, parts, kSlot, result);
+            return SMB_OK;
+        }
     }
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
+    const int dev = c->device;
+    if (int rc = begin_call(*c, stream)) return rc;
+    Scratch da, db, work;
+    DrainGuard drain;
+    drain.add(s);
+    if (on_host(ta)) { if (int rc = da.get(n * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(da.p, a, n * es, cudaMemcpyDefault, s)); a = da.p; }
+    else if (ta == MT_MANAGED) prefetch_managed(a, n * es, dev, s);
+    if (on_host(tb)) { if (int rc = db.get(n * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(db.p, b, n * es, cudaMemcpyDefault, s)); b = db.p; }
+    else if (tb == MT_MANAGED) prefetch_managed(b, n * es, dev, s);
+    if (int rc = dot_enqueue_dtype(*c, dtype, a, b, n, work, pinned.p, s)) return rc;
+    SMB_CK(cudaStreamSynchronize(s)); // a scalar result: always synchronous
+    dot_combine(dtype, pinned.p, 1, kSlot, result);
+    return SMB_OK;
 }
 
 int smb_chain(int dtype, const smb_chain_step *steps, int nsteps, const uint64_t *shape, int ndim, uint64_t n, void *out,
@@ -1130,11 +1778,17 @@ void *smb_alloc(size_t bytes, int kind) {
 int smb_free(void *ptr) {
     if (!ptr) return SMB_OK;
     if (!Pool::instance().free(ptr)) return fail(SMB_ERR_INVALID, "smb_free: %p was not returned by smb_alloc", ptr);
+    // high-water mark: beyond it the largest cached blocks go back to the driver (cudaFree waits for
+    // the device, so nothing in flight loses its memory)
+    uint64_t st[4];
+    Pool::instance().stats(st);
+    const int64_t cap = g_opt_pool_max_cached.load(std::memory_order_relaxed);
+    if (cap >= 0 && st[1] > (uint64_t)cap) Pool::instance().trim_to((uint64_t)cap);
     return SMB_OK;
 }
 
 int smb_host_written(const void *ptr) {
-    if (ptr) Pool::instance().set_host_flag(ptr, true);
+    if (ptr) Pool::instance().clear_placement(ptr);
     return SMB_OK;
 }
 
@@ -1152,6 +1806,15 @@ int smb_pool_stats(uint64_t stats[4]) {
     return SMB_OK;
 }
 
+static int fill_device(DeviceCtx &c, int dtype, void *out, const void *value, uint64_t n, cudaStream_t s) {
+    const unsigned grid = grid_for(n, kThreads * 4, c.sm_count, 16);
+    if (dtype == SMB_F64) k_fill<double><<<grid, kThreads, 0, s>>>((double *)out, n, *(const double *)value);
+    else k_fill<uint32_t><<<grid, kThreads, 0, s>>>((uint32_t *)out, n, *(const uint32_t *)value);
+    ++g_launches;
+    SMB_CK(cudaGetLastError());
+    return SMB_OK;
+}
+
 int smb_fill(int dtype, void *out, const void *value, uint64_t n, void *stream) {
     if (dtype < SMB_F32 || dtype > SMB_I32) return fail(SMB_ERR_INVALID, "unknown dtype %d", dtype);
     DeviceCtx *c = nullptr;
@@ -1160,15 +1823,29 @@ int smb_fill(int dtype, void *out, const void *value, uint64_t n, void *stream) 
     if (!out || !value) return fail(SMB_ERR_INVALID, "null pointer");
     const MemType to = mem_type(out);
     if (on_host(to)) return fail(SMB_ERR_INVALID, "smb_fill needs device or managed memory");
+    const size_t es = esize(dtype);
+    std::vector<int> devs;
+    if (to == MT_MANAGED && want_sharding(devs, n * es, stream, true)) {
+        // sm::ones / sm::zeros over the device set: the block is BORN partitioned the way the operators use it
+        const int G = (int)devs.size();
+        const ShardSplit split = split_flat(n, n, 1, 1, G, es);
+        const uint64_t shape1[1] = {n}, unit[1] = {1};
+        const void *bases[1] = {out};
+        const uint64_t *strides[1] = {unit};
+        ShardOperand ops[1];
+        if (shard_operands(devs, split, shape1, 1, bases, strides, 1, es, ops)) {
+            const ShardOperand res = ops[0];
+            return run_sharded(devs, split, ops, 0, res, es, async_mode(nullptr),
+                               [&](DeviceCtx &cg, int, uint64_t lo, uint64_t cnt, const void *const *, cudaStream_t s) {
+                                   return fill_device(cg, dtype, (char *)out + lo * es, value, cnt, s);
+                               });
+        }
+    }
     cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
-    if (to == MT_MANAGED) prefetch_managed(out, n * esize(dtype), s);
-    const unsigned grid = grid_for(n, kThreads * 4, c->sm_count, 16);
-    if (dtype == SMB_F64) k_fill<double><<<grid, kThreads, 0, s>>>((double *)out, n, *(const double *)value);
-    else k_fill<uint32_t><<<grid, kThreads, 0, s>>>((uint32_t *)out, n, *(const uint32_t *)value);
-    ++g_launches;
-    SMB_CK(cudaGetLastError());
-    if (!stream) SMB_CK(cudaStreamSynchronize(s));
-    return SMB_OK;
+    if (int rc = begin_call(*c, stream)) return rc;
+    if (to == MT_MANAGED) prefetch_managed(out, n * es, c->device, s);
+    if (int rc = fill_device(*c, dtype, out, value, n, s)) return rc;
+    return finish_call(*c, s, stream);
 }
 
 int smb_prefetch(const void *ptr, size_t bytes, int device, void *stream) {
@@ -1196,8 +1873,31 @@ int smb_get_device(void) {
     return d;
 }
 int smb_sync(void) {
-    SMB_CK(cudaDeviceSynchronize());
+    if (int rc = sync_all()) return rc;
+    SMB_CK(cudaDeviceSynchronize()); // the caller's own streams on the current device too
     return SMB_OK;
+}
+int smb_wait_pending(void) {
+    if (!g_pending.load(std::memory_order_acquire)) return SMB_OK;
+    return sync_all();
+}
+
+int smb_set_devices(const int *devices, int count) {
+    devices_from_env_once(); // an explicit call wins over SMB_DEVICES from here on
+    if (int rc = sync_all()) return rc;
+    std::lock_guard<std::mutex> lk(g_set_mu);
+    return set_devices_locked(devices, count);
+}
+int smb_get_devices(int *devices, int capacity) {
+    const std::vector<int> d = active_devices();
+    if (d.empty()) {
+        const int cur = smb_get_device();
+        if (cur < 0) return 0;
+        if (devices && capacity > 0) devices[0] = cur;
+        return 1;
+    }
+    for (int i = 0; i < (int)d.size() && i < capacity; ++i) if (devices) devices[i] = d[i];
+    return (int)d.size();
 }
 
 int smb_set_option(int key, int64_t value) {
@@ -1207,6 +1907,14 @@ int smb_set_option(int key, int64_t value) {
         case SMB_OPT_CONTIG_VARIANT: g_opt_contig_variant = value; return SMB_OK;
         case SMB_OPT_BCAST_VARIANT: g_opt_bcast_variant = value; return SMB_OK;
         case SMB_OPT_FORCE_WIDE_INDEX: g_opt_force_wide = value ? 1 : 0; return SMB_OK;
+        case SMB_OPT_ASYNC:
+            if (!value && g_opt_async.load()) { g_opt_async = 0; return sync_all(); } // leaving async mode: everything lands
+            g_opt_async = value ? 1 : 0;
+            return SMB_OK;
+        case SMB_OPT_PDL: g_opt_pdl = value ? 1 : 0; return SMB_OK;
+        case SMB_OPT_SHARD_MIN_BYTES: g_opt_shard_min_bytes = value; return SMB_OK;
+        case SMB_OPT_REPLICATE_MAX_BYTES: g_opt_replicate_max_bytes = value; return SMB_OK;
+        case SMB_OPT_POOL_MAX_CACHED_BYTES: g_opt_pool_max_cached = value; return SMB_OK;
     }
     return fail(SMB_ERR_INVALID, "unknown option %d", key);
 }
@@ -1217,6 +1925,11 @@ int64_t smb_get_option(int key) {
         case SMB_OPT_CONTIG_VARIANT: return g_opt_contig_variant;
         case SMB_OPT_BCAST_VARIANT: return g_opt_bcast_variant;
         case SMB_OPT_FORCE_WIDE_INDEX: return g_opt_force_wide;
+        case SMB_OPT_ASYNC: return g_opt_async;
+        case SMB_OPT_PDL: return g_opt_pdl;
+        case SMB_OPT_SHARD_MIN_BYTES: return g_opt_shard_min_bytes;
+        case SMB_OPT_REPLICATE_MAX_BYTES: return g_opt_replicate_max_bytes;
+        case SMB_OPT_POOL_MAX_CACHED_BYTES: return g_opt_pool_max_cached;
     }
     return -1;
 }
@@ -1253,6 +1966,26 @@ int smb_plan_elementwise(const uint64_t *stride_a, const uint64_t *stride_b, con
         if (out_stride_b) out_stride_b[k] = p.sb[k];
     }
     return p.kind;
+}
+
+int smb_plan_shards(const uint64_t *stride_a, const uint64_t *stride_b, const uint64_t *shape, int ndim, int elem_size,
+                    int ndev, uint64_t *out_bounds, uint64_t *out_range_a, uint64_t *out_range_b, int *out_modes) {
+    if (ndim < 1 || ndim > SMB_MAX_NDIM || !stride_a || !stride_b || !shape || ndev < 1 || ndev > kMaxShards ||
+        (elem_size != 4 && elem_size != 8))
+        return -SMB_ERR_INVALID;
+    const ElementwisePlan p = make_plan(stride_a, stride_b, shape, ndim);
+    const uint64_t rows = p.ndim >= 2 ? p.shape[0] : p.n, inner = p.ndim >= 2 && p.shape[0] ? p.n / p.shape[0] : 1;
+    const ShardSplit split = split_flat(p.n, rows, inner, p.ndim, ndev, (size_t)elem_size);
+    const uint64_t rmax = (uint64_t)std::max<int64_t>(0, g_opt_replicate_max_bytes.load());
+    const OperandShards oa = plan_operand(p.shape, p.sa, p.ndim, split, (size_t)elem_size, rmax);
+    const OperandShards ob = plan_operand(p.shape, p.sb, p.ndim, split, (size_t)elem_size, rmax);
+    for (int g = 0; g <= ndev; ++g) if (out_bounds) out_bounds[g] = split.bounds[g];
+    for (int g = 0; g < ndev; ++g) {
+        if (out_range_a) { out_range_a[2 * g] = oa.r[g].lo; out_range_a[2 * g + 1] = oa.r[g].hi; }
+        if (out_range_b) { out_range_b[2 * g] = ob.r[g].lo; out_range_b[2 * g + 1] = ob.r[g].hi; }
+    }
+    if (out_modes) { out_modes[0] = oa.mode; out_modes[1] = ob.mode; }
+    return oa.mode == SHARD_REFUSE || ob.mode == SHARD_REFUSE ? 0 : 1;
 }
 
 int smb_fill_uniform_f32(void *out, uint64_t first, uint64_t n, uint64_t seed, float lo, float hi, void *stream) {

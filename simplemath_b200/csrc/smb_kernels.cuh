@@ -152,6 +152,25 @@ __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t 
 }
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol, sm_90+).  Every participating kernel lets the next
+// launch on its stream become resident as soon as all of its own CTAs have started
+// (launch_dependents first thing), and waits for the PREVIOUS launch to complete and flush either
+// before its first global access (kPdlWaitFirst: the host saw a data hazard, or the stream is not
+// the library's own) or just before it exits (no hazard: the two grids overlap, and this grid's
+// completion still implies the previous one's).  Both instructions are no-ops in a launch without
+// the programmatic-stream-serialisation attribute.  The host side is in smb_api.cu (pdl_decide).
+constexpr uint32_t kPdlWaitFirst = 1u;
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter(uint32_t flags) {
+    pdl_launch_dependents();
+    if (flags & kPdlWaitFirst) pdl_wait();
+}
+__device__ __forceinline__ void pdl_exit(uint32_t flags) {
+    if (!(flags & kPdlWaitFirst)) pdl_wait();
+}
+
+// ---------------------------------------------------------------------------
 // Functors: what a launch applies to (a[i], b[i]).  `lane` tells the i32 pow
 // instantiation whether flat element i is one the reference computes in an
 // AVX2 lane (wrapping) or with scalar Op::apply (through double); see
@@ -451,10 +470,12 @@ __device__ __forceinline__ void pow_tile(const Pack<T, VB> (&in)[UNROLL], const 
 
 template<typename T, typename Fn, bool HAS_B, int VB, int UNROLL>
 __global__ void __launch_bounds__(256, fn_pow_tables<Fn>::value ? (sizeof(T) == 4 ? SMB_POW_MIN_BLOCKS : SMB_POW64_MIN_BLOCKS) : 2) k_stream(const T *__restrict__ a, const T *__restrict__ b,
-                                               T *__restrict__ out, uint64_t n, uint64_t first, Fn fn_in) {
+                                               T *__restrict__ out, uint64_t n, uint64_t first, Fn fn_in, uint32_t pdl) {
     constexpr int EPV = VB / (int)sizeof(T); // elements per vector
     Fn fn = fn_in;
-    if constexpr (fn_pow_tables<Fn>::value) fn.block_init(); // stage the lookup tables in shared memory
+    pdl_launch_dependents();
+    if constexpr (fn_pow_tables<Fn>::value) fn.block_init(); // stage the lookup tables in shared memory (constant data: before the wait)
+    if (pdl & kPdlWaitFirst) pdl_wait();
     const uint64_t nvec = n / EPV;
     constexpr uint64_t tile_vecs = (uint64_t)kBlock * UNROLL; // launches always use kBlock threads
     const uint64_t full_tiles = nvec / tile_vecs;
@@ -534,6 +555,7 @@ __global__ void __launch_bounds__(256, fn_pow_tables<Fn>::value ? (sizeof(T) == 
         const uint64_t i = tail0 + gtid;
         out[i] = fn(a[i], HAS_B ? b[i] : a[i], first + i);
     }
+    pdl_exit(pdl);
 }
 
 // Scalar-access variant for operands whose addresses do not share an alignment
@@ -1161,25 +1183,35 @@ template<typename A> __device__ __forceinline__ A dot_add(A x, A y) {
     else return x + y;
 }
 
-template<typename T, int UNROLL>
-__global__ void __launch_bounds__(256) k_dot(const T *__restrict__ a, const T *__restrict__ b, uint64_t n,
+// EPV: elements per load -- 16 / sizeof(T) when the two operands share a 16-byte phase (`head`
+// leading elements up to the first common vector boundary are then added by block 0, like the
+// ragged tail), 1 when they do not (views hand us interior pointers; the reference reads them with
+// loadu, product.h:26-71): element-wise coalesced loads.
+template<typename T, int UNROLL, int EPV>
+__global__ void __launch_bounds__(256) k_dot(const T *__restrict__ a, const T *__restrict__ b, uint64_t n, uint64_t head,
                                             typename DotAcc<T>::type *__restrict__ partials, unsigned int *__restrict__ ticket,
                                             typename DotAcc<T>::type *__restrict__ result) {
     using A = typename DotAcc<T>::type;
-    constexpr int EPV = 16 / (int)sizeof(T);
-    const uint64_t nvec = n / EPV;
+    constexpr int VB = EPV * (int)sizeof(T);
+    const uint64_t nvec = (n - head) / EPV;
+    const T *av = a + head, *bv = b + head;
     A acc[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) acc[u] = A(0);
     const uint64_t stride = (uint64_t)gridDim.x * kBlock * UNROLL;
     for (uint64_t v0 = (uint64_t)blockIdx.x * kBlock * UNROLL + threadIdx.x; v0 < nvec; v0 += stride) {
-        Pack<T, 16> pa[UNROLL], pb[UNROLL];
+        Pack<T, VB> pa[UNROLL], pb[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const uint64_t v = v0 + (uint64_t)u * kBlock;
             if (v < nvec) {
-                pa[u].raw = VecIO<16, true>::load(reinterpret_cast<const RawVec<16> *>(a) + v);
-                pb[u].raw = VecIO<16, true>::load(reinterpret_cast<const RawVec<16> *>(b) + v);
+                if constexpr (EPV == 1) {
+                    pa[u].e[0] = __ldg(av + v);
+                    pb[u].e[0] = __ldg(bv + v);
+                } else {
+                    pa[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(av) + v);
+                    pb[u].raw = VecIO<VB, true>::load(reinterpret_cast<const RawVec<VB> *>(bv) + v);
+                }
             }
         }
 #pragma unroll
@@ -1196,10 +1228,11 @@ __global__ void __launch_bounds__(256) k_dot(const T *__restrict__ a, const T *_
     A sum = acc[0];
 #pragma unroll
     for (int u = 1; u < UNROLL; ++u) sum = dot_add<A>(sum, acc[u]);
-    // scalar tail (n % EPV elements) by the first threads of block 0
-    if (blockIdx.x == 0 && threadIdx.x < n - nvec * EPV) {
-        const uint64_t i = nvec * EPV + threadIdx.x;
-        sum = dot_add<A>(sum, dot_mul<T>(a[i], b[i]));
+    // the peeled head and the ragged tail (each < one vector) by the first threads of block 0
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < head) sum = dot_add<A>(sum, dot_mul<T>(a[threadIdx.x], b[threadIdx.x]));
+        const uint64_t tail0 = head + nvec * EPV;
+        if (threadIdx.x < n - tail0) sum = dot_add<A>(sum, dot_mul<T>(a[tail0 + threadIdx.x], b[tail0 + threadIdx.x]));
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum = dot_add<A>(sum, __shfl_down_sync(0xffffffffu, sum, off));
