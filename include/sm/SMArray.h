@@ -47,6 +47,12 @@ namespace sm {
              std::same_as<T, std::complex<typename T::value_type> >);
 
     namespace storage {
+        // The host is about to read or write array memory: wait for kernels an sm::async_scope left
+        // in flight (one atomic load when there are none).
+        inline void host_access() {
+            if (smb_wait_pending() != SMB_OK) throw std::runtime_error(std::string("smb200: ") + smb_last_error());
+        }
+
         // One block of n elements of T: managed memory from the pool.  Throws
         // std::runtime_error when there is no device (no CPU fallback).
         template<typename T>
@@ -91,6 +97,7 @@ namespace sm {
             ndim = _shape.size();
             totalSize = calculateTotalSize(_shape);
             data = storage::acquire<T>(totalSize);
+            storage::host_access();
             size_t at = 0;
             for (const SMArray &row: list) {
                 std::memcpy(data + at, row.data, row.totalSize * sizeof(T));
@@ -124,7 +131,9 @@ namespace sm {
             assert(_shape.size() == other._shape.size() && "Shape mismatch in assignment");
             for (size_t i = 0; i < _shape.size(); ++i)
                 assert(_shape[i] == other._shape[i] && "Shape mismatch in assignment");
+            storage::host_access();
             for (size_t i = 0; i < totalSize; ++i) data[i] = other.data[i];
+            noteHostTouch();
             return *this;
         }
 
@@ -171,8 +180,10 @@ namespace sm {
                 if (isDense()) return broadcastCopy({totalSize, reps}, {1, 0}, {totalSize * reps});
             }
             T *fresh = storage::acquire<T>(totalSize * reps);
+            storage::host_access();
             for (size_t i = 0; i < totalSize; ++i)
                 for (size_t j = 0; j < reps; ++j) fresh[i * reps + j] = data[i];
+            smb_host_written(fresh);
             return SMArray(fresh, {totalSize * reps});
         }
 
@@ -194,6 +205,8 @@ namespace sm {
             for (size_t k = axis + 1; k < ndim; ++k) inner *= _shape[k];
             const size_t outer = totalSize / (inner * _shape[axis]);
             T *fresh = storage::acquire<T>(totalSize * reps);
+            storage::host_access();
+            smb_host_written(fresh);
             T *w = fresh;
             for (size_t o = 0; o < outer; ++o)
                 for (size_t a = 0; a < _shape[axis]; ++a) {
@@ -221,6 +234,8 @@ namespace sm {
         SMArray applyScalar(const T val) const { return withScalar<Operation>(val); }
 
         [[nodiscard]] std::string toString() const {
+            storage::host_access();
+            noteHostTouch();
             std::ostringstream os;
             std::function<void(size_t, size_t)> emit = [&](size_t offset, size_t dim) {
                 os << "[";
@@ -252,8 +267,20 @@ namespace sm {
         std::vector<size_t> _strides;
         size_t ndim = 0;
         bool isView = false;
+        // The library has been told that the host touched this array since it last went to a kernel.
+        // Element access through operator() -- the way the reference's tests fill and check arrays,
+        // tests/add.cpp:67-71 -- pulls managed pages to host memory, reads as well as writes; the next
+        // kernel then prefetches the block back in one transfer instead of demand-paging it.
+        // (smb_host_written is a lock and a map lookup: once per fill loop, not once per element.)
+        mutable bool hostTouchNoted = false;
 
         SMArray() = default;
+
+        void noteHostTouch() const {
+            if (hostTouchNoted) return;
+            smb_host_written(data);
+            hostTouchNoted = true;
+        }
 
         // Row-major strides in elements (reference SMArray.h:357-364).
         void calculateStride() {
@@ -287,6 +314,7 @@ namespace sm {
         SMArray binary(const SMArray &arr) const {
             auto bc = sm::broadcast(_shape, _strides, arr._shape, arr._strides);
             T *result = storage::acquire<T>(bc.totalSize);
+            hostTouchNoted = arr.hostTouchNoted = false; // both go to a kernel now
             try {
                 element_wise_op<T, Operation>(data, bc.newStrides1, arr.data, bc.newStrides2, bc.totalSize, result,
                                               bc.resultShape);
@@ -305,6 +333,7 @@ namespace sm {
         template<typename Operation>
         SMArray withScalar(const T val) const {
             T *result = storage::acquire<T>(totalSize);
+            hostTouchNoted = false;
             try {
                 if (isDense()) {
                     array_scalar_op<T, Operation>(data, val, totalSize, result);
@@ -342,11 +371,15 @@ namespace sm {
 
         T accessByValue(const std::initializer_list<std::size_t> &indices) const {
             assert(indices.size() <= ndim && "Number of indices exceeds number of dimensions");
+            storage::host_access();
+            noteHostTouch();
             return *locate(indices);
         }
 
         T &accessByValueRef(const std::initializer_list<std::size_t> &indices) const {
             assert(indices.size() == ndim && "Number of indices exceeds number of dimensions");
+            storage::host_access();
+            noteHostTouch();
             return *locate(indices);
         }
 

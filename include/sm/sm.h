@@ -4,4 +4,5 @@
 #pragma once
 #include "SMArray.h"
 #include "UserFunctions.h"
-#include "Lazy.h" // opt-in op-chain fusion (not in the reference)
+#include "Lazy.h"    // opt-in op-chain fusion (not in the reference)
+#include "Runtime.h" // opt-in async scope / device set (not in the reference)

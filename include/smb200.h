@@ -230,7 +230,7 @@ int smb_wait_pending(void);
  * flat range g of the result on its own stream, reading its ranges of the contiguous operands in
  * place (pages prefetched to it once, then remembered) and a private copy of shared operands.  The
  * caller still writes `a + b` and nothing else (reference include/SMArray.h:217-225).  count <= 1
- * restores single-device behaviour.  The environment variable SMB_DEVICES ("all", "0-7", "0,2")
+ * restores single-device behaviour; a device listed k times owns k ranges.  The environment variable SMB_DEVICES ("all", "0-7", "0,2")
  * presets the set for unmodified programs.  Device blocks (SMB_MEM_DEVICE) are computed where they
  * live; host operands go through the staging pipeline of the current device. */
 int smb_set_devices(const int *devices, int count);
@@ -278,6 +278,13 @@ int smb_plan_shards(const uint64_t *stride_a, const uint64_t *stride_b, const ui
  * PCIe can comfortably carry are produced in HBM and re-derived on the CPU. */
 int smb_fill_uniform_f32(void *out, uint64_t first, uint64_t n, uint64_t seed,
                          float lo, float hi, void *stream);
+
+/* Exhaustive accuracy audit of a float sm::pow result (device or managed memory, synchronous):
+ * the error of every got[i] against |x[i]|^y evaluated in double, in f32 ulps at the correctly
+ * rounded result; special pairs (C99 Annex F) must match exactly (they count as infinite error
+ * otherwise).  *count_over = elements whose error exceeds bound_ulp, *max_ulp = the largest error. */
+int smb_pow_audit_f32(const void *x, float y, const void *got, uint64_t n, float bound_ulp,
+                      uint64_t *count_over, float *max_ulp);
 
 #ifdef __cplusplus
 }

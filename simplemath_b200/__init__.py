@@ -79,6 +79,7 @@ SYMBOLS = {
     "smb_plan_elementwise": (_i, [_u64p, _u64p, _u64p, _i, _i, ctypes.POINTER(_i), _u64p, _u64p, _u64p]),
     "smb_plan_chain": (_i, [ctypes.POINTER(ChainStep), _i, _u64p, _i, ctypes.POINTER(_i), _u64p, _u64p]),
     "smb_plan_shards": (_i, [_u64p, _u64p, _u64p, _i, _i, _i, _u64p, _u64p, _u64p, ctypes.POINTER(_i)]),
+    "smb_pow_audit_f32": (_i, [_vp, ctypes.c_float, _vp, _u64, ctypes.c_float, _u64p, ctypes.POINTER(ctypes.c_float)]),
     "smb_fill_uniform_f32": (_i, [_vp, _u64, _u64, _u64, ctypes.c_float, ctypes.c_float, _vp]),
 }
 
@@ -210,6 +211,13 @@ def array_scalar_ptr(op, dtype, a_ptr, scalar, n, out_ptr, stream=0):
 
 def fill_uniform_f32_ptr(out_ptr, first, n, seed, lo, hi, stream=0):
     _check(lib().smb_fill_uniform_f32(out_ptr, int(first), int(n), int(seed), lo, hi, stream or None))
+
+
+def pow_audit_f32_ptr(x_ptr, y, got_ptr, n, bound_ulp):
+    """Exhaustive device-side audit of a float pow result: (elements above bound_ulp, largest error in ulps)."""
+    cnt, worst = ctypes.c_uint64(0), ctypes.c_float(0)
+    _check(lib().smb_pow_audit_f32(x_ptr, y, got_ptr, int(n), bound_ulp, ctypes.byref(cnt), ctypes.byref(worst)))
+    return int(cnt.value), float(worst.value)
 
 
 def set_option(key: int, value: int) -> None:

@@ -171,8 +171,9 @@ static int set_devices_locked(const int *devs, int n) {
     if (int rc = device_count_checked(&count)) return rc;
     if (n < 0 || n > kMaxDevices || (n > 0 && !devs)) return fail(SMB_ERR_INVALID, "smb_set_devices: bad device list");
     for (int i = 0; i < n; ++i) {
+        // (a device may be listed more than once: it then owns several ranges, each handled like a
+        // device of its own -- how the single-GPU tests exercise the whole sharded path)
         if (devs[i] < 0 || devs[i] >= count) return fail(SMB_ERR_INVALID, "smb_set_devices: device %d of %d does not exist", devs[i], count);
-        for (int j = 0; j < i; ++j) if (devs[j] == devs[i]) return fail(SMB_ERR_INVALID, "smb_set_devices: device %d listed twice", devs[i]);
     }
     DeviceScope scope;
     for (int i = 0; i < n; ++i) { // contexts up front; peer access so a device may read a neighbour's pages in place
@@ -181,7 +182,7 @@ static int set_devices_locked(const int *devs, int n) {
         if (n > 1) {
             SMB_CK(cudaSetDevice(devs[i]));
             for (int j = 0; j < n; ++j) {
-                if (i == j) continue;
+                if (devs[i] == devs[j]) continue;
                 int can = 0;
                 if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) == cudaSuccess && can) {
                     const cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
@@ -1988,18 +1989,69 @@ int smb_plan_shards(const uint64_t *stride_a, const uint64_t *stride_b, const ui
     return oa.mode == SHARD_REFUSE || ob.mode == SHARD_REFUSE ? 0 : 1;
 }
 
+int smb_pow_audit_f32(const void *x, float y, const void *got, uint64_t n, float bound_ulp, uint64_t *count_over, float *max_ulp) {
+    DeviceCtx *c = nullptr;
+    if (int rc = current_ctx(&c)) return rc;
+    if (!count_over || !max_ulp) return fail(SMB_ERR_INVALID, "null result pointer");
+    *count_over = 0;
+    *max_ulp = 0.0f;
+    if (n == 0) return SMB_OK;
+    if (!x || !got || on_host(mem_type(x)) || on_host(mem_type(got))) return fail(SMB_ERR_INVALID, "smb_pow_audit_f32 needs device or managed memory");
+    if (int rc = sync_all()) return rc;
+    Scratch acc;
+    if (int rc = acc.get(16, c->device)) return rc;
+    cudaStream_t s = c->main;
+    DrainGuard drain;
+    drain.add(s);
+    SMB_CK(cudaMemsetAsync(acc.p, 0, 16, s));
+    const unsigned grid = grid_for(n, kThreads * 8, c->sm_count, 16);
+    k_pow_audit_f32<<<grid, kThreads, 0, s>>>((const float *)x, (const float *)got, n, classify_exp(y), bound_ulp,
+                                             (unsigned long long *)acc.p, (unsigned int *)((char *)acc.p + 8));
+    ++g_launches;
+    SMB_CK(cudaGetLastError());
+    unsigned long long host[2] = {0, 0};
+    SMB_CK(cudaMemcpyAsync(host, acc.p, 16, cudaMemcpyDeviceToHost, s));
+    SMB_CK(cudaStreamSynchronize(s));
+    *count_over = host[0];
+    const uint32_t bits = (uint32_t)host[1];
+    memcpy(max_ulp, &bits, 4);
+    return SMB_OK;
+}
+
 int smb_fill_uniform_f32(void *out, uint64_t first, uint64_t n, uint64_t seed, float lo, float hi, void *stream) {
     DeviceCtx *c = nullptr;
     if (int rc = current_ctx(&c)) return rc;
     if (n == 0) return SMB_OK;
-    if (!out || on_host(mem_type(out))) return fail(SMB_ERR_INVALID, "smb_fill_uniform_f32 needs device or managed memory");
+    const MemType to = out ? mem_type(out) : MT_HOST;
+    if (!out || on_host(to)) return fail(SMB_ERR_INVALID, "smb_fill_uniform_f32 needs device or managed memory");
+    auto fill = [&](DeviceCtx &cg, float *dst, uint64_t at, uint64_t cnt, cudaStream_t s) {
+        const unsigned grid = grid_for(cnt, kThreads * 4, cg.sm_count, 16);
+        k_fill_uniform_f32<<<grid, kThreads, 0, s>>>(dst, first + at, cnt, seed, lo, hi);
+        ++g_launches;
+        SMB_CK(cudaGetLastError());
+        return (int)SMB_OK;
+    };
+    std::vector<int> devs;
+    if (to == MT_MANAGED && want_sharding(devs, n * 4, stream, true)) { // a function of the flat index: shards trivially
+        const int G = (int)devs.size();
+        const ShardSplit split = split_flat(n, n, 1, 1, G, 4);
+        const uint64_t shape1[1] = {n}, unit[1] = {1};
+        const void *bases[1] = {out};
+        const uint64_t *strides[1] = {unit};
+        ShardOperand ops[1];
+        if (shard_operands(devs, split, shape1, 1, bases, strides, 1, 4, ops)) {
+            const ShardOperand res = ops[0];
+            return run_sharded(devs, split, ops, 0, res, 4, async_mode(nullptr),
+                               [&](DeviceCtx &cg, int, uint64_t at, uint64_t cnt, const void *const *, cudaStream_t s) {
+                                   return fill(cg, (float *)out + at, at, cnt, s);
+                               });
+        }
+    }
     cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
-    const unsigned grid = grid_for(n, kThreads * 4, c->sm_count, 16);
-    k_fill_uniform_f32<<<grid, kThreads, 0, s>>>((float *)out, first, n, seed, lo, hi);
-    ++g_launches;
-    SMB_CK(cudaGetLastError());
-    if (!stream) SMB_CK(cudaStreamSynchronize(s));
-    return SMB_OK;
+    if (int rc = begin_call(*c, stream)) return rc;
+    if (to == MT_MANAGED) prefetch_managed(out, n * 4, c->device, s);
+    if (int rc = fill(*c, (float *)out, 0, n, s)) return rc;
+    return finish_call(*c, s, stream);
 }
 
 } // extern "C"

@@ -1266,6 +1266,60 @@ __global__ void __launch_bounds__(256) k_dot(const T *__restrict__ a, const T *_
 }
 
 // ---------------------------------------------------------------------------
+// k_pow_audit_f32 (test / bench support, smb_pow_audit_f32): the error of EVERY element of a
+// sm::pow(x, y) result against |x|^y evaluated in double -- the value of the reference-accuracy
+// pipeline before its single final rounding (log2_pos + exp2_d: relative error < 2^-31 after the
+// multiplication by y, i.e. < 0.01 f32 ulp) -- in units of the f32 ulp at the correctly rounded
+// result: the measure of oracle.ulp_error_f32, whose std::pow-in-double reference pins this one on
+// samples (tests/test_gpu_parity.py).  Special pairs (C99 Annex F table) must match exactly.  Counts
+// the elements above `bound` and keeps the maximum, so a 2^30-element result is checked
+// exhaustively at memory speed instead of through sampled windows.
+__global__ void __launch_bounds__(256) k_pow_audit_f32(const float *__restrict__ x, const float *__restrict__ got, uint64_t n,
+                                                      PowExpF32 pe, float bound, unsigned long long *__restrict__ count_over,
+                                                      unsigned int *__restrict__ max_err_bits) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned int over = 0;
+    float worst = 0.0f;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float xv = x[i], g = got[i];
+        const uint32_t ux = f2u(xv);
+        bool negate = false, special = false;
+        float want = 0.0f;
+        if (!(pe.y_class == 0 && (ux - 1u) < 0x7f7fffffu)) special = pow_special<float, PowExpF32>(xv, pe, &want, &negate);
+        float err;
+        if (special) {
+            err = (g == want && signbit(g) == signbit(want)) || (g != g && want != want) ? 0.0f : INFINITY;
+        } else {
+            double t = dmul((double)pe.y, log2_pos((double)u2f(ux & 0x7fffffffu)));
+            t = t > 200.0 ? 200.0 : t;
+            t = t < -200.0 ? -200.0 : t;
+            double rd = exp2_d(t);
+            if (negate) rd = -rd;
+            const float r32 = (float)rd;
+            if (isinf(r32) || isinf(g) || g != g) {
+                err = g == r32 ? 0.0f : INFINITY;
+            } else {
+                const uint32_t e = (f2u(r32) >> 23) & 0xffu;
+                const double ulp = e <= 1 ? 0x1p-149 : u2d((uint64_t)(e - 127 - 23 + 1023) << 52);
+                err = (float)(fabs((double)g - rd) / ulp);
+            }
+        }
+        if (!(err <= bound)) ++over;
+        worst = err > worst ? err : worst;
+    }
+    // per-warp, then one atomic pair per warp (the kernel is read-bound; atomics are rare)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        over += __shfl_down_sync(0xffffffffu, over, off);
+        worst = fmaxf(worst, __shfl_down_sync(0xffffffffu, worst, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (over) atomicAdd(count_over, (unsigned long long)over);
+        atomicMax(max_err_bits, f2u(worst)); // non-negative floats order like their bit patterns
+    }
+}
+
+// ---------------------------------------------------------------------------
 // fill (sm::ones / sm::zeros) and the counter-based uniform generator.
 template<typename T>
 __global__ void __launch_bounds__(256) k_fill(T *__restrict__ out, uint64_t n, T v) {

@@ -270,3 +270,124 @@ TEST(DropIn, AdoptedForeignBlockIsAcceptedAndReleased) {
     auto r = a + a;
     for (int i = 0; i < 64; ++i) ASSERT_EQ(r.data[i], 2.0f * float(i));
 }
+
+// ---- round 2: parity holes, async scope, device sets -----------------------------------------
+TEST(DropIn, OneDimOperandAgainstOneElement) {
+    // the reference takes its contiguous loop for every 1-D call (calculate.h:10-13)
+    // and reads past the one-element operand; here {5} + {1} broadcasts like every other rank.
+    sm::SMArray<float> a = {1.5f, -2.0f, 3.25f, 4.0f, 5.0f};
+    sm::SMArray<float> one = {10.0f};
+    auto r1 = a + one; auto r2 = one - a; auto r3 = a * one;
+    std::vector<size_t> want = {5};
+    EXPECT_EQ(r1.shape(), want); EXPECT_EQ(r2.shape(), want);
+    for (size_t i = 0; i < 5; ++i) { EXPECT_EQ(r1(i), a(i) + 10.0f); EXPECT_EQ(r2(i), 10.0f - a(i)); EXPECT_EQ(r3(i), a(i) * 10.0f); }
+    sm::SMArray<int> k = {7, -8, 9, 10, 11, 12, 13, 14, 15};
+    sm::SMArray<int> d = {3};
+    auto q = k / d;
+    for (size_t i = 0; i < 9; ++i) EXPECT_EQ(q(i), k(i) / 3);
+    sm::SMArray<double> x = {0.5, 0.25};
+    sm::SMArray<double> y = {4.0};
+    auto z = y / x;
+    EXPECT_EQ(z(0), 8.0); EXPECT_EQ(z(1), 16.0);
+}
+
+TEST(DropIn, DotProductOfViewsAtAnyOffset) {
+    // operator% passes `data` straight through (SMArray.h:208): row views are interior pointers,
+    // 20 bytes apart for a {3,5} float array; the reference's loadu path reads them anywhere.
+    auto a = sm::empty<float>(3, 5);
+    auto b = sm::empty<float>(3, 5);
+    for (size_t i = 0; i < 15; ++i) { a.data[i] = float(i) + 1.0f; b.data[i] = 0.5f * float(i) - 2.0f; }
+    for (size_t r = 0; r < 3; ++r) {
+        auto va = a(r, SLICE_ALL), vb = b(r, SLICE_ALL);
+        float want = 0.0f;
+        for (size_t j = 0; j < 5; ++j) want += a(r, j) * b(r, j);
+        EXPECT_FLOAT_EQ(va % vb, want);
+        auto v2 = b((r + 1) % 3, SLICE_ALL); // a different phase than va
+        float want2 = 0.0f;
+        for (size_t j = 0; j < 5; ++j) want2 += a(r, j) * b((r + 1) % 3, j);
+        EXPECT_FLOAT_EQ(va % v2, want2);
+    }
+    auto big = sm::empty<int>(7, 100003);
+    for (size_t i = 0; i < big.totalSize; ++i) big.data[i] = int(i % 2001) - 1000;
+    auto r3 = big(3, SLICE_ALL), r5 = big(5, SLICE_ALL);
+    uint32_t wrap = 0;
+    for (size_t j = 0; j < 100003; ++j) wrap += (uint32_t) big(3, j) * (uint32_t) big(5, j);
+    EXPECT_EQ(r3 % r5, (int) wrap);
+}
+
+TEST(DropIn, AsyncScopeHandsResultsOffWithoutWaiting) {
+    // the reference's own benchmark loop (benchmark/add.cpp:21-29): c = a + b on 10^6 floats, repeated
+    auto a = sm::ones<float>(1000000);
+    auto b = sm::ones<float>(1000000) * 2.0f;
+    sm::SMArray<float> keep = a + b;
+    {
+        sm::async_scope scope;
+        for (int i = 0; i < 200; ++i) { auto c = a + b; auto d = c * c; (void) d; }   // temporaries recycled while in flight
+        { auto c = a + b; auto d = c * c; keep = std::move(d); }                       // element-wise host copy: waits first
+        auto e = keep - a;                   // reads the last result, still on the stream
+        EXPECT_EQ(e(12345), 8.0f);           // host access waits by itself
+        sm::SMArray<float> f = (sm::lazy(a) + b) * b - e;
+        EXPECT_EQ(f(999999), -2.0f);
+    }
+    EXPECT_EQ(smb_get_option(SMB_OPT_ASYNC), 0);
+    for (size_t i = 0; i < 1000000; i += 9973) ASSERT_EQ(keep.data[i], 9.0f);
+    {
+        sm::async_scope outer;
+        { sm::async_scope inner; auto t = a + a; (void) t; }
+        EXPECT_EQ(smb_get_option(SMB_OPT_ASYNC), 1);   // the outermost scope decides
+    }
+    EXPECT_EQ(smb_get_option(SMB_OPT_ASYNC), 0);
+}
+
+TEST(DropIn, ElementWritesThroughOperatorAreSeenByTheNextKernel) {
+    // the reference's test pattern (tests/add.cpp:67-71): fill through operator(), operate, repeat
+    auto two = sm::ones<float>(1, 224, 1, 3);
+    auto big = sm::ones<float>(4, 224, 224, 3);
+    for (int round = 0; round < 3; ++round) {
+        for (size_t i = 0; i < 224; ++i) for (size_t c = 0; c < 3; ++c) two(0, i, 0, c) = float(3 + round);
+        auto v = big(1, SLICE_ALL);
+        auto r = v + two;
+        std::vector<size_t> want = {1, 224, 224, 3};
+        ASSERT_EQ(r.shape(), want);
+        for (size_t i = 0; i < r.totalSize; i += 997) ASSERT_EQ(r.data[i], float(4 + round));
+    }
+}
+
+TEST(DropIn, DeviceSetSpreadsOperatorsAndKeepsTheBits) {
+    // smb_set_devices behind the unchanged operator API.  With one GPU the set lists
+    // it several times (each entry owns a flat range); with more, all of them.
+    const int ndev = smb_device_count();
+    std::vector<int> set;
+    if (ndev >= 2) for (int d = 0; d < ndev; ++d) set.push_back(d);
+    else set = {0, 0, 0, 0};
+    const size_t R = 3000, C = 1024;
+    auto a = sm::empty<float>(R, C), b = sm::empty<float>(R, C), row = sm::empty<float>(1, C), col = sm::empty<float>(R, 1);
+    for (size_t i = 0; i < R * C; ++i) { a.data[i] = 0.001f * float(i % 7919) - 3.0f; b.data[i] = 1.0f + float(i % 13); }
+    for (size_t j = 0; j < C; ++j) row.data[j] = float(j) * 0.25f;
+    for (size_t i = 0; i < R; ++i) col.data[i] = 2.0f - float(i % 5);
+    auto s1 = a + b; auto s2 = a * row; auto s3 = col / b; auto s4 = sm::pow(b, 2.5f); auto s5 = a - 1.25f;
+    const float dot1 = a % b;
+    sm::SMArray<float> s6 = (sm::lazy(a) + row) * col - b;
+    const int64_t old_min = smb_get_option(SMB_OPT_SHARD_MIN_BYTES);
+    smb_set_option(SMB_OPT_SHARD_MIN_BYTES, 1 << 20);
+    sm::set_devices(set);
+    EXPECT_EQ(sm::devices().size(), set.size());
+    auto m1 = a + b; auto m2 = a * row; auto m3 = col / b; auto m4 = sm::pow(b, 2.5f); auto m5 = a - 1.25f;
+    const float dot2 = a % b;
+    sm::SMArray<float> m6 = (sm::lazy(a) + row) * col - b;
+    auto ones = sm::ones<float>(R, C);          // born partitioned
+    auto m7 = ones + m1;
+    sm::set_devices({});
+    smb_set_option(SMB_OPT_SHARD_MIN_BYTES, old_min);
+    for (size_t i = 0; i < R * C; ++i) {
+        ASSERT_EQ(m1.data[i], s1.data[i]); ASSERT_EQ(m2.data[i], s2.data[i]); ASSERT_EQ(m3.data[i], s3.data[i]);
+        ASSERT_EQ(m4.data[i], s4.data[i]); ASSERT_EQ(m5.data[i], s5.data[i]); ASSERT_EQ(m6.data[i], s6.data[i]);
+        ASSERT_EQ(m7.data[i], s1.data[i] + 1.0f);
+    }
+    // float dot: per-range partial sums are added in range order -- a different association than one
+    // device's, same tolerance as against the reference
+    EXPECT_TRUE(std::fabs(dot1 - dot2) <= 1e-5f * std::fabs(dot1) + 1e-3f);
+    sm::SMArray<int> x = {1, 2, 3};             // small arrays are untouched by all this
+    auto y = x + x;
+    EXPECT_EQ(y(2), 6);
+}

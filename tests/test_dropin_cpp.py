@@ -28,4 +28,4 @@ def test_reference_tests_pass_on_the_drop_in_headers():
 
 
 def test_own_cpp_acceptance():
-    assert _run("dropin_test") >= 17
+    assert _run("dropin_test") >= 22

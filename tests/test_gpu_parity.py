@@ -3,7 +3,8 @@ against the oracle / golden vectors.
 
 Bars: bit-exact for int32 and for float/double + - * /; float/double pow within
 the stated ULP bound of std::pow computed in higher precision
-(f32 <= 1 ULP vs double, f64 <= 1 ULP vs long double).
+(stated: 1 ULP; pinned here at the measured maxima plus a margin, f32 <= 0.6 ULP vs double,
+f64 <= 0.65 ULP vs long double).
 """
 import ctypes
 
@@ -16,8 +17,11 @@ from conftest import assert_same_bits
 
 pytestmark = pytest.mark.gpu
 
-F32_POW_ULP_BOUND = 1.0
-F64_POW_ULP_BOUND = 1.0
+# The stated contract is 1 ULP; the kernels measure <= 0.56 (f32) / <= 0.61 (f64) over the host-compiled
+# sweeps (tests/test_hostcheck.py), and the GPU tests pin THAT with a small margin, so a regression
+# to "just under 1 ULP" fails here.
+F32_POW_ULP_BOUND = 0.6
+F64_POW_ULP_BOUND = 0.65
 
 
 def _pow_close(got, a, y, dtype, orc):
@@ -548,9 +552,28 @@ def test_config_c3_c5_large_pow_and_add_properties(orc):
                 got = out[start:start + (1 << 20)].cpu().numpy()
                 err = oracle.ulp_error_f32(got, orc.pow_ref_f32(w, y))
                 assert err.max() <= F32_POW_ULP_BOUND, (y, start, err.max())
+            # EVERY element, on the device: error against |x|^y in double (the reference-accuracy pipeline
+            # before its rounding), none above the bound -- the declined-element slow path included
+            over, worst = smb.pow_audit_f32_ptr(x.data_ptr(), y, out.data_ptr(), n, F32_POW_ULP_BOUND)
+            assert over == 0 and worst <= F32_POW_ULP_BOUND, (y, over, worst)
             # monotone in x for y > 0: sorting inputs sorts outputs (whole array, on device)
             idx = torch.argsort(x[: 1 << 24])
             assert bool((out[: 1 << 24][idx].diff() >= 0).all())
+        # the reference benchmark's own fill, arr(i, j) = i + j + 1 on {16384, 16384} (benchmark/pow.cpp:33-47), audited whole
+        ij = (torch.arange(16384, device="cuda", dtype=torch.float32)[:, None] + torch.arange(16384, device="cuda", dtype=torch.float32)[None, :] + 1).reshape(-1)
+        for y in (2.0, 2.5):
+            smb.array_scalar_ptr(smb.OP_POW, smb.F32, ij.data_ptr(), y, n, out.data_ptr())
+            over, worst = smb.pow_audit_f32_ptr(ij.data_ptr(), y, out.data_ptr(), n, F32_POW_ULP_BOUND)
+            assert over == 0, (y, over, worst)
+        del ij
+        # every finite positive bit pattern class in one array (denormals, huge, tiny: the slow path's share)
+        bits = torch.arange(n, device="cuda", dtype=torch.int32) * 7 + 1
+        xb = bits.view(torch.float32)
+        for y in (2.5, -0.5, 31.0):
+            smb.array_scalar_ptr(smb.OP_POW, smb.F32, xb.data_ptr(), y, n, out.data_ptr())
+            over, worst = smb.pow_audit_f32_ptr(xb.data_ptr(), y, out.data_ptr(), n, F32_POW_ULP_BOUND)
+            assert over == 0, (y, over, worst)
+        del bits, xb
     finally:
         smb.set_option(smb.OPT_POW_SPECIALISE, 1)
     # pow(x, 2) specialised == x*x exactly, everywhere
@@ -563,6 +586,38 @@ def test_config_c3_c5_large_pow_and_add_properties(orc):
     assert bool((out == x + y).all())
     w = orc.fill_uniform_f32(n - 4096, 4096, 3, 0.01, 100.0), orc.fill_uniform_f32(n - 4096, 4096, 4, -1.0, 1.0)
     assert_same_bits(out[n - 4096:].cpu().numpy(), orc.elementwise("add", w[0], [1], w[1], [1], [4096]), "C5 add tail window")
+
+
+def test_config_c3_f64_pow_at_256m(orc):
+    """C3 in double at the stated size: 268 435 456 elements (2 GiB in, 2 GiB out), y = 2 (the reference
+    benchmark's exponent) and 2.5: sampled windows against powl + whole-array properties."""
+    torch = _torch()
+    n = 268_435_456
+    xf = torch.empty(n, dtype=torch.float32, device="cuda")
+    smb.fill_uniform_f32_ptr(xf.data_ptr(), 0, n, 3, 0.01, 100.0)
+    x = xf.double()
+    del xf
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+    try:
+        for y in (2.0, 2.5):
+            smb.array_scalar_ptr(smb.OP_POW, smb.F64, x.data_ptr(), y, n, out.data_ptr())
+            for start in (0, 123_456_789, n - (1 << 19)):
+                w = orc.fill_uniform_f32(start, 1 << 19, 3, 0.01, 100.0).astype(np.float64)
+                hi, lo = orc.pow_ref_f64(w, y)
+                err = oracle.ulp_error_f64(out[start:start + (1 << 19)].cpu().numpy(), hi, lo)
+                assert err.max() <= F64_POW_ULP_BOUND, (y, start, err.max())
+            idx = torch.argsort(x[: 1 << 24])
+            assert bool((out[: 1 << 24][idx].diff() >= 0).all())
+            # against torch's own double pow everywhere: both are within an ulp of the truth
+            ref = torch.pow(x, y)
+            rel = ((out - ref).abs() / ref.abs()).max().item()
+            del ref
+            assert rel <= 4 * 2.2204460492503131e-16, (y, rel)
+    finally:
+        smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+    smb.array_scalar_ptr(smb.OP_POW, smb.F64, x.data_ptr(), 2.0, n, out.data_ptr())
+    assert bool((out == x * x).all())
 
 
 # ---- SURVEY.md §8(f) row 2: dot product (SMArray::operator%) on the device --------------------

@@ -1,0 +1,391 @@
+"""GPU tests of the runtime around the kernels (need a B200; called through the C ABI):
+
+  * the parity holes the round-1 review named: 1-D stride-0 operands, operator% on
+    misaligned views, the int32 pow step of a fused chain on a broadcast intermediate;
+  * multi-GPU behind the operator API (smb_set_devices): every operator spread over a
+    device set, bit-identical to one device.  On a one-GPU box the set lists device 0 several times
+    (each entry owns a flat range), which drives the whole sharded path -- range planning, placement
+    records, replicated operands, rebased pointers, per-range launches; with >= 2 GPUs the same tests
+    also run on distinct devices;
+  * asynchronous hand-off (SMB_OPT_ASYNC), programmatic dependent launch on / off;
+  * the exhaustive device-side pow audit.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+import simplemath_b200 as smb
+from conftest import assert_same_bits
+
+pytestmark = pytest.mark.gpu
+
+_CT = {np.dtype(np.float32): ctypes.c_float, np.dtype(np.float64): ctypes.c_double, np.dtype(np.int32): ctypes.c_int32}
+
+
+class Managed:
+    """A managed (cudaMallocManaged, pooled) block seen as a numpy array: what sm::SMArray<T>::data is."""
+
+    def __init__(self, arr=None, shape=None, dtype=None):
+        if arr is not None:
+            arr = np.ascontiguousarray(arr)
+            shape, dtype = arr.shape, arr.dtype
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape)
+        n = int(np.prod(self.shape)) if len(self.shape) else 1
+        self.ptr = smb.lib().smb_alloc(max(n, 1) * self.dtype.itemsize, smb.MEM_MANAGED)
+        assert self.ptr, smb.lib().smb_last_error()
+        self.np = np.ctypeslib.as_array(ctypes.cast(self.ptr, ctypes.POINTER(_CT[self.dtype])), shape=(max(n, 1),))[:n].reshape(self.shape)
+        if arr is not None:
+            self.np[...] = arr
+            smb.lib().smb_host_written(self.ptr)
+
+    def free(self):
+        if self.ptr:
+            smb.lib().smb_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _binary_managed(op, a: np.ndarray, b: np.ndarray):
+    """smb_elementwise on managed operands / result (the SMArray operator path); returns the result as numpy."""
+    dt = smb.dtype_code(a.dtype)
+    shape, sa, sb, total = smb.broadcast(a.shape, smb.row_major_strides(a.shape), b.shape, smb.row_major_strides(b.shape))
+    ma, mb, mo = Managed(a), Managed(b), Managed(shape=shape, dtype=a.dtype)
+    smb.elementwise_ptr(smb.OPS[op], dt, ma.ptr, sa, mb.ptr, sb, shape, mo.ptr)
+    smb.sync()
+    out = mo.np.copy()
+    kern = smb.last_kernel()
+    for m in (ma, mb, mo):
+        m.free()
+    return out, kern
+
+
+def _device_sets():
+    n = smb.device_count()
+    sets = [[0, 0], [0, 0, 0], [0] * 8]
+    if n >= 2:
+        sets += [[0, 1], list(range(n))]
+    return sets
+
+
+@pytest.fixture
+def sharded():
+    """Force sharding on small results; restore single-device behaviour afterwards."""
+    old = smb.lib().smb_get_option(smb.OPT_SHARD_MIN_BYTES)
+    smb.set_option(smb.OPT_SHARD_MIN_BYTES, 0)
+    yield
+    smb.set_devices([])
+    smb.set_option(smb.OPT_SHARD_MIN_BYTES, old)
+
+
+# ---------------------------------------------------------------- parity holes of round 1 ----
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32])
+def test_f11_one_dim_stride_zero_operands(dtype):
+    """{5} + {1} and {1} + {5} (reference calculate.h:10-13 takes its contiguous loop for every 1-D
+    call and reads past the one-element operand; documented divergence: the stride table is honoured)."""
+    rng = np.random.default_rng(3)
+    for n in (5, 1, 8, 1003, 100_003):
+        a = (rng.standard_normal(n) * 50).astype(dtype)
+        one = (rng.standard_normal(1) * 7 + 9).astype(dtype)
+        for op, f in (("add", np.add), ("sub", np.subtract), ("mul", np.multiply)):
+            with np.errstate(all="ignore"):
+                assert_same_bits(smb.binary(op, a, one), f(a, one).astype(dtype), f"{{{n}}} {op} {{1}}")
+                assert_same_bits(smb.binary(op, one, a), f(one, a).astype(dtype), f"{{1}} {op} {{{n}}}")
+            got, _ = _binary_managed(op, a, one)
+            with np.errstate(all="ignore"):
+                assert_same_bits(got, f(a, one).astype(dtype), f"managed {{{n}}} {op} {{1}}")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32])
+def test_dot_on_misaligned_views(orc, dtype):
+    """SMArray::operator% hands interior pointers straight to dot_product (SMArray.h:208); the reference
+    reads them with loadu (product.h:26-71).  Same phase -> peeled head, different phases -> the
+    element-wise kernel; int32 is bit-exact either way."""
+    import torch
+    rng = np.random.default_rng(8)
+    es = np.dtype(dtype).itemsize
+    n = 100_003
+    if dtype == np.int32:
+        ha = rng.integers(-2**31, 2**31, n + 8, dtype=np.int64).astype(np.int32)
+        hb = rng.integers(-2**31, 2**31, n + 8, dtype=np.int64).astype(np.int32)
+    else:
+        ha, hb = rng.standard_normal(n + 8).astype(dtype), rng.standard_normal(n + 8).astype(dtype)
+    da, db = torch.from_numpy(ha).cuda(), torch.from_numpy(hb).cuda()
+    dt = smb.dtype_code(dtype)
+    for oa, ob, kern in ((0, 0, "k_dot"), (1, 1, "k_dot"), (3, 3, "k_dot"), (1, 2, "k_dot<unaligned>"), (0, 1, "k_dot<unaligned>"), (5, 2, "k_dot<unaligned>")):
+        if (oa * es) % 16 == (ob * es) % 16:
+            kern = "k_dot"
+        for m in (n, 1, 2, 7):
+            got = smb.dot_ptr(dt, da.data_ptr() + oa * es, db.data_ptr() + ob * es, m)
+            va, vb = ha[oa:oa + m], hb[ob:ob + m]
+            if dtype == np.int32:
+                assert np.int32(got) == orc.dot(va, vb), (oa, ob, m)
+            else:
+                exact = float(np.sum(va.astype(np.longdouble) * vb.astype(np.longdouble)))
+                bound = 8 * np.finfo(dtype).eps * float(np.sum(np.abs(va.astype(np.float64) * vb.astype(np.float64)))) + 1e-300
+                assert abs(float(got) - exact) <= bound, (oa, ob, m, got, exact)
+        assert smb.last_kernel() == kern, (oa, ob, smb.last_kernel())
+    # host views (numpy slices): staged, any offset
+    assert smb.dot(ha[1:n], hb[2:n + 1]) == (orc.dot(ha[1:n], hb[2:n + 1]) if dtype == np.int32 else smb.dot(ha[1:n].copy(), hb[2:n + 1].copy()))
+
+
+def test_chain_int32_pow_on_broadcast_intermediate(orc):
+    """sm::pow(lazy(a{1,N}), e) + B{M,N}: the unfused reference runs array_scalar_op over the N-element
+    intermediate (lane/scalar split at N - N % 8, calculate.h:139-140); the fused call evaluates that
+    prefix first.  Exponents that overflow or are negative tell the two semantics apart."""
+    rng = np.random.default_rng(14)
+    for N, M in ((13, 3), (16, 5), (1003, 7)):
+        a = rng.integers(-12, 13, size=(1, N)).astype(np.int32)
+        B = rng.integers(-1000, 1000, size=(M, N)).astype(np.int32)
+        col = rng.integers(-5, 6, size=(M, 1)).astype(np.int32)
+        for e in (3, 13, 31, 40, -1, -2):
+            want = orc.binary("add", orc.array_scalar("pow", a, e), B)
+            assert_same_bits(smb.chain(a, ("pow", e), ("add", B)), want, f"pow(a{{1,{N}}}, {e}) + B{{{M},{N}}}")
+            want2 = orc.binary("mul", orc.array_scalar("pow", orc.array_scalar("add", a, 1), e), col)
+            assert_same_bits(smb.chain(a, ("add", 1), ("pow", e), ("mul", col)), want2, f"pow(a + 1, {e}) * col")
+            # two pow steps, the first on the smaller intermediate
+            want3 = orc.array_scalar("pow", orc.binary("sub", orc.array_scalar("pow", a, e), B), 2)
+            assert_same_bits(smb.chain(a, ("pow", e), ("sub", B), ("pow", 2)), want3, "pow(pow(a, e) - B, 2)")
+
+
+# ------------------------------------------------- multi-GPU behind the operator API (§8e) ----
+def test_sharded_elementwise_bit_identical(orc, sharded):
+    rng = np.random.default_rng(77)
+    cases = [((40_000,), (40_000,)), ((300, 257), (1, 257)), ((300, 257), (300, 1)), ((129, 1), (1, 65)),
+             ((24, 1, 256), (1, 40, 256)), ((5, 6, 7, 3), (1, 6, 1, 3)), ((64, 64), (64, 64)), ((7, 2048), (2048,))]
+    for devs in _device_sets():
+        smb.set_devices(devs)
+        assert smb.get_devices() == devs
+        for s1, s2 in cases:
+            for dtype, op in ((np.float32, "add"), (np.int32, "mul"), (np.float64, "div"), (np.int32, "div")):
+                if dtype == np.int32:
+                    a = rng.integers(-1000, 1001, size=s1).astype(np.int32)
+                    b = (rng.integers(1, 98, size=s2) * rng.choice([-1, 1], size=s2)).astype(np.int32)
+                else:
+                    a, b = rng.standard_normal(s1).astype(dtype), (rng.standard_normal(s2) + 3).astype(dtype)
+                got, kern = _binary_managed(op, a, b)
+                assert_same_bits(got, orc.binary(op, a, b), f"{len(devs)} ranges {op} {np.dtype(dtype).name} {s1}x{s2} [{kern}]")
+
+
+def test_sharded_transposed_operand_falls_back_to_one_device(orc, sharded):
+    """An operand every device would need most of (a transpose) and that is too large to copy per call:
+    the operator runs on one device -- same bits."""
+    rng = np.random.default_rng(5)
+    smb.set_devices([0, 0, 0, 0])
+    old = smb.lib().smb_get_option(smb.OPT_REPLICATE_MAX_BYTES)
+    smb.set_option(smb.OPT_REPLICATE_MAX_BYTES, 1024)
+    try:
+        m = rng.standard_normal((96, 200)).astype(np.float32)
+        n = rng.standard_normal((200, 96)).astype(np.float32)
+        dt = smb.F32
+        ma, mb, mo = Managed(m), Managed(n), Managed(shape=(200, 96), dtype=np.float32)
+        smb.elementwise_ptr(smb.OP_SUB, dt, ma.ptr, [1, 200], mb.ptr, [96, 1], [200, 96], mo.ptr)
+        assert smb.last_kernel() == "k_tile<transpose>"
+        assert_same_bits(mo.np.copy(), orc.binary("sub", m.T, n), "transposed operand, device set active")
+        sharded_ok, _, _, _, modes = smb.plan_shards([1, 200], [96, 1], [200, 96], 4)
+        assert not sharded_ok and modes[0] == 2
+    finally:
+        smb.set_option(smb.OPT_REPLICATE_MAX_BYTES, old)
+
+
+def test_sharded_scalar_pow_chain_fill_dot(orc, sharded):
+    rng = np.random.default_rng(78)
+    lib = smb.lib()
+    for devs in _device_sets():
+        smb.set_devices(devs)
+        n = 100_003
+        # array (op) scalar incl. the int32 pow lane / scalar-tail split at the ABSOLUTE index
+        for dtype, op, v in ((np.float32, "mul", 1.5), (np.int32, "pow", 5), (np.int32, "pow", 31), (np.int32, "pow", -2), (np.float64, "sub", 0.25)):
+            a = rng.integers(-9, 10, n).astype(dtype) if dtype == np.int32 else rng.standard_normal(n).astype(dtype)
+            ma, mo = Managed(a), Managed(shape=(n,), dtype=dtype)
+            smb.array_scalar_ptr(smb.OPS[op], smb.dtype_code(dtype), ma.ptr, v, n, mo.ptr)
+            assert_same_bits(mo.np.copy(), orc.array_scalar(op, a, v), f"{len(devs)} ranges scalar {op} {np.dtype(dtype).name}")
+        # float pow, general kernel: every range stages its own tables
+        x = rng.uniform(0.01, 100, n).astype(np.float32)
+        mx, mo = Managed(x), Managed(shape=(n,), dtype=np.float32)
+        smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+        try:
+            smb.array_scalar_ptr(smb.OP_POW, smb.F32, mx.ptr, 2.5, n, mo.ptr)
+        finally:
+            smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+        assert oracle.ulp_error_f32(mo.np.copy(), orc.pow_ref_f32(x, 2.5)).max() <= 0.6
+        # fused chain with a broadcast row leaf (replicated) and a column leaf
+        a = rng.standard_normal((300, 256)).astype(np.float32)
+        row = rng.standard_normal((1, 256)).astype(np.float32)
+        col = rng.standard_normal((300, 1)).astype(np.float32)
+        ma, mr, mc, mo = Managed(a), Managed(row), Managed(col), Managed(shape=a.shape, dtype=np.float32)
+        leaves = [(None, False, (ma.ptr, [256, 1])), ("mul", False, (mr.ptr, [0, 1])), ("add", False, (mc.ptr, [1, 0])), ("sub", False, 0.5)]
+        smb.chain_ptr(smb.F32, leaves, list(a.shape), mo.ptr)
+        want = orc.array_scalar("sub", orc.binary("add", orc.binary("mul", a, row), col), 0.5)
+        assert_same_bits(mo.np.copy(), want, f"{len(devs)} ranges chain a*row+col-0.5 [{smb.last_kernel()}]")
+        # fill (sm::ones) born partitioned, then used
+        mf = Managed(shape=(n,), dtype=np.float32)
+        one = ctypes.c_float(1.0)
+        smb._check(lib.smb_fill(smb.F32, mf.ptr, ctypes.byref(one), n, None))
+        assert bool((mf.np == 1.0).all())
+        # dot: per-range partials added on the host; int32 wraps exactly
+        ia = rng.integers(-2**31, 2**31, n, dtype=np.int64).astype(np.int32)
+        ib = rng.integers(-2**31, 2**31, n, dtype=np.int64).astype(np.int32)
+        mia, mib = Managed(ia), Managed(ib)
+        assert np.int32(smb.dot_ptr(smb.I32, mia.ptr, mib.ptr, n)) == orc.dot(ia, ib)
+        fa, fb = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+        mfa, mfb = Managed(fa), Managed(fb)
+        exact = float(np.sum(fa.astype(np.float64) * fb.astype(np.float64)))
+        assert abs(smb.dot_ptr(smb.F32, mfa.ptr, mfb.ptr, n) - exact) <= 8 * np.finfo(np.float32).eps * float(np.sum(np.abs(fa * fb)))
+
+
+def test_sharded_reuses_placement_and_results_feed_the_next_operator(orc, sharded):
+    """c = a + b; d = c * row; e = d - c on a device set: results are born partitioned, an operand that
+    is already where its range's device wants it is not prefetched again, and the answer is the
+    single-device one."""
+    rng = np.random.default_rng(79)
+    smb.set_devices(_device_sets()[-1])
+    R, C = 2048, 2048  # 16 MiB per array: every range is at least one 2 MiB page, so operands are sharded IN PLACE
+    a = rng.standard_normal((R, C)).astype(np.float32)
+    b = rng.standard_normal((R, C)).astype(np.float32)
+    row = rng.standard_normal((1, C)).astype(np.float32)
+    ma, mb, mr = Managed(a), Managed(b), Managed(row)
+    mc, md, me = (Managed(shape=a.shape, dtype=np.float32) for _ in range(3))
+    full, rowst = [C, 1], [0, 1]
+    assert smb.plan_shards(full, full, [R, C], len(smb.get_devices()))[4] == (0, 0)
+    for _ in range(3):
+        smb.elementwise_ptr(smb.OP_ADD, smb.F32, ma.ptr, full, mb.ptr, full, [R, C], mc.ptr)
+        smb.elementwise_ptr(smb.OP_MUL, smb.F32, mc.ptr, full, mr.ptr, rowst, [R, C], md.ptr)
+        smb.elementwise_ptr(smb.OP_SUB, smb.F32, md.ptr, full, mc.ptr, full, [R, C], me.ptr)
+    c = orc.binary("add", a, b)
+    d = orc.binary("mul", c, row)
+    assert_same_bits(me.np.copy(), orc.binary("sub", d, c), "three chained operators on a device set")
+    # the host writes an operand in place (through `data`, as the reference's tests do) and says so
+    ma.np[...] = b
+    smb.lib().smb_host_written(ma.ptr)
+    smb.elementwise_ptr(smb.OP_ADD, smb.F32, ma.ptr, full, mb.ptr, full, [R, C], mc.ptr)
+    assert_same_bits(mc.np.copy(), orc.binary("add", b, b), "operand rewritten by the host between operators")
+
+
+# ------------------------------------------------------------- async hand-off, PDL on / off ----
+def test_async_mode_and_pdl_variants(orc):
+    """SMB_OPT_ASYNC: stream == NULL calls return before the kernels finish; results land at
+    smb_wait_pending().  The same sequences with programmatic dependent launch on and off, including
+    back-to-back launches WITH a data hazard (c = a + b; d = c * c) and without one."""
+    import torch
+    rng = np.random.default_rng(90)
+    n = 1 << 22
+    ha, hb = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    a, b = torch.from_numpy(ha).cuda(), torch.from_numpy(hb).cuda()
+    c, d, e, f = (torch.empty(n, dtype=torch.float32, device="cuda") for _ in range(4))
+    want_c = orc.elementwise("add", ha, [1], hb, [1], [n])
+    want_d = orc.elementwise("mul", want_c, [1], want_c, [1], [n])
+    want_e = orc.elementwise("sub", ha, [1], hb, [1], [n])
+    want_f = orc.array_scalar("mul", want_d, 0.5)
+    torch.cuda.synchronize()
+    for pdl in (1, 0):
+        smb.set_option(smb.OPT_PDL, pdl)
+        for asyn in (0, 1):
+            smb.set_option(smb.OPT_ASYNC, asyn)
+            for t in (c, d, e, f):
+                t.zero_()
+            torch.cuda.synchronize()
+            for _ in range(4):  # repeated: write-after-write and read-after-write hazards between launches
+                smb.contiguous_ptr(smb.OP_ADD, smb.F32, a.data_ptr(), b.data_ptr(), c.data_ptr(), n)      # no hazard with what follows it the first time
+                smb.contiguous_ptr(smb.OP_MUL, smb.F32, c.data_ptr(), c.data_ptr(), d.data_ptr(), n)      # reads c: must wait
+                smb.contiguous_ptr(smb.OP_SUB, smb.F32, a.data_ptr(), b.data_ptr(), e.data_ptr(), n)      # independent: may overlap
+                smb.array_scalar_ptr(smb.OP_MUL, smb.F32, d.data_ptr(), 0.5, n, f.data_ptr())             # reads d
+            smb._check(smb.lib().smb_wait_pending())
+            tag = f"pdl={pdl} async={asyn}"
+            assert_same_bits(c.cpu().numpy(), want_c, "c " + tag)
+            assert_same_bits(d.cpu().numpy(), want_d, "d " + tag)
+            assert_same_bits(e.cpu().numpy(), want_e, "e " + tag)
+            assert_same_bits(f.cpu().numpy(), want_f, "f " + tag)
+    smb.set_option(smb.OPT_ASYNC, 0)
+    smb.set_option(smb.OPT_PDL, 1)
+    # in-place update chains: x = x + b, repeated (every launch depends on the one before)
+    x = a.clone()
+    want = ha.copy()
+    smb.set_option(smb.OPT_ASYNC, 1)
+    try:
+        for _ in range(5):
+            smb.contiguous_ptr(smb.OP_ADD, smb.F32, x.data_ptr(), b.data_ptr(), x.data_ptr(), n)
+            want = orc.elementwise("add", want, [1], hb, [1], [n])
+    finally:
+        smb.set_option(smb.OPT_ASYNC, 0)  # waits
+    assert_same_bits(x.cpu().numpy(), want, "x += b five times, async")
+
+
+def test_async_mode_recycles_pool_blocks_in_stream_order(orc):
+    """The operator pattern of the C++ headers in an async scope: every result is a fresh pooled block,
+    temporaries are freed while their kernels may still be running, and the freed block is handed out
+    again at once."""
+    rng = np.random.default_rng(91)
+    lib = smb.lib()
+    n = 1 << 20
+    ha = rng.standard_normal(n).astype(np.float32)
+    ma = Managed(ha)
+    smb.set_option(smb.OPT_ASYNC, 1)
+    try:
+        cur = lib.smb_alloc(n * 4, smb.MEM_MANAGED)
+        smb.array_scalar_ptr(smb.OP_ADD, smb.F32, ma.ptr, 1.0, n, cur)
+        want = orc.array_scalar("add", ha, 1.0)
+        for k in range(12):
+            nxt = lib.smb_alloc(n * 4, smb.MEM_MANAGED)
+            smb.array_scalar_ptr(smb.OP_MUL, smb.F32, cur, 1.0009765625, n, nxt)
+            lib.smb_free(cur)  # still being read by the kernel just enqueued
+            cur = nxt
+            want = orc.array_scalar("mul", want, 1.0009765625)
+        smb._check(lib.smb_wait_pending())
+        got = np.ctypeslib.as_array(ctypes.cast(cur, ctypes.POINTER(ctypes.c_float)), shape=(n,)).copy()
+    finally:
+        smb.set_option(smb.OPT_ASYNC, 0)
+    lib.smb_free(cur)
+    assert_same_bits(got, want, "twelve dependent operators on recycled blocks")
+
+
+def test_staged_call_is_ordered_after_the_callers_stream(orc):
+    """Host (pinned) operands with stream != NULL: the H2D copies start after the work already enqueued
+    on that stream (here: the async memcpy that fills the pinned input)."""
+    import torch
+    n = 1 << 22
+    rng = np.random.default_rng(92)
+    src = torch.from_numpy(rng.standard_normal(n).astype(np.float32)).cuda()
+    pin_in = torch.zeros(n, dtype=torch.float32).pin_memory()
+    pin_out = torch.zeros(n, dtype=torch.float32).pin_memory()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(8):                       # keep the stream busy so the copy below is still pending
+            src.mul_(1.0)
+        pin_in.copy_(src, non_blocking=True)     # produces the pinned input on stream s
+    smb.array_scalar_ptr(smb.OP_MUL, smb.F32, pin_in.data_ptr(), 2.0, n, pin_out.data_ptr(), s.cuda_stream)
+    assert_same_bits(pin_out.numpy(), (src.cpu().numpy() * np.float32(2.0)), "staged call after async producer")
+
+
+# -------------------------------------------------------------- exhaustive device-side audit ----
+def test_pow_audit_agrees_with_the_oracle_and_catches_errors(orc):
+    import torch
+    rng = np.random.default_rng(93)
+    n = 1 << 20
+    hx = np.concatenate([rng.uniform(0.01, 100, n // 2).astype(np.float32),
+                         rng.integers(1, 0x7f800000, n // 2, dtype=np.uint32).view(np.float32)])
+    x = torch.from_numpy(hx).cuda()
+    out = torch.empty_like(x)
+    smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+    try:
+        for y in (2.5, -0.75, 17.0, 300.0):
+            smb.array_scalar_ptr(smb.OP_POW, smb.F32, x.data_ptr(), y, n, out.data_ptr())
+            cnt, worst = smb.pow_audit_f32_ptr(x.data_ptr(), y, out.data_ptr(), n, 0.6)
+            err = oracle.ulp_error_f32(out.cpu().numpy(), orc.pow_ref_f32(hx, y))
+            assert cnt == 0 and abs(worst - err.max()) < 0.02, (y, cnt, worst, err.max())
+    finally:
+        smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+    # a planted 2-ulp error and a wrong special are both seen
+    smb.array_scalar_ptr(smb.OP_POW, smb.F32, x.data_ptr(), 2.5, n, out.data_ptr())
+    h = out.cpu().numpy()
+    h[12345] = np.nextafter(np.nextafter(h[12345], np.float32(np.inf)), np.float32(np.inf))
+    out.copy_(torch.from_numpy(h))
+    cnt, worst = smb.pow_audit_f32_ptr(x.data_ptr(), 2.5, out.data_ptr(), n, 0.6)
+    assert cnt == 1 and 1.4 < worst < 2.6, (cnt, worst)
