@@ -112,7 +112,10 @@ enum {
     SMB_OPT_REPLICATE_MAX_BYTES = 8,
     /* Pool high-water mark: when more than this many freed bytes sit cached, smb_free returns the
      * largest blocks to the driver (default 64 GiB; negative: never). */
-    SMB_OPT_POOL_MAX_CACHED_BYTES = 9
+    SMB_OPT_POOL_MAX_CACHED_BYTES = 9,
+    /* Table-driven pow kernels: how many CTAs at the END of the grid own a single tile (they fill the
+     * ragged end the multi-tile CTAs leave); -1 (default): chosen from the SM count, 0: none. */
+    SMB_OPT_POW_TAIL_CTAS = 10
 };
 
 /* ---- the hot path ------------------------------------------------------- */

@@ -51,6 +51,7 @@ static std::atomic<int64_t> g_opt_chunk_bytes{64ll << 20};
 static std::atomic<int64_t> g_opt_contig_variant{0};
 static std::atomic<int64_t> g_opt_bcast_variant{0};
 static std::atomic<int64_t> g_opt_force_wide{0};
+static std::atomic<int64_t> g_opt_pow_tail{-1}; // single-tile CTAs at the end of a pow grid; -1: library default
 static std::atomic<int64_t> g_opt_pool_max_cached{64ll << 30}; // cached (free) pool bytes beyond which smb_free trims
 
 // ------------------------------------------------------ device context ------
@@ -548,17 +549,30 @@ static int launch_stream(DeviceCtx &c, const T *a, const T *b, T *out, uint64_t 
             // Plain streams run one tile per CTA (tools/sweep: fastest on B200); the pow kernels a few
             // consecutive tiles per CTA (pow_tiles_per_cta).  SMB_OPT_CONTIG_VARIANT overrides either.
             unsigned grid;
+            uint32_t n_small = 0;
             if (fn_pow_tables<Fn>::value && SMB_POW_BLOCKED) {
                 const int resident = sizeof(T) == 4 ? SMB_POW_MIN_BLOCKS : SMB_POW64_MIN_BLOCKS;
-                const int64_t tpc = pow_tiles_per_cta(rest / per_block, c.sm_count, resident,
+                const uint64_t full_tiles = rest / per_block;
+                const int64_t tpc = pow_tiles_per_cta(full_tiles, c.sm_count, resident,
                                                       sizeof(T) == 4 ? SMB_POW_TILES_PER_CTA : 4 * SMB_POW_TILES_PER_CTA);
-                grid = grid_for(rest, per_block * (uint64_t)tpc, c.sm_count, 0);
+                // single-tile CTAs at the end of the grid: about half a multi-tile CTA lifetime of work for
+                // every resident slot (what the ragged end of the multi-tile phase leaves idle on average)
+                const int64_t tail_opt = g_opt_pow_tail.load();
+                uint64_t small = tail_opt >= 0 ? (uint64_t)tail_opt : (uint64_t)c.sm_count * resident * (uint64_t)tpc / 2;
+                small = std::min<uint64_t>(std::min<uint64_t>(small, full_tiles / 4), (1u << 24) - 1);
+                if (tpc <= 1) small = 0;
+                const uint64_t big_tiles = full_tiles - small;
+                const uint64_t big = (big_tiles + (uint64_t)tpc - 1) / (uint64_t)tpc;
+                n_small = (uint32_t)small;
+                grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(big + small, 0x7fffffffull));
+                if ((uint64_t)grid != std::max<uint64_t>(1, big + small)) { n_small = 0; grid = grid_for(rest, per_block * (uint64_t)tpc, c.sm_count, 0); }
             } else {
                 grid = grid_for(rest, per_block, c.sm_count, fn_pow_tables<Fn>::value && cps == 0 ? 8 : cps);
             }
             const PdlDecision d = ll.decide(reads, HAS_B ? 2 : 1, write);
             SMB_CK(launch_ex(k_stream<T, Fn, HAS_B, VB, UNROLL>, dim3(grid), kThreads, 0, s, d.attr, a + head,
-                             HAS_B ? b + head : (const T *)nullptr, out + head, rest, first + head, fn, d.flags));
+                             HAS_B ? b + head : (const T *)nullptr, out + head, rest, first + head, fn,
+                             d.flags | (n_small << kPdlFlagBits)));
             ++g_launches;
             g_last_kernel = HAS_B ? "k_stream<binary>" : "k_stream<scalar>";
         }
@@ -1916,6 +1930,7 @@ int smb_set_option(int key, int64_t value) {
         case SMB_OPT_SHARD_MIN_BYTES: g_opt_shard_min_bytes = value; return SMB_OK;
         case SMB_OPT_REPLICATE_MAX_BYTES: g_opt_replicate_max_bytes = value; return SMB_OK;
         case SMB_OPT_POOL_MAX_CACHED_BYTES: g_opt_pool_max_cached = value; return SMB_OK;
+        case SMB_OPT_POW_TAIL_CTAS: g_opt_pow_tail = value; return SMB_OK;
     }
     return fail(SMB_ERR_INVALID, "unknown option %d", key);
 }
@@ -1931,6 +1946,7 @@ int64_t smb_get_option(int key) {
         case SMB_OPT_SHARD_MIN_BYTES: return g_opt_shard_min_bytes;
         case SMB_OPT_REPLICATE_MAX_BYTES: return g_opt_replicate_max_bytes;
         case SMB_OPT_POOL_MAX_CACHED_BYTES: return g_opt_pool_max_cached;
+        case SMB_OPT_POW_TAIL_CTAS: return g_opt_pow_tail;
     }
     return -1;
 }

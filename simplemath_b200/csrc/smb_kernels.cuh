@@ -160,6 +160,7 @@ __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t 
 // completion still implies the previous one's).  Both instructions are no-ops in a launch without
 // the programmatic-stream-serialisation attribute.  The host side is in smb_api.cu (pdl_decide).
 constexpr uint32_t kPdlWaitFirst = 1u;
+constexpr int kPdlFlagBits = 8; // the launch word's upper 24 bits carry a kernel-specific count (k_stream: single-tile CTAs)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter(uint32_t flags) {
@@ -489,13 +490,24 @@ __global__ void __launch_bounds__(256, fn_pow_tables<Fn>::value ? (sizeof(T) == 
         Pack<T, VB> buf0[UNROLL], buf1[UNROLL];
         const RawVec<VB> *av = reinterpret_cast<const RawVec<VB> *>(a);
 #if SMB_POW_BLOCKED
-        // CTA b owns the consecutive tiles [b * tpc, (b + 1) * tpc): the host sizes the grid so that
-        // tpc is a handful of tiles -- enough to amortise the table fill, few enough that the grid is
-        // many waves deep (a grid of resident CTAs striding over everything measured 10-15 % slower
-        // on B200 for any 1-read-1-write stream: profiles/r1_sweep_summary.md)
-        const uint64_t tpc = (full_tiles + gridDim.x - 1) / gridDim.x, tstep = 1;
-        uint64_t tile = blockIdx.x * tpc;
-        const uint64_t tiles_end = tile + tpc < full_tiles ? tile + tpc : full_tiles;
+        // CTA b owns `tpc` CONSECUTIVE tiles: the host sizes the grid so that tpc is a handful of tiles --
+        // enough to amortise the table fill, few enough that the grid is many waves deep (a grid of
+        // resident CTAs striding over everything measured 10-15 % slower on B200 for any 1-read-1-write
+        // stream: profiles/r1_sweep_summary.md).  The LAST `n_small` CTAs of the grid (the hardware hands
+        // CTAs out in index order, so they run last) own ONE tile each: multi-tile CTAs end raggedly, up
+        // to one CTA lifetime apart across the SMs, and single-tile CTAs fill those gaps -- what cost
+        // ~14 us per launch at the 8-GPU shard size (2^27 elements, a 170 us kernel).
+        const uint64_t n_small = pdl >> kPdlFlagBits;
+        const uint64_t n_big = gridDim.x - n_small, tiles_big = full_tiles - n_small; // host: n_small <= gridDim.x, full_tiles
+        const uint64_t tpc = n_big ? (tiles_big + n_big - 1) / n_big : 0, tstep = 1;
+        uint64_t tile, tiles_end;
+        if (blockIdx.x < n_big) {
+            tile = blockIdx.x * tpc;
+            tiles_end = tile + tpc < tiles_big ? tile + tpc : tiles_big;
+        } else {
+            tile = tiles_big + (blockIdx.x - n_big);
+            tiles_end = tile + 1;
+        }
 #else
         const uint64_t tstep = gridDim.x, tiles_end = full_tiles;
         uint64_t tile = blockIdx.x;

@@ -187,7 +187,11 @@ def test_pow_f64_ulp_general_kernel(orc, y):
         smb.set_option(smb.OPT_POW_SPECIALISE, 1)
     hi, lo = orc.pow_ref_f64(x, y)
     err = oracle.ulp_error_f64(got, hi, lo)
-    assert err.max() <= F64_POW_ULP_BOUND, (y, err.max(), x[err.argmax()])
+    # results in the normal range: the pinned bound; DENORMAL results are rounded twice on the way down
+    # (computed to double precision, then shifted into the subnormal grid): the stated 1 ULP there
+    normal = np.abs(hi) >= 2.2250738585072014e-308
+    assert err[normal].max() <= F64_POW_ULP_BOUND, (y, err[normal].max(), x[normal][err[normal].argmax()])
+    assert err.max() <= 1.0, (y, err.max(), x[err.argmax()])
 
 
 def test_pow_special_case_table_on_device(orc):

@@ -162,3 +162,70 @@ def test_pow_tables_header_is_what_the_generator_writes(tmp_path):
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_pow_tables.py"), str(out)], check=True, capture_output=True)
     committed = open(os.path.join(ROOT, "simplemath_b200", "csrc", "smb_pow_tables.h")).read()
     assert out.read_text() == committed
+
+
+# ---- multi-GPU planner (smb_plan_shards: csrc/smb_shard.h, no GPU needed) ---------------------------
+def _brute_touched(shape, stride, lo, hi):
+    """min / max operand offset over flat result indices [lo, hi)."""
+    idx = np.unravel_index(np.arange(lo, hi), shape)
+    off = sum(i.astype(np.int64) * s for i, s in zip(idx, stride))
+    return int(off.min()), int(off.max()) + 1
+
+
+def test_shard_planner_bounds_and_operand_ranges_match_brute_force():
+    rng = np.random.default_rng(123)
+    shapes = [((40_000,), (40_000,)), ((300, 257), (1, 257)), ((300, 257), (300, 1)), ((129, 1), (1, 65)), ((24, 1, 256), (1, 40, 256)),
+              ((5, 6, 7, 3), (1, 6, 1, 3)), ((64, 64), (64, 64)), ((7, 2048), (2048,)), ((2, 3, 4, 5, 6, 7), (2, 1, 4, 1, 6, 1)), ((5,), (1,))]
+    for s1, s2 in shapes:
+        shape, sa, sb, n = smb.broadcast(s1, smb.row_major_strides(s1), s2, smb.row_major_strides(s2))
+        for ndev in (1, 2, 3, 8, 64):
+            ok, bounds, ra, rb, modes = smb.plan_shards(sa, sb, shape, ndev)
+            assert bounds[0] == 0 and bounds[-1] == n and all(x <= y for x, y in zip(bounds, bounds[1:])), (s1, s2, ndev, bounds)
+            for g in range(ndev):
+                lo, hi = bounds[g], bounds[g + 1]
+                if lo == hi:
+                    assert ra[g][0] == ra[g][1] and rb[g][0] == rb[g][1]
+                    continue
+                assert ra[g] == _brute_touched(shape, sa, lo, hi), (s1, s2, ndev, g, "a")
+                assert rb[g] == _brute_touched(shape, sb, lo, hi), (s1, s2, ndev, g, "b")
+    # a transposed operand: offsets are not monotone in the flat index, the hull still is exact
+    for r, c in ((37, 53), (200, 96), (8, 8)):
+        shape, sa, sb = [r, c], [1, r], [c, 1]
+        for ndev in (2, 5):
+            ok, bounds, ra, rb, modes = smb.plan_shards(sa, sb, shape, ndev)
+            for g in range(ndev):
+                if bounds[g] < bounds[g + 1]:
+                    assert ra[g] == _brute_touched(shape, sa, bounds[g], bounds[g + 1])
+    # random strided views (every stride table a result dim could see)
+    for _ in range(60):
+        nd = int(rng.integers(1, 5))
+        shape = [int(v) for v in rng.integers(1, 9, nd)]
+        sa = [int(v) for v in rng.integers(0, 40, nd)]
+        sb = [int(v) for v in rng.integers(0, 3, nd)]
+        ndev = int(rng.integers(1, 6))
+        ok, bounds, ra, rb, modes = smb.plan_shards(sa, sb, shape, ndev)
+        for g in range(ndev):
+            if bounds[g] < bounds[g + 1]:
+                assert ra[g] == _brute_touched(shape, sa, bounds[g], bounds[g + 1]), (shape, sa, ndev, g)
+                assert rb[g] == _brute_touched(shape, sb, bounds[g], bounds[g + 1]), (shape, sb, ndev, g)
+
+
+def test_shard_planner_on_the_baseline_configs():
+    """C5 / C2 x 16 / C4 at 8 devices: page-aligned or whole-row cuts, the streaming operand split in place,
+    the broadcast operand replicated; a large transposed operand refuses (one device runs it)."""
+    page = (2 << 20) // 4
+    ok, bounds, ra, rb, modes = smb.plan_shards([1], [1], [1 << 30], 8)
+    assert ok and modes == (0, 0) and all(b % page == 0 for b in bounds) and ra == rb == list(zip(bounds, bounds[1:]))
+    shape, sa, sb, n = smb.broadcast((65536, 4096), (4096, 1), (1, 4096), (4096, 1))
+    ok, bounds, ra, rb, modes = smb.plan_shards(sa, sb, shape, 8)
+    assert ok and modes == (0, 1) and all(b % page == 0 and b % 4096 == 0 for b in bounds) and all(r == (0, 4096) for r in rb)
+    shape, sa, sb, n = smb.broadcast((512, 1, 1024), (1024, 1024, 1), (1, 512, 1024), (512 * 1024, 1024, 1))
+    ok, bounds, ra, rb, modes = smb.plan_shards(sa, sb, shape, 8)
+    assert ok and modes == (1, 1) and all(b % (512 * 1024) == 0 for b in bounds)    # whole dim-0 slabs: k_outer applies
+    assert ra == [(g * 65536, (g + 1) * 65536) for g in range(8)] and all(r == (0, 524288) for r in rb)
+    ok, bounds, ra, rb, modes = smb.plan_shards([1, 8192], [8192, 1], [8192, 8192], 4)
+    assert not ok and modes[0] == 2 and modes[1] == 0
+    # uneven: 3 devices, 10 rows
+    shape, sa, sb, n = smb.broadcast((10, 1000), (1000, 1), (1, 1000), (1000, 1))
+    ok, bounds, ra, rb, modes = smb.plan_shards(sa, sb, shape, 3)
+    assert bounds == [0, 4000, 7000, 10000]
