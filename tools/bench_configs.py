@@ -26,12 +26,16 @@ try:
     PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
-stream = torch.cuda.current_stream()
+# an explicit NON-default stream: handle 0 (the legacy default stream) means "synchronous call on the library's
+# private stream" to the C ABI, which would time a host round trip per call instead of the kernel
+stream = torch.cuda.Stream()
 sp = stream.cuda_stream
+assert sp != 0
 TD = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32}
 
 
 def timed(fn, reps):
+    torch.cuda.synchronize()
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -83,6 +87,23 @@ def binary_case(name, op, a, b, note=""):
     ms = timed(fn, args.reps)
     bytes_ = a.itemsize * (n + a.size + b.size)
     cpu_ms = cpu_time(lambda: ref.smarray_binary(op, a, b, want_result=False)) if ref is not None else None
+    if bytes_ < (256 << 20):
+        # launch-bound sizes, per CALL through the operator-style ABI (stream == NULL), host wall clock:
+        # the reference's synchronous contract vs the asynchronous hand-off (SMB_OPT_ASYNC, one sync at the end)
+        argn = argv[:-1] + (None,)
+        k = max(200, args.reps)
+        for mode in (0, 1):
+            smb.set_option(smb.OPT_ASYNC, mode)
+            for _ in range(20):
+                lib.smb_elementwise(*argn)
+            smb.sync()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                lib.smb_elementwise(*argn)
+            smb.sync()
+            us = (time.perf_counter() - t0) / k * 1e6
+            note += f"; stream==NULL {'async hand-off' if mode else 'synchronous'}: {us:.2f} us per call = {bytes_ / us / 1e3:.0f} GB/s"
+        smb.set_option(smb.OPT_ASYNC, 0)
     if bytes_ < (256 << 20):
         # launch-bound sizes: the same launches captured in a CUDA graph (no host gaps between them)
         try:
@@ -138,10 +159,11 @@ scalar_case("C3 f32 pow(arr,9.25) 256M uniform, medium-|y| tier", "pow", x, 9.25
 x1 = (1 + rng.uniform(-2e-2, 2e-2, 1 << 28)).astype(np.float32)
 scalar_case("C3 f32 pow(arr,1000.5) 256M in [0.98,1.02], large-|y| tier (p-series)", "pow", x1, 1000.5, 0)
 del x1
-xd = x[: 1 << 27].astype(np.float64)
+xd = x.astype(np.float64)   # C3 in double at the stated size: 268 435 456 elements, 2 GiB in + 2 GiB out
 del x
-scalar_case("C3 f64 pow(arr,2.5) 128M uniform, general kernel (FP64-pipe bound)", "pow", xd, 2.5, 0)
-scalar_case("C3 f64 pow(arr,2.0) 128M specialised", "pow", xd, 2.0, 1)
+scalar_case("C3 f64 pow(arr,2.5) 256M uniform, general kernel (FP64-pipe bound)", "pow", xd, 2.5, 0)
+scalar_case("C3 f64 pow(arr,2.0) 256M general kernel (the reference benchmark's exponent)", "pow", xd, 2.0, 0)
+scalar_case("C3 f64 pow(arr,2.0) 256M specialised", "pow", xd, 2.0, 1)
 del xd
 # C4: int32 3-D broadcast
 ia = rng.integers(-1000, 1001, size=(512, 1, 1024)).astype(np.int32)
@@ -172,6 +194,21 @@ def transposed_case(name, n0, n1):
     report(name, 12 * n0 * n1, n0 * n1, ms, cpu_ms, f"verified={ok}")
 
 
+def generic_case(name, rows, cols):
+    """w[:, ::2] + w[:, 1::2]: inner stride 2 on both operands -- neither {0,1}-inner nor a transpose: k_generic."""
+    w = torch.rand(rows * cols, device="cuda")
+    half = cols // 2
+    out = torch.empty(rows * half, device="cuda")
+    lib, u = smb.lib(), smb._u64arr
+    argv = (smb.OP_ADD, smb.F32, w.data_ptr(), u([cols, 2]), w.data_ptr() + 4, u([cols, 2]), u([rows, half]), 2, rows * half, out.data_ptr(), sp)
+    ms = timed(lambda: lib.smb_elementwise(*argv), args.reps)
+    wv = w.view(rows, cols)
+    ok = bool(torch.equal(out.view(rows, half), wv[:, ::2] + wv[:, 1::2]))
+    # algorithmic bytes: both operands' distinct elements (together: every element of w once) + the result
+    report(name, 4 * (rows * cols + rows * half), rows * half, ms, None, f"verified={ok}; the two operands interleave in the same cache lines")
+
+
+generic_case("G f32 w[:, ::2] + w[:, 1::2], w {16384,16384} (generic strides)", 16384, 16384)
 transposed_case("T f32 {8192,8192}^T + {8192,8192} (transposed operand)", 8192, 8192)
 transposed_case("T f32 {16384,1000}^T + {1000,16384}... shape {1000,16384}", 1000, 16384)
 
