@@ -32,16 +32,16 @@ namespace sm {
 
         // acc = acc (Operation) leaf   /   acc = leaf (Operation) acc
         template<typename Operation> Lazy &&then(const SMArray<T> &leaf, bool leaf_on_left = false) && {
-            push(smb::OpTag<Operation>::value, leaf_on_left, &leaf, T{});
+            push(smb::OpTag<Operation>::id(), leaf_on_left, &leaf, T{});
             return std::move(*this);
         }
         template<typename Operation> Lazy &&then(T value, bool leaf_on_left = false) && {
-            push(smb::OpTag<Operation>::value, leaf_on_left, nullptr, value);
+            push(smb::OpTag<Operation>::id(), leaf_on_left, nullptr, value);
             return std::move(*this);
         }
         template<typename Operation> Lazy &&then(Lazy &&rhs, bool leaf_on_left = false) && {
             owned_.push_back(std::make_unique<SMArray<T> >(rhs.eval())); // a nested chain becomes a leaf
-            push(smb::OpTag<Operation>::value, leaf_on_left, owned_.back().get(), T{});
+            push(smb::OpTag<Operation>::id(), leaf_on_left, owned_.back().get(), T{});
             return std::move(*this);
         }
 

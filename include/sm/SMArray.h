@@ -342,7 +342,7 @@ namespace sm {
                     smb_chain_step steps[2] = {};
                     steps[0].data = data;
                     for (size_t k = 0; k < ndim; ++k) steps[0].stride[k] = _strides[k];
-                    steps[1].op = smb::OpTag<Operation>::value;
+                    steps[1].op = smb::OpTag<Operation>::id();
                     if constexpr (std::is_same_v<T, float>) steps[1].value.f32 = val;
                     else if constexpr (std::is_same_v<T, double>) steps[1].value.f64 = val;
                     else steps[1].value.i32 = val;

@@ -24,7 +24,7 @@ namespace smb {
 
 template<typename T, typename Operation>
 void handle_contiguous_arrays(const T *a, const T *b, T *result, size_t n) {
-    smb::check(smb_contiguous(smb::OpTag<Operation>::value, smb::DTypeTag<T>::value, a, b, result, n, nullptr));
+    smb::check(smb_contiguous(smb::OpTag<Operation>::id(), smb::DTypeTag<T>::value, a, b, result, n, nullptr));
 }
 
 template<typename T, typename Operation>
@@ -32,11 +32,11 @@ void element_wise_op(const T *a, const std::vector<size_t> &stride_a,
                      const T *b, const std::vector<size_t> &stride_b,
                      size_t n, T *result, const std::vector<size_t> &shape) {
     if (shape.size() > MAX_NDIM) throw std::runtime_error("smb200: rank exceeds MAX_NDIM");
-    smb::check(smb_elementwise(smb::OpTag<Operation>::value, smb::DTypeTag<T>::value, a, smb::u64(stride_a), b,
+    smb::check(smb_elementwise(smb::OpTag<Operation>::id(), smb::DTypeTag<T>::value, a, smb::u64(stride_a), b,
                                smb::u64(stride_b), smb::u64(shape), static_cast<int>(shape.size()), n, result, nullptr));
 }
 
 template<typename T, typename Operation>
 void array_scalar_op(const T *a, T value, const size_t n, T *result) {
-    smb::check(smb_array_scalar(smb::OpTag<Operation>::value, smb::DTypeTag<T>::value, a, &value, n, result, nullptr));
+    smb::check(smb_array_scalar(smb::OpTag<Operation>::id(), smb::DTypeTag<T>::value, a, &value, n, result, nullptr));
 }

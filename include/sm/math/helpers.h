@@ -6,6 +6,8 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <stdexcept>
+#include <string>
 #include <type_traits>
 #include <vector>
 
@@ -23,16 +25,32 @@ namespace smb {
     template<> struct DTypeTag<double> { static constexpr int value = SMB_F64; };
     template<> struct DTypeTag<int32_t> { static constexpr int value = SMB_I32; };
 
-    // Op struct -> device op tag.  An Op without `device_op` has no device
+    // Op struct -> device op id.  An Op without `device_op` has no device
     // specialisation and cannot be launched: compile error, not a CPU fallback.
+    //   built-in Ops:      static constexpr int device_op = SMB_OP_*;
+    //   user-defined Ops:  static int device_op() { return smb::op_id("MyOp"); }   (README.md:86-133 recipe;
+    //                      the device side registers "MyOp" from a .cu file, include/smb200_plugin.cuh)
     template<typename Operation, typename = void> struct OpTag {
         static_assert(dependent_false<Operation>::value,
-                      "this Op struct has no device specialisation (static constexpr int device_op = SMB_OP_*)");
+                      "this Op struct has no device specialisation (static constexpr int device_op = SMB_OP_*, "
+                      "or static int device_op() for an op registered through smb200_plugin.cuh)");
     };
     template<typename Operation>
-    struct OpTag<Operation, std::void_t<decltype(Operation::device_op)>> {
-        static constexpr int value = Operation::device_op;
+    struct OpTag<Operation, std::enable_if_t<std::is_convertible_v<decltype(Operation::device_op), int>>> {
+        static int id() { return Operation::device_op; }
     };
+    template<typename Operation>
+    struct OpTag<Operation, std::enable_if_t<std::is_convertible_v<decltype(Operation::device_op()), int>>> {
+        static int id() { return Operation::device_op(); }
+    };
+
+    // The id a user-defined Op was registered under (smb_register_op); throws when the device side
+    // of that Op was never linked / loaded -- no CPU fallback.
+    inline int op_id(const char *name) {
+        const int id = smb_find_op(name);
+        if (id < 0) throw std::runtime_error(std::string("smb200: no device Op registered under the name \"") + name + "\"");
+        return id;
+    }
 }
 
 // Row-major contiguity predicate, reference helpers.h:130-139.

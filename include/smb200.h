@@ -51,7 +51,8 @@ enum {
     SMB_OP_SUB = 1, /* SubtractOp<T>  include/math/subtract.h:5-14   */
     SMB_OP_MUL = 2, /* MultiplyOp<T>  include/math/multiply.h:7-16   */
     SMB_OP_DIV = 3, /* DivideOp<T>    include/math/division.h:8-17,67-70 */
-    SMB_OP_POW = 4  /* PowOp<T>       include/math/pow.h:6-14, math/simd/crafted_pow.h:54-103 */
+    SMB_OP_POW = 4, /* PowOp<T>       include/math/pow.h:6-14, math/simd/crafted_pow.h:54-103 */
+    SMB_OP_USER = 16 /* first id smb_register_op hands out (user-defined Op structs, README.md:86-133) */
 };
 
 /* Element types: exactly the SimdTraits<T> specialisations of the reference
@@ -114,7 +115,7 @@ enum {
      * largest blocks to the driver (default 64 GiB; negative: never). */
     SMB_OPT_POOL_MAX_CACHED_BYTES = 9,
     /* Table-driven pow kernels: how many CTAs at the END of the grid own a single tile (they fill the
-     * ragged end the multi-tile CTAs leave); -1 (default): chosen from the SM count, 0: none. */
+     * ragged end the multi-tile CTAs leave).  0 (default): none -- measured no gain on B200. */
     SMB_OPT_POW_TAIL_CTAS = 10
 };
 
@@ -192,6 +193,31 @@ int smb_chain(int dtype, const smb_chain_step *steps, int nsteps,
 int smb_chain_range(int dtype, const smb_chain_step *steps, int nsteps,
                     const uint64_t *shape, int ndim, uint64_t lin_begin, uint64_t lin_count,
                     void *out, void *stream);
+
+/* ---- user-defined device Ops ------------------------------------------------------------------
+ * The reference's "Extending with Custom Operations" recipe (README.md:86-133: an Op struct with
+ * apply / apply_simd, used through element_wise_op<T, MyOp<T>>) without patching this library.  The
+ * user's .cu file includes include/smb200_plugin.cuh, which instantiates this library's kernel
+ * templates over MyOp<T>::apply_device and fills an smb_user_op; smb_register_op files it under a
+ * name and returns the op id (>= SMB_OP_USER) that smb_elementwise / smb_elementwise_range /
+ * smb_contiguous / smb_array_scalar then accept like a built-in one (host operands, views, device
+ * sets and async mode included; smb_chain takes built-in ops only).  Registering the same name for
+ * another dtype returns the same id.  The launchers return a cudaError_t value (0 = success). */
+typedef struct smb_launch_env { void *stream; int sm_count; int device; } smb_launch_env;
+typedef struct smb_user_op {
+    /* out[i] = op(a[i], b[i]), i < n: dense streams at any element-aligned addresses */
+    int (*contiguous)(const smb_launch_env *env, const void *a, const void *b, void *out, uint64_t n);
+    /* out[i] = op(a[i], *scalar) */
+    int (*scalar)(const smb_launch_env *env, const void *a, const void *scalar, void *out, uint64_t n);
+    /* the broadcast / strided loop over a prepared stride table (smb::BcastTable of table_bytes bytes):
+     * generic != 0: arbitrary element strides; else inner strides in {0,1} and `vector_bytes` (16, or the
+     * element size) is the widest access the addresses and strides allow; wide != 0: 64-bit index math */
+    int (*strided)(const smb_launch_env *env, const void *a, const void *b, void *out, const void *table, int table_bytes,
+                   int generic, int wide, int vector_bytes, int a_reused, int b_reused);
+} smb_user_op;
+int smb_register_op(const char *name, int dtype, const smb_user_op *launchers);
+/* The id a name was registered under, or a negative value. */
+int smb_find_op(const char *name);
 
 /* ---- storage: replaces `new T[n]` / `delete[]` of SMArray<T>::data ------- */
 /* include/SMArray.h:33-34,70-76,219,342-346; include/UserFunctions.h:8-40.

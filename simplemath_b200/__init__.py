@@ -79,6 +79,8 @@ SYMBOLS = {
     "smb_plan_elementwise": (_i, [_u64p, _u64p, _u64p, _i, _i, ctypes.POINTER(_i), _u64p, _u64p, _u64p]),
     "smb_plan_chain": (_i, [ctypes.POINTER(ChainStep), _i, _u64p, _i, ctypes.POINTER(_i), _u64p, _u64p]),
     "smb_plan_shards": (_i, [_u64p, _u64p, _u64p, _i, _i, _i, _u64p, _u64p, _u64p, ctypes.POINTER(_i)]),
+    "smb_register_op": (_i, [ctypes.c_char_p, _i, _vp]),
+    "smb_find_op": (_i, [ctypes.c_char_p]),
     "smb_pow_audit_f32": (_i, [_vp, ctypes.c_float, _vp, _u64, ctypes.c_float, _u64p, ctypes.POINTER(ctypes.c_float)]),
     "smb_fill_uniform_f32": (_i, [_vp, _u64, _u64, _u64, ctypes.c_float, ctypes.c_float, _vp]),
 }

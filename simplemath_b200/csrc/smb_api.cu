@@ -51,7 +51,7 @@ static std::atomic<int64_t> g_opt_chunk_bytes{64ll << 20};
 static std::atomic<int64_t> g_opt_contig_variant{0};
 static std::atomic<int64_t> g_opt_bcast_variant{0};
 static std::atomic<int64_t> g_opt_force_wide{0};
-static std::atomic<int64_t> g_opt_pow_tail{-1}; // single-tile CTAs at the end of a pow grid; -1: library default
+static std::atomic<int64_t> g_opt_pow_tail{0}; // single-tile CTAs at the end of a pow grid (0: none, the default)
 static std::atomic<int64_t> g_opt_pool_max_cached{64ll << 30}; // cached (free) pool bytes beyond which smb_free trims
 
 // ------------------------------------------------------ device context ------
@@ -555,10 +555,12 @@ static int launch_stream(DeviceCtx &c, const T *a, const T *b, T *out, uint64_t 
                 const uint64_t full_tiles = rest / per_block;
                 const int64_t tpc = pow_tiles_per_cta(full_tiles, c.sm_count, resident,
                                                       sizeof(T) == 4 ? SMB_POW_TILES_PER_CTA : 4 * SMB_POW_TILES_PER_CTA);
-                // single-tile CTAs at the end of the grid: about half a multi-tile CTA lifetime of work for
-                // every resident slot (what the ragged end of the multi-tile phase leaves idle on average)
+                // Single-tile CTAs at the end of the grid (SMB_OPT_POW_TAIL_CTAS) to fill the ragged end of the
+                // multi-tile phase: built, measured, and OFF by default -- with the tile count per CTA already
+                // shrunk for small arrays it changes nothing up to one wave of them and loses beyond
+                // (profiles/r2_pow_grid_sweep.md).
                 const int64_t tail_opt = g_opt_pow_tail.load();
-                uint64_t small = tail_opt >= 0 ? (uint64_t)tail_opt : (uint64_t)c.sm_count * resident * (uint64_t)tpc / 2;
+                uint64_t small = tail_opt > 0 ? (uint64_t)tail_opt : 0;
                 small = std::min<uint64_t>(std::min<uint64_t>(small, full_tiles / 4), (1u << 24) - 1);
                 if (tpc <= 1) small = 0;
                 const uint64_t big_tiles = full_tiles - small;
@@ -894,12 +896,83 @@ static int bcast_t(DeviceCtx &c, int op, const ElementwisePlan &p, const T *a, c
     return fail(SMB_ERR_INVALID, "unknown op %d", op);
 }
 
+// ------------------------------------------------ user-defined device Ops ----
+// The reference's "Extending with Custom Operations" recipe (README.md:86-133: an Op struct with apply /
+// apply_simd, then element_wise_op<T, MyOp<T>> from an operator) on the device, without patching this
+// library: the user's .cu includes include/smb200_plugin.cuh, which instantiates the SAME kernel
+// templates (k_stream, k_row, k_generic) over a functor that calls MyOp<T>::apply_device, and registers
+// three launchers under a name.  From then on the op id goes through every path a built-in op takes --
+// planning, host-operand staging, views, flat-range sharding over a device set, async mode.
+constexpr int kUserOpBase = SMB_OP_USER;
+struct UserOpEntry {
+    std::string name;
+    smb_user_op fn[3];
+    bool have[3] = {false, false, false};
+};
+static std::mutex g_user_mu;
+static std::vector<UserOpEntry> g_user_ops;
+static bool user_op_lookup(int op, int dtype, smb_user_op *out) {
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    const int i = op - kUserOpBase;
+    if (i < 0 || i >= (int)g_user_ops.size() || dtype < 0 || dtype > 2 || !g_user_ops[i].have[dtype]) return false;
+    *out = g_user_ops[i].fn[dtype];
+    return true;
+}
+static int user_rc(int e, const char *what) {
+    if (e == 0) return SMB_OK;
+    cudaGetLastError();
+    return fail(SMB_ERR_CUDA, "user op %s launch: %s", what, cudaGetErrorString((cudaError_t)e));
+}
+static int user_contiguous(DeviceCtx &c, int op, int dtype, const void *a, const void *b, void *out, uint64_t n, cudaStream_t s) {
+    smb_user_op u;
+    if (!user_op_lookup(op, dtype, &u)) return fail(SMB_ERR_INVALID, "op %d is not registered for dtype %d", op, dtype);
+    const smb_launch_env env{s, c.sm_count, c.device};
+    ++g_launches;
+    g_last_kernel = "user<k_stream>";
+    return user_rc(u.contiguous(&env, a, b, out, n), "contiguous");
+}
+static int user_scalar(DeviceCtx &c, int op, int dtype, const void *a, const void *scalar, void *out, uint64_t n, cudaStream_t s) {
+    smb_user_op u;
+    if (!user_op_lookup(op, dtype, &u)) return fail(SMB_ERR_INVALID, "op %d is not registered for dtype %d", op, dtype);
+    const smb_launch_env env{s, c.sm_count, c.device};
+    ++g_launches;
+    g_last_kernel = "user<k_stream,scalar>";
+    return user_rc(u.scalar(&env, a, scalar, out, n), "scalar");
+}
+template<typename T>
+static int row_vector_bytes(const ElementwisePlan &p, const T *a, const T *b, const T *out, uint64_t lin_base, uint64_t count);
+static BcastTable make_table(const ElementwisePlan &p, uint64_t lin_base, uint64_t count, uint64_t lane_base, bool *wide);
+static bool operand_reused(const ElementwisePlan &p, const uint64_t *s);
+static int user_strided(DeviceCtx &c, int op, int dtype, const ElementwisePlan &p, const void *a, const void *b, void *out,
+                        uint64_t lin_base, uint64_t count, cudaStream_t s) {
+    smb_user_op u;
+    if (!user_op_lookup(op, dtype, &u)) return fail(SMB_ERR_INVALID, "op %d is not registered for dtype %d", op, dtype);
+    if (count == 0) return SMB_OK;
+    bool wide = false;
+    const BcastTable t = make_table(p, lin_base, count, lin_base, &wide);
+    int vb = dtype == SMB_F64 ? 8 : 4;
+    if (p.kind == PLAN_ROW) {
+        if (dtype == SMB_F64) vb = row_vector_bytes<double>(p, (const double *)a, (const double *)b, (const double *)out, lin_base, count);
+        else vb = row_vector_bytes<float>(p, (const float *)a, (const float *)b, (const float *)out, lin_base, count);
+    }
+    const smb_launch_env env{s, c.sm_count, c.device};
+    ++g_launches;
+    g_last_kernel = p.kind == PLAN_GENERIC ? "user<k_generic>" : "user<k_row>";
+    return user_rc(u.strided(&env, a, b, out, &t, (int)sizeof t, p.kind == PLAN_GENERIC, wide, vb, operand_reused(p, p.sa), operand_reused(p, p.sb)), "strided");
+}
+
 // One elementwise launch on DEVICE-ACCESSIBLE operands.  `a`/`b` address the
 // operands of plan `p`; the launch produces flat elements
 // [lin_base, lin_base+count) of the plan's result into out[0..count).
 static int elementwise_device(DeviceCtx &c, int op, int dtype, const ElementwisePlan &p, const void *a, const void *b,
                               void *out, uint64_t lin_base, uint64_t count, uint64_t lane_base, uint64_t lane_end,
                               cudaStream_t s) {
+    if (op >= kUserOpBase) {
+        const size_t es = esize(dtype);
+        if (p.kind == PLAN_CONTIGUOUS)
+            return user_contiguous(c, op, dtype, (const char *)a + lin_base * es, (const char *)b + lin_base * es, out, count, s);
+        return user_strided(c, op, dtype, p, a, b, out, lin_base, count, s);
+    }
     if (p.kind == PLAN_CONTIGUOUS) {
         switch (dtype) {
             case SMB_F32: return contiguous_t<float>(c, op, (const float *)a + lin_base, (const float *)b + lin_base, (float *)out, count, lane_base, lane_end, s);
@@ -918,6 +991,7 @@ static int elementwise_device(DeviceCtx &c, int op, int dtype, const Elementwise
 
 static int scalar_device(DeviceCtx &c, int op, int dtype, const void *a, const void *scalar, void *out, uint64_t n,
                          uint64_t first, uint64_t lane_end, cudaStream_t s) {
+    if (op >= kUserOpBase) return user_scalar(c, op, dtype, a, scalar, out, n, s);
     switch (dtype) {
         case SMB_F32: return scalar_t<float>(c, op, (const float *)a, *(const float *)scalar, (float *)out, n, first, lane_end, s);
         case SMB_F64: return scalar_t<double>(c, op, (const double *)a, *(const double *)scalar, (double *)out, n, first, lane_end, s);
@@ -1162,8 +1236,13 @@ static int scalar_staged(DeviceCtx &c, int op, int dtype, const void *a, MemType
 }
 
 static int check_args(int op, int dtype) {
-    if (op < SMB_OP_ADD || op > SMB_OP_POW) return fail(SMB_ERR_INVALID, "unknown op %d", op);
     if (dtype < SMB_F32 || dtype > SMB_I32) return fail(SMB_ERR_INVALID, "unknown dtype %d (float, double, int32 only)", dtype);
+    if (op >= kUserOpBase) {
+        smb_user_op u;
+        if (!user_op_lookup(op, dtype, &u)) return fail(SMB_ERR_INVALID, "op %d has no device launchers registered for dtype %d (smb_register_op)", op, dtype);
+        return SMB_OK;
+    }
+    if (op < SMB_OP_ADD || op > SMB_OP_POW) return fail(SMB_ERR_INVALID, "unknown op %d", op);
     return SMB_OK;
 }
 
@@ -2003,6 +2082,26 @@ int smb_plan_shards(const uint64_t *stride_a, const uint64_t *stride_b, const ui
     }
     if (out_modes) { out_modes[0] = oa.mode; out_modes[1] = ob.mode; }
     return oa.mode == SHARD_REFUSE || ob.mode == SHARD_REFUSE ? 0 : 1;
+}
+
+int smb_register_op(const char *name, int dtype, const smb_user_op *launchers) {
+    if (!name || !*name || !launchers || dtype < SMB_F32 || dtype > SMB_I32 || !launchers->contiguous || !launchers->scalar || !launchers->strided) {
+        fail(SMB_ERR_INVALID, "smb_register_op: name, dtype and all three launchers are required");
+        return -SMB_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    int idx = -1;
+    for (size_t i = 0; i < g_user_ops.size(); ++i) if (g_user_ops[i].name == name) idx = (int)i;
+    if (idx < 0) { g_user_ops.emplace_back(); idx = (int)g_user_ops.size() - 1; g_user_ops[idx].name = name; }
+    g_user_ops[idx].fn[dtype] = *launchers;
+    g_user_ops[idx].have[dtype] = true;
+    return kUserOpBase + idx;
+}
+int smb_find_op(const char *name) {
+    if (!name) return -SMB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    for (size_t i = 0; i < g_user_ops.size(); ++i) if (g_user_ops[i].name == name) return kUserOpBase + (int)i;
+    return -SMB_ERR_INVALID;
 }
 
 int smb_pow_audit_f32(const void *x, float y, const void *got, uint64_t n, float bound_ulp, uint64_t *count_over, float *max_ulp) {

@@ -29,3 +29,14 @@ def test_reference_tests_pass_on_the_drop_in_headers():
 
 def test_own_cpp_acceptance():
     assert _run("dropin_test") >= 22
+
+
+def test_user_defined_op_plugin():
+    """tests/plugin: ModOp<T> / MyOp<T> defined OUTSIDE the library (reference README.md:86-133 recipe), device
+    bodies registered from an nvcc-compiled .cu, operators written with element_wise_op<T, Op<T>>."""
+    path = os.path.join(ROOT, "tests", "plugin", "bin", "plugin_test")
+    if not os.path.exists(path):
+        pytest.skip("plugin_test was not prebuilt")
+    r = subprocess.run([path], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert int(r.stdout.strip().splitlines()[-1].split()[0]) >= 5

@@ -187,10 +187,11 @@ def test_pow_f64_ulp_general_kernel(orc, y):
         smb.set_option(smb.OPT_POW_SPECIALISE, 1)
     hi, lo = orc.pow_ref_f64(x, y)
     err = oracle.ulp_error_f64(got, hi, lo)
-    # results in the normal range: the pinned bound; DENORMAL results are rounded twice on the way down
-    # (computed to double precision, then shifted into the subnormal grid): the stated 1 ULP there
-    normal = np.abs(hi) >= 2.2250738585072014e-308
-    assert err[normal].max() <= F64_POW_ULP_BOUND, (y, err[normal].max(), x[normal][err[normal].argmax()])
+    # results comfortably inside the normal range (what the fast core takes): the pinned bound.  Results that are
+    # denormal or within 2^22 of the underflow / overflow thresholds go through the double-double path, whose
+    # final scaling rounds a second time there: the stated 1 ULP
+    inside = (np.abs(hi) >= 2.0 ** -1000) & (np.abs(hi) <= 2.0 ** 1000)
+    assert err[inside].max() <= F64_POW_ULP_BOUND, (y, err[inside].max(), x[inside][err[inside].argmax()])
     assert err.max() <= 1.0, (y, err.max(), x[err.argmax()])
 
 
@@ -565,6 +566,7 @@ def test_config_c3_c5_large_pow_and_add_properties(orc):
             assert bool((out[: 1 << 24][idx].diff() >= 0).all())
         # the reference benchmark's own fill, arr(i, j) = i + j + 1 on {16384, 16384} (benchmark/pow.cpp:33-47), audited whole
         ij = (torch.arange(16384, device="cuda", dtype=torch.float32)[:, None] + torch.arange(16384, device="cuda", dtype=torch.float32)[None, :] + 1).reshape(-1)
+        torch.cuda.synchronize()   # torch filled it on ITS stream; the library's private stream does not wait for that one
         for y in (2.0, 2.5):
             smb.array_scalar_ptr(smb.OP_POW, smb.F32, ij.data_ptr(), y, n, out.data_ptr())
             over, worst = smb.pow_audit_f32_ptr(ij.data_ptr(), y, out.data_ptr(), n, F32_POW_ULP_BOUND)
@@ -573,6 +575,7 @@ def test_config_c3_c5_large_pow_and_add_properties(orc):
         # every finite positive bit pattern class in one array (denormals, huge, tiny: the slow path's share)
         bits = torch.arange(n, device="cuda", dtype=torch.int32) * 7 + 1
         xb = bits.view(torch.float32)
+        torch.cuda.synchronize()
         for y in (2.5, -0.5, 31.0):
             smb.array_scalar_ptr(smb.OP_POW, smb.F32, xb.data_ptr(), y, n, out.data_ptr())
             over, worst = smb.pow_audit_f32_ptr(xb.data_ptr(), y, out.data_ptr(), n, F32_POW_ULP_BOUND)
@@ -602,6 +605,7 @@ def test_config_c3_f64_pow_at_256m(orc):
     x = xf.double()
     del xf
     out = torch.empty(n, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
     smb.set_option(smb.OPT_POW_SPECIALISE, 0)
     try:
         for y in (2.0, 2.5):

@@ -144,7 +144,7 @@ static void run_add(const float *a, const float *b, float *out, uint64_t n) {
         uint64_t blocks = (n + per_block - 1) / per_block;
         if (cap) blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * cap);
         using Fn = BinaryFn<OP_ADD, float>;
-        float ms = time_ms([&] { k_stream<float, Fn, true, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, b, out, n, 0, Fn{0}); });
+        float ms = time_ms([&] { k_stream<float, Fn, true, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, b, out, n, 0, Fn{0}, smb::kPdlWaitFirst); });
         char p[128];
         snprintf(p, sizeof p, "vb=%d unroll=%d ctas_per_sm=%d", VB, UNROLL, cap);
         report("add_f32_ldg", p, 12.0 * n, ms);
@@ -170,7 +170,7 @@ static void run_pow_loop_only(const float *a, float *out, uint64_t n) {
         constexpr uint64_t per_block = 256ull * UNROLL * (VB / 4);
         uint64_t blocks = (n + per_block - 1) / per_block;
         blocks = (blocks + cap - 1) / cap;
-        float ms = time_ms([&] { k_stream<float, PowLoopOnlyFn, false, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, nullptr, out, n, 0, PowLoopOnlyFn{0}); });
+        float ms = time_ms([&] { k_stream<float, PowLoopOnlyFn, false, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, nullptr, out, n, 0, PowLoopOnlyFn{0}, smb::kPdlWaitFirst); });
         char p[128];
         snprintf(p, sizeof p, "vb=%d unroll=%d tiles_per_cta=%d", VB, UNROLL, cap);
         report("pow_loop_only", p, 8.0 * n, ms);
@@ -186,7 +186,7 @@ static void run_pow(const float *a, float *out, uint64_t n, float y) {
         blocks = (blocks + cap - 1) / cap;
         using Fn = PowF32Fn<SMALL ? POW_TIER_SMALL : POW_TIER_LARGE, POW_SIGN_REJECT, false>;
         Fn fn = Fn::make(y, 0);
-        float ms = time_ms([&] { k_stream<float, Fn, false, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, nullptr, out, n, 0, fn); });
+        float ms = time_ms([&] { k_stream<float, Fn, false, VB, UNROLL><<<(unsigned)blocks, 256>>>(a, nullptr, out, n, 0, fn, smb::kPdlWaitFirst); });
         char p[128];
         snprintf(p, sizeof p, "y=%.2f small_y=%d vb=%d unroll=%d tiles_per_cta=%d", y, (int)SMALL, VB, UNROLL, cap);
         report("pow_f32_general", p, 8.0 * n, ms);
