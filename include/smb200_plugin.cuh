@@ -49,6 +49,17 @@ template<typename T, typename Op> struct ScalarRightFn { // the scalar is the RI
     __device__ __forceinline__ T operator()(T a, T, uint64_t) const { return Op::apply_device(a, v); }
 };
 
+// The plugin's translation unit carries its own (static) CUDA runtime, whose idea of the calling thread's
+// current device is separate from the library's: make the launch device current here for the launch.
+struct DeviceGuard {
+    int saved = -1;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&saved) != cudaSuccess) saved = -1;
+        if (saved != device) cudaSetDevice(device); else saved = -1;
+    }
+    ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
 inline unsigned grid_for(uint64_t items, uint64_t per_block, int sm_count, int ctas_per_sm) {
     uint64_t blocks = (items + per_block - 1) / per_block;
     if (blocks == 0) blocks = 1;
@@ -61,6 +72,7 @@ inline unsigned grid_for(uint64_t items, uint64_t per_block, int sm_count, int c
 template<typename T, typename Fn, bool HAS_B>
 inline int stream(const smb_launch_env *env, const T *a, const T *b, T *out, uint64_t n, Fn fn) {
     if (n == 0) return 0;
+    const DeviceGuard guard(env->device);
     cudaStream_t s = (cudaStream_t)env->stream;
     constexpr int VB = 16, UNROLL = 4;
     const uintptr_t ma = (uintptr_t)a % VB, mb = HAS_B ? (uintptr_t)b % VB : ma, mo = (uintptr_t)out % VB;
@@ -93,6 +105,7 @@ int launch_strided(const smb_launch_env *env, const void *a, const void *b, void
                    int generic, int wide, int vector_bytes, int a_reused, int b_reused) {
     if (table_bytes != (int)sizeof(BcastTable)) return (int)cudaErrorInvalidValue; // header / library mismatch
     const BcastTable t = *(const BcastTable *)table;
+    const DeviceGuard guard(env->device);
     cudaStream_t s = (cudaStream_t)env->stream;
     using Fn = BinFn<T, Op>;
     const Fn fn{0};

@@ -21,6 +21,11 @@ NVCC_FLAGS = [
     # no flush-to-zero, correctly rounded div/sqrt (all nvcc defaults except fmad).
     "-fmad=false", "-ftz=false", "-prec-div=true", "-prec-sqrt=true",
     "--shared", "-Xcompiler", "-fPIC",
+    # The CUDA runtime is linked statically and stays PRIVATE to this library: its symbols are not exported
+    # (--exclude-libs) and the library's own calls bind to its own definitions (-Bsymbolic).  Otherwise a program
+    # that links this library AND carries its own static runtime (any nvcc-built user plugin, tests/plugin) has
+    # half of its <<<>>> launch sequence resolved into our copy and half into its own.
+    "-Xlinker", "--exclude-libs,ALL", "-Xlinker", "-Bsymbolic",
 ]
 
 
@@ -69,8 +74,8 @@ def build_sweep(force: bool = False) -> str:
     deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if force or _stale(out, deps):
         flags = [f for f in NVCC_FLAGS if f not in ("--shared",)]
-        # drop "-Xcompiler -fPIC" pair too
-        flags = [f for i, f in enumerate(flags) if not (f == "-Xcompiler" or (i > 0 and flags[i - 1] == "-Xcompiler"))]
+        # drop the "-Xcompiler -fPIC" and "-Xlinker ..." pairs too (shared-library options)
+        flags = [f for i, f in enumerate(flags) if not (f in ("-Xcompiler", "-Xlinker") or (i > 0 and flags[i - 1] in ("-Xcompiler", "-Xlinker")))]
         subprocess.run([_nvcc(), *flags, "-o", out, src], check=True)
     return out
 
