@@ -116,7 +116,11 @@ enum {
     SMB_OPT_POOL_MAX_CACHED_BYTES = 9,
     /* Table-driven pow kernels: how many CTAs at the END of the grid own a single tile (they fill the
      * ragged end the multi-tile CTAs leave).  0 (default): none -- measured no gain on B200. */
-    SMB_OPT_POW_TAIL_CTAS = 10
+    SMB_OPT_POW_TAIL_CTAS = 10,
+    /* Fused chains with an f32 pow step and at most 3 leaves (sm::pow(a + b, e)): vectors per thread and
+     * register prefetch of the next tile's leaves -- 0: one vector, no prefetch (round 1); 1 (default): one
+     * vector + prefetch; 2: two vectors; 3: two vectors + prefetch. */
+    SMB_OPT_CHAIN_POW_VARIANT = 11
 };
 
 /* ---- the hot path ------------------------------------------------------- */

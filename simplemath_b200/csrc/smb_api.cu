@@ -51,6 +51,7 @@ static std::atomic<int64_t> g_opt_chunk_bytes{64ll << 20};
 static std::atomic<int64_t> g_opt_contig_variant{0};
 static std::atomic<int64_t> g_opt_bcast_variant{0};
 static std::atomic<int64_t> g_opt_force_wide{0};
+static std::atomic<int64_t> g_opt_chain_pow_variant{1}; // fused pow chains of <= 3 leaves: 0 U1, 1 U1+prefetch, 2 U2, 3 U2+prefetch
 static std::atomic<int64_t> g_opt_pow_tail{0}; // single-tile CTAs at the end of a pow grid (0: none, the default)
 static std::atomic<int64_t> g_opt_pool_max_cached{64ll << 30}; // cached (free) pool bytes beyond which smb_free trims
 
@@ -1558,13 +1559,25 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
             powfast = true;
         }
     }
-    t.tiles_per_cta = powfast ? 32 : 1; // amortise the 24 KB table copy, stay many waves deep
+    const int powvar = (int)g_opt_chain_pow_variant.load();
+    t.tiles_per_cta = powfast ? (powvar >= 2 ? 16 : 32) : 1; // amortise the 24 KB table copy, stay many waves deep
     // compiled-in chain capacity / vectors per thread: short chains keep more loads in flight
 #define SMB_CHAIN_LAUNCH(E, W, NS, U, PF, ND)                                                                     \
     k_chain<T, E, W, NS, U, PF, ND><<<grid_for(items, (uint64_t)kThreads * U * t.tiles_per_cta, c.sm_count, 0), kThreads, 0, s>>>(out, t)
+#define SMB_CHAIN_LAUNCH_PF(E, W, U, ND, PRE)                                                                     \
+    k_chain<T, E, W, 3, U, true, ND, PRE><<<grid_for(items, (uint64_t)kThreads * U * t.tiles_per_cta, c.sm_count, 0), kThreads, 0, s>>>(out, t)
 #define SMB_CHAIN_BY_LEN(E, W, PF, ND)                                                            \
     do {                                                                                          \
-        if (p.nleaf <= 3 && PF) SMB_CHAIN_LAUNCH(E, W, 3, 1, PF, ND); /* pow: fewer registers, more CTAs */ \
+        if (p.nleaf <= 3 && PF) { /* sm::pow(a (op) b, e): vectors per thread x register prefetch, SMB_OPT_CHAIN_POW_VARIANT */ \
+            if constexpr (PF) {                                                                   \
+                switch (powvar) {                                                                 \
+                    case 0: SMB_CHAIN_LAUNCH_PF(E, W, 1, ND, false); break;                       \
+                    case 2: SMB_CHAIN_LAUNCH_PF(E, W, 2, ND, false); break;                       \
+                    case 3: SMB_CHAIN_LAUNCH_PF(E, W, 2, ND, true); break;                        \
+                    default: SMB_CHAIN_LAUNCH_PF(E, W, 1, ND, true); break;                       \
+                }                                                                                 \
+            }                                                                                     \
+        }                                                                                         \
         else if (p.nleaf <= 3) SMB_CHAIN_LAUNCH(E, W, 3, 4, PF, ND);                              \
         else if (p.nleaf <= 5) SMB_CHAIN_LAUNCH(E, W, 5, 2, PF, ND);                              \
         else SMB_CHAIN_LAUNCH(E, W, 8, 1, PF, ND);                                                \
@@ -1591,6 +1604,7 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
     }
 #undef SMB_CHAIN_BY_RANK
 #undef SMB_CHAIN_BY_LEN
+#undef SMB_CHAIN_LAUNCH_PF
 #undef SMB_CHAIN_LAUNCH
     ++g_launches;
     SMB_CK(cudaGetLastError());
@@ -2010,6 +2024,7 @@ int smb_set_option(int key, int64_t value) {
         case SMB_OPT_REPLICATE_MAX_BYTES: g_opt_replicate_max_bytes = value; return SMB_OK;
         case SMB_OPT_POOL_MAX_CACHED_BYTES: g_opt_pool_max_cached = value; return SMB_OK;
         case SMB_OPT_POW_TAIL_CTAS: g_opt_pow_tail = value; return SMB_OK;
+        case SMB_OPT_CHAIN_POW_VARIANT: g_opt_chain_pow_variant = value; return SMB_OK;
     }
     return fail(SMB_ERR_INVALID, "unknown option %d", key);
 }
@@ -2026,6 +2041,7 @@ int64_t smb_get_option(int key) {
         case SMB_OPT_REPLICATE_MAX_BYTES: return g_opt_replicate_max_bytes;
         case SMB_OPT_POOL_MAX_CACHED_BYTES: return g_opt_pool_max_cached;
         case SMB_OPT_POW_TAIL_CTAS: return g_opt_pow_tail;
+        case SMB_OPT_CHAIN_POW_VARIANT: return g_opt_chain_pow_variant;
     }
     return -1;
 }

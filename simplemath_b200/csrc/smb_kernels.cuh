@@ -976,7 +976,9 @@ enum { CH_ADD = 0, CH_SUB = 1, CH_MUL = 2, CH_DIV = 3, CH_POW = 4, CH_RSUB = 5, 
 // index and offset loops are then straight-line code on constant-bank operands -- with the rank a
 // run-time value the guarded 6-dim loops were 58 instructions per element, most of them IMAD / MOV /
 // ISETP / BRA), 0: any rank, guarded loops.
-template<typename T, int EPV, bool WIDE, int NS, int UNROLL, int NDIM>
+// PIN: the vector loads are ordinary coherent loads with a memory clobber, which ptxas keeps where they are
+// written (a prefetch issued a whole tile ahead is otherwise sunk down to its first use, see pow_tile).
+template<typename T, int EPV, bool WIDE, int NS, int UNROLL, int NDIM, bool PIN = false>
 __device__ __forceinline__ void chain_load(const ChainTable &t, uint64_t tile, uint64_t nvec, T (&leaf)[UNROLL][NS][EPV]) {
     using Idx = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
     constexpr int KMAX = NDIM ? NDIM : SMB_MAX_NDIM;
@@ -1012,7 +1014,8 @@ __device__ __forceinline__ void chain_load(const ChainTable &t, uint64_t tile, u
                         if (k < ndim) off += (uint64_t)idx[k] * t.stride[s][k];
                     if (EPV > 1 && t.stride[s][ndim - 1] == 1) {
                         Pack<T, 16> pk; // EPV * sizeof(T) == 16
-                        pk.raw = VecIO<16, false>::load(base + off);
+                        if constexpr (PIN) pk.raw = load_stream_pinned(reinterpret_cast<const RawVec<16> *>(base + off));
+                        else pk.raw = VecIO<16, false>::load(base + off);
 #pragma unroll
                         for (int e = 0; e < EPV; ++e) leaf[u][s][e] = pk.e[e];
                     } else {
@@ -1115,7 +1118,7 @@ __device__ __forceinline__ void chain_compute(const ChainTable &t, uint64_t tile
 // first tile's loads) and a pow step goes through the FFMA2 core, two elements per call, the
 // reference-accuracy path only for the vectors it declines -- sm::pow(a + b, e) in one pass.  Such a
 // CTA runs several consecutive tiles to amortise the copy; plain chains run one tile per CTA.
-template<typename T, int EPV, bool WIDE, int NS, int UNROLL, bool POWFAST, int NDIM>
+template<typename T, int EPV, bool WIDE, int NS, int UNROLL, bool POWFAST, int NDIM, bool PREFETCH = false>
 __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid_constant__ ChainTable t) {
     const uint64_t nvec = t.count / EPV; // host guarantees count % EPV == 0
     const uint64_t ntiles = (nvec + kBlock * UNROLL - 1) / (kBlock * UNROLL);
@@ -1140,19 +1143,39 @@ __global__ void __launch_bounds__(256) k_chain(T *__restrict__ out, const __grid
             mbar_wait(&tab_bar, 0);
             return;
         }
-        // No register prefetch here: with the leaf buffers doubled the kernel drops to two CTAs per
-        // SM and measured slower; occupancy (one vector per thread, four CTAs) hides the loads instead.
-        bool first = true;
+        if constexpr (PREFETCH) {
+            // The pow step is ~120 issue slots per vector: with the NEXT tile's leaf loads issued before this
+            // tile's arithmetic (two leaf buffers swapping roles) HBM latency hides under the warp's own
+            // math instead of relying on the other resident warps (sm::pow(a + b, e): 4.4 -> see profiles/).
+            T leaf0[UNROLL][NS][EPV], leaf1[UNROLL][NS][EPV];
+            chain_load<T, EPV, WIDE, NS, UNROLL, NDIM, true>(t, tile, nvec, leaf0);
+            mbar_wait(&tab_bar, 0); // the tables have landed (the copy overlapped the loads above)
+            asm volatile("" : "+r"(lane.log_off), "+r"(lane.exp_off) :: "memory"); // ties the lookups to the wait
 #pragma unroll 1
-        for (; tile < tile_end; ++tile) {
-            T leaf[UNROLL][NS][EPV];
-            chain_load<T, EPV, WIDE, NS, UNROLL, NDIM>(t, tile, nvec, leaf);
-            if (first) {
-                mbar_wait(&tab_bar, 0); // the tables have landed (the copy overlapped the loads above)
-                asm volatile("" : "+r"(lane.log_off), "+r"(lane.exp_off) :: "memory"); // ties the lookups to the wait
-                first = false;
+            while (tile < tile_end) {
+                if (tile + 1 < tile_end) chain_load<T, EPV, WIDE, NS, UNROLL, NDIM, true>(t, tile + 1, nvec, leaf1);
+                SMB_POW_SCHED_FENCE();
+                chain_compute<T, EPV, NS, UNROLL, true>(t, tile, nvec, leaf0, out, lane);
+                if (++tile >= tile_end) break;
+                if (tile + 1 < tile_end) chain_load<T, EPV, WIDE, NS, UNROLL, NDIM, true>(t, tile + 1, nvec, leaf0);
+                SMB_POW_SCHED_FENCE();
+                chain_compute<T, EPV, NS, UNROLL, true>(t, tile, nvec, leaf1, out, lane);
+                ++tile;
             }
-            chain_compute<T, EPV, NS, UNROLL, true>(t, tile, nvec, leaf, out, lane);
+        } else {
+            // No register prefetch: occupancy (one vector per thread, four CTAs) hides the loads instead.
+            bool first = true;
+#pragma unroll 1
+            for (; tile < tile_end; ++tile) {
+                T leaf[UNROLL][NS][EPV];
+                chain_load<T, EPV, WIDE, NS, UNROLL, NDIM>(t, tile, nvec, leaf);
+                if (first) {
+                    mbar_wait(&tab_bar, 0); // the tables have landed (the copy overlapped the loads above)
+                    asm volatile("" : "+r"(lane.log_off), "+r"(lane.exp_off) :: "memory"); // ties the lookups to the wait
+                    first = false;
+                }
+                chain_compute<T, EPV, NS, UNROLL, true>(t, tile, nvec, leaf, out, lane);
+            }
         }
     }
 }

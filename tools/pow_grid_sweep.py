@@ -15,40 +15,10 @@ import torch
 
 import simplemath_b200 as smb
 
-try:
-    import pynvml
-    pynvml.nvmlInit()
-    _h = pynvml.nvmlDeviceGetHandleByIndex(0)
+from pow_grid_sweep_util import timed, stream, sp  # noqa: E402
 
-    def sm_clock():
-        return pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM)
-except Exception:
-    def sm_clock():
-        return None
-
-stream = torch.cuda.Stream()
-sp = stream.cuda_stream
 smb.set_option(smb.OPT_POW_SPECIALISE, 0)
 FULL = "--full" in sys.argv
-
-
-def timed(fn, reps=20):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(reps):
-        fn()
-    e1.record(stream)
-    clocks = []
-    while not e1.query():
-        c = sm_clock()
-        if c is not None:
-            clocks.append(c)
-    e1.synchronize()
-    clocks.sort()
-    return e0.elapsed_time(e1) / reps, (clocks[len(clocks) // 2] if clocks else None)
 
 
 for logn in (27, 30):
