@@ -830,6 +830,24 @@ static int launch_bcast(DeviceCtx &c, const ElementwisePlan &p, const T *a, cons
             return SMB_OK;
         }
     }
+    // small constant inner strides (w[:, ::2], every third column): vector loads + register picks
+    if (p.kind == PLAN_GENERIC && g_opt_bcast_variant.load() != 2) {
+        constexpr uint64_t epv = 16 / sizeof(T);
+        const int m = p.ndim;
+        bool ok = p.sa[m - 1] <= epv && p.sb[m - 1] <= epv && p.shape[m - 1] % epv == 0 && lin_base % epv == 0 && count % epv == 0 &&
+                  (uintptr_t)out % 16 == 0 && (uintptr_t)a % sizeof(T) == 0 && (uintptr_t)b % sizeof(T) == 0;
+        for (int k = 0; k + 1 < m && ok; ++k) ok = p.sa[k] % epv == 0 && p.sb[k] % epv == 0;
+        if (ok) {
+            const int pha = (int)(((uintptr_t)a % 16) / sizeof(T)), phb = (int)(((uintptr_t)b % 16) / sizeof(T));
+            const unsigned grid = grid_for(count / epv, kThreads, c.sm_count, 0);
+            if (wide) k_sgather<T, Fn, true><<<grid, kThreads, 0, s>>>(a, b, out, t, pha, phb, fn);
+            else k_sgather<T, Fn, false><<<grid, kThreads, 0, s>>>(a, b, out, t, pha, phb, fn);
+            g_last_kernel = wide ? "k_sgather<wide>" : "k_sgather";
+            ++g_launches;
+            SMB_CK(cudaGetLastError());
+            return SMB_OK;
+        }
+    }
     if (p.kind == PLAN_GENERIC) {
         const unsigned grid = grid_for(count, kThreads, c.sm_count, 32);
         if (wide) k_generic<T, Fn, true><<<grid, kThreads, 0, s>>>(a, b, out, t, fn);

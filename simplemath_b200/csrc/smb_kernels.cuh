@@ -1195,6 +1195,87 @@ __global__ void __launch_bounds__(256) k_generic(const T *__restrict__ a, const 
 }
 
 // ---------------------------------------------------------------------------
+// k_sgather: small constant inner strides (w[:, ::2] + w[:, 1::2], every third column, ...).  k_generic reads
+// such operands one 4-byte element per thread: the warp still pulls every sector of the rows it touches, but
+// pays one load instruction, one index computation and one scalar store per ELEMENT.  Here a thread produces
+// one 16-byte vector of consecutive outputs; an operand with inner stride S <= EPV is covered by at most
+// S + 1 ALIGNED 16-byte loads (the span from its first to its last wanted element, aligned down by the
+// operand's phase), and the wanted elements are picked in registers -- lane positions are compile-time
+// constants, selected by ONE uniform switch on (stride, phase) per operand.  Every loaded vector contains
+// at least one wanted element (S <= EPV), so nothing outside the operand's pages is touched.  Host
+// guarantees: row length, range bounds and every outer stride are multiples of EPV (the phase is then the
+// same for every vector), inner strides <= EPV, 16-byte aligned result.
+template<typename T, int S, int PH>
+__device__ __forceinline__ void sg_pick(const T *__restrict__ p_aligned, T (&v)[16 / sizeof(T)]) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    if constexpr (S == 0) {
+        const T x = __ldg(p_aligned + PH);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) v[e] = x;
+    } else {
+        constexpr int NV = (PH + (EPV - 1) * S) / EPV + 1;
+        Pack<T, 16> pk[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) pk[k].raw = VecIO<16, false>::load(p_aligned + k * EPV);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) v[e] = pk[(PH + e * S) / EPV].e[(PH + e * S) % EPV];
+    }
+}
+template<typename T, int S>
+__device__ __forceinline__ void sg_load_phase(const T *__restrict__ p, int phase, T (&v)[16 / sizeof(T)]) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const T *pa = p - phase;
+    if constexpr (EPV == 4) {
+        switch (phase) {
+            case 0: sg_pick<T, S, 0>(pa, v); break;
+            case 1: sg_pick<T, S, 1>(pa, v); break;
+            case 2: sg_pick<T, S, 2>(pa, v); break;
+            default: sg_pick<T, S, 3>(pa, v); break;
+        }
+    } else {
+        if (phase == 0) sg_pick<T, S, 0>(pa, v);
+        else sg_pick<T, S, 1>(pa, v);
+    }
+}
+template<typename T>
+__device__ __forceinline__ void sg_load(const T *__restrict__ p, int stride, int phase, T (&v)[16 / sizeof(T)]) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    switch (stride) { // uniform
+        case 0: sg_load_phase<T, 0>(p, phase, v); break;
+        case 1: sg_load_phase<T, 1>(p, phase, v); break;
+        case 2: sg_load_phase<T, 2>(p, phase, v); break;
+        default:
+            if constexpr (EPV == 4) {
+                if (stride == 3) sg_load_phase<T, 3>(p, phase, v);
+                else sg_load_phase<T, 4>(p, phase, v);
+            } else {
+                sg_load_phase<T, 2>(p, phase, v); // (not reached: the host admits strides <= EPV)
+            }
+            break;
+    }
+}
+template<typename T, typename Fn, bool WIDE>
+__global__ void __launch_bounds__(256) k_sgather(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
+                                                const __grid_constant__ BcastTable t, int phase_a, int phase_b, Fn fn) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const uint64_t nvec = t.count / EPV;
+    const int m = t.ndim;
+    const int sa = (int)t.sa[m - 1], sb = (int)t.sb[m - 1];
+    const uint64_t step = (uint64_t)gridDim.x * kBlock;
+    for (uint64_t v = (uint64_t)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += step) {
+        uint64_t oa, ob;
+        offsets_of<WIDE>(t, t.lin_base + v * EPV, oa, ob);
+        T va[EPV], vb[EPV];
+        sg_load<T>(a + oa, sa, phase_a, va);
+        sg_load<T>(b + ob, sb, phase_b, vb);
+        Pack<T, 16> r;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) r.e[e] = fn(va[e], vb[e], t.lane_base + v * EPV + e);
+        VecIO<16, true>::store(reinterpret_cast<RawVec<16> *>(out) + v, r.raw);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // k_dot: sum_i a[i]*b[i]  (SMArray::operator%, reference math/product.h:8-224) -- the first
 // "next" row after the elementwise path.  HBM-bound reduction: each thread
 // accumulates UNROLL independent vector products per iteration, then warp shuffle -> shared

@@ -377,6 +377,57 @@ def test_transposed_operands_tile_kernel(orc):
     assert smb.last_kernel().startswith("k_generic")
 
 
+def test_small_inner_strides_vector_gather_kernel(orc):
+    """w[:, ::2] + w[:, 1::2] and friends: inner strides 0..4 (f64: 0..2) take k_sgather -- aligned 16-byte loads,
+    elements picked in registers -- for every operand phase; anything it cannot take stays on k_generic."""
+    torch = _torch()
+    rng = np.random.default_rng(71)
+    for dtype, tdt in ((np.float32, torch.float32), (np.int32, torch.int32), (np.float64, torch.float64)):
+        epv = 16 // np.dtype(dtype).itemsize
+        rows, cols = 37, 96 * epv
+        hw = (rng.standard_normal(rows * cols + 16) * 100).astype(dtype)
+        dw = torch.from_numpy(hw).cuda()
+        es = hw.itemsize
+        for s_a in range(0, epv + 1):
+            for s_b in range(0, epv + 1):
+                if max(s_a, s_b) < 2:
+                    continue
+                L = cols // max(s_a, s_b, 1)
+                L -= L % epv
+                for off_a in range(epv):
+                    off_b = (off_a * 3 + 1) % epv
+                    va = np.lib.stride_tricks.as_strided(hw[off_a:], (rows, L), (cols * es, s_a * es))
+                    vb = np.lib.stride_tricks.as_strided(hw[off_b:], (rows, L), (cols * es, s_b * es))
+                    want = orc.elementwise("sub", hw[off_a:], [cols, s_a], hw[off_b:], [cols, s_b], [rows, L]).reshape(rows, L)
+                    assert_same_bits(want, (va - vb).astype(dtype), "oracle == numpy on the strided views")
+                    out = torch.empty(rows * L, dtype=tdt, device="cuda")
+                    smb.elementwise_ptr(smb.OP_SUB, smb.dtype_code(dtype), dw.data_ptr() + off_a * es, [cols, s_a],
+                                        dw.data_ptr() + off_b * es, [cols, s_b], [rows, L], out.data_ptr())
+                    assert smb.last_kernel() == "k_sgather", (dtype, s_a, s_b, off_a, smb.last_kernel())
+                    assert_same_bits(out.cpu().numpy().reshape(rows, L), want, f"sgather {np.dtype(dtype).name} strides {s_a},{s_b} phases {off_a},{off_b}")
+    # 3-D with a broadcast outer dim, flat sub-ranges (shards), and the fallbacks
+    hw = rng.standard_normal(8 * 16 * 64).astype(np.float32)
+    dw = torch.from_numpy(hw).cuda()
+    hb = rng.standard_normal(16 * 32).astype(np.float32)
+    db = torch.from_numpy(hb).cuda()
+    shape, sa, sb = [8, 16, 32], [16 * 64, 64, 2], [0, 32, 1]
+    want = orc.elementwise("mul", hw, sa, hb, sb, shape).ravel()
+    out = torch.empty(8 * 16 * 32, dtype=torch.float32, device="cuda")
+    smb.elementwise_ptr(smb.OP_MUL, smb.F32, dw.data_ptr(), sa, db.data_ptr(), sb, shape, out.data_ptr())
+    assert smb.last_kernel() == "k_sgather"
+    assert_same_bits(out.cpu().numpy(), want, "3-D strided x broadcast")
+    part = torch.empty(1024, dtype=torch.float32, device="cuda")
+    smb.elementwise_range_ptr(smb.OP_MUL, smb.F32, dw.data_ptr(), sa, db.data_ptr(), sb, shape, 512, 1024, part.data_ptr())
+    assert smb.last_kernel() == "k_sgather"
+    assert_same_bits(part.cpu().numpy(), want[512:1536], "strided, flat sub-range")
+    smb.elementwise_range_ptr(smb.OP_MUL, smb.F32, dw.data_ptr(), sa, db.data_ptr(), sb, shape, 510, 1024, part.data_ptr())
+    assert smb.last_kernel() == "k_generic"     # range not on a vector boundary
+    assert_same_bits(part.cpu().numpy(), want[510:1534], "strided, ragged sub-range")
+    smb.elementwise_ptr(smb.OP_MUL, smb.F32, dw.data_ptr(), [16 * 64, 64, 5], db.data_ptr(), sb, [8, 16, 12], out.data_ptr())
+    assert smb.last_kernel() == "k_generic"     # stride 5 > 4
+    assert_same_bits(out.cpu().numpy()[:8 * 16 * 12], orc.elementwise("mul", hw, [16 * 64, 64, 5], hb, sb, [8, 16, 12]).ravel(), "stride 5")
+
+
 def test_wide_index_path_on_small_shapes(orc):
     """The 64-bit index kernels (results beyond 2^31 elements) forced on small shapes."""
     rng = np.random.default_rng(31)
@@ -392,7 +443,10 @@ def test_wide_index_path_on_small_shapes(orc):
         m = rng.standard_normal((37, 53)).astype(np.float64)
         n = rng.standard_normal((53, 37)).astype(np.float64)
         w2 = rng.standard_normal((64, 100))
-        assert_same_bits(smb.binary("div", w2[:, ::2], w2[:, 1::2]), orc.binary("div", w2[:, ::2], w2[:, 1::2]), "wide generic")
+        assert_same_bits(smb.binary("div", w2[:, ::2], w2[:, 1::2]), orc.binary("div", w2[:, ::2], w2[:, 1::2]), "wide strided")
+        assert smb.last_kernel() == "k_sgather<wide>"
+        w3 = rng.standard_normal((64, 99))
+        assert_same_bits(smb.binary("div", w3[:, ::3], w3[:, 1::3]), orc.binary("div", w3[:, ::3], w3[:, 1::3]), "wide generic")
         assert smb.last_kernel() == "k_generic<wide>"
     finally:
         smb.set_option(smb.OPT_FORCE_WIDE_INDEX, 0)
