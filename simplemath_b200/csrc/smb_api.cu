@@ -516,15 +516,16 @@ static inline Span span_of(const void *p, uint64_t bytes) { return Span{(uintptr
 
 // Consecutive tiles per CTA of the table-driven pow kernels.  Enough to amortise the table fill (one
 // bulk copy for f32, an in-kernel fill of 40 KB for f64) and the first tile's unhidden load latency,
-// few enough that the grid stays MANY waves deep: a grid of resident CTAs measured 10-15 % slower,
-// and at the 8-GPU shard size (2^27 elements) the library default of 8 left only 9 waves, whose last
-// one costs 5 % -- so the count shrinks with the array (>= 24 waves of `resident` CTAs).
+// few enough that the grid stays several waves deep: a grid of resident CTAs measured 10-15 % slower.
+// At the 8-GPU shard size (2^27 elements) the default of 8 still gives nine waves and measured best
+// (profiles/r2_pow_grid_sweep.md: 6376 vs 6274 / 6140 GB/s for 4 / 3 tiles at full clock); only arrays
+// small enough to leave fewer than four waves get fewer tiles per CTA.
 static int64_t pow_tiles_per_cta(uint64_t full_tiles, int sm_count, int resident_per_sm, int64_t dflt) {
     const int64_t cps = g_opt_contig_variant.load();
     if (cps > 0) return cps;
     const uint64_t per_wave = (uint64_t)sm_count * (uint64_t)resident_per_sm;
-    const uint64_t fit = full_tiles / (per_wave * 24);
-    return (int64_t)std::max<uint64_t>(2, std::min<uint64_t>((uint64_t)dflt, fit));
+    const uint64_t fit = full_tiles / (per_wave * 4);
+    return (int64_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)dflt, fit));
 }
 
 template<typename T, typename Fn, bool HAS_B>
