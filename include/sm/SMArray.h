@@ -84,6 +84,7 @@ namespace sm {
             _strides = {1};
             ndim = 1;
             data = storage::acquire<T>(totalSize);
+            storage::host_access(); // a recycled block may still be in use by kernels an async scope left in flight
             std::memcpy(data, list.begin(), totalSize * sizeof(T));
             smb_host_written(data); // pages are on the host now: prefetch before the first kernel
         }

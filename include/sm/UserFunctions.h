@@ -14,6 +14,7 @@ namespace sm {
     SMArray<T> empty(Args... args) {
         std::vector<size_t> shape = {static_cast<size_t>(args)...};
         T *data = storage::acquire<T>(calculateTotalSize(shape));
+        storage::host_access(); // the caller fills it on the host: a recycled block must not have kernels of an async scope in flight
         smb_host_written(data); // the caller fills it through data / operator() on the host
         return {data, std::move(shape)};
     }
@@ -25,6 +26,7 @@ namespace sm {
             if constexpr (requires { smb::DTypeTag<T>::value; }) {
                 smb::check(smb_fill(smb::DTypeTag<T>::value, data, &value, n, nullptr));
             } else {
+                host_access();
                 for (size_t i = 0; i < n; ++i) data[i] = value; // element types outside the hot path
             }
             return data;

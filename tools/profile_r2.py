@@ -38,7 +38,10 @@ if "generic" in which:
     out = torch.empty(rows * cols // 2, device="cuda")
     torch.cuda.synchronize()
     argv = (smb.OP_ADD, smb.F32, w.data_ptr(), u([cols, 2]), w.data_ptr() + 4, u([cols, 2]), u([rows, cols // 2]), 2, rows * cols // 2, out.data_ptr(), sp)
-    run(lambda: smb._check(lib.smb_elementwise(*argv)))
+    run(lambda: smb._check(lib.smb_elementwise(*argv)))   # inner stride 2 on both operands: k_sgather
+    cols5 = cols // 5
+    argv5 = (smb.OP_ADD, smb.F32, w.data_ptr(), u([cols, 5]), w.data_ptr() + 4, u([cols, 5]), u([rows, cols5]), 2, rows * cols5, out.data_ptr(), sp)
+    run(lambda: smb._check(lib.smb_elementwise(*argv5)))  # inner stride 5: k_generic
     del w, out
 if "dot" in which:
     n = 1 << 27
