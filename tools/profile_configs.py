@@ -10,7 +10,9 @@ import torch
 import simplemath_b200 as smb
 
 lib, u = smb.lib(), smb._u64arr
-sp = torch.cuda.current_stream().cuda_stream
+stream = torch.cuda.Stream()  # explicit: handle 0 would mean "synchronous call on the private stream"
+sp = stream.cuda_stream
+torch.cuda.synchronize()
 
 
 def bcast(op, dt, tdt, s1, s2, reps=2):
@@ -24,6 +26,7 @@ def bcast(op, dt, tdt, s1, s2, reps=2):
     a = torch.ones(n1, dtype=tdt, device="cuda") * 3
     b = torch.ones(n2, dtype=tdt, device="cuda") * 2
     out = torch.empty(n, dtype=tdt, device="cuda")
+    torch.cuda.synchronize()
     for _ in range(reps):
         smb._check(lib.smb_elementwise(op, dt, a.data_ptr(), u(sa), b.data_ptr(), u(sb), u(shape), len(shape), n, out.data_ptr(), sp))
     torch.cuda.synchronize()
@@ -38,10 +41,12 @@ smb.set_option(smb.OPT_POW_SPECIALISE, 0)
 n = 1 << 27
 x = torch.rand(n, dtype=torch.float64, device="cuda") * 100 + 0.01
 o = torch.empty_like(x)
+torch.cuda.synchronize()
 for _ in range(2):
     smb.array_scalar_ptr(smb.OP_POW, smb.F64, x.data_ptr(), 2.5, n, o.data_ptr(), sp)
 xf = torch.rand(1 << 28, dtype=torch.float32, device="cuda") * 100 + 0.01
 of = torch.empty_like(xf)
+torch.cuda.synchronize()
 for _ in range(2):
     smb.array_scalar_ptr(smb.OP_POW, smb.F32, xf.data_ptr(), 9.25, 1 << 28, of.data_ptr(), sp)
 torch.cuda.synchronize()

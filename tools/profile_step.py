@@ -14,7 +14,9 @@ lg = int(sys.argv[1]) if len(sys.argv) > 1 else 28
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 n = 1 << lg
 a, b, x, out, pw = (torch.empty(n, dtype=torch.float32, device="cuda") for _ in range(5))
-sp = torch.cuda.current_stream().cuda_stream
+stream = torch.cuda.Stream()  # explicit: handle 0 would mean "synchronous call on the private stream"
+sp = stream.cuda_stream
+torch.cuda.synchronize()
 smb.fill_uniform_f32_ptr(a.data_ptr(), 0, n, 1, -1.0, 1.0, sp)
 smb.fill_uniform_f32_ptr(b.data_ptr(), 0, n, 2, -1.0, 1.0, sp)
 smb.fill_uniform_f32_ptr(x.data_ptr(), 0, n, 3, 0.01, 100.0, sp)
