@@ -117,9 +117,11 @@ enum {
     /* Table-driven pow kernels: how many CTAs at the END of the grid own a single tile (they fill the
      * ragged end the multi-tile CTAs leave).  0 (default): none -- measured no gain on B200. */
     SMB_OPT_POW_TAIL_CTAS = 10,
-    /* Fused chains with an f32 pow step and at most 3 leaves (sm::pow(a + b, e)): vectors per thread and
-     * register prefetch of the next tile's leaves -- 0: one vector, no prefetch (round 1); 1 (default): one
-     * vector + prefetch; 2: two vectors; 3: two vectors + prefetch. */
+    /* Fused chains with an f32 pow step and at most 3 leaves (sm::pow(a + b, e)).  4 (default): dense same-shape
+     * operands run the pow kernel itself with the operator applied to the loaded operands (bit-identical to the
+     * operator followed by sm::pow); everything else, and the values 0..3, use the general chain kernel --
+     * 0: one vector per thread, no prefetch (round 1); 1: one vector + register prefetch of the next tile's
+     * leaves; 2: two vectors; 3: two vectors + prefetch. */
     SMB_OPT_CHAIN_POW_VARIANT = 11
 };
 

@@ -51,7 +51,7 @@ static std::atomic<int64_t> g_opt_chunk_bytes{64ll << 20};
 static std::atomic<int64_t> g_opt_contig_variant{0};
 static std::atomic<int64_t> g_opt_bcast_variant{0};
 static std::atomic<int64_t> g_opt_force_wide{0};
-static std::atomic<int64_t> g_opt_chain_pow_variant{1}; // fused pow chains of <= 3 leaves: 0 U1, 1 U1+prefetch, 2 U2, 3 U2+prefetch
+static std::atomic<int64_t> g_opt_chain_pow_variant{4}; // fused pow chains of <= 3 leaves: 4 the pow kernel with a pre-operator; k_chain forms: 0 U1, 1 U1+prefetch, 2 U2, 3 U2+prefetch
 static std::atomic<int64_t> g_opt_pow_tail{0}; // single-tile CTAs at the end of a pow grid (0: none, the default)
 static std::atomic<int64_t> g_opt_pool_max_cached{64ll << 30}; // cached (free) pool bytes beyond which smb_free trims
 
@@ -512,6 +512,10 @@ static unsigned grid_for(uint64_t work_items, uint64_t items_per_block, int sm_c
     return (unsigned)std::min<uint64_t>(blocks, 0x7fffffffull);
 }
 
+// vectors in flight per thread: the library default, unless the functor carries two operand streams through the pow loop
+template<typename Fn, typename = void> struct fn_unroll : std::integral_constant<int, SMB_STREAM_UNROLL> {};
+template<typename Fn> struct fn_unroll<Fn, std::void_t<decltype(Fn::UNROLL_OVERRIDE)>> : std::integral_constant<int, Fn::UNROLL_OVERRIDE> {};
+
 static inline Span span_of(const void *p, uint64_t bytes) { return Span{(uintptr_t)p, (uintptr_t)p + bytes}; }
 
 // Consecutive tiles per CTA of the table-driven pow kernels.  Enough to amortise the table fill (one
@@ -532,7 +536,7 @@ template<typename T, typename Fn, bool HAS_B>
 static int launch_stream(DeviceCtx &c, const T *a, const T *b, T *out, uint64_t n, uint64_t first, Fn fn,
                          cudaStream_t s) {
     if (n == 0) return SMB_OK;
-    constexpr int VB = SMB_STREAM_VB, UNROLL = SMB_STREAM_UNROLL;
+    constexpr int VB = SMB_STREAM_VB, UNROLL = fn_unroll<Fn>::value;
     const uintptr_t ma = (uintptr_t)a % VB, mb = HAS_B ? (uintptr_t)b % VB : ma, mo = (uintptr_t)out % VB;
     const int64_t cps = g_opt_contig_variant.load();
     const Span reads[2] = {span_of(a, n * sizeof(T)), span_of(HAS_B ? b : a, n * sizeof(T))};
@@ -556,7 +560,7 @@ static int launch_stream(DeviceCtx &c, const T *a, const T *b, T *out, uint64_t 
                 const int resident = sizeof(T) == 4 ? SMB_POW_MIN_BLOCKS : SMB_POW64_MIN_BLOCKS;
                 const uint64_t full_tiles = rest / per_block;
                 const int64_t tpc = pow_tiles_per_cta(full_tiles, c.sm_count, resident,
-                                                      sizeof(T) == 4 ? SMB_POW_TILES_PER_CTA : 4 * SMB_POW_TILES_PER_CTA);
+                                                      (sizeof(T) == 4 ? SMB_POW_TILES_PER_CTA : 4 * SMB_POW_TILES_PER_CTA) * SMB_STREAM_UNROLL / UNROLL);
                 // Single-tile CTAs at the end of the grid (SMB_OPT_POW_TAIL_CTAS) to fill the ragged end of the
                 // multi-tile phase: built, measured, and OFF by default -- with the tile count per CTA already
                 // shrunk for small arrays it changes nothing up to one wave of them and loses beyond
@@ -1579,7 +1583,36 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
         }
     }
     const int powvar = (int)g_opt_chain_pow_variant.load();
-    t.tiles_per_cta = powfast ? (powvar >= 2 ? 16 : 32) : 1; // amortise the 24 KB table copy, stay many waves deep
+    // sm::pow(a (op) b, y) on dense same-shape arrays -- THE fused pow (SMB_OPT_CHAIN_POW_VARIANT = 4, the default): the
+    // pow kernel itself with the operator applied to the two loaded operands (k_stream<PowF32FnPre>), bit-identical to
+    // the operator followed by the pow kernel and at that kernel's speed; the general chain kernel below was
+    // instruction-bound at 4.4-4.7 TB/s whatever its shape (profiles/r2_chain_pow_sweep.md).
+    if constexpr (std::is_same<T, float>::value) {
+        if (powvar == 4 && p.nleaf == 3 && p.ndim == 1 && data[0] && data[1] && !data[2] && steps[2].op == SMB_OP_POW &&
+            p.stride[0][0] == 1 && p.stride[1][0] == 1 && steps[1].op != SMB_OP_POW && pow_f32_fast_ok(classify_exp(steps[2].value.f32))) {
+            // (any length and alignment: launch_stream peels heads and tails exactly as it does for sm::pow itself)
+            const float y = steps[2].value.f32;
+            const PowExpF32 pe = classify_exp(y);
+            const int pre = steps[1].op == SMB_OP_ADD ? PRE_ADD : steps[1].op == SMB_OP_MUL ? PRE_MUL
+                            : steps[1].op == SMB_OP_SUB ? (steps[1].swap ? PRE_RSUB : PRE_SUB) : (steps[1].swap ? PRE_RDIV : PRE_DIV);
+            const float *pa = (const float *)data[0] + lin_begin, *pb = (const float *)data[1] + lin_begin;
+            const bool lt1 = pow_f32_y_lt_1(pe);
+            const int tier = pow_f32_tier(pe), sign = pow_f32_sign_mode(pe);
+            g_last_kernel = "k_stream<pow,fused-pre>";
+#define SMB_POWPRE(S, G, L) launch_stream<float, PowF32FnPre<S, G, L>, true>(c, pa, pb, (float *)out, lin_count, lin_begin, PowF32FnPre<S, G, L>::make(y, 0, pre), s)
+#define SMB_POWPRE_BY_SIGN(S) (sign == POW_SIGN_REJECT ? SMB_POWPRE(S, POW_SIGN_REJECT, false) : sign == POW_SIGN_EVEN ? SMB_POWPRE(S, POW_SIGN_EVEN, false) : SMB_POWPRE(S, POW_SIGN_ODD, false))
+            int rc;
+            if (lt1) rc = SMB_POWPRE(POW_TIER_SMALL, POW_SIGN_REJECT, true);
+            else if (tier == POW_TIER_SMALL) rc = SMB_POWPRE_BY_SIGN(POW_TIER_SMALL);
+            else if (tier == POW_TIER_MEDIUM) rc = SMB_POWPRE_BY_SIGN(POW_TIER_MEDIUM);
+            else rc = SMB_POWPRE_BY_SIGN(POW_TIER_LARGE);
+#undef SMB_POWPRE_BY_SIGN
+#undef SMB_POWPRE
+            if (rc == SMB_OK) g_last_kernel = "k_stream<pow,fused-pre>";
+            return rc;
+        }
+    }
+    t.tiles_per_cta = powfast ? (powvar == 2 || powvar == 3 ? 16 : 32) : 1; // amortise the 24 KB table copy, stay many waves deep
     // compiled-in chain capacity / vectors per thread: short chains keep more loads in flight
 #define SMB_CHAIN_LAUNCH(E, W, NS, U, PF, ND)                                                                     \
     k_chain<T, E, W, NS, U, PF, ND><<<grid_for(items, (uint64_t)kThreads * U * t.tiles_per_cta, c.sm_count, 0), kThreads, 0, s>>>(out, t)
@@ -1593,7 +1626,8 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
                     case 0: SMB_CHAIN_LAUNCH_PF(E, W, 1, ND, false); break;                       \
                     case 2: SMB_CHAIN_LAUNCH_PF(E, W, 2, ND, false); break;                       \
                     case 3: SMB_CHAIN_LAUNCH_PF(E, W, 2, ND, true); break;                        \
-                    default: SMB_CHAIN_LAUNCH_PF(E, W, 1, ND, true); break;                       \
+                    case 1: SMB_CHAIN_LAUNCH_PF(E, W, 1, ND, true); break;                        \
+                    default: SMB_CHAIN_LAUNCH_PF(E, W, 1, ND, false); break; /* what does not fit the fused pow kernel */ \
                 }                                                                                 \
             }                                                                                     \
         }                                                                                         \

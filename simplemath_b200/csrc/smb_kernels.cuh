@@ -245,6 +245,7 @@ template<int TIER, int SIGN, bool Y_LT_1> struct PowF32Fn {
     uint64_t *tab_bar; // mbarrier the table copy completes on
     __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return pow_f32_slow(a, pe); }
     __device__ __forceinline__ float slow(float a) const { return pow_f32(a, pe); } // inlined, see pow_tile
+    __device__ __forceinline__ float slow_call(float a) const { return pow_f32_slow(a, pe); } // out of line (ragged tile)
     // Two elements through the branch-free fast core; false = redo on the slow path.
     __device__ __forceinline__ bool pair(float a0, float a1, float &r0, float &r1) const {
         return pow_f32_pair_fast<TIER, SIGN, Y_LT_1>(a0, a1, pe.y, lane, nullptr, nullptr, &r0, &r1);
@@ -278,6 +279,37 @@ template<int TIER, int SIGN, bool Y_LT_1> struct PowF32Fn {
         return fn;
     }
 };
+// sm::pow(a (op) b, y) in ONE pass at the pow kernel's speed (the ≤ 3-leaf contiguous case of a fused chain,
+// smb_chain: leaf (op) leaf, then pow by a constant): the same functor with a binary pre-operator applied to the two
+// loaded operands -- rounded to float by the same DevOp bodies the separate operator uses, so the result is
+// bit-identical to `add` followed by the pow kernel.  The pre-operator is a run-time (uniform) code, not a template
+// parameter: one instantiation per pow variant instead of six.
+enum { PRE_ADD = 0, PRE_SUB = 1, PRE_MUL = 2, PRE_DIV = 3, PRE_RSUB = 4, PRE_RDIV = 5 };
+template<int TIER, int SIGN, bool Y_LT_1> struct PowF32FnPre : PowF32Fn<TIER, SIGN, Y_LT_1> {
+    static constexpr bool PREOP = true;
+    static constexpr int UNROLL_OVERRIDE = 2; // two operand streams: half the vectors per thread keep the register buffers the same size
+    int pre_op;
+    __device__ __forceinline__ float pre(float a, float b) const {
+        switch (pre_op) { // uniform
+            case PRE_ADD: return DevOp<OP_ADD, float>::apply(a, b);
+            case PRE_SUB: return DevOp<OP_SUB, float>::apply(a, b);
+            case PRE_MUL: return DevOp<OP_MUL, float>::apply(a, b);
+            case PRE_DIV: return DevOp<OP_DIV, float>::apply(a, b);
+            case PRE_RSUB: return DevOp<OP_SUB, float>::apply(b, a);
+            default: return DevOp<OP_DIV, float>::apply(b, a);
+        }
+    }
+    __device__ __forceinline__ float operator()(float a, float b, uint64_t) const { return pow_f32_slow(pre(a, b), this->pe); }
+    static PowF32FnPre make(float y, uint64_t lane_end_, int pre_op_) {
+        PowF32FnPre fn;
+        static_cast<PowF32Fn<TIER, SIGN, Y_LT_1> &>(fn) = PowF32Fn<TIER, SIGN, Y_LT_1>::make(y, lane_end_);
+        fn.pre_op = pre_op_;
+        return fn;
+    }
+};
+template<typename Fn, typename = void> struct fn_preop : std::false_type {};
+template<typename Fn> struct fn_preop<Fn, std::void_t<decltype(Fn::PREOP)>> : std::bool_constant<Fn::PREOP> {};
+
 // sm::pow(arr, y) for double: table-driven fast core per element, double-double
 // reference-accuracy path (out of line) for whatever it declines.
 __device__ __noinline__ double pow_f64_slow(double x, PowExpF64 pe) { return pow_f64(x, pe); }
@@ -379,15 +411,22 @@ template<typename T, typename Fn, bool HAS_B, int VB>
 __device__ __forceinline__ void stream_vec(const Pack<T, VB> &pa, const Pack<T, VB> &pb, Pack<T, VB> &r, uint64_t first_elem,
                                            const Fn &fn) {
     constexpr int EPV = VB / (int)sizeof(T);
-    if constexpr (fn_pairwise<Fn>::value && !HAS_B && (EPV % 2 == 0)) {
+    if constexpr (fn_pairwise<Fn>::value && (!HAS_B || fn_preop<Fn>::value) && (EPV % 2 == 0)) {
         // Pairwise functors (f32 pow): branch-free fast core on every pair, ONE check per vector;
-        // a vector with any declined element is redone whole on the slow path (rare).
+        // a vector with any declined element is redone whole on the slow path (rare).  With a fused
+        // pre-operator the pair is (a (op) b), exactly what the multi-tile loop feeds the core.
+        Pack<T, VB> x;
+#pragma unroll
+        for (int k = 0; k < EPV; ++k) {
+            if constexpr (fn_preop<Fn>::value) x.e[k] = fn.pre(pa.e[k], pb.e[k]);
+            else x.e[k] = pa.e[k];
+        }
         bool ok = true;
 #pragma unroll
-        for (int k = 0; k < EPV; k += 2) ok &= fn.pair(pa.e[k], pa.e[k + 1], r.e[k], r.e[k + 1]);
+        for (int k = 0; k < EPV; k += 2) ok &= fn.pair(x.e[k], x.e[k + 1], r.e[k], r.e[k + 1]);
         if (!ok) {
 #pragma unroll
-            for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa.e[k], pa.e[k], 0);
+            for (int k = 0; k < EPV; ++k) r.e[k] = fn.slow_call(x.e[k]);
         }
     } else if constexpr (fn_checked<Fn>::value && !HAS_B) {
         bool ok = true;
@@ -432,21 +471,27 @@ __device__ __forceinline__ void stream_tile(const T *__restrict__ a, const T *__
 // rare) are redone afterwards on the reference-accuracy path, ONE branch per tile.  Their input
 // is re-read from memory rather than kept in registers; it has not been overwritten even when
 // out aliases a, because the declined vector's store was skipped.
-template<typename T, typename Fn, int VB, int UNROLL>
-__device__ __forceinline__ void pow_tile(const Pack<T, VB> (&in)[UNROLL], const T *__restrict__ a, T *__restrict__ out,
+template<typename T, typename Fn, int VB, int UNROLL, bool PRE = false>
+__device__ __forceinline__ void pow_tile(const Pack<T, VB> (&in)[UNROLL], [[maybe_unused]] const Pack<T, VB> (&in_b)[UNROLL],
+                                         const T *__restrict__ a, [[maybe_unused]] const T *__restrict__ b, T *__restrict__ out,
                                          uint64_t v0, const Fn &fn) {
     constexpr int EPV = VB / (int)sizeof(T);
     bool ok[UNROLL], all = true;
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-        Pack<T, VB> r;
+        Pack<T, VB> r, x;
+#pragma unroll
+        for (int k = 0; k < EPV; ++k) {
+            if constexpr (PRE) x.e[k] = fn.pre(in[u].e[k], in_b[u].e[k]);
+            else x.e[k] = in[u].e[k];
+        }
         ok[u] = true;
         if constexpr (fn_pairwise<Fn>::value) {
 #pragma unroll
-            for (int k = 0; k < EPV; k += 2) ok[u] &= fn.pair(in[u].e[k], in[u].e[k + 1], r.e[k], r.e[k + 1]);
+            for (int k = 0; k < EPV; k += 2) ok[u] &= fn.pair(x.e[k], x.e[k + 1], r.e[k], r.e[k + 1]);
         } else {
 #pragma unroll
-            for (int k = 0; k < EPV; ++k) ok[u] &= fn.fast(in[u].e[k], r.e[k]);
+            for (int k = 0; k < EPV; ++k) ok[u] &= fn.fast(x.e[k], r.e[k]);
         }
         if (ok[u]) VecIO<VB, true>::store(reinterpret_cast<RawVec<VB> *>(out) + v0 + (uint64_t)u * kBlock, r.raw);
         all &= ok[u];
@@ -463,7 +508,8 @@ __device__ __forceinline__ void pow_tile(const Pack<T, VB> (&in)[UNROLL], const 
             const int u = e / EPV;
             if ((bad >> u) & 1u) {
                 const uint64_t i = (v0 + (uint64_t)u * kBlock) * EPV + (uint64_t)(e % EPV);
-                out[i] = fn.slow(a[i]);
+                if constexpr (PRE) out[i] = fn.slow(fn.pre(a[i], b[i]));
+                else out[i] = fn.slow(a[i]);
             }
         }
     }
@@ -481,14 +527,28 @@ __global__ void __launch_bounds__(256, fn_pow_tables<Fn>::value ? (sizeof(T) == 
     constexpr uint64_t tile_vecs = (uint64_t)kBlock * UNROLL; // launches always use kBlock threads
     const uint64_t full_tiles = nvec / tile_vecs;
     // full tiles: no bounds checks in the loop body
-    if constexpr (fn_pow_tables<Fn>::value && !HAS_B) {
+    if constexpr (fn_pow_tables<Fn>::value && (!HAS_B || fn_preop<Fn>::value)) {
+        constexpr bool PRE = fn_preop<Fn>::value;
         // Compute-heavy functor on a persistent grid: the next tile's loads are issued BEFORE this
         // tile's arithmetic (register double buffer), so HBM latency hides under ~500 issue slots of
         // math instead of stalling the warp (ncu: long_scoreboard was the top stall without it).
         // The two buffers swap roles every other tile (loop unrolled by two) -- copying one into
         // the other cost a MOV per element.
         Pack<T, VB> buf0[UNROLL], buf1[UNROLL];
+        Pack<T, VB> bb0[PRE ? UNROLL : 1], bb1[PRE ? UNROLL : 1]; // the second operand's tiles (fused pre-operator only)
         const RawVec<VB> *av = reinterpret_cast<const RawVec<VB> *>(a);
+        [[maybe_unused]] const RawVec<VB> *bv = reinterpret_cast<const RawVec<VB> *>(b);
+        // one tile of loads into a buffer pair; the pow body needs operand b only with a pre-operator
+#define SMB_POW_LOAD_TILE(BA, BB, TILE)                                                                     \
+        _Pragma("unroll") for (int u = 0; u < UNROLL; ++u) {                                                \
+            BA[u].raw = load_stream_pinned(av + (TILE) * tile_vecs + threadIdx.x + u * kBlock);             \
+            if constexpr (PRE) BB[u].raw = load_stream_pinned(bv + (TILE) * tile_vecs + threadIdx.x + u * kBlock); \
+        }
+#define SMB_POW_RUN_TILE(BA, BB, TILE)                                                                      \
+        do {                                                                                                \
+            if constexpr (PRE) pow_tile<T, Fn, VB, UNROLL, true>(BA, BB, a, b, out, (TILE) * tile_vecs + threadIdx.x, fn); \
+            else pow_tile<T, Fn, VB, UNROLL, false>(BA, BA, a, a, out, (TILE) * tile_vecs + threadIdx.x, fn); \
+        } while (0)
 #if SMB_POW_BLOCKED
         // CTA b owns `tpc` CONSECUTIVE tiles: the host sizes the grid so that tpc is a handful of tiles --
         // enough to amortise the table fill, few enough that the grid is many waves deep (a grid of
@@ -512,46 +572,39 @@ __global__ void __launch_bounds__(256, fn_pow_tables<Fn>::value ? (sizeof(T) == 
         const uint64_t tstep = gridDim.x, tiles_end = full_tiles;
         uint64_t tile = blockIdx.x;
 #endif
-        if (tile < tiles_end) {
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) buf0[u].raw = load_stream_pinned(av + tile * tile_vecs + threadIdx.x + u * kBlock);
-        }
+        if (tile < tiles_end) { SMB_POW_LOAD_TILE(buf0, bb0, tile) }
         fn.block_wait(); // the tables have landed (the copy overlapped the loads above)
 #if SMB_POW_PINGPONG
 #pragma unroll 1
         while (tile < tiles_end) {
             uint64_t next = tile + tstep;
-            if (next < tiles_end) {
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) buf1[u].raw = load_stream_pinned(av + next * tile_vecs + threadIdx.x + u * kBlock);
-            }
+            if (next < tiles_end) { SMB_POW_LOAD_TILE(buf1, bb1, next) }
             SMB_POW_SCHED_FENCE();
-            pow_tile<T, Fn, VB, UNROLL>(buf0, a, out, tile * tile_vecs + threadIdx.x, fn);
+            SMB_POW_RUN_TILE(buf0, bb0, tile);
             tile = next;
             if (tile >= tiles_end) break;
             next = tile + tstep;
-            if (next < tiles_end) {
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) buf0[u].raw = load_stream_pinned(av + next * tile_vecs + threadIdx.x + u * kBlock);
-            }
+            if (next < tiles_end) { SMB_POW_LOAD_TILE(buf0, bb0, next) }
             SMB_POW_SCHED_FENCE();
-            pow_tile<T, Fn, VB, UNROLL>(buf1, a, out, tile * tile_vecs + threadIdx.x, fn);
+            SMB_POW_RUN_TILE(buf1, bb1, tile);
             tile = next;
         }
 #else
 #pragma unroll 1
         for (; tile < tiles_end; tile += tstep) {
             const uint64_t next = tile + tstep;
-            if (next < tiles_end) {
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) buf1[u].raw = load_stream_pinned(av + next * tile_vecs + threadIdx.x + u * kBlock);
-            }
+            if (next < tiles_end) { SMB_POW_LOAD_TILE(buf1, bb1, next) }
             SMB_POW_SCHED_FENCE();
-            pow_tile<T, Fn, VB, UNROLL>(buf0, a, out, tile * tile_vecs + threadIdx.x, fn);
+            SMB_POW_RUN_TILE(buf0, bb0, tile);
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) buf0[u].raw = buf1[u].raw;
+            for (int u = 0; u < UNROLL; ++u) {
+                buf0[u].raw = buf1[u].raw;
+                if constexpr (PRE) bb0[u].raw = bb1[u].raw;
+            }
         }
 #endif
+#undef SMB_POW_LOAD_TILE
+#undef SMB_POW_RUN_TILE
     } else {
 #pragma unroll 1
         for (uint64_t tile = blockIdx.x; tile < full_tiles; tile += gridDim.x)

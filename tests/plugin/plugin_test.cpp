@@ -93,8 +93,8 @@ TEST(Plugin, UserOpsOnADeviceSetAndInAnAsyncScope) {
         sm::async_scope scope;
         auto t = apply_op<ModOp<int>>(a, row);
         auto u = apply_op<MyOp<int>>(t, row);
-        for (size_t i = 0; i < R * C; i += 4099) ASSERT_EQ(u.data[i] , (one.data[i] + row.data[i % C]) * 2);   // .data after sm::sync only ...
-        (void) u(0, 0);                                                                                          // ... or after an accessor, which waits
+        (void) u(0, 0);                                                                                          // an accessor waits for what the scope left in flight
+        for (size_t i = 0; i < R * C; i += 4099) ASSERT_EQ(u.data[i], (one.data[i] + row.data[i % C]) * 2);     // raw .data only after that (or after sm::sync)
     }
     sm::set_devices({});
     smb_set_option(SMB_OPT_SHARD_MIN_BYTES, old_min);

@@ -374,6 +374,8 @@ def test_transposed_operands_tile_kernel(orc):
     # a strided slice that is not a transpose stays on the generic kernel
     w = rng.standard_normal((64, 100)).astype(np.float32)
     assert_same_bits(smb.binary("add", w[:, ::2], w[:, 1::2]), orc.binary("add", w[:, ::2], w[:, 1::2]), "stride-2 columns")
+    assert smb.last_kernel().startswith("k_sgather")      # {64,50} with strides {100,2} coalesces to one stride-2 dim of 3200
+    assert_same_bits(smb.binary("add", w[:, ::7], w[:, 1::7]), orc.binary("add", w[:, ::7], w[:, 1::7]), "stride-7 columns")
     assert smb.last_kernel().startswith("k_generic")
 
 

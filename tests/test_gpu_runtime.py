@@ -389,3 +389,43 @@ def test_pow_audit_agrees_with_the_oracle_and_catches_errors(orc):
     out.copy_(torch.from_numpy(h))
     cnt, worst = smb.pow_audit_f32_ptr(x.data_ptr(), 2.5, out.data_ptr(), n, 0.6)
     assert cnt == 1 and 1.4 < worst < 2.6, (cnt, worst)
+
+
+# ------------------------------------------ sm::pow(a (op) b, y): the pow kernel with a fused pre-operator ----
+def test_fused_pow_of_a_binary_operator_is_bit_identical_to_the_two_operators(orc):
+    """smb_chain [a, (op) b, pow y] on dense same-shape f32 arrays runs the pow kernel itself with the operator applied to
+    the loaded operands: the same bits as the operator followed by sm::pow (same DevOp rounding, same pow variant), every
+    tier / sign variant, ragged sizes, both operand orders of - and /."""
+    rng = np.random.default_rng(97)
+    smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+    try:
+        for n in (100_003, 1 << 20, 8, 3):
+            a = rng.uniform(0.05, 9.0, n).astype(np.float32)
+            b = rng.uniform(0.05, 9.0, n).astype(np.float32)
+            sgn = np.where(rng.random(n) < 0.3, -1, 1).astype(np.float32)
+            for y in (2.5, 0.5, 17.0, 300.5, 3.0, 2.0, -1.5):
+                for op in ("add", "sub", "mul", "div", "rsub", "rdiv"):
+                    aa = a * sgn if float(y).is_integer() else a
+                    bb = b
+                    if not float(y).is_integer() and op in ("sub", "rsub"):
+                        aa, bb = (a + 9.5, b) if op == "sub" else (a, b + 9.5)   # keep the base positive
+                    base_op = op[1:] if op.startswith("r") else op
+                    mid = smb.binary(base_op, bb, aa) if op.startswith("r") else smb.binary(base_op, aa, bb)
+                    want = smb.pow(mid, y)
+                    got = smb.chain(aa, (op, bb), ("pow", y))
+                    assert smb.last_kernel() == "k_stream<pow,fused-pre>", (n, y, op, smb.last_kernel())
+                    assert_same_bits(got, want, f"pow({op}(a, b), {y}) n={n}")
+            # and within the stated accuracy of std::pow in double on the exactly rounded intermediate
+            mid = orc.binary("add", a, b)
+            err = oracle.ulp_error_f32(smb.chain(a, ("add", b), ("pow", 2.5)), orc.pow_ref_f32(mid, 2.5))
+            assert err.max() <= 0.6, err.max()
+        # what does not fit (a broadcast leaf, a constant second operand, a longer chain) stays on the chain kernel
+        m = rng.uniform(0.1, 5, (64, 256)).astype(np.float32)
+        row = rng.uniform(0.1, 5, (1, 256)).astype(np.float32)
+        got = smb.chain(m, ("add", row), ("pow", 2.5))
+        assert smb.last_kernel().startswith("k_chain")
+        assert oracle.ulp_error_f32(got, orc.pow_ref_f32(orc.binary("add", m, row), 2.5)).max() <= 0.6
+        got = smb.chain(m, ("mul", 2.0), ("pow", 2.5))
+        assert smb.last_kernel().startswith("k_chain")
+    finally:
+        smb.set_option(smb.OPT_POW_SPECIALISE, 1)
