@@ -844,9 +844,18 @@ static int launch_bcast(DeviceCtx &c, const ElementwisePlan &p, const T *a, cons
         for (int k = 0; k + 1 < m && ok; ++k) ok = p.sa[k] % epv == 0 && p.sb[k] % epv == 0;
         if (ok) {
             const int pha = (int)(((uintptr_t)a % 16) / sizeof(T)), phb = (int)(((uintptr_t)b % 16) / sizeof(T));
+            // 256-bit loads for an operand whose every vector span starts on 32 bytes: even inner stride (a span is
+            // 16 * stride bytes from the previous one), aligned-down base and all outer strides on 32 bytes
+            auto spans32 = [&](const T *ptr, const uint64_t *st) {
+                if (st[m - 1] % 2 != 0 || st[m - 1] == 0) return 0;
+                if (((uintptr_t)ptr & ~(uintptr_t)15) % 32 != 0) return 0;
+                for (int k = 0; k + 1 < m; ++k) if (st[k] % (2 * epv) != 0) return 0;
+                return 1; // (the inner part of a span's offset is 16 * stride * q bytes: on 32 for every q when the stride is even)
+            };
+            const int wide32 = spans32(a, p.sa) | (spans32(b, p.sb) << 1);
             const unsigned grid = grid_for(count / epv, kThreads, c.sm_count, 0);
-            if (wide) k_sgather<T, Fn, true><<<grid, kThreads, 0, s>>>(a, b, out, t, pha, phb, fn);
-            else k_sgather<T, Fn, false><<<grid, kThreads, 0, s>>>(a, b, out, t, pha, phb, fn);
+            if (wide) k_sgather<T, Fn, true><<<grid, kThreads, 0, s>>>(a, b, out, t, pha, phb, wide32, fn);
+            else k_sgather<T, Fn, false><<<grid, kThreads, 0, s>>>(a, b, out, t, pha, phb, wide32, fn);
             g_last_kernel = wide ? "k_sgather<wide>" : "k_sgather";
             ++g_launches;
             SMB_CK(cudaGetLastError());

@@ -44,6 +44,9 @@ constexpr int kBlock = 256; // threads per CTA of every kernel in this file
 #ifndef SMB_POW_MIN_BLOCKS
 #define SMB_POW_MIN_BLOCKS 3 // resident CTAs per SM the f32 pow kernel is compiled for
 #endif
+#ifndef SMB_DOT_MIN_BLOCKS
+#define SMB_DOT_MIN_BLOCKS 4 // k_dot: four CTAs per SM (64 registers): the f64 instantiation sat at 70 registers = three CTAs and was latency-bound
+#endif
 
 // ---------------------------------------------------------------------------
 // 16-byte and 32-byte global vector access with streaming cache hints.
@@ -1258,7 +1261,10 @@ __global__ void __launch_bounds__(256) k_generic(const T *__restrict__ a, const 
 // at least one wanted element (S <= EPV), so nothing outside the operand's pages is touched.  Host
 // guarantees: row length, range bounds and every outer stride are multiples of EPV (the phase is then the
 // same for every vector), inner strides <= EPV, 16-byte aligned result.
-template<typename T, int S, int PH>
+// V32: the span is an even number of vectors starting on a 32-byte boundary (host-checked, uniform): one 256-bit load per
+// vector PAIR (LDG.E.256, new with sm_100).  A warp's lanes sit S vectors apart, so 128-bit loads fill only every S-th
+// 16 bytes of each L1 wavefront -- ncu had the LSU data pipe at 98 % on w[:, ::2] + w[:, 1::2] with DRAM at 65 %.
+template<typename T, int S, int PH, bool V32>
 __device__ __forceinline__ void sg_pick(const T *__restrict__ p_aligned, T (&v)[16 / sizeof(T)]) {
     constexpr int EPV = 16 / (int)sizeof(T);
     if constexpr (S == 0) {
@@ -1267,50 +1273,65 @@ __device__ __forceinline__ void sg_pick(const T *__restrict__ p_aligned, T (&v)[
         for (int e = 0; e < EPV; ++e) v[e] = x;
     } else {
         constexpr int NV = (PH + (EPV - 1) * S) / EPV + 1;
-        Pack<T, 16> pk[NV];
+        if constexpr (V32 && NV % 2 == 0) {
+            Pack<T, 32> pk[NV / 2];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) pk[k].raw = VecIO<16, false>::load(p_aligned + k * EPV);
+            for (int k = 0; k < NV / 2; ++k) pk[k].raw = VecIO<32, false>::load(p_aligned + k * 2 * EPV);
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) v[e] = pk[(PH + e * S) / EPV].e[(PH + e * S) % EPV];
+            for (int e = 0; e < EPV; ++e) v[e] = pk[(PH + e * S) / (2 * EPV)].e[(PH + e * S) % (2 * EPV)];
+        } else {
+            Pack<T, 16> pk[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) pk[k].raw = VecIO<16, false>::load(p_aligned + k * EPV);
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) v[e] = pk[(PH + e * S) / EPV].e[(PH + e * S) % EPV];
+        }
     }
 }
-template<typename T, int S>
+template<typename T, int S, bool V32>
 __device__ __forceinline__ void sg_load_phase(const T *__restrict__ p, int phase, T (&v)[16 / sizeof(T)]) {
     constexpr int EPV = 16 / (int)sizeof(T);
     const T *pa = p - phase;
     if constexpr (EPV == 4) {
         switch (phase) {
-            case 0: sg_pick<T, S, 0>(pa, v); break;
-            case 1: sg_pick<T, S, 1>(pa, v); break;
-            case 2: sg_pick<T, S, 2>(pa, v); break;
-            default: sg_pick<T, S, 3>(pa, v); break;
+            case 0: sg_pick<T, S, 0, V32>(pa, v); break;
+            case 1: sg_pick<T, S, 1, V32>(pa, v); break;
+            case 2: sg_pick<T, S, 2, V32>(pa, v); break;
+            default: sg_pick<T, S, 3, V32>(pa, v); break;
         }
     } else {
-        if (phase == 0) sg_pick<T, S, 0>(pa, v);
-        else sg_pick<T, S, 1>(pa, v);
+        if (phase == 0) sg_pick<T, S, 0, V32>(pa, v);
+        else sg_pick<T, S, 1, V32>(pa, v);
     }
 }
+// wide32: the host found every vector span of this operand 32-byte aligned (even stride, base and outer strides on
+// 32 bytes); only the strides whose spans can be an even number of vectors have a 256-bit form
 template<typename T>
-__device__ __forceinline__ void sg_load(const T *__restrict__ p, int stride, int phase, T (&v)[16 / sizeof(T)]) {
+__device__ __forceinline__ void sg_load(const T *__restrict__ p, int stride, int phase, bool wide32, T (&v)[16 / sizeof(T)]) {
     constexpr int EPV = 16 / (int)sizeof(T);
     switch (stride) { // uniform
-        case 0: sg_load_phase<T, 0>(p, phase, v); break;
-        case 1: sg_load_phase<T, 1>(p, phase, v); break;
-        case 2: sg_load_phase<T, 2>(p, phase, v); break;
+        case 0: sg_load_phase<T, 0, false>(p, phase, v); break;
+        case 1: sg_load_phase<T, 1, false>(p, phase, v); break;
+        case 2:
+            if (wide32) sg_load_phase<T, 2, true>(p, phase, v);
+            else sg_load_phase<T, 2, false>(p, phase, v);
+            break;
         default:
             if constexpr (EPV == 4) {
-                if (stride == 3) sg_load_phase<T, 3>(p, phase, v);
-                else sg_load_phase<T, 4>(p, phase, v);
+                if (stride == 3) sg_load_phase<T, 3, false>(p, phase, v);
+                else if (wide32) sg_load_phase<T, 4, true>(p, phase, v);
+                else sg_load_phase<T, 4, false>(p, phase, v);
             } else {
-                sg_load_phase<T, 2>(p, phase, v); // (not reached: the host admits strides <= EPV)
+                sg_load_phase<T, 2, false>(p, phase, v); // (not reached: the host admits strides <= EPV)
             }
             break;
     }
 }
 template<typename T, typename Fn, bool WIDE>
 __global__ void __launch_bounds__(256) k_sgather(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
-                                                const __grid_constant__ BcastTable t, int phase_a, int phase_b, Fn fn) {
+                                                const __grid_constant__ BcastTable t, int phase_a, int phase_b, int wide32, Fn fn) {
     constexpr int EPV = 16 / (int)sizeof(T);
+    const bool wa = wide32 & 1, wb = (wide32 >> 1) & 1;
     const uint64_t nvec = t.count / EPV;
     const int m = t.ndim;
     const int sa = (int)t.sa[m - 1], sb = (int)t.sb[m - 1];
@@ -1319,8 +1340,8 @@ __global__ void __launch_bounds__(256) k_sgather(const T *__restrict__ a, const 
         uint64_t oa, ob;
         offsets_of<WIDE>(t, t.lin_base + v * EPV, oa, ob);
         T va[EPV], vb[EPV];
-        sg_load<T>(a + oa, sa, phase_a, va);
-        sg_load<T>(b + ob, sb, phase_b, vb);
+        sg_load<T>(a + oa, sa, phase_a, wa, va);
+        sg_load<T>(b + ob, sb, phase_b, wb, vb);
         Pack<T, 16> r;
 #pragma unroll
         for (int e = 0; e < EPV; ++e) r.e[e] = fn(va[e], vb[e], t.lane_base + v * EPV + e);
@@ -1357,7 +1378,7 @@ template<typename A> __device__ __forceinline__ A dot_add(A x, A y) {
 // ragged tail), 1 when they do not (views hand us interior pointers; the reference reads them with
 // loadu, product.h:26-71): element-wise coalesced loads.
 template<typename T, int UNROLL, int EPV>
-__global__ void __launch_bounds__(256) k_dot(const T *__restrict__ a, const T *__restrict__ b, uint64_t n, uint64_t head,
+__global__ void __launch_bounds__(256, SMB_DOT_MIN_BLOCKS) k_dot(const T *__restrict__ a, const T *__restrict__ b, uint64_t n, uint64_t head,
                                             typename DotAcc<T>::type *__restrict__ partials, unsigned int *__restrict__ ticket,
                                             typename DotAcc<T>::type *__restrict__ result) {
     using A = typename DotAcc<T>::type;
