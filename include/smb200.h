@@ -122,7 +122,12 @@ enum {
      * operator followed by sm::pow); everything else, and the values 0..3, use the general chain kernel --
      * 0: one vector per thread, no prefetch (round 1); 1: one vector + register prefetch of the next tile's
      * leaves; 2: two vectors; 3: two vectors + prefetch. */
-    SMB_OPT_CHAIN_POW_VARIANT = 11
+    SMB_OPT_CHAIN_POW_VARIANT = 11,
+    /* Device set: how an operand several devices read (or whose per-device ranges are below a page) reaches them.
+     * 0 (default): the operand is advised read-mostly and each device's range prefetched to it ONCE -- the driver keeps a
+     * read-only duplicate per device and invalidates them on any write (raw host writes included); 1: a private copy per
+     * call in pooled device scratch (subject to SMB_OPT_REPLICATE_MAX_BYTES). */
+    SMB_OPT_REPLICA_MODE = 12
 };
 
 /* ---- the hot path ------------------------------------------------------- */

@@ -31,6 +31,10 @@ struct Block {
     // written by a kernel / fill stay where they are.  A stale record is only a performance matter --
     // the GPU then demand-pages what moved.
     uint64_t placement = 0;
+    // Managed blocks only: the block carries cudaMemAdviseSetReadMostly (it was last used as an operand several
+    // devices read: the driver keeps a read-only duplicate on each, and invalidates them on any write -- the
+    // host's raw writes through SMArray::data included).  Cleared, with the advice, when it becomes a result.
+    bool read_mostly = false;
 };
 
 class Pool {
@@ -45,7 +49,8 @@ public:
     bool owns(const void *ptr, Block *out = nullptr);
     // For a managed address: returns the containing block and whether its recorded placement
     // already was `want` (and records `want`).  false when the address is not in a live pool block.
-    bool take_placement(const void *ptr, uint64_t want, Block *out, bool *matched);
+    // rm_action: -1 leave the read-mostly mark, 0 clear it, 1 set it; *was_rm = the mark before.
+    bool take_placement(const void *ptr, uint64_t want, Block *out, bool *matched, int rm_action = -1, bool *was_rm = nullptr);
     void clear_placement(const void *ptr);
     // Give cached blocks back to the driver until at most `keep_bytes` stay cached (largest first).
     void trim_to(uint64_t keep_bytes);

@@ -55,6 +55,13 @@ static std::atomic<int64_t> g_opt_chain_pow_variant{4}; // fused pow chains of <
 static std::atomic<int64_t> g_opt_pow_tail{0}; // single-tile CTAs at the end of a pow grid (0: none, the default)
 static std::atomic<int64_t> g_opt_pool_max_cached{64ll << 30}; // cached (free) pool bytes beyond which smb_free trims
 
+// Every copy / prefetch / memset / event wait the library enqueues bumps this counter.  The overlapping launch form
+// reasons about KERNELS only (what earlier kernels read and write, and that each kernel's completion implies its
+// predecessor's); a kernel that follows anything else on its stream -- a replica copy it is about to read, a prefetch --
+// is launched plainly: full stream order, no attribute.
+static std::atomic<uint64_t> g_other_ops{0};
+static inline void note_other_op() { g_other_ops.fetch_add(1, std::memory_order_relaxed); }
+
 // ------------------------------------------------------ device context ------
 constexpr int kSlots = 3;       // staging pipeline depth (H2D | kernel | D2H in flight)
 constexpr int kMaxDevices = 64;
@@ -65,6 +72,7 @@ struct StreamTrack {
     static constexpr int kCap = 24;
     Span reads[kCap], writes[kCap];
     int nr = 0, nw = 0;
+    uint64_t other_ops_seen = ~0ull; // g_other_ops when the stream's last overlappable launch was decided
     void reset() { nr = nw = 0; }
 };
 struct DeviceCtx {
@@ -300,7 +308,7 @@ bool Pool::owns(const void *ptr, Block *out) {
     if (out) *out = b;
     return true;
 }
-bool Pool::take_placement(const void *ptr, uint64_t want, Block *out, bool *matched) {
+bool Pool::take_placement(const void *ptr, uint64_t want, Block *out, bool *matched, int rm_action, bool *was_rm) {
     std::lock_guard<std::mutex> lk(mu_);
     auto it = live_.upper_bound((uintptr_t)ptr);
     if (it == live_.begin()) return false;
@@ -310,6 +318,8 @@ bool Pool::take_placement(const void *ptr, uint64_t want, Block *out, bool *matc
     *out = b;
     *matched = b.placement == want;
     b.placement = want;
+    if (was_rm) *was_rm = b.read_mostly;
+    if (rm_action >= 0) b.read_mostly = rm_action != 0;
     return true;
 }
 void Pool::clear_placement(const void *ptr) {
@@ -405,14 +415,21 @@ static inline bool on_host(MemType t) { return t == MT_HOST || t == MT_PINNED; }
 // managed memory is always prefetched.
 static inline uint64_t mix64(uint64_t h, uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); return h; }
 static inline uint64_t placement_single(int dev) { return 0x5100000000000000ull | (uint64_t)(dev + 1); }
-static void prefetch_managed(const void *p, size_t bytes, int dev, cudaStream_t s) {
+// A block that becomes a RESULT loses the read-mostly advice an earlier use as a shared operand left on it
+// (writes to read-duplicated pages work, but every one of them invalidates the duplicates first).
+static void drop_read_mostly(const Block &blk) {
+    if (cudaMemAdvise(blk.base, blk.bytes, cudaMemAdviseUnsetReadMostly, 0) != cudaSuccess) cudaGetLastError();
+}
+static void prefetch_managed(const void *p, size_t bytes, int dev, cudaStream_t s, bool is_result = false) {
     Block blk;
-    bool matched = false;
-    if (Pool::instance().take_placement(p, placement_single(dev), &blk, &matched)) {
+    bool matched = false, was_rm = false;
+    if (Pool::instance().take_placement(p, placement_single(dev), &blk, &matched, is_result ? 0 : -1, &was_rm)) {
+        if (is_result && was_rm) drop_read_mostly(blk);
         if (matched) return;
         p = blk.base;        // whole block: views of it become resident too
         bytes = blk.bytes;
     }
+    note_other_op();
     if (cudaMemPrefetchAsync(p, bytes, dev, s) != cudaSuccess) cudaGetLastError(); // best effort
 }
 
@@ -440,6 +457,14 @@ struct PdlDecision { bool attr; uint32_t flags; };
 static inline bool spans_overlap(const Span &x, const Span &y) { return x.lo < y.hi && y.lo < x.hi; }
 static PdlDecision pdl_decide(StreamTrack &t, const Span *reads, int nr, const Span &write) {
     if (!g_opt_pdl.load(std::memory_order_relaxed)) { t.reset(); return {false, kPdlWaitFirst}; }
+    const uint64_t ops = g_other_ops.load(std::memory_order_relaxed);
+    if (ops != t.other_ops_seen) { // something that is not one of our kernels may sit right before this launch: plain launch
+        t.other_ops_seen = ops;
+        t.reset();
+        for (int j = 0; j < nr; ++j) if (reads[j].hi > reads[j].lo) t.reads[t.nr++] = reads[j];
+        t.writes[t.nw++] = write;
+        return {false, kPdlWaitFirst};
+    }
     bool conflict = t.nr + nr > StreamTrack::kCap || t.nw + 1 > StreamTrack::kCap;
     for (int i = 0; i < t.nw && !conflict; ++i) {
         if (spans_overlap(t.writes[i], write)) conflict = true;
@@ -1093,6 +1118,7 @@ static int async_order(const int *devs, int n, uint64_t sig) {
         for (int e = 0; others >> e; ++e) {
             if (!((others >> e) & 1ull)) continue;
             if (!((recorded >> e) & 1ull)) { SMB_CK(cudaEventRecord(g_ctx[e].ev_done, g_ctx[e].main)); recorded |= 1ull << e; }
+            note_other_op();
             SMB_CK(cudaStreamWaitEvent(g_ctx[devs[i]].main, g_ctx[e].ev_done, 0));
         }
     }
@@ -1142,6 +1168,7 @@ static int sync_all() {
 static int order_slots_after(DeviceCtx &c, cudaStream_t after, int nslots) {
     if (!after) return SMB_OK;
     SMB_CK(cudaEventRecord(c.ev_user, after));
+    note_other_op();
     for (int i = 0; i < nslots; ++i) SMB_CK(cudaStreamWaitEvent(c.slot[i], c.ev_user, 0));
     return SMB_OK;
 }
@@ -1183,18 +1210,21 @@ static int elementwise_staged(DeviceCtx &c, int op, int dtype, const Elementwise
     bool need_ev = false;
     if (on_host(ta) && !a_var) {
         if (int rc = inv_a.get(p.extent_a * es, dev)) return rc;
+        note_other_op();
         SMB_CK(cudaMemcpyAsync(inv_a.p, a, p.extent_a * es, cudaMemcpyHostToDevice, c.slot[0]));
         da_inv = inv_a.p;
         need_ev = true;
     }
     if (on_host(tb) && !b_var) {
         if (int rc = inv_b.get(p.extent_b * es, dev)) return rc;
+        note_other_op();
         SMB_CK(cudaMemcpyAsync(inv_b.p, b, p.extent_b * es, cudaMemcpyHostToDevice, c.slot[0]));
         db_inv = inv_b.p;
         need_ev = true;
     }
     if (need_ev) {
         SMB_CK(cudaEventRecord(c.ev, c.slot[0]));
+        note_other_op();
         for (int i = 1; i < nslots; ++i) SMB_CK(cudaStreamWaitEvent(c.slot[i], c.ev, 0));
     }
     const uint64_t slab_ea = a_var ? (chunk_rows - 1) * p.sa[0] + ea1 : 0;
@@ -1215,6 +1245,7 @@ static int elementwise_staged(DeviceCtx &c, int op, int dtype, const Elementwise
         if (a_var) {
             const char *src = (const char *)a + r0 * p.sa[0] * es;
             if (on_host(ta)) {
+                note_other_op();
                 SMB_CK(cudaMemcpyAsync(sa_[sl].p, src, ((r - 1) * p.sa[0] + ea1) * es, cudaMemcpyHostToDevice, s));
                 pa = (const char *)sa_[sl].p;
             } else pa = src;
@@ -1222,6 +1253,7 @@ static int elementwise_staged(DeviceCtx &c, int op, int dtype, const Elementwise
         if (b_var) {
             const char *src = (const char *)b + r0 * p.sb[0] * es;
             if (on_host(tb)) {
+                note_other_op();
                 SMB_CK(cudaMemcpyAsync(sb_[sl].p, src, ((r - 1) * p.sb[0] + eb1) * es, cudaMemcpyHostToDevice, s));
                 pb = (const char *)sb_[sl].p;
             } else pb = src;
@@ -1229,6 +1261,7 @@ static int elementwise_staged(DeviceCtx &c, int op, int dtype, const Elementwise
         char *po = on_host(to) ? (char *)so_[sl].p : (char *)out + r0 * inner * es;
         if (int rc = elementwise_device(c, op, dtype, sub, pa, pb, po, 0, sub.n, r0 * inner, lane_end, s)) return rc;
         if (on_host(to))
+            note_other_op();
             SMB_CK(cudaMemcpyAsync((char *)out + r0 * inner * es, po, sub.n * es, cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < kSlots; ++i) SMB_CK(cudaStreamSynchronize(c.slot[i]));
@@ -1257,11 +1290,13 @@ static int scalar_staged(DeviceCtx &c, int op, int dtype, const void *a, MemType
         const uint64_t i0 = ci * chunk, cnt = std::min(chunk, n - i0);
         const char *pa = (const char *)a + i0 * es;
         if (on_host(ta)) {
+            note_other_op();
             SMB_CK(cudaMemcpyAsync(sa_[sl].p, pa, cnt * es, cudaMemcpyHostToDevice, s));
             pa = (const char *)sa_[sl].p;
         }
         char *po = on_host(to) ? (char *)so_[sl].p : (char *)out + i0 * es;
         if (int rc = scalar_device(c, op, dtype, pa, scalar, po, cnt, i0, lane_end, s)) return rc;
+        note_other_op();
         if (on_host(to)) SMB_CK(cudaMemcpyAsync((char *)out + i0 * es, po, cnt * es, cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < nslots; ++i) SMB_CK(cudaStreamSynchronize(c.slot[i]));
@@ -1290,13 +1325,18 @@ static int check_args(int op, int dtype) {
 static std::atomic<int64_t> g_opt_shard_min_bytes{32ll << 20};   // results below this stay on one device
 static std::atomic<int64_t> g_opt_replicate_max_bytes{64ll << 20};
 
+static std::atomic<int64_t> g_opt_replica_mode{0}; // shared operands: 0 read-mostly duplicates kept by the driver, 1 a private copy per call
+
 struct ShardOperand {
     const void *base = nullptr;  // the operand as the caller passed it
     OperandShards plan;
-    bool need_prefetch = false;  // in place: the block's recorded placement is not this partition
+    bool need_prefetch = false;  // the block's recorded placement is not this partition: prefetch each device's range
+    bool duplicate = false;      // shared operand kept as read-mostly duplicates (no private copy)
+    bool need_advise = false;    // ... and the advice has not been given yet
+    uint64_t hull_lo = 0, hull_hi = 0; // elements any device reads (the advised range)
 };
-static uint64_t placement_sharded(const std::vector<int> &devs, const void *base, const OperandShards &o) {
-    uint64_t h = 0xA5ull;
+static uint64_t placement_sharded(const std::vector<int> &devs, const void *base, const OperandShards &o, uint64_t tag = 0) {
+    uint64_t h = 0xA5ull ^ tag;
     for (size_t i = 0; i < devs.size(); ++i) {
         h = mix64(h, (uint64_t)devs[i]);
         h = mix64(h, o.r[i].lo);
@@ -1307,26 +1347,45 @@ static uint64_t placement_sharded(const std::vector<int> &devs, const void *base
 }
 // Decide how every operand reaches the devices; false: some operand is both shared between devices
 // and too large to copy per call -- the caller runs the operator on one device instead.
+//   in place        ranges disjoint and at least a page each: device g's range is prefetched to it once;
+//   shared / small  SMB_OPT_REPLICA_MODE 0 (default): the operand is advised READ-MOSTLY and each device's range is
+//                   prefetched to it once -- the driver then keeps a read-only duplicate on every device that reads
+//                   it and invalidates them on ANY write, raw host writes through SMArray::data included, which is
+//                   what a cache of private copies could not promise; the kernels read the original pointer.
+//                   Mode 1: a private copy per call in pooled device scratch (kept for comparison).
 static bool shard_operands(const std::vector<int> &devs, const ShardSplit &split, const uint64_t *shape, int ndim,
                            const void *const *bases, const uint64_t *const *strides, int nops, size_t es, ShardOperand *ops) {
     const uint64_t rmax = (uint64_t)std::max<int64_t>(0, g_opt_replicate_max_bytes.load());
+    const bool dupmode = g_opt_replica_mode.load() == 0;
     for (int o = 0; o < nops; ++o) {
         ops[o].base = bases[o];
         if (!bases[o]) continue; // a constant
-        ops[o].plan = plan_operand(shape, strides[o], ndim, split, es, rmax);
+        ops[o].plan = plan_operand(shape, strides[o], ndim, split, es, rmax); // (a large shared operand -- a big transpose -- keeps the operator on one device, where k_tile applies)
         if (ops[o].plan.mode == SHARD_REFUSE) return false;
     }
     for (int o = 0; o < nops; ++o) {
-        if (!bases[o] || ops[o].plan.mode != SHARD_IN_PLACE) continue;
+        if (!bases[o]) continue;
+        const bool shared = ops[o].plan.mode != SHARD_IN_PLACE;
+        if (shared && !dupmode) continue; // private copies: nothing to record
+        ops[o].duplicate = shared;
+        ops[o].hull_lo = ~0ull;
+        for (int g = 0; g < split.g; ++g) {
+            if (ops[o].plan.r[g].hi == ops[o].plan.r[g].lo) continue;
+            ops[o].hull_lo = std::min(ops[o].hull_lo, ops[o].plan.r[g].lo);
+            ops[o].hull_hi = std::max(ops[o].hull_hi, ops[o].plan.r[g].hi);
+        }
         Block blk;
-        bool matched = false;
-        ops[o].need_prefetch = !(Pool::instance().take_placement(bases[o], placement_sharded(devs, bases[o], ops[o].plan), &blk, &matched) && matched);
+        bool matched = false, was_rm = false;
+        const bool pooled = Pool::instance().take_placement(bases[o], placement_sharded(devs, bases[o], ops[o].plan, shared ? 0x0D0Dull : 0), &blk,
+                                                            &matched, shared ? 1 : -1, &was_rm);
+        ops[o].need_prefetch = !(pooled && matched);
+        ops[o].need_advise = shared && !(pooled && was_rm);
     }
     return true;
 }
 // Operand `op` for device index g (the current device), on stream s: returns the base pointer the
-// kernels of that device use (the caller's pointer, or a rebased scratch copy).
-static int shard_operand_on_device(const ShardOperand &op, int g, int dev, size_t es, cudaStream_t s, Scratch &scratch,
+// kernels of that device use (the caller's pointer, or a rebased private copy in replica mode 1).
+static int shard_operand_on_device(ShardOperand &op, int g, int dev, size_t es, cudaStream_t s, Scratch &scratch,
                                    const void **use) {
     *use = op.base;
     if (!op.base) return SMB_OK;
@@ -1334,18 +1393,42 @@ static int shard_operand_on_device(const ShardOperand &op, int g, int dev, size_
     if (r.hi == r.lo) return SMB_OK;
     const char *src = (const char *)op.base + r.lo * es;
     const size_t bytes = (r.hi - r.lo) * es;
-    if (op.plan.mode == SHARD_IN_PLACE) {
-        if (op.need_prefetch && cudaMemPrefetchAsync(src, bytes, dev, s) != cudaSuccess) cudaGetLastError(); // best effort
+    if (op.plan.mode == SHARD_IN_PLACE || op.duplicate) {
+        if (op.need_advise) { // once per operand: before the first device's prefetch
+            if (cudaMemAdvise((const char *)op.base + op.hull_lo * es, (op.hull_hi - op.hull_lo) * es, cudaMemAdviseSetReadMostly, dev) != cudaSuccess)
+                cudaGetLastError();
+            op.need_advise = false;
+        }
+        if (op.need_prefetch) {
+            note_other_op();
+            if (cudaMemPrefetchAsync(src, bytes, dev, s) != cudaSuccess) cudaGetLastError(); // best effort
+        }
         return SMB_OK;
     }
-    // replica: same 16-byte phase as the original so the vector kernels still qualify; the kernels
+    // private copy: same 16-byte phase as the original so the vector kernels still qualify; the kernels
     // index from the operand's element 0, so the base is moved back by the range's offset
     const size_t pad = (uintptr_t)src & 15;
     if (int rc = scratch.get(bytes + 16, dev)) return rc;
     char *dst = (char *)scratch.p + pad;
+    note_other_op();
     SMB_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
     *use = dst - r.lo * es;
     return SMB_OK;
+}
+
+// The RESULT of a sharded operator: dense, device g writes exactly [bounds[g], bounds[g + 1]); always in place.  Its
+// pages are prefetched to their devices unless the block is already partitioned this way; a read-mostly mark left by an
+// earlier life as a shared operand goes (with the advice).
+static ShardOperand shard_result(const std::vector<int> &devs, const ShardSplit &split, void *out) {
+    ShardOperand res;
+    res.base = out;
+    res.plan.mode = SHARD_IN_PLACE;
+    for (int g = 0; g < split.g; ++g) res.plan.r[g] = ElemRange{split.bounds[g], split.bounds[g + 1]};
+    Block blk;
+    bool matched = false, was_rm = false;
+    res.need_prefetch = !(Pool::instance().take_placement(out, placement_sharded(devs, out, res.plan), &blk, &matched, 0, &was_rm) && matched);
+    if (was_rm) drop_read_mostly(blk);
+    return res;
 }
 
 // Runs `launch(ctx, g, lo, count, operand bases..., stream)` for every non-empty range of the split.
@@ -1376,6 +1459,7 @@ static int run_sharded(const std::vector<int> &devs, const ShardSplit &split, Sh
         if (rc != SMB_OK) break;
         if (result.base && result.need_prefetch) {
             const ElemRange r = result.plan.r[g];
+            note_other_op();
             if (cudaMemPrefetchAsync((const char *)result.base + r.lo * es, (r.hi - r.lo) * es, devs[g], c->main) != cudaSuccess) cudaGetLastError();
         }
         rc = launch(*c, g, lo, cnt, use, c->main);
@@ -1413,15 +1497,7 @@ static int elementwise_sharded(const std::vector<int> &devs, int op, int dtype, 
     ShardOperand ops[2], res;
     *done = false;
     if (!shard_operands(devs, split, p.shape, p.ndim, bases, strides, 2, es, ops)) return SMB_OK;
-    // the result: dense, range g is exactly [bounds[g], bounds[g + 1])
-    res.base = out;
-    res.plan.mode = SHARD_IN_PLACE;
-    for (int g = 0; g < G; ++g) res.plan.r[g] = ElemRange{split.bounds[g], split.bounds[g + 1]};
-    {
-        Block blk;
-        bool matched = false;
-        res.need_prefetch = !(Pool::instance().take_placement(out, placement_sharded(devs, out, res.plan), &blk, &matched) && matched);
-    }
+    res = shard_result(devs, split, out);
     *done = true;
     return run_sharded(devs, split, ops, 2, res, es, async_mode(nullptr),
                        [&](DeviceCtx &c, int, uint64_t lo, uint64_t cnt, const void *const *use, cudaStream_t s) {
@@ -1461,10 +1537,13 @@ static int elementwise_entry(int op, int dtype, const void *a, const uint64_t *s
             void *po = out;
             cudaStream_t s = c->slot[0];
             if (int rc = order_slots_after(*c, after, 1)) return rc;
+            note_other_op();
             if (on_host(ta)) { if (int rc = da.get(p.extent_a * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(da.p, a, p.extent_a * es, cudaMemcpyHostToDevice, s)); pa = da.p; }
+            note_other_op();
             if (on_host(tb)) { if (int rc = db.get(p.extent_b * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(db.p, b, p.extent_b * es, cudaMemcpyHostToDevice, s)); pb = db.p; }
             if (on_host(to)) { if (int rc = dout.get(lin_count * es, dev)) return rc; po = dout.p; }
             if (int rc = elementwise_device(*c, op, dtype, p, pa, pb, po, lin_begin, lin_count, lin_begin, lane_end, s)) return rc;
+            note_other_op();
             if (on_host(to)) SMB_CK(cudaMemcpyAsync(out, po, lin_count * es, cudaMemcpyDeviceToHost, s));
             SMB_CK(cudaStreamSynchronize(s));
             return SMB_OK;
@@ -1481,7 +1560,7 @@ static int elementwise_entry(int op, int dtype, const void *a, const uint64_t *s
     if (int rc = begin_call(*c, stream)) return rc;
     if (ta == MT_MANAGED) prefetch_managed(a, p.extent_a * es, c->device, s);
     if (tb == MT_MANAGED) prefetch_managed(b, p.extent_b * es, c->device, s);
-    if (to == MT_MANAGED) prefetch_managed(out, lin_count * es, c->device, s);
+    if (to == MT_MANAGED) prefetch_managed(out, lin_count * es, c->device, s, true);
     if (int rc = elementwise_device(*c, op, dtype, p, a, b, out, lin_begin, lin_count, lin_begin, lane_end, s)) return rc;
     return finish_call(*c, s, stream);
 }
@@ -1509,12 +1588,14 @@ static int dot_enqueue(DeviceCtx &c, const T *a, const T *b, uint64_t n, Scratch
     unsigned int *ticket = (unsigned int *)scratch.p;
     A *res = (A *)((char *)scratch.p + 8);
     A *partials = (A *)((char *)scratch.p + 16);
+    note_other_op();
     SMB_CK(cudaMemsetAsync(scratch.p, 0, 16, s));
     if (vec) k_dot<T, UNROLL, EPVV><<<grid, kThreads, 0, s>>>(a, b, n, head, partials, ticket, res);
     else k_dot<T, UNROLL, 1><<<grid, kThreads, 0, s>>>(a, b, n, 0, partials, ticket, res);
     ++g_launches;
     g_last_kernel = vec ? "k_dot" : "k_dot<unaligned>";
     SMB_CK(cudaGetLastError());
+    note_other_op();
     SMB_CK(cudaMemcpyAsync(result_pinned, res, sizeof(A), cudaMemcpyDeviceToHost, s));
     return SMB_OK;
 }
@@ -1768,12 +1849,7 @@ static int chain_entry(int dtype, const smb_chain_step *steps, int nsteps, const
         for (int i = 0; i < nsteps; ++i) { bases[i] = steps[i].data; cstr[i] = p.stride[i]; }
         ShardOperand ops[SMB_CHAIN_MAX], res;
         if (shard_operands(devs, split, p.shape, p.ndim, bases, cstr, nsteps, es, ops)) {
-            res.base = out;
-            res.plan.mode = SHARD_IN_PLACE;
-            for (int g = 0; g < G; ++g) res.plan.r[g] = ElemRange{split.bounds[g], split.bounds[g + 1]};
-            Block blk;
-            bool matched = false;
-            res.need_prefetch = !(Pool::instance().take_placement(out, placement_sharded(devs, out, res.plan), &blk, &matched) && matched);
+            res = shard_result(devs, split, out);
             return run_sharded(devs, split, ops, nsteps, res, es, async_mode(nullptr),
                                [&](DeviceCtx &cg, int, uint64_t lo, uint64_t cnt, const void *const *use, cudaStream_t sg) {
                                    return chain_dispatch(cg, dtype, p, steps, use, lo, cnt, lane_end, (char *)out + lo * es, sg);
@@ -1792,6 +1868,7 @@ static int chain_entry(int dtype, const smb_chain_step *steps, int nsteps, const
         if (!data[i]) continue;
         if (on_host(mt[i])) {
             if (int rc = scratch[i].get(p.extent[i] * es, dev)) return rc;
+            note_other_op();
             SMB_CK(cudaMemcpyAsync(scratch[i].p, data[i], p.extent[i] * es, cudaMemcpyDefault, s));
             data[i] = scratch[i].p;
         } else if (mt[i] == MT_MANAGED) prefetch_managed(data[i], p.extent[i] * es, dev, s);
@@ -1800,8 +1877,9 @@ static int chain_entry(int dtype, const smb_chain_step *steps, int nsteps, const
     if (on_host(to)) {
         if (int rc = dout.get(lin_count * es, dev)) return rc;
         po = dout.p;
-    } else if (to == MT_MANAGED) prefetch_managed(out, lin_count * es, dev, s);
+    } else if (to == MT_MANAGED) prefetch_managed(out, lin_count * es, dev, s, true);
     if (int rc = chain_dispatch(*c, dtype, p, steps, data, lin_begin, lin_count, lane_end, po, s)) return rc;
+    note_other_op();
     if (on_host(to)) SMB_CK(cudaMemcpyAsync(out, po, lin_count * es, cudaMemcpyDefault, s));
     if (any_host) { SMB_CK(cudaStreamSynchronize(s)); return SMB_OK; } // scratch in use: synchronous whatever the mode
     return finish_call(*c, s, stream);
@@ -1846,11 +1924,11 @@ int smb_array_scalar(int op, int dtype, const void *a, const void *scalar, uint6
         const int G = (int)devs.size();
         const ShardSplit split = split_flat(n, n, 1, 1, G, es);
         const uint64_t shape1[1] = {n}, unit[1] = {1};
-        const void *bases[2] = {a, out};
-        const uint64_t *strides[2] = {unit, unit};
-        ShardOperand ops[2];
-        if (shard_operands(devs, split, shape1, 1, bases, strides, 2, es, ops)) {
-            const ShardOperand res = ops[1];
+        const void *bases[1] = {a};
+        const uint64_t *strides[1] = {unit};
+        ShardOperand ops[1];
+        if (shard_operands(devs, split, shape1, 1, bases, strides, 1, es, ops)) {
+            const ShardOperand res = shard_result(devs, split, out);
             return run_sharded(devs, split, ops, 1, res, es, async_mode(nullptr),
                                [&](DeviceCtx &cg, int, uint64_t lo, uint64_t cnt, const void *const *use, cudaStream_t s) {
                                    return scalar_device(cg, op, dtype, (const char *)use[0] + lo * es, scalar, (char *)out + lo * es, cnt, lo, lane_end, s);
@@ -1860,7 +1938,7 @@ int smb_array_scalar(int op, int dtype, const void *a, const void *scalar, uint6
     cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
     if (int rc = begin_call(*c, stream)) return rc;
     if (ta == MT_MANAGED) prefetch_managed(a, n * es, c->device, s);
-    if (to == MT_MANAGED) prefetch_managed(out, n * es, c->device, s);
+    if (to == MT_MANAGED) prefetch_managed(out, n * es, c->device, s, true);
     if (int rc = scalar_device(*c, op, dtype, a, scalar, out, n, 0, lane_end, s)) return rc;
     return finish_call(*c, s, stream);
 }
@@ -1909,8 +1987,10 @@ int smb_dot(int dtype, const void *a, const void *b, uint64_t n, void *result, v
     Scratch da, db, work;
     DrainGuard drain;
     drain.add(s);
+    note_other_op();
     if (on_host(ta)) { if (int rc = da.get(n * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(da.p, a, n * es, cudaMemcpyDefault, s)); a = da.p; }
     else if (ta == MT_MANAGED) prefetch_managed(a, n * es, dev, s);
+    note_other_op();
     if (on_host(tb)) { if (int rc = db.get(n * es, dev)) return rc; SMB_CK(cudaMemcpyAsync(db.p, b, n * es, cudaMemcpyDefault, s)); b = db.p; }
     else if (tb == MT_MANAGED) prefetch_managed(b, n * es, dev, s);
     if (int rc = dot_enqueue_dtype(*c, dtype, a, b, n, work, pinned.p, s)) return rc;
@@ -1999,12 +2079,9 @@ int smb_fill(int dtype, void *out, const void *value, uint64_t n, void *stream) 
         // sm::ones / sm::zeros over the device set: the block is BORN partitioned the way the operators use it
         const int G = (int)devs.size();
         const ShardSplit split = split_flat(n, n, 1, 1, G, es);
-        const uint64_t shape1[1] = {n}, unit[1] = {1};
-        const void *bases[1] = {out};
-        const uint64_t *strides[1] = {unit};
-        ShardOperand ops[1];
-        if (shard_operands(devs, split, shape1, 1, bases, strides, 1, es, ops)) {
-            const ShardOperand res = ops[0];
+        {
+            ShardOperand ops[1];
+            const ShardOperand res = shard_result(devs, split, out);
             return run_sharded(devs, split, ops, 0, res, es, async_mode(nullptr),
                                [&](DeviceCtx &cg, int, uint64_t lo, uint64_t cnt, const void *const *, cudaStream_t s) {
                                    return fill_device(cg, dtype, (char *)out + lo * es, value, cnt, s);
@@ -2013,7 +2090,7 @@ int smb_fill(int dtype, void *out, const void *value, uint64_t n, void *stream) 
     }
     cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
     if (int rc = begin_call(*c, stream)) return rc;
-    if (to == MT_MANAGED) prefetch_managed(out, n * es, c->device, s);
+    if (to == MT_MANAGED) prefetch_managed(out, n * es, c->device, s, true);
     if (int rc = fill_device(*c, dtype, out, value, n, s)) return rc;
     return finish_call(*c, s, stream);
 }
@@ -2023,6 +2100,7 @@ int smb_prefetch(const void *ptr, size_t bytes, int device, void *stream) {
     if (int rc = current_ctx(&c)) return rc;
     if (mem_type(ptr) != MT_MANAGED) return SMB_OK; // nothing to migrate
     cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
+    note_other_op();
     SMB_CK(cudaMemPrefetchAsync(ptr, bytes, device < 0 ? cudaCpuDeviceId : device, s));
     if (!stream) SMB_CK(cudaStreamSynchronize(s));
     return SMB_OK;
@@ -2087,6 +2165,7 @@ int smb_set_option(int key, int64_t value) {
         case SMB_OPT_POOL_MAX_CACHED_BYTES: g_opt_pool_max_cached = value; return SMB_OK;
         case SMB_OPT_POW_TAIL_CTAS: g_opt_pow_tail = value; return SMB_OK;
         case SMB_OPT_CHAIN_POW_VARIANT: g_opt_chain_pow_variant = value; return SMB_OK;
+        case SMB_OPT_REPLICA_MODE: g_opt_replica_mode = value; return SMB_OK;
     }
     return fail(SMB_ERR_INVALID, "unknown option %d", key);
 }
@@ -2104,6 +2183,7 @@ int64_t smb_get_option(int key) {
         case SMB_OPT_POOL_MAX_CACHED_BYTES: return g_opt_pool_max_cached;
         case SMB_OPT_POW_TAIL_CTAS: return g_opt_pow_tail;
         case SMB_OPT_CHAIN_POW_VARIANT: return g_opt_chain_pow_variant;
+        case SMB_OPT_REPLICA_MODE: return g_opt_replica_mode;
     }
     return -1;
 }
@@ -2196,6 +2276,7 @@ int smb_pow_audit_f32(const void *x, float y, const void *got, uint64_t n, float
     cudaStream_t s = c->main;
     DrainGuard drain;
     drain.add(s);
+    note_other_op();
     SMB_CK(cudaMemsetAsync(acc.p, 0, 16, s));
     const unsigned grid = grid_for(n, kThreads * 8, c->sm_count, 16);
     k_pow_audit_f32<<<grid, kThreads, 0, s>>>((const float *)x, (const float *)got, n, classify_exp(y), bound_ulp,
@@ -2203,6 +2284,7 @@ int smb_pow_audit_f32(const void *x, float y, const void *got, uint64_t n, float
     ++g_launches;
     SMB_CK(cudaGetLastError());
     unsigned long long host[2] = {0, 0};
+    note_other_op();
     SMB_CK(cudaMemcpyAsync(host, acc.p, 16, cudaMemcpyDeviceToHost, s));
     SMB_CK(cudaStreamSynchronize(s));
     *count_over = host[0];
@@ -2228,12 +2310,9 @@ int smb_fill_uniform_f32(void *out, uint64_t first, uint64_t n, uint64_t seed, f
     if (to == MT_MANAGED && want_sharding(devs, n * 4, stream, true)) { // a function of the flat index: shards trivially
         const int G = (int)devs.size();
         const ShardSplit split = split_flat(n, n, 1, 1, G, 4);
-        const uint64_t shape1[1] = {n}, unit[1] = {1};
-        const void *bases[1] = {out};
-        const uint64_t *strides[1] = {unit};
-        ShardOperand ops[1];
-        if (shard_operands(devs, split, shape1, 1, bases, strides, 1, 4, ops)) {
-            const ShardOperand res = ops[0];
+        {
+            ShardOperand ops[1];
+            const ShardOperand res = shard_result(devs, split, out);
             return run_sharded(devs, split, ops, 0, res, 4, async_mode(nullptr),
                                [&](DeviceCtx &cg, int, uint64_t at, uint64_t cnt, const void *const *, cudaStream_t s) {
                                    return fill(cg, (float *)out + at, at, cnt, s);
@@ -2242,7 +2321,7 @@ int smb_fill_uniform_f32(void *out, uint64_t first, uint64_t n, uint64_t seed, f
     }
     cudaStream_t s = stream ? (cudaStream_t)stream : c->main;
     if (int rc = begin_call(*c, stream)) return rc;
-    if (to == MT_MANAGED) prefetch_managed(out, n * 4, c->device, s);
+    if (to == MT_MANAGED) prefetch_managed(out, n * 4, c->device, s, true);
     if (int rc = fill(*c, (float *)out, 0, n, s)) return rc;
     return finish_call(*c, s, stream);
 }

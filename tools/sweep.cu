@@ -159,6 +159,7 @@ struct PowLoopOnlyFn {
     uint64_t lane_end;
     __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return a; }
     __device__ __forceinline__ float slow(float a) const { return a; }
+    __device__ __forceinline__ float slow_call(float a) const { return a; }
     __device__ __forceinline__ bool pair(float a0, float a1, float &r0, float &r1) const { r0 = a0 + 1.0f; r1 = a1 + 1.0f; return true; }
     __device__ __forceinline__ void block_init() {}
     __device__ __forceinline__ void block_wait() {}
