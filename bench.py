@@ -307,7 +307,7 @@ def run_smb(args):
     smb.fill_uniform_f32_ptr(x.data_ptr(), lo, m, 3, 0.01, 100.0, sp)
     stream.synchronize()
     smb.set_option(smb.OPT_POW_SPECIALISE, 0)  # headline = the general pow kernel
-    smb.set_option(smb.OPT_PDL, args.pdl)
+    smb.set_option(smb.OPT_PDL, 2 if args.pdl else 0)  # 2: also on the streams this script owns (only this library's kernels and events go there)
 
     # The step's two operators are independent (a+b -> out, pow(x) -> pw): with --streams 2 (default)
     # they are enqueued on two streams, so one kernel's last wave overlaps the other's first; within a

@@ -100,9 +100,11 @@ enum {
      * Calls with host (non-pinned or pinned) operands and smb_dot stay synchronous in either mode.
      * Setting it back to 0 waits for everything pending. */
     SMB_OPT_ASYNC = 5,
-    /* 1 (default): back-to-back kernels on one stream use programmatic dependent launch -- the next
-     * grid's CTAs become resident while the previous grid drains (and overlap it outright on the
-     * private stream when the host sees no data hazard); 0: plain stream order. */
+    /* 1 (default): back-to-back kernels on the library's PRIVATE stream (stream == NULL calls) use programmatic
+     * dependent launch -- the next grid's CTAs become resident while the previous grid drains, and overlap it
+     * outright when the host sees no data hazard; a kernel that follows a copy / prefetch is launched plainly.
+     * 2: also on the streams callers pass in (always waiting first) -- the caller vouches that only this
+     * library's kernels, events and ordinary copies precede them there (bench.py does).  0: plain stream order. */
     SMB_OPT_PDL = 6,
     /* Device set (smb_set_devices): results smaller than this many bytes stay on one device
      * (default 32 MiB). */

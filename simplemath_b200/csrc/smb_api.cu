@@ -449,8 +449,10 @@ static void prefetch_managed(const void *p, size_t bytes, int dev, cudaStream_t 
 // attribute off (plain stream order).
 static std::atomic<int64_t> g_opt_pdl{1};
 // The overlapping form is used on the library's PRIVATE stream only (stream == NULL calls): there
-// every kernel is ours.  On a caller's stream the previous kernel may be anyone's (and may itself
-// trigger early), so launches there always wait first.
+// every operation is ours, and a kernel that follows anything but one of our kernels (a copy, a
+// prefetch) is launched plainly.  On a caller's stream the library cannot know what precedes it, so
+// launches there are plain unless the caller opts in (SMB_OPT_PDL = 2: only this library's kernels,
+// events and ordinary copies are enqueued on the streams it is handed), and then always wait first.
 static std::mutex g_launch_mu; // decision + launch are one unit per stream; launches are cheap, one lock serves all
 
 struct PdlDecision { bool attr; uint32_t flags; };
@@ -486,7 +488,9 @@ struct LaunchLock {
     LaunchLock(DeviceCtx &c, cudaStream_t s) : lk(g_launch_mu), t(s == c.main ? &c.track : nullptr) {}
     PdlDecision decide(const Span *reads, int nr, const Span &write) {
         if (t) return pdl_decide(*t, reads, nr, write);
-        return {g_opt_pdl.load(std::memory_order_relaxed) != 0, kPdlWaitFirst};
+        // a caller's stream: the attribute only when the caller vouches for what precedes us there (SMB_OPT_PDL = 2),
+        // and then always with the initial wait
+        return {g_opt_pdl.load(std::memory_order_relaxed) >= 2, kPdlWaitFirst};
     }
     void barrier() { if (t) pdl_barrier(*t); }
 };
@@ -2159,7 +2163,7 @@ int smb_set_option(int key, int64_t value) {
             if (!value && g_opt_async.load()) { g_opt_async = 0; return sync_all(); } // leaving async mode: everything lands
             g_opt_async = value ? 1 : 0;
             return SMB_OK;
-        case SMB_OPT_PDL: g_opt_pdl = value ? 1 : 0; return SMB_OK;
+        case SMB_OPT_PDL: g_opt_pdl = value < 0 ? 0 : value > 2 ? 2 : value; return SMB_OK;
         case SMB_OPT_SHARD_MIN_BYTES: g_opt_shard_min_bytes = value; return SMB_OK;
         case SMB_OPT_REPLICATE_MAX_BYTES: g_opt_replicate_max_bytes = value; return SMB_OK;
         case SMB_OPT_POOL_MAX_CACHED_BYTES: g_opt_pool_max_cached = value; return SMB_OK;

@@ -285,7 +285,7 @@ def test_async_mode_and_pdl_variants(orc):
     want_e = orc.elementwise("sub", ha, [1], hb, [1], [n])
     want_f = orc.array_scalar("mul", want_d, 0.5)
     torch.cuda.synchronize()
-    for pdl in (1, 0):
+    for pdl in (2, 1, 0):
         smb.set_option(smb.OPT_PDL, pdl)
         for asyn in (0, 1):
             smb.set_option(smb.OPT_ASYNC, asyn)

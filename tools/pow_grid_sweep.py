@@ -39,7 +39,7 @@ for logn in (27, 30):
     cfgs += [("pow", 2.0, 1, 0, 0), ("pow", 2.0, 1, 8, 0)]
     for pass_ in (0, 1):
         for kind, y, pdl, tpc, tail in (cfgs if pass_ == 0 else cfgs[::-1]):
-            smb.set_option(smb.OPT_PDL, pdl)
+            smb.set_option(smb.OPT_PDL, 2 if pdl else 0)
             smb.set_option(smb.OPT_CONTIG_VARIANT, tpc)
             smb.set_option(smb.OPT_POW_TAIL_CTAS, tail)
             if kind == "add":
