@@ -1442,8 +1442,16 @@ static int run_sharded(const std::vector<int> &devs, const ShardSplit &split, Sh
     const int G = (int)devs.size();
     std::vector<Scratch> scratch((size_t)G * (size_t)std::max(nops, 1));
     DeviceScope scope;
-    bool pure = true; // every operand in place: each device touches only its own ranges
-    for (int o = 0; o < nops; ++o) if (ops[o].base && ops[o].plan.mode != SHARD_IN_PLACE) pure = false;
+    // "Pure": every operand and the result already sit in exactly this partition (their records matched, nothing is
+    // prefetched or advised by this call) -- in place, or as read-mostly duplicates nobody has written since.  Each device
+    // then reads and writes only what its own stream produced or what no device writes, so an operator with the same
+    // partition as the one before it needs no cross-device ordering.
+    bool pure = !(result.base && result.need_prefetch);
+    for (int o = 0; o < nops; ++o) {
+        if (!ops[o].base) continue;
+        if (ops[o].need_prefetch || ops[o].need_advise) pure = false;
+        if (ops[o].plan.mode != SHARD_IN_PLACE && !ops[o].duplicate) pure = false; // private copies are made by this call
+    }
     if (async) {
         uint64_t sig = 0;
         if (pure) { sig = 0x51ull; for (int g = 0; g <= G; ++g) sig = mix64(sig, split.bounds[g]); for (int d : devs) sig = mix64(sig, (uint64_t)d); sig |= 1; }

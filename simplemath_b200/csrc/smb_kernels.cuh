@@ -45,7 +45,9 @@ constexpr int kBlock = 256; // threads per CTA of every kernel in this file
 #define SMB_POW_MIN_BLOCKS 3 // resident CTAs per SM the f32 pow kernel is compiled for
 #endif
 #ifndef SMB_DOT_MIN_BLOCKS
-#define SMB_DOT_MIN_BLOCKS 4 // k_dot: four CTAs per SM (64 registers): the f64 instantiation sat at 70 registers = three CTAs and was latency-bound
+// k_dot: the 4-byte instantiations fit four CTAs per SM as they are; capping the f64 one to 64 registers for a fourth
+// CTA was tried and lost (5.70 -> 5.32 TB/s: the spills cost more than the extra CTA hides), so it keeps its 70.
+#define SMB_DOT_MIN_BLOCKS(T) (sizeof(T) == 8 ? 3 : 4)
 #endif
 
 // ---------------------------------------------------------------------------
@@ -1378,7 +1380,7 @@ template<typename A> __device__ __forceinline__ A dot_add(A x, A y) {
 // ragged tail), 1 when they do not (views hand us interior pointers; the reference reads them with
 // loadu, product.h:26-71): element-wise coalesced loads.
 template<typename T, int UNROLL, int EPV>
-__global__ void __launch_bounds__(256, SMB_DOT_MIN_BLOCKS) k_dot(const T *__restrict__ a, const T *__restrict__ b, uint64_t n, uint64_t head,
+__global__ void __launch_bounds__(256, SMB_DOT_MIN_BLOCKS(T)) k_dot(const T *__restrict__ a, const T *__restrict__ b, uint64_t n, uint64_t head,
                                             typename DotAcc<T>::type *__restrict__ partials, unsigned int *__restrict__ ticket,
                                             typename DotAcc<T>::type *__restrict__ result) {
     using A = typename DotAcc<T>::type;

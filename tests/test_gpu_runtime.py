@@ -429,3 +429,44 @@ def test_fused_pow_of_a_binary_operator_is_bit_identical_to_the_two_operators(or
         assert smb.last_kernel().startswith("k_chain")
     finally:
         smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+
+
+def test_device_set_in_async_mode_keeps_order_across_devices(orc, sharded):
+    """Async hand-off on a device set: dependent operators whose partitions differ (a small result feeding a large one as a
+    broadcast operand, a result reused as an operand with another shape), recycled blocks, and the steady state where the
+    same partition repeats and the cross-device waits are skipped."""
+    rng = np.random.default_rng(101)
+    lib = smb.lib()
+    for devs in _device_sets():
+        smb.set_devices(devs)
+        R, C = 1024, 2048                                   # 8 MiB per array
+        a = rng.standard_normal((R, C)).astype(np.float32)
+        b = rng.standard_normal((R, C)).astype(np.float32)
+        row = rng.standard_normal((1, C)).astype(np.float32)
+        ma, mb, mrow = Managed(a), Managed(b), Managed(row)
+        mrow2, mc, md, me = Managed(shape=(1, C), dtype=np.float32), Managed(shape=(R, C), dtype=np.float32), Managed(shape=(R, C), dtype=np.float32), Managed(shape=(R, C), dtype=np.float32)
+        full, rowst = [C, 1], [0, 1]
+        smb.set_option(smb.OPT_ASYNC, 1)
+        try:
+            for it in range(4):
+                smb.array_scalar_ptr(smb.OP_MUL, smb.F32, mrow.ptr, 1.0 + it, C, mrow2.ptr)                        # small: one device
+                smb.elementwise_ptr(smb.OP_ADD, smb.F32, ma.ptr, full, mb.ptr, full, [R, C], mc.ptr)                # large: every device
+                smb.elementwise_ptr(smb.OP_MUL, smb.F32, mc.ptr, full, mrow2.ptr, rowst, [R, C], md.ptr)            # reads the small result on every device
+                smb.elementwise_ptr(smb.OP_SUB, smb.F32, md.ptr, full, mc.ptr, full, [R, C], me.ptr)                # same partition as before: no waits
+                smb.elementwise_ptr(smb.OP_ADD, smb.F32, me.ptr, full, mrow.ptr, rowst, [R, C], mc.ptr)             # overwrites c, which the previous two read
+                tmp = lib.smb_alloc(R * C * 4, smb.MEM_MANAGED)                                                     # a temporary freed while in flight
+                smb.elementwise_ptr(smb.OP_MUL, smb.F32, mc.ptr, full, mc.ptr, full, [R, C], tmp)
+                smb.elementwise_ptr(smb.OP_ADD, smb.F32, tmp, full, mb.ptr, full, [R, C], md.ptr)
+                lib.smb_free(tmp)
+            smb._check(lib.smb_wait_pending())
+        finally:
+            smb.set_option(smb.OPT_ASYNC, 0)
+        row2 = orc.array_scalar("mul", row, 4.0)
+        c1 = orc.binary("add", a, b)
+        d1 = orc.binary("mul", c1, row2)
+        e1 = orc.binary("sub", d1, c1)
+        c2 = orc.binary("add", e1, row)
+        d2 = orc.binary("add", orc.binary("mul", c2, c2), b)
+        assert_same_bits(me.np.copy(), e1, f"e on {devs}")
+        assert_same_bits(mc.np.copy(), c2, f"c on {devs}")
+        assert_same_bits(md.np.copy(), d2, f"d on {devs}")
