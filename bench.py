@@ -36,6 +36,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "elementwise algorithmic GB/s, f32 add + pow on 4 GiB arrays (C5)"
+WORKLOAD = "C5: f32 contiguous add (a+b) + pow(x, 2.5) on 2^30-element (4 GiB) arrays"  # the same string in both arms
 UNIT = "GB/s"
 N_TOTAL = 1 << 30
 POW_Y = 2.5
@@ -222,8 +223,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C5: f32 contiguous add (a+b) + pow(x, 2.5) on 2^30-element (4 GiB) arrays" +
-                               ("" if elems == N_TOTAL else f"; bounded CPU sample of {elems} elements per array"),
+        "config": {"workload": WORKLOAD + ("" if elems == N_TOTAL else f"; bounded CPU sample of {elems} elements per array"),
                    "elements": elems, "pow_exponent": POW_Y},
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -603,9 +603,9 @@ def run_smb(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "C5: f32 contiguous add (a+b) + pow(x, 2.5) on 2^30-element (4 GiB) arrays, sharded by "
-                                   "flat output index range" + (" (weak: 2^30 elements PER GPU)" if args.scaling == "weak" else ""), "elements": n, "elements_per_gpu": m, "pow_exponent": POW_Y,
-                       "pow_kernel": "general exp2(y*log2 x), specialisation off", "parallelism": f"flat-range shards x{world}",
+            "config": {"workload": WORKLOAD + (" (weak: 2^30 elements PER GPU)" if args.scaling == "weak" else ""), "elements": n, "pow_exponent": POW_Y,
+                       "elements_per_gpu": m, "pow_kernel": "general exp2(y*log2 x), specialisation off",
+                       "parallelism": f"sharded by flat output index range x{world}, one process per GPU, no data-path collective",
                        "streams": args.streams, "programmatic_dependent_launch": bool(args.pdl),
                        "l2": f"inputs larger than L2 ({m * 4 >> 20} MiB per array per GPU vs 126 MiB L2)",
                        "inputs": "splitmix64 counter generator of the flat index, produced in HBM",
