@@ -129,7 +129,10 @@ enum {
      * 0 (default): the operand is advised read-mostly and each device's range prefetched to it ONCE -- the driver keeps a
      * read-only duplicate per device and invalidates them on any write (raw host writes included); 1: a private copy per
      * call in pooled device scratch (subject to SMB_OPT_REPLICATE_MAX_BYTES). */
-    SMB_OPT_REPLICA_MODE = 12
+    SMB_OPT_REPLICA_MODE = 12,
+    /* Device set, synchronous mode: 1 (default) every device of the set has a persistent launcher thread that prepares,
+     * launches and waits for its device's range, all devices at once; 0: the calling thread walks the devices. */
+    SMB_OPT_LAUNCHER_THREADS = 13
 };
 
 /* ---- the hot path ------------------------------------------------------- */

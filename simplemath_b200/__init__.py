@@ -26,7 +26,7 @@ F32, F64, I32 = range(3)
 MEM_DEVICE, MEM_MANAGED, MEM_PINNED = range(3)
 (OPT_POW_SPECIALISE, OPT_STAGE_CHUNK_BYTES, OPT_CONTIG_VARIANT, OPT_BCAST_VARIANT, OPT_FORCE_WIDE_INDEX, OPT_ASYNC, OPT_PDL,
  OPT_SHARD_MIN_BYTES, OPT_REPLICATE_MAX_BYTES, OPT_POOL_MAX_CACHED_BYTES, OPT_POW_TAIL_CTAS, OPT_CHAIN_POW_VARIANT,
- OPT_REPLICA_MODE) = range(13)
+ OPT_REPLICA_MODE, OPT_LAUNCHER_THREADS) = range(14)
 PLAN_CONTIGUOUS, PLAN_ROW, PLAN_GENERIC = range(3)
 MAX_NDIM = 6
 CHAIN_MAX = 8

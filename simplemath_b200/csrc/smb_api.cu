@@ -6,8 +6,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <cstdlib>
+#include <deque>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <utility>
 #include <string>
 #include <vector>
@@ -86,6 +90,7 @@ struct DeviceCtx {
     cudaEvent_t ev_done = nullptr; // async mode, several devices: end of this device's part of the last operator
     bool dirty = false;            // async mode: work enqueued on `main` since the last synchronisation
     StreamTrack track;             // of `main`
+    std::mutex launch_mu;          // decision + launch on this device's streams are one unit (one lock per device: the launcher threads run side by side)
 };
 static DeviceCtx g_ctx[kMaxDevices];
 static std::mutex g_ctx_mu;
@@ -165,6 +170,62 @@ struct DeviceScope {
     ~DeviceScope() { if (saved >= 0) cudaSetDevice(saved); }
 };
 
+// ------------------------------------------------ one launcher thread per device ----
+// The default (synchronous) mode of a device set used to walk the devices from the calling thread: set device, prepare
+// operands, launch -- about 6 us per device -- and then wait for the streams one after another.  With 8 GPUs that is
+// ~50 us of host time around kernels that take 20-40 us per device on the broadcast configs (C2 x 16: 3.7x, C4: 2.4x one GPU),
+// and it held the streams to 6.4-6.8x.  Each device of the set gets a persistent launcher thread that stays on its
+// device: the calling thread hands every range to its device's thread and waits for all of them; a launcher prepares,
+// launches AND waits for its stream, so the eight waits overlap.  Launchers spin briefly for the next operator before they
+// block, so back-to-back operators find them awake.  (Async mode keeps the single-thread walk: nothing waits there.)
+static std::atomic<int64_t> g_opt_launcher_threads{1};
+struct LaunchWorker {
+    int dev = -1;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    std::atomic<int> queued{0};
+};
+static LaunchWorker *g_workers[kMaxDevices]; // created once per device (g_set_mu), never destroyed: they outlive static destruction
+static void worker_main(LaunchWorker *w) {
+    if (cudaSetDevice(w->dev) != cudaSuccess) cudaGetLastError();
+    for (;;) {
+        std::function<void()> job;
+        for (int spin = 0; spin < 20000 && w->queued.load(std::memory_order_acquire) == 0; ++spin) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        {
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv.wait(lk, [&] { return !w->q.empty(); });
+            job = std::move(w->q.front());
+            w->q.pop_front();
+            w->queued.fetch_sub(1, std::memory_order_release);
+        }
+        job();
+    }
+}
+static LaunchWorker *worker_of(int dev) { // g_set_mu held by the caller
+    if (!g_workers[dev]) {
+        LaunchWorker *w = new LaunchWorker;
+        w->dev = dev;
+        w->th = std::thread(worker_main, w);
+        w->th.detach();
+        g_workers[dev] = w;
+    }
+    return g_workers[dev];
+}
+static void worker_post(LaunchWorker *w, std::function<void()> job) {
+    {
+        std::lock_guard<std::mutex> lk(w->mu);
+        w->q.push_back(std::move(job));
+        w->queued.fetch_add(1, std::memory_order_release);
+    }
+    w->cv.notify_one();
+}
+
 // ------------------------------------------------------- the device set -----
 // smb_set_devices: the devices an operator on MANAGED arrays is spread over (the
 // broadcast output's flat index range is split, contiguous operands are split by the same ranges,
@@ -202,6 +263,7 @@ static int set_devices_locked(const int *devs, int n) {
             }
         }
     }
+    if (n > 1) for (int i = 0; i < n; ++i) worker_of(devs[i]); // one launcher thread per device of the set
     g_devices.assign(devs, devs + n);
     g_ndevices.store(n);
     return SMB_OK;
@@ -453,7 +515,6 @@ static std::atomic<int64_t> g_opt_pdl{1};
 // prefetch) is launched plainly.  On a caller's stream the library cannot know what precedes it, so
 // launches there are plain unless the caller opts in (SMB_OPT_PDL = 2: only this library's kernels,
 // events and ordinary copies are enqueued on the streams it is handed), and then always wait first.
-static std::mutex g_launch_mu; // decision + launch are one unit per stream; launches are cheap, one lock serves all
 
 struct PdlDecision { bool attr; uint32_t flags; };
 static inline bool spans_overlap(const Span &x, const Span &y) { return x.lo < y.hi && y.lo < x.hi; }
@@ -485,7 +546,7 @@ static inline void pdl_barrier(StreamTrack &t) { t.reset(); }
 struct LaunchLock {
     std::unique_lock<std::mutex> lk;
     StreamTrack *t; // nullptr: a caller's stream
-    LaunchLock(DeviceCtx &c, cudaStream_t s) : lk(g_launch_mu), t(s == c.main ? &c.track : nullptr) {}
+    LaunchLock(DeviceCtx &c, cudaStream_t s) : lk(c.launch_mu), t(s == c.main ? &c.track : nullptr) {}
     PdlDecision decide(const Span *reads, int nr, const Span &write) {
         if (t) return pdl_decide(*t, reads, nr, write);
         // a caller's stream: the attribute only when the caller vouches for what precedes us there (SMB_OPT_PDL = 2),
@@ -1452,6 +1513,13 @@ static int run_sharded(const std::vector<int> &devs, const ShardSplit &split, Sh
         if (ops[o].need_prefetch || ops[o].need_advise) pure = false;
         if (ops[o].plan.mode != SHARD_IN_PLACE && !ops[o].duplicate) pure = false; // private copies are made by this call
     }
+    // read-mostly advice: once per shared operand, before any device prefetches it
+    for (int o = 0; o < nops; ++o) {
+        if (!ops[o].base || !ops[o].need_advise) continue;
+        if (cudaMemAdvise((const char *)ops[o].base + ops[o].hull_lo * es, (ops[o].hull_hi - ops[o].hull_lo) * es, cudaMemAdviseSetReadMostly, devs[0]) != cudaSuccess)
+            cudaGetLastError();
+        ops[o].need_advise = false;
+    }
     if (async) {
         uint64_t sig = 0;
         if (pure) { sig = 0x51ull; for (int g = 0; g <= G; ++g) sig = mix64(sig, split.bounds[g]); for (int d : devs) sig = mix64(sig, (uint64_t)d); sig |= 1; }
@@ -1459,6 +1527,54 @@ static int run_sharded(const std::vector<int> &devs, const ShardSplit &split, Sh
     }
     int rc = SMB_OK;
     int launched = 0;
+    if (!async && g_opt_launcher_threads.load(std::memory_order_relaxed) != 0) {
+        // one launcher thread per device: prepare + launch + wait for the stream there, all devices at once
+        struct Slot { int rc = SMB_OK; std::string err; const char *kernel = nullptr; };
+        std::vector<Slot> slots((size_t)G);
+        std::atomic<int> remaining{0};
+        LaunchWorker *workers[kMaxShards];
+        bool have_all = true;
+        for (int g = 0; g < G; ++g) { workers[g] = g_workers[devs[g]]; if (!workers[g]) have_all = false; }
+        if (have_all) {
+            for (int g = 0; g < G; ++g) if (split.bounds[g + 1] > split.bounds[g]) remaining.fetch_add(1, std::memory_order_relaxed);
+            for (int g = 0; g < G; ++g) {
+                const uint64_t lo = split.bounds[g], cnt = split.bounds[g + 1] - lo;
+                if (cnt == 0) continue;
+                worker_post(workers[g], [&, g, lo, cnt] {
+                    Slot &sl = slots[(size_t)g];
+                    DeviceCtx *c = nullptr;
+                    int r = ctx_of(devs[g], &c); // (the launcher already sits on its device; the context exists since smb_set_devices)
+                    const void *use[SMB_CHAIN_MAX + 2];
+                    for (int o = 0; o < nops && r == SMB_OK; ++o)
+                        r = shard_operand_on_device(ops[o], g, devs[g], es, c->main, scratch[(size_t)g * nops + o], &use[o]);
+                    if (r == SMB_OK && result.base && result.need_prefetch) {
+                        const ElemRange rr = result.plan.r[g];
+                        note_other_op();
+                        if (cudaMemPrefetchAsync((const char *)result.base + rr.lo * es, (rr.hi - rr.lo) * es, devs[g], c->main) != cudaSuccess) cudaGetLastError();
+                    }
+                    if (r == SMB_OK) r = launch(*c, g, lo, cnt, use, c->main);
+                    if (c) {
+                        const cudaError_t e = cudaStreamSynchronize(c->main);
+                        if (e != cudaSuccess && r == SMB_OK) { cudaGetLastError(); r = fail(SMB_ERR_CUDA, "device %d: %s", devs[g], cudaGetErrorString(e)); }
+                    }
+                    sl.rc = r;
+                    if (r != SMB_OK) sl.err = g_err;       // the launcher's thread-local message
+                    sl.kernel = g_last_kernel;
+                    remaining.fetch_sub(1, std::memory_order_release);
+                });
+            }
+            while (remaining.load(std::memory_order_acquire) != 0) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            for (int g = 0; g < G; ++g) {
+                if (slots[(size_t)g].kernel) g_last_kernel = slots[(size_t)g].kernel;
+                if (slots[(size_t)g].rc != SMB_OK && rc == SMB_OK) { rc = slots[(size_t)g].rc; g_err = slots[(size_t)g].err; }
+            }
+            return rc;
+        }
+    }
     for (int g = 0; g < G && rc == SMB_OK; ++g) {
         const uint64_t lo = split.bounds[g], cnt = split.bounds[g + 1] - lo;
         if (cnt == 0) continue;
@@ -1980,16 +2096,15 @@ int smb_dot(int dtype, const void *a, const void *b, uint64_t n, void *result, v
         ShardOperand ops[2], none;
         if (shard_operands(devs, split, shape1, 1, bases, strides, 2, es, ops)) {
             std::vector<Scratch> partial_scratch((size_t)G);
-            int parts = 0;
+            memset(pinned.p, 0, kSlot * (size_t)G); // a device without elements contributes zero; slot g belongs to device g (the launchers run side by side)
             // a scalar result: always synchronous (async = false), every device's stream is drained before the sum
             const int rc = run_sharded(devs, split, ops, 2, none, es, false,
                                        [&](DeviceCtx &cg, int g, uint64_t lo, uint64_t cnt, const void *const *use, cudaStream_t s) {
-                                           ++parts;
                                            return dot_enqueue_dtype(cg, dtype, (const char *)use[0] + lo * es, (const char *)use[1] + lo * es, cnt,
-                                                                    partial_scratch[(size_t)g], (char *)pinned.p + kSlot * (size_t)(parts - 1), s);
+                                                                    partial_scratch[(size_t)g], (char *)pinned.p + kSlot * (size_t)g, s);
                                        });
             if (rc) return rc;
-            dot_combine(dtype, pinned.p, parts, kSlot, result);
+            dot_combine(dtype, pinned.p, G, kSlot, result);
             return SMB_OK;
         }
     }
@@ -2178,6 +2293,7 @@ int smb_set_option(int key, int64_t value) {
         case SMB_OPT_POW_TAIL_CTAS: g_opt_pow_tail = value; return SMB_OK;
         case SMB_OPT_CHAIN_POW_VARIANT: g_opt_chain_pow_variant = value; return SMB_OK;
         case SMB_OPT_REPLICA_MODE: g_opt_replica_mode = value; return SMB_OK;
+        case SMB_OPT_LAUNCHER_THREADS: g_opt_launcher_threads = value ? 1 : 0; return SMB_OK;
     }
     return fail(SMB_ERR_INVALID, "unknown option %d", key);
 }
@@ -2196,6 +2312,7 @@ int64_t smb_get_option(int key) {
         case SMB_OPT_POW_TAIL_CTAS: return g_opt_pow_tail;
         case SMB_OPT_CHAIN_POW_VARIANT: return g_opt_chain_pow_variant;
         case SMB_OPT_REPLICA_MODE: return g_opt_replica_mode;
+        case SMB_OPT_LAUNCHER_THREADS: return g_opt_launcher_threads;
     }
     return -1;
 }
