@@ -638,6 +638,7 @@ static int launch_stream(DeviceCtx &c, const T *a, const T *b, T *out, uint64_t 
         if (head) { // peel up to the first common vector boundary (views give interior pointers)
             k_stream_unaligned<T, Fn, HAS_B><<<1, kThreads, 0, s>>>(a, b, out, head, first, fn);
             ++g_launches;
+            note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
         }
         const uint64_t rest = n - head;
         if (rest) {
@@ -678,6 +679,7 @@ static int launch_stream(DeviceCtx &c, const T *a, const T *b, T *out, uint64_t 
         const unsigned grid = grid_for(n, kThreads, c.sm_count, 32);
         k_stream_unaligned<T, Fn, HAS_B><<<grid, kThreads, 0, s>>>(a, b, out, n, first, fn);
         ++g_launches;
+        note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
         g_last_kernel = "k_stream_unaligned";
     }
     SMB_CK(cudaGetLastError());
@@ -873,6 +875,7 @@ static int launch_bcast(DeviceCtx &c, const ElementwisePlan &p, const T *a, cons
                 else k_outer<T, Fn, TI, TJ, false><<<grid, kThreads, 0, s>>>(pa, pb, out, op, fn);
                 g_last_kernel = "k_outer<4x4>";
                 ++g_launches;
+                note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
                 SMB_CK(cudaGetLastError());
                 return SMB_OK;
             }
@@ -921,6 +924,7 @@ static int launch_bcast(DeviceCtx &c, const ElementwisePlan &p, const T *a, cons
             else k_tile<T, Fn, false, true, TR, TC><<<grid, kThreads, 0, s>>>(a, b, out, tp, fn);
             g_last_kernel = "k_tile<transpose>";
             ++g_launches;
+            note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
             SMB_CK(cudaGetLastError());
             return SMB_OK;
         }
@@ -948,6 +952,7 @@ static int launch_bcast(DeviceCtx &c, const ElementwisePlan &p, const T *a, cons
             else k_sgather<T, Fn, false><<<grid, kThreads, 0, s>>>(a, b, out, t, pha, phb, wide32, fn);
             g_last_kernel = wide ? "k_sgather<wide>" : "k_sgather";
             ++g_launches;
+            note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
             SMB_CK(cudaGetLastError());
             return SMB_OK;
         }
@@ -1002,6 +1007,7 @@ static int launch_bcast(DeviceCtx &c, const ElementwisePlan &p, const T *a, cons
         }
     }
     ++g_launches;
+    note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
     SMB_CK(cudaGetLastError());
     return SMB_OK;
 }
@@ -1051,6 +1057,7 @@ static int user_contiguous(DeviceCtx &c, int op, int dtype, const void *a, const
     if (!user_op_lookup(op, dtype, &u)) return fail(SMB_ERR_INVALID, "op %d is not registered for dtype %d", op, dtype);
     const smb_launch_env env{s, c.sm_count, c.device};
     ++g_launches;
+    note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
     g_last_kernel = "user<k_stream>";
     return user_rc(u.contiguous(&env, a, b, out, n), "contiguous");
 }
@@ -1059,6 +1066,7 @@ static int user_scalar(DeviceCtx &c, int op, int dtype, const void *a, const voi
     if (!user_op_lookup(op, dtype, &u)) return fail(SMB_ERR_INVALID, "op %d is not registered for dtype %d", op, dtype);
     const smb_launch_env env{s, c.sm_count, c.device};
     ++g_launches;
+    note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
     g_last_kernel = "user<k_stream,scalar>";
     return user_rc(u.scalar(&env, a, scalar, out, n), "scalar");
 }
@@ -1080,6 +1088,7 @@ static int user_strided(DeviceCtx &c, int op, int dtype, const ElementwisePlan &
     }
     const smb_launch_env env{s, c.sm_count, c.device};
     ++g_launches;
+    note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
     g_last_kernel = p.kind == PLAN_GENERIC ? "user<k_generic>" : "user<k_row>";
     return user_rc(u.strided(&env, a, b, out, &t, (int)sizeof t, p.kind == PLAN_GENERIC, wide, vb, operand_reused(p, p.sa), operand_reused(p, p.sb)), "strided");
 }
@@ -1721,6 +1730,7 @@ static int dot_enqueue(DeviceCtx &c, const T *a, const T *b, uint64_t n, Scratch
     if (vec) k_dot<T, UNROLL, EPVV><<<grid, kThreads, 0, s>>>(a, b, n, head, partials, ticket, res);
     else k_dot<T, UNROLL, 1><<<grid, kThreads, 0, s>>>(a, b, n, 0, partials, ticket, res);
     ++g_launches;
+    note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
     g_last_kernel = vec ? "k_dot" : "k_dot<unaligned>";
     SMB_CK(cudaGetLastError());
     note_other_op();
@@ -1878,6 +1888,7 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
 #undef SMB_CHAIN_LAUNCH_PF
 #undef SMB_CHAIN_LAUNCH
     ++g_launches;
+    note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
     SMB_CK(cudaGetLastError());
     return SMB_OK;
 }
@@ -2188,6 +2199,7 @@ static int fill_device(DeviceCtx &c, int dtype, void *out, const void *value, ui
     if (dtype == SMB_F64) k_fill<double><<<grid, kThreads, 0, s>>>((double *)out, n, *(const double *)value);
     else k_fill<uint32_t><<<grid, kThreads, 0, s>>>((uint32_t *)out, n, *(const uint32_t *)value);
     ++g_launches;
+    note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
     SMB_CK(cudaGetLastError());
     return SMB_OK;
 }
@@ -2411,6 +2423,7 @@ int smb_pow_audit_f32(const void *x, float y, const void *got, uint64_t n, float
     k_pow_audit_f32<<<grid, kThreads, 0, s>>>((const float *)x, (const float *)got, n, classify_exp(y), bound_ulp,
                                              (unsigned long long *)acc.p, (unsigned int *)((char *)acc.p + 8));
     ++g_launches;
+    note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
     SMB_CK(cudaGetLastError());
     unsigned long long host[2] = {0, 0};
     note_other_op();
@@ -2432,6 +2445,7 @@ int smb_fill_uniform_f32(void *out, uint64_t first, uint64_t n, uint64_t seed, f
         const unsigned grid = grid_for(cnt, kThreads * 4, cg.sm_count, 16);
         k_fill_uniform_f32<<<grid, kThreads, 0, s>>>(dst, first + at, cnt, seed, lo, hi);
         ++g_launches;
+        note_other_op(); // a plain launch: the next stream kernel after it is launched plainly too
         SMB_CK(cudaGetLastError());
         return (int)SMB_OK;
     };
