@@ -163,7 +163,7 @@ __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t 
 // before its first global access (kPdlWaitFirst: the host saw a data hazard, or the stream is not
 // the library's own) or just before it exits (no hazard: the two grids overlap, and this grid's
 // completion still implies the previous one's).  Both instructions are no-ops in a launch without
-// the programmatic-stream-serialisation attribute.  The host side is in smb_api.cu (pdl_decide).
+// the programmatic-stream-serialisation attribute.  The host side is in smb_runtime.inl (pdl_decide).
 constexpr uint32_t kPdlWaitFirst = 1u;
 constexpr int kPdlFlagBits = 8; // the launch word's upper 24 bits carry a kernel-specific count (k_stream: single-tile CTAs)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -218,7 +218,7 @@ static __device__ const PowTabExp d_pow_exp_tab[SMB_POW_EXP_ENTRIES] = SMB_POW_E
 // The replicated shared-memory layout of the two f32 pow tables, kept ready-made in global memory
 // ([0] small-y, [1] large-y; 24 KB each, L2 resident) so that a CTA stages them with ONE bulk copy
 // instead of ~60 instructions per thread -- which is what lets the pow grid be many waves deep
-// (a few tiles per CTA).  Built once per device by k_pow_image_init (smb_api.cu: current_ctx).
+// (a few tiles per CTA).  Built once per device by k_pow_image_init (smb_runtime.inl: init_ctx).
 static __device__ __align__(128) SmbPowTabs g_pow_image[2];
 __global__ void k_pow_image_init() {
     const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;

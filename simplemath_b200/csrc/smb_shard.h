@@ -6,7 +6,7 @@
 // the output is split by the ranges its device touches, and an operand several devices need (a
 // broadcast row, a small outer-product factor) is replicated.  This header only does the
 // arithmetic -- where to cut, which elements of an operand a flat range touches -- so it is testable
-// without a GPU (smb_plan_shards); the launcher that acts on it is in smb_api.cu.
+// without a GPU (smb_plan_shards); the launcher that acts on it is in smb_devices.inl.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>

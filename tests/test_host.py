@@ -43,7 +43,7 @@ def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "simplemath_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inl", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "liboracle" not in txt and "libsmref" not in txt, f
     for dirpath, _, files in os.walk(os.path.join(ROOT, "include")):
