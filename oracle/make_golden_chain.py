@@ -7,7 +7,7 @@ tests/test_chain.py checks the fused smb_chain result against these outputs bit 
 reference's float sm::pow does not link, SURVEY.md F7).
 
 Run here (the container that has /root/reference):
-    make -C oracle ref && python oracle/make_golden_chain.py
+    make -C oracle ref && python oracle/make_golden_chain.py [v1|v2|all]
 """
 from __future__ import annotations
 
@@ -19,7 +19,9 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle  # noqa: E402
 
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "golden_chain_v1.npz")
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+OUT = os.path.join(GOLDEN, "golden_chain_v1.npz")
+OUT_V2 = os.path.join(GOLDEN, "golden_chain_v2.npz")
 
 
 def main():
@@ -98,5 +100,52 @@ def main():
     print(f"wrote {OUT}: {idx} chains, {os.path.getsize(OUT)} bytes")
 
 
+def main_v2():
+    """golden_chain_v2.npz: int32 sm::pow applied to an intermediate SMALLER than the chain's output
+    (a later leaf broadcasts it up).  The reference's lane / scalar-tail split (include/math/
+    calculate.h:172-215 through include/UserFunctions.h:42-48) follows the flat index inside the
+    temporary sm::pow materialises -- N elements -- not the M*N-element result; a fused kernel that
+    derives the split from its output index gets the tail elements of every row wrong."""
+    ref = oracle.reference()
+    if ref is None:
+        raise SystemExit("oracle/_ref/libsmref.so missing: run `make -C oracle ref` where /root/reference exists")
+    rng = np.random.default_rng(20261101)
+    cases, idx = {}, 0
+
+    def emit(first, steps):
+        nonlocal idx
+        p = f"k{idx:03d}_"
+        acc = first
+        for s, (op, leaf) in enumerate(steps):
+            if isinstance(leaf, np.ndarray):
+                acc = ref.smarray_binary(op, acc, leaf)[0]
+                cases[p + f"leaf{s}"] = leaf
+            else:
+                acc = ref.smarray_scalar(op, acc, leaf)
+                cases[p + f"leaf{s}"] = np.array(leaf, np.int32)
+        cases[p + "first"] = first
+        cases[p + "ops"] = np.array([op for op, _ in steps])
+        cases[p + "out"] = acc
+        idx += 1
+
+    def small(shape, lo=-6, hi=7):
+        return rng.integers(lo, hi, size=shape).astype(np.int32)
+
+    for m, n in ((3, 5), (4, 8), (3, 13), (2, 21), (3, 203)):
+        for e in (3, 13, 31, 40, -1, -2, 0):
+            emit(small((1, n)), [("pow", e), ("add", small((m, n), -1000, 1000))])            # pow(row, e) + B
+            emit(small((1, n)), [("add", 1), ("pow", e), ("mul", small((m, 1), -9, 10))])      # pow(row + 1, e) * col
+            emit(small((n,)), [("pow", e), ("sub", small((m, n), -1000, 1000))])               # 1-D first leaf
+        # the temporary is already M x N: lanes run over the flat M*N index, across row boundaries
+        emit(small((m, 1)), [("mul", small((1, n))), ("pow", 3), ("add", small((n,)))])
+        emit(small((m, 1)), [("add", small((1, n))), ("pow", -2), ("mul", 7)])
+    np.savez_compressed(OUT_V2, **cases)
+    print(f"wrote {OUT_V2}: {idx} chains, {os.path.getsize(OUT_V2)} bytes")
+
+
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "v1"):
+        main()
+    if which in ("all", "v2"):
+        main_v2()

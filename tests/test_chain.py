@@ -96,13 +96,14 @@ def test_chain_planner_coalescing_keeps_every_offset():
     assert vec and sh == [512, 512, 1024] and st == [[1024, 0, 1], [0, 1024, 1]]
 
 
-def load_golden_chains():
+def load_golden_chains(name="golden_chain_v1.npz"):
     """tests/golden/golden_chain_v1.npz: chains evaluated operator by operator on the UNMODIFIED
     reference (oracle/make_golden_chain.py).  Yields (first, steps, out); a "fix" entry replaces the
     accumulator before a `leaf / acc` step (the generator made it a safe divisor), so such a chain
-    is checked in two pieces."""
+    is checked in two pieces.  golden_chain_v2.npz (same layout, same generator): int32 sm::pow on an
+    intermediate that a LATER leaf broadcasts up."""
     import os
-    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_chain_v1.npz"))
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
     i = 0
     while f"k{i:03d}_first" in z:
         p = f"k{i:03d}_"
@@ -127,6 +128,17 @@ def test_golden_chain_fixtures_agree_with_the_oracle(orc):
     assert n == 38
 
 
+def test_golden_int32_pow_on_broadcast_intermediates_agrees_with_the_oracle(orc):
+    """golden_chain_v2: the reference's lane / scalar-tail split of int32 sm::pow follows the flat index
+    of the N-element temporary it is applied to, not of the M*N-element chain result."""
+    n = 0
+    for i, first, steps, out in load_golden_chains("golden_chain_v2.npz"):
+        want, _ = oracle_chain(orc, first, steps)
+        assert_same_bits(np.asarray(want).reshape(out.shape), out, f"golden chain v2 {i}")
+        n += 1
+    assert n == 115
+
+
 # ------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 def test_chain_matches_reference_golden_fixtures():
@@ -136,6 +148,17 @@ def test_chain_matches_reference_golden_fixtures():
         assert_same_bits(smb.chain(first, *steps).reshape(out.shape), out, f"golden chain {i}: {[s[0] for s in steps]}")
         n += 1
     assert n == 38
+
+
+@pytest.mark.gpu
+def test_chain_int32_pow_on_broadcast_intermediates_matches_reference_golden():
+    """golden_chain_v2 through the fused smb_chain: `pow(row, e) + B`, `pow(row + 1, e) * col`, ... must
+    split lanes / tail by the intermediate's own flat index (the round-1 kernel used the output's)."""
+    n = 0
+    for i, first, steps, out in load_golden_chains("golden_chain_v2.npz"):
+        assert_same_bits(smb.chain(first, *steps).reshape(out.shape), out, f"golden chain v2 {i}: {[s[0] for s in steps]}")
+        n += 1
+    assert n == 115
 
 
 pytestmark_gpu = pytest.mark.gpu
