@@ -333,8 +333,10 @@ int smb_array_scalar(int op, int dtype, const void *a, const void *scalar, uint6
     const uint64_t lane_end = scalar_lane_end(dtype, n);
     const MemType ta = mem_type(a), to = mem_type(out);
     const size_t es = esize(dtype);
-    if (on_host(ta) || on_host(to))
-        return scalar_staged(*c, op, dtype, a, ta, scalar, out, to, n, lane_end, stream ? (cudaStream_t)stream : (c->dirty ? c->main : nullptr));
+    if (on_host(ta) || on_host(to)) { // always synchronous; pending asynchronous work may be producing `a`
+        if (!stream && g_pending.load(std::memory_order_acquire)) if (int rc = sync_all()) return rc;
+        return scalar_staged(*c, op, dtype, a, ta, scalar, out, to, n, lane_end, (cudaStream_t)stream);
+    }
     std::vector<int> devs;
     if (ta == MT_MANAGED && to == MT_MANAGED && want_sharding(devs, n * es, stream, true)) {
         const int G = (int)devs.size();

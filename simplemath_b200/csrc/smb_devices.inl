@@ -123,6 +123,9 @@ template<typename Launch>
 static int run_sharded(const std::vector<int> &devs, const ShardSplit &split, ShardOperand *ops, int nops,
                        const ShardOperand &result, size_t es, bool async, Launch &&launch) {
     const int G = (int)devs.size();
+    // A synchronous operator (the dot product always is) while asynchronous work is pending: that work may be producing
+    // an operand on ANOTHER device's stream (a small array computed on one device, a different partition) -- land it first.
+    if (!async && g_pending.load(std::memory_order_acquire)) if (int rc = sync_all()) return rc;
     std::vector<Scratch> scratch((size_t)G * (size_t)std::max(nops, 1));
     DeviceScope scope;
     // "Pure": every operand and the result already sit in exactly this partition (their records matched, nothing is
@@ -275,11 +278,14 @@ static int elementwise_entry(int op, int dtype, const void *a, const uint64_t *s
     const size_t es = esize(dtype);
     if (on_host(ta) || on_host(tb) || on_host(to)) {
         // Host operands: always synchronous (the result is in host memory on return); the copies are
-        // ordered after what is already enqueued on `stream` (or on the private stream in async mode).
-        cudaStream_t after = stream ? (cudaStream_t)stream : (c->dirty ? c->main : nullptr);
+        // ordered after what is already enqueued on `stream`; with stream == NULL, pending asynchronous work
+        // (on any device of the set) is waited for first -- it may be producing one of the operands.
+        cudaStream_t after = (cudaStream_t)stream;
+        if (!stream && g_pending.load(std::memory_order_acquire)) if (int rc = sync_all()) return rc;
         if (lin_begin != 0 || lin_count != p.n) {
             // partial range with host operands: stage the touched operands whole
             const int dev = c->device;
+            std::lock_guard<std::mutex> stage(c->stage_mu);
             Scratch da, db, dout;
             DrainGuard drain;
             drain.add(c->slot[0]);

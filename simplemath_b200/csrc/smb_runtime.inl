@@ -65,8 +65,9 @@ struct DeviceCtx {
     cudaEvent_t ev = nullptr;
     cudaEvent_t ev_user = nullptr; // orders the library's private streams after the caller's stream
     cudaEvent_t ev_done = nullptr; // async mode, several devices: end of this device's part of the last operator
-    bool dirty = false;            // async mode: work enqueued on `main` since the last synchronisation
+    std::atomic<bool> dirty{false}; // async mode: work enqueued on `main` since the last synchronisation
     StreamTrack track;             // of `main`
+    std::mutex stage_mu;           // one staged (host-operand) call at a time per device: they share the slot streams and the two ordering events
     std::mutex launch_mu;          // decision + launch on this device's streams are one unit (one lock per device: the launcher threads run side by side)
 };
 static DeviceCtx g_ctx[kMaxDevices];

@@ -115,6 +115,7 @@ static int elementwise_staged(DeviceCtx &c, int op, int dtype, const Elementwise
     const int nslots = (int)std::min<uint64_t>(kSlots, nchunks);
 
     // invariant operands: upload once on slot 0, everyone else waits on the event
+    std::lock_guard<std::mutex> stage(c.stage_mu);
     Scratch inv_a, inv_b;
     Scratch sa_[kSlots], sb_[kSlots], so_[kSlots];
     DrainGuard drain; // after the scratch blocks: drained before they are released, on every way out
@@ -174,9 +175,10 @@ static int elementwise_staged(DeviceCtx &c, int op, int dtype, const Elementwise
         }
         char *po = on_host(to) ? (char *)so_[sl].p : (char *)out + r0 * inner * es;
         if (int rc = elementwise_device(c, op, dtype, sub, pa, pb, po, 0, sub.n, r0 * inner, lane_end, s)) return rc;
-        if (on_host(to))
+        if (on_host(to)) {
             note_other_op();
             SMB_CK(cudaMemcpyAsync((char *)out + r0 * inner * es, po, sub.n * es, cudaMemcpyDeviceToHost, s));
+        }
     }
     for (int i = 0; i < kSlots; ++i) SMB_CK(cudaStreamSynchronize(c.slot[i]));
     return SMB_OK;
@@ -190,6 +192,7 @@ static int scalar_staged(DeviceCtx &c, int op, int dtype, const void *a, MemType
     const uint64_t chunk = std::min<uint64_t>(n, std::max<uint64_t>(1, chunk_bytes / es));
     const uint64_t nchunks = (n + chunk - 1) / chunk;
     const int nslots = (int)std::min<uint64_t>(kSlots, nchunks);
+    std::lock_guard<std::mutex> stage(c.stage_mu);
     Scratch sa_[kSlots], so_[kSlots];
     DrainGuard drain;
     for (int i = 0; i < kSlots; ++i) drain.add(c.slot[i]);

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 #include <random>
+#include <thread>
 #include "sm.h"
 
 namespace {
@@ -390,4 +391,67 @@ TEST(DropIn, DeviceSetSpreadsOperatorsAndKeepsTheBits) {
     sm::SMArray<int> x = {1, 2, 3};             // small arrays are untouched by all this
     auto y = x + x;
     EXPECT_EQ(y(2), 6);
+}
+
+// "Concurrent ops on distinct arrays are safe" (the reference has no global state on the path, SURVEY.md §8b Threading):
+// here the contexts, the pool, the launch bookkeeping and the async hand-off are shared -- several host threads run
+// operator sequences on their own arrays at once, synchronously, inside an async scope, and over a device set.
+static int concurrent_sequence(int seed, int rounds) {
+    int bad = 0;
+    const size_t R = 257, C = 1031;   // ragged on purpose
+    auto a = sm::empty<float>(R, C), b = sm::empty<float>(R, C), row = sm::empty<float>(1, C);
+    auto ia = sm::empty<int>(R * C);
+    for (size_t i = 0; i < R * C; ++i) { a.data[i] = float((i * 7 + seed) % 1013) * 0.5f - 100.0f; b.data[i] = 1.0f + float((i + seed) % 17); ia.data[i] = int(i % 2001) - 1000 + seed; }
+    for (size_t j = 0; j < C; ++j) row.data[j] = float(j % 29) - float(seed);
+    for (int r = 0; r < rounds; ++r) {
+        auto s = a + b;
+        auto m = s * row;
+        auto q = m / b;
+        auto p = sm::pow(b, 2.0f);
+        sm::SMArray<float> f = (sm::lazy(a) - row) * b;
+        auto i2 = ia * ia;
+        const int d = ia % ia;
+        uint32_t want_d = 0;
+        for (size_t i = 0; i < R * C; ++i) want_d += uint32_t(ia.data[i]) * uint32_t(ia.data[i]);
+        if (d != int(want_d)) ++bad;
+        for (size_t i = size_t(r) % 7; i < R * C; i += 7) {
+            const float sv = a.data[i] + b.data[i], mv = sv * row.data[i % C];
+            if (s.data[i] != sv || m.data[i] != mv || q.data[i] != mv / b.data[i] || p.data[i] != b.data[i] * b.data[i] ||
+                f.data[i] != (a.data[i] - row.data[i % C]) * b.data[i] || i2.data[i] != int(uint32_t(ia.data[i]) * uint32_t(ia.data[i])))
+                ++bad;
+        }
+    }
+    return bad;
+}
+static int run_concurrently(int nthreads, int rounds) {
+    std::vector<std::thread> th;
+    std::vector<int> bad((size_t) nthreads, -1);
+    for (int t = 0; t < nthreads; ++t) th.emplace_back([&bad, t, rounds] {
+        try { bad[(size_t) t] = concurrent_sequence(t + 1, rounds); } catch (const std::exception &) { bad[(size_t) t] = -2; }
+    });
+    for (auto &t : th) t.join();
+    int total = 0;
+    for (int v : bad) total += v == 0 ? 0 : 1;
+    return total;
+}
+TEST(DropIn, ConcurrentHostThreadsOnDistinctArrays) {
+    EXPECT_EQ(run_concurrently(4, 6), 0);                       // the reference's contract: complete on return
+    {
+        sm::async_scope scope;                                   // hand-off mode: one private stream, recycled temporaries
+        EXPECT_EQ(run_concurrently(4, 6), 0);
+    }
+    const int ndev = smb_device_count();
+    std::vector<int> set;
+    if (ndev >= 2) for (int d = 0; d < ndev; ++d) set.push_back(d);
+    else set = {0, 0, 0};
+    const int64_t old_min = smb_get_option(SMB_OPT_SHARD_MIN_BYTES);
+    smb_set_option(SMB_OPT_SHARD_MIN_BYTES, 1 << 18);            // the 1 MiB arrays above are spread over the set
+    sm::set_devices(set);
+    EXPECT_EQ(run_concurrently(3, 4), 0);
+    {
+        sm::async_scope scope;
+        EXPECT_EQ(run_concurrently(3, 4), 0);
+    }
+    sm::set_devices({});
+    smb_set_option(SMB_OPT_SHARD_MIN_BYTES, old_min);
 }

@@ -364,6 +364,69 @@ def test_staged_call_is_ordered_after_the_callers_stream(orc):
     assert_same_bits(pin_out.numpy(), (src.cpu().numpy() * np.float32(2.0)), "staged call after async producer")
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.int32])
+def test_operands_of_mixed_memory_kinds(orc, dtype):
+    """One call may mix host, device and managed operands (element_wise_op takes raw pointers): host inputs are
+    staged slab by slab, a device / managed result is written in place (no copy back), a host result is copied
+    back -- whole results and flat sub-ranges, several slabs per call."""
+    import torch
+    tdt = {np.float32: torch.float32, np.int32: torch.int32}[dtype]
+    rng = np.random.default_rng(97)
+    rows, cols = 96, 1024
+    a = (rng.standard_normal((rows, cols)) * 50).astype(dtype)
+    b = (rng.standard_normal((1, cols)) * 50).astype(dtype)           # invariant along the slabs: uploaded once
+    c = (rng.standard_normal((rows, cols)) * 50).astype(dtype)
+    dt = smb.dtype_code(np.dtype(dtype))
+    shape = [rows, cols]
+    smb.set_option(smb.OPT_STAGE_CHUNK_BYTES, 1 << 16)                       # 16 rows per slab: 6 slabs over 3 slots
+    try:
+        for name, y, sy in (("row", b, [0, 1]), ("dense", c, [cols, 1])):
+            want = orc.binary("sub", a, y)
+            dy = torch.from_numpy(y).cuda()
+            da = torch.from_numpy(a).cuda()
+            my = Managed(y)
+            # host a, host y -> DEVICE result
+            out = torch.zeros(rows * cols, dtype=tdt, device="cuda")
+            torch.cuda.synchronize()
+            smb.elementwise_ptr(smb.OP_SUB, dt, a.ctypes.data, [cols, 1], y.ctypes.data, sy, shape, out.data_ptr())
+            assert_same_bits(out.cpu().numpy().reshape(rows, cols), want, f"host,host({name}) -> device")
+            # host a, DEVICE y -> host result
+            got = np.zeros((rows, cols), dtype)
+            smb.elementwise_ptr(smb.OP_SUB, dt, a.ctypes.data, [cols, 1], dy.data_ptr(), sy, shape, got.ctypes.data)
+            assert_same_bits(got, want, f"host,device({name}) -> host")
+            # DEVICE a, MANAGED y -> host result
+            got = np.zeros((rows, cols), dtype)
+            smb.elementwise_ptr(smb.OP_SUB, dt, da.data_ptr(), [cols, 1], my.ptr, sy, shape, got.ctypes.data)
+            assert_same_bits(got, want, f"device,managed({name}) -> host")
+            # host a, managed y -> MANAGED result
+            mo = Managed(shape=(rows, cols), dtype=dtype)
+            smb.elementwise_ptr(smb.OP_SUB, dt, a.ctypes.data, [cols, 1], my.ptr, sy, shape, mo.ptr)
+            smb.sync()
+            assert_same_bits(mo.np.copy(), want, f"host,managed({name}) -> managed")
+            # a flat sub-range with host inputs and a device result, and with a host result
+            lo, cnt = 5 * cols + 17, 40 * cols + 3
+            part = torch.zeros(cnt, dtype=tdt, device="cuda")
+            torch.cuda.synchronize()
+            smb.elementwise_range_ptr(smb.OP_SUB, dt, a.ctypes.data, [cols, 1], y.ctypes.data, sy, shape, lo, cnt, part.data_ptr())
+            assert_same_bits(part.cpu().numpy(), want.ravel()[lo:lo + cnt], f"range host,host({name}) -> device")
+            hpart = np.zeros(cnt, dtype)
+            smb.elementwise_range_ptr(smb.OP_SUB, dt, da.data_ptr(), [cols, 1], y.ctypes.data, sy, shape, lo, cnt, hpart.ctypes.data)
+            assert_same_bits(hpart, want.ravel()[lo:lo + cnt], f"range device,host({name}) -> host")
+            my.free(); mo.free()
+        # array (op) scalar: host in -> device out, device in -> host out
+        flat = a.ravel()
+        want = orc.array_scalar("mul", flat, 3)
+        out = torch.zeros(flat.size, dtype=tdt, device="cuda")
+        torch.cuda.synchronize()
+        smb.array_scalar_ptr(smb.OP_MUL, dt, flat.ctypes.data, 3, flat.size, out.data_ptr())
+        assert_same_bits(out.cpu().numpy(), want, "scalar host -> device")
+        got = np.zeros(flat.size, dtype)
+        smb.array_scalar_ptr(smb.OP_MUL, dt, torch.from_numpy(flat).cuda().data_ptr(), 3, flat.size, got.ctypes.data)
+        assert_same_bits(got, want, "scalar device -> host")
+    finally:
+        smb.set_option(smb.OPT_STAGE_CHUNK_BYTES, 64 << 20)
+
+
 # -------------------------------------------------------------- exhaustive device-side audit ----
 def test_pow_audit_agrees_with_the_oracle_and_catches_errors(orc):
     import torch
@@ -470,3 +533,51 @@ def test_device_set_in_async_mode_keeps_order_across_devices(orc, sharded):
         assert_same_bits(me.np.copy(), e1, f"e on {devs}")
         assert_same_bits(mc.np.copy(), c2, f"c on {devs}")
         assert_same_bits(md.np.copy(), d2, f"d on {devs}")
+
+
+def test_synchronous_calls_land_pending_async_work_of_other_devices_first(orc):
+    """In async mode an operand may still be in flight on ANOTHER device's stream when a synchronous call needs it:
+    a small array computed on one device feeding a dot product that is spread over the set (2n bytes count there), and a
+    host-operand call (always synchronous) reading a result the whole set is still producing."""
+    rng = np.random.default_rng(103)
+    lib = smb.lib()
+    n = 1 << 20
+    a = rng.integers(-2**31, 2**31, size=n, dtype=np.int64).astype(np.int32)
+    b = rng.integers(-2**31, 2**31, size=n, dtype=np.int64).astype(np.int32)
+    h = rng.integers(-1000, 1000, size=n).astype(np.int32)
+    old = lib.smb_get_option(smb.OPT_SHARD_MIN_BYTES)
+    try:
+        for devs in _device_sets():
+            smb.set_devices(devs)
+            ma, mb = Managed(a), Managed(b)
+            mc, md = Managed(shape=(n,), dtype=np.int32), Managed(shape=(n,), dtype=np.int32)
+            smb.set_option(smb.OPT_ASYNC, 1)
+            try:
+                for it in range(3):
+                    # 4 MiB results stay on one device, the 8 MiB dot product is spread over the set
+                    smb.set_option(smb.OPT_SHARD_MIN_BYTES, 6 << 20)
+                    smb.contiguous_ptr(smb.OP_MUL, smb.I32, ma.ptr, mb.ptr, mc.ptr, n)
+                    for _ in range(6):
+                        smb.array_scalar_ptr(smb.OP_ADD, smb.I32, mc.ptr, 1 + it, n, mc.ptr)
+                    got = smb.dot_ptr(smb.I32, mc.ptr, mb.ptr, n)
+                    c = (a * b + np.int32(6 * (1 + it))).astype(np.int32)
+                    want = int(np.sum(c.astype(np.int64) * b.astype(np.int64)) & 0xffffffff)
+                    assert (got & 0xffffffff) == want, (devs, it)
+                    # every device produces d; a host-operand call reads it right away
+                    smb.set_option(smb.OPT_SHARD_MIN_BYTES, 0)
+                    smb.contiguous_ptr(smb.OP_SUB, smb.I32, mc.ptr, ma.ptr, md.ptr, n)
+                    out = np.zeros(n, np.int32)
+                    smb.contiguous_ptr(smb.OP_ADD, smb.I32, h.ctypes.data, md.ptr, out.ctypes.data, n)
+                    assert_same_bits(out, (h + (c - a)).astype(np.int32), f"host + pending sharded result on {devs}")
+                    hs = np.zeros(n, np.int32)
+                    smb.contiguous_ptr(smb.OP_MUL, smb.I32, md.ptr, md.ptr, mc.ptr, n)      # pending again
+                    smb.array_scalar_ptr(smb.OP_SUB, smb.I32, mc.ptr, 7, n, hs.ctypes.data)  # managed in, host out
+                    d = (c - a).astype(np.int32)
+                    assert_same_bits(hs, (d * d - np.int32(7)).astype(np.int32), f"scalar to host on {devs}")
+            finally:
+                smb.set_option(smb.OPT_ASYNC, 0)
+            for m in (ma, mb, mc, md):
+                m.free()
+    finally:
+        smb.set_devices([])
+        smb.set_option(smb.OPT_SHARD_MIN_BYTES, old)
