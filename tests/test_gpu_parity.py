@@ -730,3 +730,71 @@ def test_dot_device_pointers_and_sharded_sum(orc):
         lo, hi = smb.shard_range(n, r, 4, align=4)
         parts += smb.dot_ptr(smb.F32, x.data_ptr() + 4 * lo, y.data_ptr() + 4 * lo, hi - lo)
     assert abs(parts - ref) <= 1e-6 * n ** 0.5 + 1e-3 * abs(ref)
+
+
+# ---- randomized views of device-resident parents: the kernels see the real base alignment and strides ----
+def _random_view(rng, dtype, want_shape, op_is_divisor):
+    """A numpy view with shape `want_shape` (1 = broadcast dim) cut out of a larger parent: random start, step and
+    axis order per dim, optional leading-dim drop.  Returns (parent, view)."""
+    nd = len(want_shape)
+    perm = rng.permutation(nd) if rng.random() < 0.35 else np.arange(nd)      # memory order of the parent's axes
+    steps = [int(rng.choice([1, 1, 1, 1, 2, 3])) for _ in range(nd)]
+    starts = [int(rng.integers(0, 4)) for _ in range(nd)]
+    pshape = [starts[k] + (want_shape[k] - 1) * steps[k] + 1 + int(rng.integers(0, 3)) for k in range(nd)]
+    mem_shape = [pshape[perm[k]] for k in range(nd)]
+    n = int(np.prod(mem_shape))
+    if dtype == np.int32:
+        flat = rng.integers(1, 60, size=n).astype(np.int32) * rng.choice(np.array([-1, 1], np.int32), size=n) if op_is_divisor \
+            else rng.integers(-2**31, 2**31, size=n, dtype=np.int64).astype(np.int32)
+    else:
+        flat = (rng.uniform(0.5, 3, size=n) * rng.choice([-1, 1], size=n)).astype(dtype) if op_is_divisor \
+            else (rng.standard_normal(n) * 100).astype(dtype)
+    parent = flat.reshape(mem_shape)
+    logical = parent.transpose(np.argsort(perm))                                # axes back in logical order
+    view = logical[tuple(slice(starts[k], starts[k] + (want_shape[k] - 1) * steps[k] + 1, steps[k]) for k in range(nd))]
+    assert view.shape == tuple(want_shape)
+    return parent, view
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32])
+def test_fuzz_random_views_of_device_arrays_vs_oracle(orc, dtype):
+    """~250 random (shape, broadcast pattern, slicing step, axis order, interior offset) pairs per dtype on DEVICE-resident
+    parents, every operator, bit for bit against the oracle -- whichever kernel the planner picks."""
+    torch = _torch()
+    rng = np.random.default_rng(20261102 + np.dtype(dtype).itemsize + (7 if dtype == np.int32 else 0))
+    dims = [1, 2, 3, 4, 5, 8, 12, 16, 24, 33, 64, 100]
+    dt = smb.dtype_code(np.dtype(dtype))
+    kernels = {}
+    for case in range(250):
+        nd = int(rng.integers(1, 6))
+        shape = [int(rng.choice(dims)) for _ in range(nd)]
+        while int(np.prod(shape)) > 400_000:
+            shape[int(rng.integers(0, nd))] = 2
+        op = ["add", "sub", "mul", "div"][case % 4]
+        views = []
+        for o in range(2):
+            want = [1 if rng.random() < 0.25 else d for d in shape]
+            drop = int(rng.integers(0, nd)) if rng.random() < 0.2 else 0      # missing leading dims (rank padding)
+            want = want[drop:]
+            views.append(_random_view(rng, dtype, want, op == "div" and o == 1))
+        (pa, va), (pb, vb) = views
+        want = orc.binary(op, va, vb)
+        dpa, dpb = torch.from_numpy(pa.copy()).cuda(), torch.from_numpy(pb.copy()).cuda()
+        es = np.dtype(dtype).itemsize
+        a_ptr = dpa.data_ptr() + (va.__array_interface__["data"][0] - pa.__array_interface__["data"][0])
+        b_ptr = dpb.data_ptr() + (vb.__array_interface__["data"][0] - pb.__array_interface__["data"][0])
+        rshape, sa, sb, total = smb.broadcast(va.shape, [s // es for s in va.strides], vb.shape, [s // es for s in vb.strides])
+        assert tuple(rshape) == want.shape
+        pad = int(rng.integers(0, 4))                                          # the result may start off a vector boundary too
+        out = torch.zeros(total + pad + 3, dtype={np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32}[dtype], device="cuda")
+        torch.cuda.synchronize()
+        smb.elementwise_ptr(smb.OPS[op], dt, a_ptr, sa, b_ptr, sb, rshape, out.data_ptr() + pad * es)
+        k = smb.last_kernel()
+        kernels[k] = kernels.get(k, 0) + 1
+        host = out.cpu().numpy()
+        assert_same_bits(host[pad:pad + total].reshape(want.shape), want,
+                         f"case {case}: {op} {va.shape}/{va.strides} x {vb.shape}/{vb.strides} [{k}]")
+        assert not host[:pad].any() and not host[pad + total:].any(), f"case {case}: wrote outside the result [{k}]"
+    families = {k.split("<")[0] for k in kernels}
+    assert {"k_row", "k_generic", "k_stream"} <= families, kernels
+    assert len(kernels) >= 5, kernels
