@@ -389,3 +389,59 @@ def test_chain_randomised_shapes_ranks_and_leaf_kinds(orc):
         kernels.add(smb.last_kernel())
         assert_same_bits(got, np.asarray(want).reshape(got.shape), f"fuzz case {case}: {np.dtype(dt).name} {shape} {[s[0] for s in steps]}")
     assert {"k_chain<vec16>", "k_chain<scalar>", "k_chain<vec16,wide>", "k_chain<scalar,wide>"} <= kernels, kernels
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32])
+def test_fuzz_chains_over_random_views_of_device_arrays(orc, dt):
+    """~120 random chains per dtype: 2-7 steps, each leaf a random strided / permuted / broadcast view of a DEVICE-resident
+    parent (interior pointers, odd bases) or a constant, operators + - * / in both operand orders -- fused result against
+    the oracle's operator-by-operator sequence, bit for bit."""
+    import torch
+    from test_gpu_parity import _random_view
+    tdt = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32}[dt]
+    rng = np.random.default_rng(20261103 + np.dtype(dt).itemsize + (5 if dt == np.int32 else 0))
+    dims = [1, 2, 3, 4, 8, 12, 16, 33, 64, 100]
+    code = smb.dtype_code(np.dtype(dt))
+    es = np.dtype(dt).itemsize
+    kernels = {}
+    for case in range(120):
+        nd = int(rng.integers(1, 5))
+        shape = [int(rng.choice(dims)) for _ in range(nd)]
+        while int(np.prod(shape)) > 300_000:
+            shape[int(rng.integers(0, nd))] = 2
+        friendly = case % 2 == 0                    # every other case qualifies for the vector kernel
+        if friendly:
+            shape[-1] = int(rng.choice([4, 8, 16, 64, 100]))
+        nsteps = int(rng.integers(2, 8))
+        keep = []                                   # device parents stay alive until the launch is checked
+        steps_np, leaves = [], []
+        for s in range(nsteps):
+            op = "add" if s == 0 else str(rng.choice(["add", "sub", "mul", "div", "rsub", "add", "mul"]))
+            if s > 0 and rng.random() < 0.2:        # a constant
+                v = int(rng.integers(1, 9)) if dt == np.int32 else float(np.float32(rng.uniform(0.5, 4.0)))
+                steps_np.append((op, v))
+                leaves.append((op[1:] if op == "rsub" else op, op == "rsub", v))
+                continue
+            want = [1 if (s > 0 and rng.random() < 0.3) else d for d in shape]
+            drop = int(rng.integers(0, nd)) if (s > 0 and rng.random() < 0.2) else 0
+            parent, view = _random_view(rng, dt, want[drop:], op == "div", friendly)
+            dev = torch.from_numpy(parent.copy()).cuda()
+            keep.append(dev)
+            ptr = dev.data_ptr() + (view.__array_interface__["data"][0] - parent.__array_interface__["data"][0])
+            st = [0] * drop + [x // es for x in view.strides]
+            dd = [1] * drop + list(view.shape)
+            st = [0 if d == 1 and r > 1 else x for d, r, x in zip(dd, shape, st)]
+            steps_np.append((op, view))
+            leaves.append((None if s == 0 else (op[1:] if op == "rsub" else op), op == "rsub", (ptr, st)))
+        first = steps_np[0][1]
+        want_out, _ = oracle_chain(orc, np.broadcast_to(first, shape) if first.shape != tuple(shape) else first, steps_np[1:])
+        out = torch.zeros(int(np.prod(shape)) + 4, dtype=tdt, device="cuda")
+        torch.cuda.synchronize()
+        smb.chain_ptr(code, leaves, shape, out.data_ptr())
+        k = smb.last_kernel()
+        kernels[k] = kernels.get(k, 0) + 1
+        host = out.cpu().numpy()
+        assert_same_bits(host[:-4].reshape(shape), np.asarray(want_out).reshape(shape), f"chain case {case}: {[o for o, _ in steps_np]} {shape} [{k}]")
+        assert not host[-4:].any(), f"chain case {case}: wrote past the result [{k}]"
+    assert any(k.startswith("k_chain<vec16") for k in kernels) and any(k.startswith("k_chain<scalar") for k in kernels), kernels
