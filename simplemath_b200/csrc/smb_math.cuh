@@ -398,7 +398,7 @@ SMB_HD float pow_f32(float x, const PowExpF32 &pe) {
 //   -- float(biased exponent) + (L_hi - 127) is exact because L_hi is a multiple of 2^-15;
 //   the bracket is kept as two floats;
 //   t = y*log2|x| as th + tl; k = rint(64 t): 2^t = 2^n * T[j] * 2^f, n = k >> 6,
-//   j = k & 63, |f| <= 2^-7, T[j] = 2^(j/64) as T_hi + T_lo,
+//   j = k & 63, |f| <= 2^-7, T[j] = 2^(j/64) as T_hi (1 + T_rel),
 //   2^f - 1 = f*(E1 + f*(E2 + f*E3)).
 // Error: <= 0.5 (final rounding) + ~0.06 ULP; tests bound it by 1 ULP.
 // The core declines (returns false) anything that is not "normal positive
@@ -450,7 +450,7 @@ SMB_HD float rcp_seed(float x) {
     return 1.0f / x;
 #endif
 }
-struct PowTabExp { float t_hi, t_lo; };
+struct PowTabExp { float t_hi, t_rel; }; // 2^(j/64) = t_hi (1 + t_rel)
 
 // Table access.  Host build: the compact tables behind `tab_*`.  Device: the tables live in
 // shared memory (smb_s_pow below, filled per CTA by PowF32Fn::block_init) with each
@@ -525,7 +525,7 @@ SMB_HD PowTabExp pow_tab_exp_at(const PowTabExp *tab, uint32_t lane_off, uint32_
     const uint32_t off = ((k << 7) & (63u << 7)) | lane_off; // entry j = k & 63 starts at byte j * 128
     PowTabExp e;
     asm("{\n\t.reg .u32 a;\n\t.reg .u64 b;\n\tmov.u64 b, smb_s_pow;\n\tcvt.u32.u64 a, b;\n\tadd.u32 a, a, %2;\n\t"
-        "ld.shared.v2.f32 {%0,%1}, [a+16384];\n\t}" : "=f"(e.t_hi), "=f"(e.t_lo) : "r"(off));
+        "ld.shared.v2.f32 {%0,%1}, [a+16384];\n\t}" : "=f"(e.t_hi), "=f"(e.t_rel) : "r"(off));
     return e;
 #else
     (void)lane_off;
@@ -585,14 +585,16 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
     // ---- log2 |x|,  |x| = 2^E * m,  m in [1, 2) ----------------------------------
     const f2 m = f2_make(u2f((u0 & 0x007fffffu) | lane.c.one), u2f((u1 & 0x007fffffu) | lane.c.one));
     const PowTabLog t0 = pow_tab_log_at(tab_log, lane.log_off, u0), t1 = pow_tab_log_at(tab_log, lane.log_off, u1);
-    f2 lh, ll; // log2(m * invc) [or log2(m / c)] as lh + ll
+    // log2(m * invc) [or log2(m / c)] = lead_a * lead_b (the leading product, never rounded on its own: it joins
+    // E + L_hi inside one fma below) + tail_a * tail_b (+ tail2_a * tail2_b, large tier)
+    f2 lead_a, lead_b, tail_a, tail_b, tail2_a, tail2_b;
+    tail2_a = tail2_b = f2_splat(0.0f);
     if (TIER != POW_TIER_LARGE) {
         // exact; .c holds invc here.  Scalar FMAs: the operands come straight from the LDS
         // registers, packing them first would cost more moves than the packed form saves.
         const f2 r = f2_make(ffma(m.x, t0.c, -1.0f), ffma(m.y, t1.c, -1.0f));
         const f2 c1h = f2_splat(SMB_POW_C1H);              // 1/ln2 = c1h + c1l
-        lh = f2_mul(c1h, r);
-        ll = f2_fma(c1h, r, f2_neg(lh));                   // the rounding error of lh, exactly
+        lead_a = c1h; lead_b = r;
         f2 q;
         if (TIER == POW_TIER_SMALL) {
             q = f2_fma(r, f2_splat(lane.c.s_c3), f2_splat(SMB_POW_S_C2));
@@ -602,7 +604,7 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
             q = f2_fma(r, q, f2_splat(SMB_POW_L_C2));
         }
         q = f2_fma(r, q, f2_splat(SMB_POW_C1L));
-        ll = f2_fma(r, q, ll);
+        tail_a = r; tail_b = q;
     } else {
         // The r-series would need its r^2 term in two floats once y is large; the odd series in
         // p = (m - c)/(m + c), |p| <= 0.0059, has p^3 as its second term and does not.
@@ -623,10 +625,9 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
         const f2 c0h = f2_splat(2.885390043258667f);       // 2/ln2 = c0h + c0l
         f2 qq = f2_fma(s, f2_splat(0.5767093896865845f), f2_splat(0.9617967009544373f));
         qq = f2_fma(s, qq, f2_splat(3.851926067000022e-08f));
-        lh = f2_mul(c0h, p_hi);
-        ll = f2_fma(c0h, p_hi, f2_neg(lh));
-        ll = f2_fma(c0h, p_lo, ll);
-        ll = f2_fma(p_hi, qq, ll);
+        lead_a = c0h; lead_b = p_hi;
+        tail_a = c0h; tail_b = p_lo;
+        tail2_a = p_hi; tail2_b = qq;
     }
     // E + L_hi, exactly.  The upper half-word of x is [sign | biased exponent | j] with j the
     // table index, so float(u >> 16) / 128 = 256 sign + biased exponent + j/128 (one I2F with a
@@ -635,9 +636,14 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
     // A rejected sign rides along as +256.  Scalar -- the table words are used once.
     const float e0 = (float)(uint16_t)(u0 >> 16), e1 = (float)(uint16_t)(u1 >> 16);
     const f2 h1 = f2_make(ffma(e0, 0.0078125f, t0.l_hi), ffma(e1, 0.0078125f, t1.l_hi));
-    const f2 h2 = f2_add(h1, lh);                          // fast two-sum: |h1| >= |lh| or h1 == 0
-    const f2 l2 = f2_add(f2_sub(h1, h2), lh);
-    f2 lo = f2_add(f2_make(fadd(t0.l_lo, l2.x), fadd(t1.l_lo, l2.y)), ll);
+    // h2 = RN(h1 + a*b) from the exact product; h1 - h2 is exact (|a*b| <= |h1| / 2 or h1 == 0, so h2 lies within a
+    // factor 2 of h1: Sterbenz), and a*b + (h1 - h2) -- the rounding error of h2, at most ulp(h2)/2 -- is again one fma:
+    // three packed operations where the product, its error, the sum and the sum's error took five.
+    const f2 h2 = f2_fma(lead_a, lead_b, h1);
+    const f2 l2 = f2_fma(lead_a, lead_b, f2_sub(h1, h2));
+    f2 lo = f2_fma(tail_a, tail_b, l2);
+    if (TIER == POW_TIER_LARGE) lo = f2_fma(tail2_a, tail2_b, lo);
+    lo = f2_make(fadd(t0.l_lo, lo.x), fadd(t1.l_lo, lo.y));
     f2 h3 = h2;
     if (TIER == POW_TIER_LARGE) {
         // renormalise: L_lo alone can reach 2^-16, too coarse a tail once multiplied by a large y
@@ -646,9 +652,12 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
     }
     // ---- t = y * log2|x| as th + tl ---------------------------------------------
     const f2 y2 = f2_splat(y);
-    const f2 th = f2_mul(y2, h3);
-    f2 tl = f2_fma(y2, h3, f2_neg(th));
-    tl = f2_fma(y2, lo, tl);
+    // k = rint(64 y h3) straight from the exact product: the sum with 1.5 * 2^17 (ulp 2^-6) leaves k in the low mantissa
+    // bits and k/64 after subtracting the constant again; kd stands in for th in the range test (they differ by < 2^-6).
+    const f2 s17 = f2_splat(196608.0f);
+    const f2 tk = f2_fma(y2, h3, s17);
+    const f2 kd = f2_sub(tk, s17);                         // k / 64, exactly
+    const f2 th = kd;
     // The one validity test.  Results outside the comfortable normal range (incl. overflow and
     // underflow) go to the slow path, and so does every input that is not a normal number: a zero
     // or denormal has log2 <= -126 here, inf / NaN >= 128, a rejected negative base >= 129.
@@ -656,21 +665,18 @@ SMB_HD bool pow_f32_pair_fast(float x0, float x1, float y, PowLane lane,
     bool ok = fabsf(rng.x) < 125.0f && fabsf(rng.y) < 125.0f;
     if (SIGN == POW_SIGN_RUNTIME) ok = ok && fabsf(h3.x) < 125.0f && fabsf(h3.y) < 125.0f; // |y| unknown: both
     // ---- 2^t --------------------------------------------------------------------
-    const f2 shifter = f2_splat(12582912.0f);              // 1.5 * 2^23
-    const f2 tk = f2_fma(th, f2_splat(lane.c.k64), shifter);    // low mantissa bits hold k = rint(64 th)
-    const uint32_t k0 = f2u(tk.x), k1 = f2u(tk.y);         // biased by 0x4b400000, a multiple of 64
-    const f2 kf = f2_sub(tk, shifter);
-    f2 f = f2_fma(kf, f2_splat(-0.015625f), th);           // th - k/64, exact
-    f = f2_add(f, tl);
+    const uint32_t k0 = f2u(tk.x), k1 = f2u(tk.y);         // biased by 0x48400000, a multiple of 64 that vanishes << 17
+    f2 f = f2_fma(y2, h3, f2_neg(kd));                     // y h3 - k/64 from the exact product: |f| <= 2^-7, error <= 2^-32
+    f = f2_fma(y2, lo, f);
     const PowTabExp x0e = pow_tab_exp_at(tab_exp, lane.exp_off, k0), x1e = pow_tab_exp_at(tab_exp, lane.exp_off, k1);
     f2 g = f2_fma(f, f2_splat(lane.c.e3), f2_splat(0.24022682011127472f));
     g = f2_fma(f, g, f2_splat(0.6931471824645996f));
-    const f2 w = f2_mul(f, g);                             // 2^f - 1
-    // T_hi + (T_hi*w + T_lo), scalar: the table words feed straight from the LDS registers
-    const float z0 = fadd(x0e.t_hi, ffma(x0e.t_hi, w.x, x0e.t_lo));
-    const float z1 = fadd(x1e.t_hi, ffma(x1e.t_hi, w.y, x1e.t_lo));   // in [0.99, 2.01): 2^(j/64 + f)
+    // 2^(j/64 + f) = T_hi (1 + T_rel) (1 + w),  w = 2^f - 1 = f g:  T_hi + T_hi (f g + T_rel)  (T_rel w < 2^-31 dropped).
+    // Scalar: the table words feed straight from the LDS registers, and the per-entry T_rel rides in the fma's addend.
+    const float z0 = ffma(x0e.t_hi, ffma(f.x, g.x, x0e.t_rel), x0e.t_hi);
+    const float z1 = ffma(x1e.t_hi, ffma(f.y, g.y, x1e.t_rel), x1e.t_hi);   // in [0.99, 2.01)
     // scale by 2^n, n = k >> 6, through the exponent field (|n| <= 125 keeps the result normal):
-    // (k & ~63) << 17 == n << 23 (the bias 0x4b400000 << 17 vanishes mod 2^32)
+    // (k & ~63) << 17 == n << 23 (the bias 0x48400000 << 17 vanishes mod 2^32)
     uint32_t b0 = pow_scale_bits(k0, f2u(z0)), b1 = pow_scale_bits(k1, f2u(z1));
     if (SIGN == POW_SIGN_ODD) { b0 |= s0 & 0x80000000u; b1 |= s1 & 0x80000000u; } // keep the base's sign
     if (SIGN == POW_SIGN_RUNTIME) { b0 |= s0 & sign_or; b1 |= s1 & sign_or; }
@@ -890,7 +896,7 @@ SMB_HD double pow_f64(double x, const PowExpF64 &pe) {
 struct PowTabLog64 { double c, l_hi, l_lo, pad; };   // generated (compact) form
 struct PowTabLog64A { double c, l_hi; };             // device layout: split so that every lookup is
 struct PowTabLog64B { double l_lo; };                // one conflict-free LDS.128 / LDS.64
-struct PowTabExp64 { double t_hi, t_lo; };
+struct PowTabExp64 { double t_hi, t_rel; }; // 2^(j/64) = t_hi (1 + t_rel)
 #if defined(__CUDA_ARCH__)
 #define SMB_POW64_A_STRIDE 8    /* 16-byte entries: the 8 lanes of a wavefront get their own replica */
 #define SMB_POW64_B_STRIDE 16   /*  8-byte entries: 16 lanes per wavefront */
@@ -940,29 +946,30 @@ SMB_HD bool pow_f64_fast(double x, double y, uint64_t sign_reject, const PowTabL
     q = dfma(s, q, 0.9617966939259756);
     q = dfma(s, q, 4.0710547481862066e-17);                // c0l + s*Q
     const double c0h = 2.8853900817779268;
-    const double lh = dmul(c0h, p_hi);
-    double ll = dfma(c0h, p_hi, -lh);
+    const double h1 = dadd((double)(int32_t)eb, t.l_hi);   // exact: integer + multiple of 2^-40
+    // The leading product c0h * p_hi joins h1 inside ONE fma (never rounded on its own): h2 = RN(h1 + c0h p_hi);
+    // h1 - h2 is exact (|c0h p_hi| <= |h1| / 2 or h1 == 0 -- the unit entries c = 1, c = 2 -- so h2 lies within a factor 2
+    // of h1), and the rounding error of h2 is again one fma.  Six FP64 operations where the separately rounded product
+    // needed nine.
+    const double h2 = dfma(c0h, p_hi, h1);
+    double ll = dfma(c0h, p_hi, dsub(h1, h2));
     ll = dfma(c0h, p_lo, ll);
     ll = dfma(p_hi, q, ll);
-    const double h1 = dadd((double)(int32_t)eb, t.l_hi);   // exact: integer + multiple of 2^-40
-    const double h2 = dadd(h1, lh);                        // fast two-sum: |h1| >= |lh| or h1 == 0
-    const double l2 = dadd(dsub(h1, h2), lh);
-    const double lo_raw = dadd(dadd(t_l_lo, l2), ll);
+    const double lo_raw = dadd(t_l_lo, ll);
     double h3 = h2, lo = lo_raw;
     if (!SMALL_Y) { // renormalise: the tail alone can reach 2^-41, too coarse once multiplied by a large y
         h3 = dadd(h2, lo_raw);
         lo = dadd(dsub(h2, h3), lo_raw);
     }
-    const double th = dmul(y, h3);
-    double tl = dfma(y, h3, -th);
-    tl = dfma(y, lo, tl);
-    ok = ok && fabs(th) < 1000.0;                          // result well inside the normal range
-    const double shifter = 6755399441055744.0;             // 1.5 * 2^52
-    const double tk = dfma(th, 64.0, shifter);
-    const uint32_t k = (uint32_t)d2u(tk);                  // low word: rint(64 th), two's complement
-    const double kf = dsub(tk, shifter);
-    double f = dfma(kf, -0.015625, th);                    // exact
-    f = dadd(f, tl);
+    // k = rint(64 y h3) from the exact product: 1.5 * 2^46 has ulp 2^-6, so the sum leaves k in the low mantissa bits
+    // and k/64 once the constant is subtracted again; f = y h3 - k/64 is ONE fma (|f| <= 2^-7, error <= 2^-61).
+    const double s46 = 105553116266496.0;                  // 1.5 * 2^46
+    const double tk = dfma(y, h3, s46);
+    const uint32_t k = (uint32_t)d2u(tk);                  // low word: rint(64 y h3), two's complement
+    const double kd = dsub(tk, s46);                       // k / 64, exactly
+    ok = ok && fabs(kd) < 1000.0;                          // result well inside the normal range
+    double f = dfma(y, h3, -kd);
+    f = dfma(y, lo, f);
     const PowTabExp64 e = tab_exp[(k & 63u) * SMB_POW64_EXP_STRIDE];
     double g = dfma(f, 1.5252733804059841e-05, 0.0001540353039338161);
     g = dfma(f, g, 0.0013333558146428443);
@@ -970,8 +977,7 @@ SMB_HD bool pow_f64_fast(double x, double y, uint64_t sign_reject, const PowTabL
     g = dfma(f, g, 0.05550410866482158);
     g = dfma(f, g, 0.24022650695910072);
     g = dfma(f, g, 0.6931471805599453);
-    const double w = dmul(f, g);                           // 2^f - 1
-    const double z = dadd(e.t_hi, dfma(e.t_hi, w, e.t_lo));
+    const double z = dfma(e.t_hi, dfma(f, g, e.t_rel), e.t_hi); // T_hi (1 + T_rel)(1 + f g), T_rel f g < 2^-60 dropped
     // scale by 2^n, n = (int32)k >> 6 (|n| <= 1000 keeps the result normal)
     const int64_t n = (int64_t)((int32_t)k >> 6);
     uint64_t b = d2u(z) + ((uint64_t)n << 52);

@@ -16,7 +16,8 @@ f32 LOG table, 128 entries indexed by the top 7 mantissa bits of |x| = 2^E * m, 
   and the coefficients of log2(1 + r) = C1*r + r^2*(C2 + C3 r [+ C4 r^2 + C5 r^3]) fitted on the
   table's actual range of r (Chebyshev-node interpolation, near-minimax).
 f64 LOG table: {c, L_hi - 1023, L_lo} with p = (m - c)/(m + c) (see pow_f64_fast).
-EXP table, 64 entries: 2^(j/64) as T_hi + T_lo (two f32 / two f64).
+EXP table, 64 entries: 2^(j/64) as T_hi * (1 + T_rel) (two f32 / two f64): the relative form folds the
+           correction into the exp2 polynomial's last fma.
 """
 import os
 import struct
@@ -115,8 +116,8 @@ def main():
     for j in range(NE):
         t = mp.power(2, mp.mpf(j) / NE)
         t_hi = f32(t)
-        t_lo = f32(t - mp.mpf(t_hi))
-        exp_rows.append((t_hi, t_lo))
+        t_rel = f32((t - mp.mpf(t_hi)) / mp.mpf(t_hi))
+        exp_rows.append((t_hi, t_rel))
     # ---- f64 tables: same indexing, L_hi a multiple of 2^-40 minus the double bias 1023
     log64, exp64 = [], []
     for j in range(NL):
@@ -134,7 +135,7 @@ def main():
     for j in range(NE):
         t = mp.power(2, mp.mpf(j) / NE)
         t_hi = float(t)
-        exp64.append((t_hi, float(t - mp.mpf(t_hi))))
+        exp64.append((t_hi, float((t - mp.mpf(t_hi)) / mp.mpf(t_hi))))
     with open(OUT, "w") as f:
         f.write("// GENERATED by tools/gen_pow_tables.py -- do not edit.\n")
         f.write("// Lookup tables of the table-driven f32 / f64 pow cores (smb_math.cuh).\n")
@@ -154,14 +155,14 @@ def main():
         f.write(f"#define SMB_POW_S_C2 {poly_small[0]!r}f\n#define SMB_POW_S_C3 {poly_small[1]!r}f\n")
         for d in range(4):
             f.write(f"#define SMB_POW_L_C{d + 2} {poly_large[d]!r}f\n")
-        f.write("\n// {T_hi, T_lo}: 2^(j/64) = T_hi + T_lo\n#define SMB_POW_EXP_TABLE_INIT { \\\n")
+        f.write("\n// {T_hi, T_rel}: 2^(j/64) = T_hi * (1 + T_rel)\n#define SMB_POW_EXP_TABLE_INIT { \\\n")
         for th, tl in exp_rows:
             f.write(f"    {{{th!r}f, {tl!r}f}}, \\\n")
         f.write("}\n\n// f64: {c, L_hi - 1023, L_lo, 0}: log2(c) = L_hi + L_lo, L_hi a multiple of 2^-40\n")
         f.write("#define SMB_POW64_LOG_TABLE_INIT { \\\n")
         for c, lh, ll in log64:
             f.write(f"    {{{c!r}, {lh!r}, {ll!r}, 0.0}}, \\\n")
-        f.write("}\n\n// f64: {T_hi, T_lo}: 2^(j/64) = T_hi + T_lo\n#define SMB_POW64_EXP_TABLE_INIT { \\\n")
+        f.write("}\n\n// f64: {T_hi, T_rel}: 2^(j/64) = T_hi * (1 + T_rel)\n#define SMB_POW64_EXP_TABLE_INIT { \\\n")
         for th, tl in exp64:
             f.write(f"    {{{th!r}, {tl!r}}}, \\\n")
         f.write("}\n")
