@@ -112,7 +112,17 @@ def binary_case(name, op, a, b, note=""):
                 gsp = torch.cuda.current_stream().cuda_stream
                 for _ in range(args.reps):
                     lib.smb_elementwise(*argv[:-1], gsp)
-            gms = timed(g.replay, 3) / args.reps
+            # events on the stream the graph replays on (torch's current stream), not on the explicit stream `timed` uses
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(5):
+                g.replay()
+            g1.record()
+            g1.synchronize()
+            gms = g0.elapsed_time(g1) / 5 / args.reps
             note += f"; CUDA-graph replay of {args.reps} launches: {gms:.4f} ms each = {bytes_ / gms / 1e6:.0f} GB/s"
         except Exception as e:  # capture is an extra, never the measurement
             note += f"; graph capture unavailable: {type(e).__name__}"
