@@ -117,6 +117,29 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
             return rc;
         }
     }
+    // sm::pow(a (op) constant, y), op in + - *, on a dense array: the pow kernel with a one-operand pre-operator (PowF32FnPre1).
+    if constexpr (std::is_same<T, float>::value) {
+        if (powvar == 4 && p.nleaf == 3 && p.ndim == 1 && data[0] && !data[1] && !data[2] && steps[2].op == SMB_OP_POW &&
+            p.stride[0][0] == 1 && steps[1].op != SMB_OP_POW && steps[1].op != SMB_OP_DIV && pow_f32_fast_ok(classify_exp(steps[2].value.f32))) {
+            const float y = steps[2].value.f32, cst = steps[1].value.f32;
+            const PowExpF32 pe = classify_exp(y);
+            const int pre = steps[1].op == SMB_OP_ADD ? PRE_ADD : steps[1].op == SMB_OP_MUL ? PRE_MUL : (steps[1].swap ? PRE_RSUB : PRE_SUB);
+            const float *pa = (const float *)data[0] + lin_begin;
+            const bool lt1 = pow_f32_y_lt_1(pe);
+            const int tier = pow_f32_tier(pe), sign = pow_f32_sign_mode(pe);
+#define SMB_POWPRE1(S, G, L) launch_stream<float, PowF32FnPre1<S, G, L>, false>(c, pa, nullptr, (float *)out, lin_count, lin_begin, PowF32FnPre1<S, G, L>::make(y, 0, pre, cst), s)
+#define SMB_POWPRE1_BY_SIGN(S) (sign == POW_SIGN_REJECT ? SMB_POWPRE1(S, POW_SIGN_REJECT, false) : sign == POW_SIGN_EVEN ? SMB_POWPRE1(S, POW_SIGN_EVEN, false) : SMB_POWPRE1(S, POW_SIGN_ODD, false))
+            int rc;
+            if (lt1) rc = SMB_POWPRE1(POW_TIER_SMALL, POW_SIGN_REJECT, true);
+            else if (tier == POW_TIER_SMALL) rc = SMB_POWPRE1_BY_SIGN(POW_TIER_SMALL);
+            else if (tier == POW_TIER_MEDIUM) rc = SMB_POWPRE1_BY_SIGN(POW_TIER_MEDIUM);
+            else rc = SMB_POWPRE1_BY_SIGN(POW_TIER_LARGE);
+#undef SMB_POWPRE1_BY_SIGN
+#undef SMB_POWPRE1
+            if (rc == SMB_OK) g_last_kernel = "k_stream<pow,fused-pre1>";
+            return rc;
+        }
+    }
     t.tiles_per_cta = powfast ? (powvar == 2 || powvar == 3 ? 16 : 32) : 1; // amortise the 24 KB table copy, stay many waves deep
     // compiled-in chain capacity / vectors per thread: short chains keep more loads in flight
 #define SMB_CHAIN_LAUNCH(E, W, NS, U, PF, ND)                                                                     \

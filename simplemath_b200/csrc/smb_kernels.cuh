@@ -314,6 +314,31 @@ template<int TIER, int SIGN, bool Y_LT_1> struct PowF32FnPre : PowF32Fn<TIER, SI
 };
 template<typename Fn, typename = void> struct fn_preop : std::false_type {};
 template<typename Fn> struct fn_preop<Fn, std::void_t<decltype(Fn::PREOP)>> : std::bool_constant<Fn::PREOP> {};
+// sm::pow(a (op) constant, y) -- the same idea with ONE operand stream: the pre-operator combines the loaded element with a
+// uniform constant (either operand order), so the kernel is the plain pow kernel plus one instruction per element.
+template<int TIER, int SIGN, bool Y_LT_1> struct PowF32FnPre1 : PowF32Fn<TIER, SIGN, Y_LT_1> {
+    static constexpr bool PREOP1 = true;
+    // a + c, a - c, c - a and a * c are ONE fma with uniform operands -- fma(a, 1, c), fma(a, 1, -c), fma(a, -1, c),
+    // fma(a, c, -0.0) round exactly like the add / subtract / multiply they stand for (signed zeros included) -- so the
+    // pre-operator costs one instruction per element and no branch.  (The two divisions stay on the chain kernel: an
+    // inlined, predicated division per element cost this kernel 8 %.)
+    float pre_mul, pre_add;
+    __device__ __forceinline__ float pre1(float a) const { return __fmaf_rn(a, pre_mul, pre_add); }
+    __device__ __forceinline__ float operator()(float a, float, uint64_t) const { return pow_f32_slow(pre1(a), this->pe); }
+    static PowF32FnPre1 make(float y, uint64_t lane_end_, int pre_op_, float c) { // PRE_ADD, PRE_SUB, PRE_RSUB or PRE_MUL
+        PowF32FnPre1 fn;
+        static_cast<PowF32Fn<TIER, SIGN, Y_LT_1> &>(fn) = PowF32Fn<TIER, SIGN, Y_LT_1>::make(y, lane_end_);
+        fn.pre_mul = pre_op_ == PRE_MUL ? c : pre_op_ == PRE_RSUB ? -1.0f : 1.0f;
+        fn.pre_add = pre_op_ == PRE_MUL ? -0.0f : pre_op_ == PRE_SUB ? -c : c;
+        return fn;
+    }
+};
+template<typename Fn, typename = void> struct fn_preop1 : std::false_type {};
+template<typename Fn> struct fn_preop1<Fn, std::void_t<decltype(Fn::PREOP1)>> : std::bool_constant<Fn::PREOP1> {};
+template<typename T, typename Fn> __device__ __forceinline__ T apply_pre1(const Fn &fn, T a) {
+    if constexpr (fn_preop1<Fn>::value) return fn.pre1(a);
+    else return a;
+}
 
 // sm::pow(arr, y) for double: table-driven fast core per element, double-double
 // reference-accuracy path (out of line) for whatever it declines.
@@ -424,7 +449,7 @@ __device__ __forceinline__ void stream_vec(const Pack<T, VB> &pa, const Pack<T, 
 #pragma unroll
         for (int k = 0; k < EPV; ++k) {
             if constexpr (fn_preop<Fn>::value) x.e[k] = fn.pre(pa.e[k], pb.e[k]);
-            else x.e[k] = pa.e[k];
+            else x.e[k] = apply_pre1(fn, pa.e[k]);
         }
         bool ok = true;
 #pragma unroll
@@ -488,7 +513,7 @@ __device__ __forceinline__ void pow_tile(const Pack<T, VB> (&in)[UNROLL], [[mayb
 #pragma unroll
         for (int k = 0; k < EPV; ++k) {
             if constexpr (PRE) x.e[k] = fn.pre(in[u].e[k], in_b[u].e[k]);
-            else x.e[k] = in[u].e[k];
+            else x.e[k] = apply_pre1(fn, in[u].e[k]);
         }
         ok[u] = true;
         if constexpr (fn_pairwise<Fn>::value) {
@@ -514,7 +539,7 @@ __device__ __forceinline__ void pow_tile(const Pack<T, VB> (&in)[UNROLL], [[mayb
             if ((bad >> u) & 1u) {
                 const uint64_t i = (v0 + (uint64_t)u * kBlock) * EPV + (uint64_t)(e % EPV);
                 if constexpr (PRE) out[i] = fn.slow(fn.pre(a[i], b[i]));
-                else out[i] = fn.slow(a[i]);
+                else out[i] = fn.slow(apply_pre1(fn, a[i]));
             }
         }
     }

@@ -386,7 +386,7 @@ SMB_HD float pow_f32(float x, const PowExpF32 &pe) {
 // The double core runs on the half-rate FP64 pipe and made sm::pow compute-bound
 // at a third of the HBM rate (2.15 TB/s measured on B200).  This core keeps the
 // arithmetic on the FP32 pipe and issues it as packed fma.rn.f32x2 (SASS FFMA2,
-// new with sm_100): two elements per instruction, ~30 instructions per element in
+// new with sm_100): two elements per instruction, ~25 instructions per element in
 // all, which is what fits under the memory roofline.
 //
 //   |x| = 2^E * m, m in [1, 2); the top 7 mantissa bits select {invc, L_hi, L_lo} with
@@ -394,12 +394,13 @@ SMB_HD float pow_f32(float x, const PowExpF32 &pe) {
 //   r = fma(m, invc, -1) is then exact (|r| <= 2^-7, M*k - 2^31 fits 24 bits) -- no division,
 //   no reciprocal, no error term to carry.  invc = 1 for the first entry and 1/2 for the last
 //   two, so x near 1 keeps full RELATIVE accuracy (E + L == 0 there).
-//   log2|x| = (E + L_hi) + [C1h*r + L_lo + (C1h*r)_err + r*(C1l + r*(C2 + r*C3 ...))]
-//   -- float(biased exponent) + (L_hi - 127) is exact because L_hi is a multiple of 2^-15;
-//   the bracket is kept as two floats;
-//   t = y*log2|x| as th + tl; k = rint(64 t): 2^t = 2^n * T[j] * 2^f, n = k >> 6,
-//   j = k & 63, |f| <= 2^-7, T[j] = 2^(j/64) as T_hi (1 + T_rel),
-//   2^f - 1 = f*(E1 + f*(E2 + f*E3)).
+//   log2|x| = (E + L_hi) + C1h*r + [L_lo + r*(C1l + r*(C2 + r*C3 ...))]
+//   -- h1 = float(biased exponent) + (L_hi - 127) is exact because L_hi is a multiple of 2^-15;
+//   the leading product C1h*r is never rounded on its own: h = fma(C1h, r, h1), and the rounding
+//   error of that sum, fma(C1h, r, h1 - h), joins the bracket (lo);
+//   k = rint(64 y h) straight from fma(y, h, 1.5 * 2^17): 2^t = 2^n * T[j] * 2^f, n = k >> 6,
+//   j = k & 63, f = fma(y, lo, fma(y, h, -k/64)), |f| <= 2^-7, T[j] = 2^(j/64) as T_hi (1 + T_rel),
+//   2^f - 1 = f*(E1 + f*(E2 + f*E3)), result = T_hi + T_hi*(f*g + T_rel).
 // Error: <= 0.5 (final rounding) + ~0.06 ULP; tests bound it by 1 ULP.
 // The core declines (returns false) anything that is not "normal positive
 // magnitude, result comfortably inside the normal range"; the caller then uses
@@ -486,8 +487,8 @@ namespace smb {
 // PowConsts: constants that ride in as kernel parameters (uniform registers) -- `one` keeps
 // `(u & 0x007fffff) | one` ONE three-input LOP3 (with both words literal ptxas emits an AND and an
 // OR), the floats feed FFMA2's scalar-splat operand without a per-vector MOV.
-struct PowConsts { uint32_t one; float k64, s_c3, e3; };
-SMB_HD PowConsts pow_consts() { PowConsts c; c.one = 0x3f800000u; c.k64 = 64.0f; c.s_c3 = SMB_POW_S_C3; c.e3 = 0.05547422543168068f; return c; }
+struct PowConsts { uint32_t one; float s_c3, e3; };
+SMB_HD PowConsts pow_consts() { PowConsts c; c.one = 0x3f800000u; c.s_c3 = SMB_POW_S_C3; c.e3 = 0.05547422543168068f; return c; }
 struct PowLane { uint32_t log_off, exp_off; PowConsts c; };
 #if defined(__CUDACC__)
 static __device__ uint2 d_pow_lane_tab[16] = {{0, 0}, {16, 8}, {32, 16}, {48, 24}, {64, 32}, {80, 40}, {96, 48}, {112, 56},

@@ -482,14 +482,53 @@ def test_fused_pow_of_a_binary_operator_is_bit_identical_to_the_two_operators(or
             mid = orc.binary("add", a, b)
             err = oracle.ulp_error_f32(smb.chain(a, ("add", b), ("pow", 2.5)), orc.pow_ref_f32(mid, 2.5))
             assert err.max() <= 0.6, err.max()
-        # what does not fit (a broadcast leaf, a constant second operand, a longer chain) stays on the chain kernel
+        # what does not fit (a broadcast leaf, a longer chain) stays on the chain kernel
         m = rng.uniform(0.1, 5, (64, 256)).astype(np.float32)
         row = rng.uniform(0.1, 5, (1, 256)).astype(np.float32)
         got = smb.chain(m, ("add", row), ("pow", 2.5))
         assert smb.last_kernel().startswith("k_chain")
         assert oracle.ulp_error_f32(got, orc.pow_ref_f32(orc.binary("add", m, row), 2.5)).max() <= 0.6
-        got = smb.chain(m, ("mul", 2.0), ("pow", 2.5))
+        got = smb.chain(m, ("mul", 2.0), ("add", 1.0), ("pow", 2.5))
         assert smb.last_kernel().startswith("k_chain")
+    finally:
+        smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+
+
+def test_fused_pow_of_an_array_and_a_constant_is_bit_identical_to_the_two_operators(orc):
+    """smb_chain [a, (op) constant, pow y] on a dense f32 array: the pow kernel with a one-operand pre-operator -- the same
+    bits as the scalar operator followed by sm::pow, every tier / sign variant, ragged sizes, both operand orders of -
+    (the two divisions stay on the chain kernel, equally bit-identical)."""
+    rng = np.random.default_rng(98)
+    smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+    try:
+        for n, off in ((100_003, 0), (1 << 20, 0), (4099, 1), (8, 0), (3, 0)):
+            a = rng.uniform(0.05, 9.0, n + off).astype(np.float32)[off:]
+            sgn = np.where(rng.random(n) < 0.3, -1, 1).astype(np.float32)
+            for y in (2.5, 0.5, 17.0, 300.5, 3.0, 2.0, -1.5):
+                for op, cst in (("add", 1.5), ("sub", -0.25), ("mul", 1.75), ("div", 3.0), ("rsub", 20.0), ("rdiv", 2.0)):
+                    aa = (a * sgn).astype(np.float32) if float(y).is_integer() else a
+                    if op.startswith("r"):
+                        mid = smb.binary(op[1:], np.full(n, cst, np.float32), aa)
+                    else:
+                        mid = smb.scalar(op, aa, cst)
+                    want = smb.pow(mid, y)
+                    got = smb.chain(aa, (op, cst), ("pow", y))
+                    if "div" in op:   # stays on the chain kernel (its scalar form runs the reference-accuracy pow): ULP-bounded, not bit-identical
+                        if n > 8:
+                            assert smb.last_kernel().startswith("k_chain"), (n, y, op, smb.last_kernel())
+                        if abs(y) < 8:
+                            ref = orc.pow_ref_f32(mid, y)
+                            fin = np.isfinite(ref) & (np.abs(ref) > 1e-30) & (np.abs(ref) < 1e30)
+                            assert oracle.ulp_error_f32(got[fin], ref[fin]).max() <= 0.6, (op, y, n)
+                        continue
+                    if n > 8:
+                        assert smb.last_kernel() == "k_stream<pow,fused-pre1>", (n, y, op, smb.last_kernel())
+                    assert_same_bits(got, want, f"pow({op}(a, {cst}), {y}) n={n} off={off}")
+        # and against the oracle's accuracy contract
+        a = rng.uniform(0.05, 9.0, 1 << 16).astype(np.float32)
+        got = smb.chain(a, ("mul", 1.75), ("pow", 2.5))
+        err = oracle.ulp_error_f32(got, orc.pow_ref_f32(orc.array_scalar("mul", a, 1.75), 2.5))
+        assert err.max() <= 0.6, err.max()
     finally:
         smb.set_option(smb.OPT_POW_SPECIALISE, 1)
 

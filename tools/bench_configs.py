@@ -283,4 +283,17 @@ chain_case("F4 f32 pow(a+b, 2.5), 2^28 elements, fused", n,
            lambda: (smb.contiguous_ptr(smb.OP_ADD, smb.F32, P(fa), P(fb), P(ft1), n, sp),
                     smb.array_scalar_ptr(smb.OP_POW, smb.F32, P(ft1), 2.5, n, P(fo), sp)), 2,
            "sm::pow(a+b, e) in one pass")
+stepsp1 = smb.chain_steps(smb.F32, [L(None, fa), ("add", False, 1.5), ("pow", False, 2.5)], [n])
+chain_case("F5 f32 pow(a + 1.5, 2.5), 2^28 elements, fused", n,
+           lambda: smb.lib().smb_chain(smb.F32, stepsp1, 3, smb._u64arr([n]), 1, n, P(fo), sp),
+           lambda: (smb.array_scalar_ptr(smb.OP_ADD, smb.F32, P(fa), 1.5, n, P(ft1), sp),
+                    smb.array_scalar_ptr(smb.OP_POW, smb.F32, P(ft1), 2.5, n, P(fo), sp)), 1,
+           "sm::pow(a + c, e) in one pass: the pow kernel with a one-operand pre-operator")
+stepsp2 = smb.chain_steps(smb.F32, [L(None, fa), L("add", fb), ("pow", False, 2.5), L("mul", fc)], [n])
+chain_case("F6 f32 pow(a+b, 2.5)*c, 2^28 elements, fused (general chain kernel)", n,
+           lambda: smb.lib().smb_chain(smb.F32, stepsp2, 4, smb._u64arr([n]), 1, n, P(fo), sp),
+           lambda: (smb.contiguous_ptr(smb.OP_ADD, smb.F32, P(fa), P(fb), P(ft1), n, sp),
+                    smb.array_scalar_ptr(smb.OP_POW, smb.F32, P(ft1), 2.5, n, P(ft2), sp),
+                    smb.contiguous_ptr(smb.OP_MUL, smb.F32, P(ft2), P(fc), P(fo), n, sp)), 3,
+           "a pow step in the MIDDLE of a chain stays on k_chain (instruction-bound)")
 smb.set_option(smb.OPT_POW_SPECIALISE, 1)
