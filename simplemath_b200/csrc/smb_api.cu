@@ -36,6 +36,16 @@ using namespace smb;
 
 // =============================================================== C ABI =====
 // ---- op-chain fusion ---------------------------------
+// sm::pow by 2, 0.5, -1, 1 has an exact single-operation form that the eager operator uses (SMB_OPT_POW_SPECIALISE, on by
+// default); a pow step of a chain takes the same form, so that lazy and eager results agree bit for bit there too:
+// CH_SQR, CH_SQRT, 1 / acc (CH_RDIV with the constant 1), and -- exponent 1 -- acc * 1.  -1: an ordinary pow step.
+template<typename T>
+static int chain_pow_special(const smb_chain_step &st) {
+    if constexpr (!std::is_floating_point<T>::value) return -1;
+    if (st.op != SMB_OP_POW || !g_opt_pow_specialise.load()) return -1;
+    const double y = sizeof(T) == 8 ? st.value.f64 : (double)st.value.f32;
+    return y == 2.0 ? CH_SQR : y == 0.5 ? CH_SQRT : y == -1.0 ? CH_RDIV : y == 1.0 ? CH_MUL : -1;
+}
 template<typename T>
 static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *steps, const void *const *data,
                         uint64_t lin_begin, uint64_t lin_count, uint64_t lane_end, T *out, cudaStream_t s) {
@@ -58,10 +68,16 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
         t.data[i] = data[i];
         // leaf (op) acc: only - and / care which side the leaf is on
         t.op[i] = (uint8_t)(steps[i].swap && steps[i].op == SMB_OP_SUB ? CH_RSUB : steps[i].swap && steps[i].op == SMB_OP_DIV ? CH_RDIV : steps[i].op);
+        const int special = i > 0 ? chain_pow_special<T>(steps[i]) : -1;
+        if (special >= 0) t.op[i] = (uint8_t)special;
         for (int k = 0; k < SMB_MAX_NDIM; ++k) t.stride[i][k] = p.stride[i][k];
         if (!data[i]) {
             if (sizeof(T) == 8) memcpy(&t.cbits[i], &steps[i].value.f64, 8);
             else { uint32_t w; memcpy(&w, &steps[i].value.f32, 4); t.cbits[i] = w; } // f32 and i32 share the low word
+            if (special == CH_RDIV || special == CH_MUL) { // 1 / acc, acc * 1: the constant becomes 1
+                if constexpr (sizeof(T) == 8) { const double one = 1.0; memcpy(&t.cbits[i], &one, 8); }
+                else t.cbits[i] = 0x3f800000u;
+            }
         } else if (p.stride[i][p.ndim - 1] == 1) {
             if ((uintptr_t)data[i] % 16 != 0) vec = false;
             for (int k = 0; k + 1 < p.ndim; ++k) if (p.stride[i][k] % EPVV != 0) vec = false;
@@ -77,7 +93,7 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
     t.pow_small = 1;
     if constexpr (std::is_same<T, float>::value) {
         for (int i = 1; i < p.nleaf && vec; ++i) {
-            if (steps[i].op != SMB_OP_POW) continue;
+            if (steps[i].op != SMB_OP_POW || chain_pow_special<T>(steps[i]) >= 0) continue;
             const PowExpF32 pe = classify_exp(steps[i].value.f32);
             if (!pow_f32_fast_ok(pe)) continue;
             t.pow_fast[i] = 1;
@@ -93,7 +109,7 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
     // the operator followed by the pow kernel and at that kernel's speed; the general chain kernel below was
     // instruction-bound at 4.4-4.7 TB/s whatever its shape (profiles/r2_chain_pow_sweep.md).
     if constexpr (std::is_same<T, float>::value) {
-        if (powvar == 4 && p.nleaf == 3 && p.ndim == 1 && data[0] && data[1] && !data[2] && steps[2].op == SMB_OP_POW &&
+        if (powvar == 4 && p.nleaf == 3 && p.ndim == 1 && data[0] && data[1] && !data[2] && steps[2].op == SMB_OP_POW && chain_pow_special<T>(steps[2]) < 0 &&
             p.stride[0][0] == 1 && p.stride[1][0] == 1 && steps[1].op != SMB_OP_POW && pow_f32_fast_ok(classify_exp(steps[2].value.f32))) {
             // (any length and alignment: launch_stream peels heads and tails exactly as it does for sm::pow itself)
             const float y = steps[2].value.f32;
@@ -119,7 +135,7 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
     }
     // sm::pow(a (op) constant, y), op in + - *, on a dense array: the pow kernel with a one-operand pre-operator (PowF32FnPre1).
     if constexpr (std::is_same<T, float>::value) {
-        if (powvar == 4 && p.nleaf == 3 && p.ndim == 1 && data[0] && !data[1] && !data[2] && steps[2].op == SMB_OP_POW &&
+        if (powvar == 4 && p.nleaf == 3 && p.ndim == 1 && data[0] && !data[1] && !data[2] && steps[2].op == SMB_OP_POW && chain_pow_special<T>(steps[2]) < 0 &&
             p.stride[0][0] == 1 && steps[1].op != SMB_OP_POW && steps[1].op != SMB_OP_DIV && pow_f32_fast_ok(classify_exp(steps[2].value.f32))) {
             const float y = steps[2].value.f32, cst = steps[1].value.f32;
             const PowExpF32 pe = classify_exp(y);

@@ -1051,7 +1051,18 @@ template<typename T> __device__ __noinline__ T chain_pow(T a, T b, bool lane) {
     else return DevOp<OP_POW, T>::apply(a, b);
 }
 // step codes: the four ops, the two non-commutative ones mirrored (leaf on the left), pow
-enum { CH_ADD = 0, CH_SUB = 1, CH_MUL = 2, CH_DIV = 3, CH_POW = 4, CH_RSUB = 5, CH_RDIV = 6 };
+enum { CH_ADD = 0, CH_SUB = 1, CH_MUL = 2, CH_DIV = 3, CH_POW = 4, CH_RSUB = 5, CH_RDIV = 6, CH_SQR = 7, CH_SQRT = 8 };
+// pow(x, 0.5) exactly as the specialised sm::pow kernel computes it (PowSpecialFn<POWS_SQRT>); never reached for int32
+template<typename T> __device__ __forceinline__ T chain_sqrt(T a) {
+    if constexpr (std::is_floating_point<T>::value) {
+        if (a == (T)0) return (T)0;                 // +-0 -> +0
+        if (a == -(T)INFINITY) return (T)INFINITY;  // -inf -> +inf
+        if constexpr (sizeof(T) == 4) return __fsqrt_rn(a);
+        else return __dsqrt_rn(a);
+    } else {
+        return a;
+    }
+}
 // NS: compiled-in capacity of the chain (leaf registers); UNROLL: vectors per thread, all of whose
 // leaf loads are issued before the first operator (UNROLL * NS independent loads in flight per
 // thread -- a single vector per thread left HBM half idle).  One tile of 256 * UNROLL vectors per CTA.
@@ -1142,6 +1153,8 @@ __device__ __forceinline__ void chain_compute(const ChainTable &t, uint64_t tile
                 SMB_CHAIN_CASE(CH_DIV, (DevOp<OP_DIV, T>::apply(x, y)))
                 SMB_CHAIN_CASE(CH_RSUB, (DevOp<OP_SUB, T>::apply(y, x)))
                 SMB_CHAIN_CASE(CH_RDIV, (DevOp<OP_DIV, T>::apply(y, x)))
+                SMB_CHAIN_CASE(CH_SQR, ((void)y, DevOp<OP_MUL, T>::apply(x, x)))
+                SMB_CHAIN_CASE(CH_SQRT, ((void)y, chain_sqrt<T>(x)))
                 default: // CH_POW
 #pragma unroll
                     for (int u = 0; u < UNROLL; ++u) {

@@ -226,6 +226,16 @@ TEST(DropIn, LazyPowJoinsTheChain) {
         const float got2 = fused.data[i] * 2.0f;                            // ... and * 0.5f is exact
         ASSERT_TRUE(std::fabs((double) got2 - want) <= std::fabs((double) std::nextafter(p, INFINITY) - (double) p));
     }
+    // sm::pow(a (op) b, y) and sm::pow(a (op) constant, y): the pow kernel with a pre-operator -- the bits of the two eager operators
+    auto big = sm::empty<float>(100003), big2 = sm::empty<float>(100003);
+    for (size_t i = 0; i < big.totalSize; ++i) { big.data[i] = 0.05f + 0.0007f * float(i % 9973); big2.data[i] = 1.0f + float(i % 17) * 0.125f; }
+    sm::SMArray<float> f1 = sm::pow(sm::lazy(big) * big2, 1.5f);
+    sm::SMArray<float> f2 = sm::pow(sm::lazy(big) * 0.5f, 1.5f);
+    sm::SMArray<float> f3 = sm::pow(8.0f - sm::lazy(big), 2.5f);
+    auto e1m = big * big2; auto e1 = sm::pow(e1m, 1.5f);
+    auto e2m = big * 0.5f; auto e2 = sm::pow(e2m, 1.5f);
+    auto eight = sm::ones<float>(100003) * 8.0f; auto e3m = eight - big; auto e3 = sm::pow(e3m, 2.5f);
+    for (size_t i = 0; i < big.totalSize; ++i) { ASSERT_EQ(f1.data[i], e1.data[i]); ASSERT_EQ(f2.data[i], e2.data[i]); ASSERT_EQ(f3.data[i], e3.data[i]); }
     sm::SMArray<int> k = {1, 2, 3, -2, 5, 6, 7, 8, 9, 10, 11};
     sm::SMArray<int> ip = sm::pow(sm::lazy(k) + 1, 3);
     auto k1 = k + 1; auto ie = sm::pow(k1, 3);

@@ -232,7 +232,8 @@ def test_chain_float_pow_within_ulp_bound(orc, dt, bound):
         _, base = oracle_chain(orc, a, steps)          # base = a + b, bit-exact
         got = smb.chain(a, *steps)
         if dt == np.float32:
-            assert smb.last_kernel() == "k_chain<vec16,pow>", smb.last_kernel()   # the table-driven core, staged tables
+            # the table-driven core with staged tables -- except y = 2, which takes its exact form (acc * acc) like the eager operator
+            assert smb.last_kernel() == ("k_chain<vec16>" if y == 2.0 else "k_chain<vec16,pow>"), smb.last_kernel()
         assert_same_bits(smb.chain(a, ("add", b)), base, "pow base")
         if dt == np.float32:
             err = oracle.ulp_error_f32(got.ravel(), orc.pow_ref_f32(base.ravel(), float(np.float32(y))))

@@ -533,6 +533,27 @@ def test_fused_pow_of_an_array_and_a_constant_is_bit_identical_to_the_two_operat
         smb.set_option(smb.OPT_POW_SPECIALISE, 1)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_specialised_exponents_inside_chains_match_the_eager_operator_bit_for_bit(orc, dtype):
+    """sm::pow by 2, 0.5, -1, 1 has an exact one-operation form (SMB_OPT_POW_SPECIALISE, the default); a pow step of a chain
+    takes the same form, so lazy and eager agree bit for bit there -- specials and negative bases included."""
+    rng = np.random.default_rng(99)
+    n = 100_003
+    a = np.concatenate([rng.uniform(-9, 9, n - 8), [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-42, -1e-42, 3e38]]).astype(dtype)
+    b = rng.uniform(0.5, 2.0, n).astype(dtype)
+    for y in (2.0, 0.5, -1.0, 1.0):
+        mid = smb.binary("mul", a, b)
+        assert_same_bits(smb.chain(a, ("mul", b), ("pow", y)), smb.pow(mid, y), f"pow(a*b, {y})")
+        assert smb.last_kernel().startswith("k_")
+        mid = smb.scalar("add", a, 0.25)
+        assert_same_bits(smb.chain(a, ("add", 0.25), ("pow", y)), smb.pow(mid, y), f"pow(a+c, {y})")
+        assert_same_bits(smb.chain(a, ("pow", y), ("sub", b)), smb.binary("sub", smb.pow(a, y), b), f"pow(a, {y}) - b")
+        m2 = a.reshape(-1)[: 96 * 1024].reshape(96, 1024)
+        row = b[:1024].reshape(1, 1024)
+        assert_same_bits(smb.chain(m2, ("add", row), ("pow", y), ("mul", row)),
+                         smb.binary("mul", smb.pow(smb.binary("add", m2, row), y).reshape(96, 1024), row), f"(pow(m+row, {y}))*row")
+
+
 def test_device_set_in_async_mode_keeps_order_across_devices(orc, sharded):
     """Async hand-off on a device set: dependent operators whose partitions differ (a small result feeding a large one as a
     broadcast operand, a result reused as an operand with another shape), recycled blocks, and the steady state where the
