@@ -159,7 +159,7 @@ static int run_sharded(const std::vector<int> &devs, const ShardSplit &split, Sh
         std::atomic<int> remaining{0};
         LaunchWorker *workers[kMaxShards];
         bool have_all = true;
-        for (int g = 0; g < G; ++g) { workers[g] = g_workers[devs[g]]; if (!workers[g]) have_all = false; }
+        for (int g = 0; g < G; ++g) { workers[g] = g_workers[devs[g]].load(std::memory_order_acquire); if (!workers[g]) have_all = false; }
         if (have_all) {
             for (int g = 0; g < G; ++g) if (split.bounds[g + 1] > split.bounds[g]) remaining.fetch_add(1, std::memory_order_relaxed);
             for (int g = 0; g < G; ++g) {
@@ -188,7 +188,8 @@ static int run_sharded(const std::vector<int> &devs, const ShardSplit &split, Sh
                     remaining.fetch_sub(1, std::memory_order_release);
                 });
             }
-            while (remaining.load(std::memory_order_acquire) != 0) {
+            for (unsigned spins = 0; remaining.load(std::memory_order_acquire) != 0; ++spins) {
+                if (spins > 50000) { std::this_thread::yield(); continue; } // a long kernel: stop hogging the core
 #if defined(__x86_64__)
                 __builtin_ia32_pause();
 #endif

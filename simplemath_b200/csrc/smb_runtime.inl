@@ -165,7 +165,7 @@ struct LaunchWorker {
     std::deque<std::function<void()>> q;
     std::atomic<int> queued{0};
 };
-static LaunchWorker *g_workers[kMaxDevices]; // created once per device (g_set_mu), never destroyed: they outlive static destruction
+static std::atomic<LaunchWorker *> g_workers[kMaxDevices]; // created once per device (g_set_mu), never destroyed: they outlive static destruction
 static void worker_main(LaunchWorker *w) {
     if (cudaSetDevice(w->dev) != cudaSuccess) cudaGetLastError();
     for (;;) {
@@ -186,14 +186,15 @@ static void worker_main(LaunchWorker *w) {
     }
 }
 static LaunchWorker *worker_of(int dev) { // g_set_mu held by the caller
-    if (!g_workers[dev]) {
-        LaunchWorker *w = new LaunchWorker;
+    LaunchWorker *w = g_workers[dev].load(std::memory_order_acquire);
+    if (!w) {
+        w = new LaunchWorker;
         w->dev = dev;
         w->th = std::thread(worker_main, w);
         w->th.detach();
-        g_workers[dev] = w;
+        g_workers[dev].store(w, std::memory_order_release);
     }
-    return g_workers[dev];
+    return w;
 }
 static void worker_post(LaunchWorker *w, std::function<void()> job) {
     {
