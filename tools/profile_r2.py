@@ -59,6 +59,16 @@ if "chain" in which:
     steps = smb.chain_steps(smb.F32, [(None, False, (fa.data_ptr(), [1])), ("add", False, (fb.data_ptr(), [1])), ("pow", False, 2.5)], [n])
     run(lambda: smb._check(lib.smb_chain(smb.F32, steps, 3, u([n]), 1, n, fo.data_ptr(), sp)))
     del fa, fb, fo
+if "chainmid" in which:  # a pow step in the MIDDLE of a chain: the general chain kernel with the fast pow core
+    n = 1 << 28
+    fa, fb, fc = (torch.rand(n, device="cuda") + 0.5 for _ in range(3))
+    fo = torch.empty(n, device="cuda")
+    torch.cuda.synchronize()
+    smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+    steps = smb.chain_steps(smb.F32, [(None, False, (fa.data_ptr(), [1])), ("add", False, (fb.data_ptr(), [1])), ("pow", False, 2.5),
+                                      ("mul", False, (fc.data_ptr(), [1]))], [n])
+    run(lambda: smb._check(lib.smb_chain(smb.F32, steps, 4, u([n]), 1, n, fo.data_ptr(), sp)))
+    del fa, fb, fc, fo
 if "pow" in which:
     n = 1 << 30
     x = torch.empty(n, dtype=torch.float32, device="cuda")
