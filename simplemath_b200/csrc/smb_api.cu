@@ -156,6 +156,35 @@ static int chain_launch(DeviceCtx &c, const ChainPlan &p, const smb_chain_step *
             return rc;
         }
     }
+    // the same two shapes for double (PowF64FnPre / PowF64FnPre1)
+    if constexpr (std::is_same<T, double>::value) {
+        const bool shape_ok = powvar == 4 && p.nleaf == 3 && p.ndim == 1 && data[0] && !data[2] && steps[2].op == SMB_OP_POW &&
+                              chain_pow_special<T>(steps[2]) < 0 && p.stride[0][0] == 1 && steps[1].op != SMB_OP_POW;
+        const bool two = shape_ok && data[1] && p.stride[1][0] == 1, one = shape_ok && !data[1] && steps[1].op != SMB_OP_DIV;
+        if (two || one) {
+            const double y = steps[2].value.f64;
+            const PowExpF64 pe = classify_exp(y);
+            const bool small = pow_f64_small_y(pe), odd = pe.y_is_odd != 0;
+            const int pre = steps[1].op == SMB_OP_ADD ? PRE_ADD : steps[1].op == SMB_OP_MUL ? PRE_MUL
+                            : steps[1].op == SMB_OP_SUB ? (steps[1].swap ? PRE_RSUB : PRE_SUB) : (steps[1].swap ? PRE_RDIV : PRE_DIV);
+            const double *pa = (const double *)data[0] + lin_begin;
+            int rc;
+            if (two) {
+                const double *pb = (const double *)data[1] + lin_begin;
+#define SMB_POW64PRE(S, O) launch_stream<double, PowF64FnPre<S, O>, true>(c, pa, pb, (double *)out, lin_count, lin_begin, PowF64FnPre<S, O>::make(y, 0, pre), s)
+                rc = small ? (odd ? SMB_POW64PRE(true, true) : SMB_POW64PRE(true, false)) : (odd ? SMB_POW64PRE(false, true) : SMB_POW64PRE(false, false));
+#undef SMB_POW64PRE
+                if (rc == SMB_OK) g_last_kernel = "k_stream<pow,fused-pre>";
+            } else {
+                const double cst = steps[1].value.f64;
+#define SMB_POW64PRE1(S, O) launch_stream<double, PowF64FnPre1<S, O>, false>(c, pa, nullptr, (double *)out, lin_count, lin_begin, PowF64FnPre1<S, O>::make(y, 0, pre, cst), s)
+                rc = small ? (odd ? SMB_POW64PRE1(true, true) : SMB_POW64PRE1(true, false)) : (odd ? SMB_POW64PRE1(false, true) : SMB_POW64PRE1(false, false));
+#undef SMB_POW64PRE1
+                if (rc == SMB_OK) g_last_kernel = "k_stream<pow,fused-pre1>";
+            }
+            return rc;
+        }
+    }
     t.tiles_per_cta = powfast ? (powvar == 2 || powvar == 3 ? 16 : 32) : 1; // amortise the 24 KB table copy, stay many waves deep
     // compiled-in chain capacity / vectors per thread: short chains keep more loads in flight
 #define SMB_CHAIN_LAUNCH(E, W, NS, U, PF, ND)                                                                     \

@@ -394,6 +394,45 @@ template<bool SMALL_Y, bool ODD_Y> struct PowF64Fn {
     }
 };
 template<> struct ScalarFn<OP_POW, double> : PowF64Fn<false, true> {};
+// sm::pow(a (op) b, y) and sm::pow(a (op) constant, y) for double: the f64 pow kernel with a pre-operator, like PowF32FnPre /
+// PowF32FnPre1 (same DevOp rounding of the intermediate, same pow variant: bit-identical to the two eager operators).  Without them
+// a double chain with a pow step runs the double-double reference path per element (k_chain has no f64 table staging) -- slower than
+// the eager operators it was meant to fuse.
+template<bool SMALL_Y, bool ODD_Y> struct PowF64FnPre : PowF64Fn<SMALL_Y, ODD_Y> {
+    static constexpr bool PREOP = true;
+    static constexpr int UNROLL_OVERRIDE = 2; // two operand streams: half the vectors per thread keep the register buffers the same size
+    int pre_op;
+    __device__ __forceinline__ double pre(double a, double b) const {
+        switch (pre_op) { // uniform
+            case PRE_ADD: return DevOp<OP_ADD, double>::apply(a, b);
+            case PRE_SUB: return DevOp<OP_SUB, double>::apply(a, b);
+            case PRE_MUL: return DevOp<OP_MUL, double>::apply(a, b);
+            case PRE_DIV: return DevOp<OP_DIV, double>::apply(a, b);
+            case PRE_RSUB: return DevOp<OP_SUB, double>::apply(b, a);
+            default: return DevOp<OP_DIV, double>::apply(b, a);
+        }
+    }
+    __device__ __forceinline__ double operator()(double a, double b, uint64_t) const { return pow_f64_slow(pre(a, b), this->pe); }
+    static PowF64FnPre make(double y, uint64_t lane_end_, int pre_op_) {
+        PowF64FnPre fn;
+        static_cast<PowF64Fn<SMALL_Y, ODD_Y> &>(fn) = PowF64Fn<SMALL_Y, ODD_Y>::make(y, lane_end_);
+        fn.pre_op = pre_op_;
+        return fn;
+    }
+};
+template<bool SMALL_Y, bool ODD_Y> struct PowF64FnPre1 : PowF64Fn<SMALL_Y, ODD_Y> {
+    static constexpr bool PREOP1 = true;
+    double pre_mul, pre_add; // a + c, a - c, c - a, a * c as ONE fma with uniform operands (see PowF32FnPre1)
+    __device__ __forceinline__ double pre1(double a) const { return __fma_rn(a, pre_mul, pre_add); }
+    __device__ __forceinline__ double operator()(double a, double, uint64_t) const { return pow_f64_slow(pre1(a), this->pe); }
+    static PowF64FnPre1 make(double y, uint64_t lane_end_, int pre_op_, double c) { // PRE_ADD, PRE_SUB, PRE_RSUB or PRE_MUL
+        PowF64FnPre1 fn;
+        static_cast<PowF64Fn<SMALL_Y, ODD_Y> &>(fn) = PowF64Fn<SMALL_Y, ODD_Y>::make(y, lane_end_);
+        fn.pre_mul = pre_op_ == PRE_MUL ? c : pre_op_ == PRE_RSUB ? -1.0 : 1.0;
+        fn.pre_add = pre_op_ == PRE_MUL ? -0.0 : pre_op_ == PRE_SUB ? -c : c;
+        return fn;
+    }
+};
 
 template<typename Fn, typename = void> struct fn_pairwise : std::false_type {};
 template<typename Fn> struct fn_pairwise<Fn, std::void_t<decltype(Fn::PAIRWISE)>> : std::bool_constant<Fn::PAIRWISE> {};
@@ -458,13 +497,19 @@ __device__ __forceinline__ void stream_vec(const Pack<T, VB> &pa, const Pack<T, 
 #pragma unroll
             for (int k = 0; k < EPV; ++k) r.e[k] = fn.slow_call(x.e[k]);
         }
-    } else if constexpr (fn_checked<Fn>::value && !HAS_B) {
+    } else if constexpr (fn_checked<Fn>::value && (!HAS_B || fn_preop<Fn>::value)) {
+        // (with a pre-operator too: the ragged tile must take the same fast / slow decision as the full tiles)
         bool ok = true;
 #pragma unroll
-        for (int k = 0; k < EPV; ++k) ok &= fn.fast(pa.e[k], r.e[k]);
+        for (int k = 0; k < EPV; ++k) {
+            T x;
+            if constexpr (fn_preop<Fn>::value) x = fn.pre(pa.e[k], pb.e[k]);
+            else x = apply_pre1(fn, pa.e[k]);
+            ok &= fn.fast(x, r.e[k]);
+        }
         if (!ok) {
 #pragma unroll
-            for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa.e[k], pa.e[k], 0);
+            for (int k = 0; k < EPV; ++k) r.e[k] = fn(pa.e[k], HAS_B ? pb.e[k] : pa.e[k], 0);
         }
     } else {
 #pragma unroll

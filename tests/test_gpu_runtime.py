@@ -533,6 +533,42 @@ def test_fused_pow_of_an_array_and_a_constant_is_bit_identical_to_the_two_operat
         smb.set_option(smb.OPT_POW_SPECIALISE, 1)
 
 
+def test_fused_pow_in_double_is_bit_identical_to_the_two_operators(orc):
+    """The two fused shapes for double -- sm::pow(a (op) b, y) and sm::pow(a (op) constant, y) -- run the f64 pow kernel with a
+    pre-operator: the bits of the eager operator followed by sm::pow (small / large |y|, odd / even / non-integer y, ragged sizes)."""
+    rng = np.random.default_rng(100)
+    smb.set_option(smb.OPT_POW_SPECIALISE, 0)
+    try:
+        for n in (100_003, 1 << 19, 6, 3):
+            a = rng.uniform(0.05, 9.0, n)
+            b = rng.uniform(0.05, 9.0, n)
+            sgn = np.where(rng.random(n) < 0.3, -1.0, 1.0)
+            for y in (2.5, 0.5, 17.0, 300.5, 3.0, 2.0, -1.5):
+                aa = a * sgn if float(y).is_integer() else a
+                for op in ("add", "sub", "mul", "div", "rsub", "rdiv"):
+                    x, z = aa, b
+                    if not float(y).is_integer() and op in ("sub", "rsub"):
+                        x, z = (a + 9.5, b) if op == "sub" else (a, b + 9.5)   # keep the base positive
+                    base_op = op[1:] if op.startswith("r") else op
+                    mid = smb.binary(base_op, z, x) if op.startswith("r") else smb.binary(base_op, x, z)
+                    got = smb.chain(x, (op, z), ("pow", y))
+                    if n > 8:
+                        assert smb.last_kernel() == "k_stream<pow,fused-pre>", (n, y, op, smb.last_kernel())
+                    assert_same_bits(got, smb.pow(mid, y), f"f64 pow({op}(a, b), {y}) n={n}")
+                for op, cst in (("add", 1.5), ("sub", -0.25), ("mul", 1.75), ("rsub", 20.0)):
+                    mid = smb.binary("sub", np.full(n, cst), aa) if op == "rsub" else smb.scalar(op, aa, cst)
+                    got = smb.chain(aa, (op, cst), ("pow", y))
+                    if n > 8:
+                        assert smb.last_kernel() == "k_stream<pow,fused-pre1>", (n, y, op, smb.last_kernel())
+                    assert_same_bits(got, smb.pow(mid, y), f"f64 pow({op}(a, {cst}), {y}) n={n}")
+        a = rng.uniform(0.05, 9.0, 1 << 16)
+        b = rng.uniform(0.05, 9.0, 1 << 16)
+        hi, lo = orc.pow_ref_f64(orc.binary("add", a, b), 2.5)
+        assert oracle.ulp_error_f64(smb.chain(a, ("add", b), ("pow", 2.5)), hi, lo).max() <= 0.65
+    finally:
+        smb.set_option(smb.OPT_POW_SPECIALISE, 1)
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_specialised_exponents_inside_chains_match_the_eager_operator_bit_for_bit(orc, dtype):
     """sm::pow by 2, 0.5, -1, 1 has an exact one-operation form (SMB_OPT_POW_SPECIALISE, the default); a pow step of a chain

@@ -296,4 +296,25 @@ chain_case("F6 f32 pow(a+b, 2.5)*c, 2^28 elements, fused (general chain kernel)"
                     smb.array_scalar_ptr(smb.OP_POW, smb.F32, P(ft1), 2.5, n, P(ft2), sp),
                     smb.contiguous_ptr(smb.OP_MUL, smb.F32, P(ft2), P(fc), P(fo), n, sp)), 3,
            "a pow step in the MIDDLE of a chain stays on k_chain (instruction-bound)")
+n64 = 1 << 27
+da, db = (torch.rand(n64, device="cuda", dtype=torch.float64) + 0.5 for _ in range(2))
+do, dt1 = (torch.empty(n64, device="cuda", dtype=torch.float64) for _ in range(2))
+steps64 = smb.chain_steps(smb.F64, [L(None, da), L("add", db), ("pow", False, 2.5)], [n64])
+
+
+def chain_case64(name, leaves_fn, unfused_fn, arrays_in, note):
+    ms = timed(leaves_fn, args.reps)
+    kern = smb.last_kernel()
+    ms_unfused = timed(unfused_fn, args.reps)
+    bytes_ = 8 * n64 * (arrays_in + 1)
+    print(json.dumps({"config": name, "elements": n64, "algorithmic_bytes": bytes_, "gpu_ms": ms, "gpu_gbs": bytes_ / ms / 1e6,
+                      "gpu_gelem_s": n64 / ms / 1e6, "frac_measured_peak": bytes_ / ms / 1e6 / PEAK, "frac_nominal_8000": bytes_ / ms / 1e6 / 8000,
+                      "kernel": kern, "unfused_ms": ms_unfused, "fusion_speedup": ms_unfused / ms, "note": note}), flush=True)
+
+
+chain_case64("F7 f64 pow(a+b, 2.5), 2^27 elements, fused",
+             lambda: smb.lib().smb_chain(smb.F64, steps64, 3, smb._u64arr([n64]), 1, n64, P(do), sp),
+             lambda: (smb.contiguous_ptr(smb.OP_ADD, smb.F64, P(da), P(db), P(dt1), n64, sp),
+                      smb.array_scalar_ptr(smb.OP_POW, smb.F64, P(dt1), 2.5, n64, P(do), sp)), 2,
+             "the f64 pow kernel with a pre-operator (a double chain with a pow step would otherwise run the double-double path per element)")
 smb.set_option(smb.OPT_POW_SPECIALISE, 1)
