@@ -168,9 +168,13 @@ constexpr uint32_t kPdlWaitFirst = 1u;
 constexpr int kPdlFlagBits = 8; // the launch word's upper 24 bits carry a kernel-specific count (k_stream: single-tile CTAs)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// A launch that must wait for its predecessors lets ITS dependents in only after the wait has returned: the host drops its
+// record of earlier launches' operand ranges at such a launch ("when its work starts, everything before it is done"), and a
+// dependent admitted before the wait could start -- and read what an earlier, still running grid writes -- while this grid is
+// still blocked in griddepcontrol.wait.
 __device__ __forceinline__ void pdl_enter(uint32_t flags) {
-    pdl_launch_dependents();
-    if (flags & kPdlWaitFirst) pdl_wait();
+    if (flags & kPdlWaitFirst) { pdl_wait(); pdl_launch_dependents(); }
+    else pdl_launch_dependents();
 }
 __device__ __forceinline__ void pdl_exit(uint32_t flags) {
     if (!(flags & kPdlWaitFirst)) pdl_wait();
@@ -595,9 +599,9 @@ __global__ void __launch_bounds__(256, fn_pow_tables<Fn>::value ? (sizeof(T) == 
                                                T *__restrict__ out, uint64_t n, uint64_t first, Fn fn_in, uint32_t pdl) {
     constexpr int EPV = VB / (int)sizeof(T); // elements per vector
     Fn fn = fn_in;
-    pdl_launch_dependents();
+    if (!(pdl & kPdlWaitFirst)) pdl_launch_dependents();
     if constexpr (fn_pow_tables<Fn>::value) fn.block_init(); // stage the lookup tables in shared memory (constant data: before the wait)
-    if (pdl & kPdlWaitFirst) pdl_wait();
+    if (pdl & kPdlWaitFirst) { pdl_wait(); pdl_launch_dependents(); } // dependents only after the wait, see pdl_enter
     const uint64_t nvec = n / EPV;
     constexpr uint64_t tile_vecs = (uint64_t)kBlock * UNROLL; // launches always use kBlock threads
     const uint64_t full_tiles = nvec / tile_vecs;

@@ -485,7 +485,9 @@ static void prefetch_managed(const void *p, size_t bytes, int dev, cudaStream_t 
 //     point) write, and writes nothing they read, runs right away and executes
 //     griddepcontrol.wait only at its END -- so that ITS completion still implies theirs;
 //   * any other launch executes griddepcontrol.wait first (the wait returns once the previous grid
-//     has completed and flushed): it only saves the scheduling ramp.
+//     has completed and flushed): it only saves the scheduling ramp.  It triggers its own dependents
+//     AFTER that wait (smb_kernels.cuh: pdl_enter): pdl_decide forgets the earlier launches' ranges
+//     at a waiting launch, which is only sound if nothing later can start before the wait is over.
 // The host knows every operand range of its own launches, so it decides; SMB_OPT_PDL = 0 turns the
 // attribute off (plain stream order).
 static std::atomic<int64_t> g_opt_pdl{1};

@@ -677,3 +677,48 @@ def test_synchronous_calls_land_pending_async_work_of_other_devices_first(orc):
     finally:
         smb.set_devices([])
         smb.set_option(smb.OPT_SHARD_MIN_BYTES, old)
+
+
+def test_async_launches_queued_behind_a_long_kernel_keep_their_order(orc):
+    """Python enqueues more slowly than the GPU drains 4 us kernels, so dependent launches rarely overlap in the other tests.
+    Here every round starts with a long kernel: the small operators queue up behind it and become eligible back to back --
+    the situation in which a launch admitted behind a WAITING launch once started before that wait was over and read what an
+    earlier grid was still writing (tools/pdl_stress.py; profiles/r2_pdl_stress.jsonl: 1175 of 1800 rounds wrong before the
+    fix, 0 after).  One device (producer, then two consumers of its result) and one device listed twice (two ranges)."""
+    lib = smb.lib()
+    rng = np.random.default_rng(104)
+    nbig, n = 1 << 27, 1 << 20
+    big_a, big_o = lib.smb_alloc(nbig * 4, smb.MEM_MANAGED), lib.smb_alloc(nbig * 4, smb.MEM_MANAGED)
+    old = lib.smb_get_option(smb.OPT_SHARD_MIN_BYTES)
+    try:
+        for devs in ([], [0, 0]):
+            smb.set_option(smb.OPT_SHARD_MIN_BYTES, 0 if devs else old)
+            smb.set_devices(devs)
+            a = rng.standard_normal(n).astype(np.float32)
+            b = rng.standard_normal(n).astype(np.float32)
+            ma, mb = Managed(a), Managed(b)
+            mc, md, me = (Managed(shape=(n,), dtype=np.float32) for _ in range(3))
+            smb.contiguous_ptr(smb.OP_ADD, smb.F32, big_a, big_a, big_o, nbig)
+            smb.sync()
+            smb.set_option(smb.OPT_ASYNC, 1)
+            try:
+                wrong = 0
+                for r in range(150):
+                    k = np.float32(1 + r % 7)
+                    smb.contiguous_ptr(smb.OP_ADD, smb.F32, big_a, big_a, big_o, nbig)           # the queue fills behind this one
+                    smb.array_scalar_ptr(smb.OP_MUL, smb.F32, ma.ptr, float(k), n, mc.ptr)          # c = a * k      (producer)
+                    smb.array_scalar_ptr(smb.OP_ADD, smb.F32, mc.ptr, 2.0, n, md.ptr)               # d = c + 2      (conflicts: waits)
+                    smb.contiguous_ptr(smb.OP_ADD, smb.F32, mc.ptr, mb.ptr, me.ptr, n)              # e = c + b      (no conflict with d's launch)
+                    smb.sync()
+                    c = a * k
+                    wrong += int(not (np.array_equal(md.np, c + np.float32(2.0)) and np.array_equal(me.np, c + b)))
+                assert wrong == 0, (devs, wrong)
+            finally:
+                smb.set_option(smb.OPT_ASYNC, 0)
+            for m in (ma, mb, mc, md, me):
+                m.free()
+    finally:
+        smb.set_devices([])
+        smb.set_option(smb.OPT_SHARD_MIN_BYTES, old)
+        lib.smb_free(big_a)
+        lib.smb_free(big_o)
