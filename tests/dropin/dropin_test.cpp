@@ -465,3 +465,36 @@ TEST(DropIn, ConcurrentHostThreadsOnDistinctArrays) {
     sm::set_devices({});
     smb_set_option(SMB_OPT_SHARD_MIN_BYTES, old_min);
 }
+
+// Dependent operators at the C++ launch rate, queued behind a long kernel so that they become eligible back to back: a
+// producer, a consumer that has to wait for it, and a second consumer that conflicts only with the producer (the shape that
+// once slipped through the overlapping-launch rules).  Results are kept and checked after the scope ends.
+TEST(DropIn, AsyncDependentOperatorsQueuedBehindALongKernel) {
+    const size_t N = 1 << 20, NBIG = size_t(1) << 27;
+    auto big = sm::ones<float>(NBIG);
+    auto a = sm::empty<float>(N), b = sm::empty<float>(N);
+    for (size_t i = 0; i < N; ++i) { a.data[i] = float(i % 1013) * 0.25f - 100.0f; b.data[i] = float(i % 17) + 0.5f; }
+    int bad = 0;
+    for (int round = 0; round < 12; ++round) {
+        std::vector<sm::SMArray<float>> ds, es;
+        {
+            sm::async_scope scope;
+            auto sink = big + big;                                  // ~0.25 ms: the queue fills behind it
+            for (int it = 0; it < 24; ++it) {
+                const float k = float(1 + (round * 24 + it) % 9);
+                auto c = a * k;                                      // producer
+                ds.push_back(c + 2.0f);                              // reads c: waits for the producer
+                es.push_back(c + b);                                 // reads c as well, touches nothing of the launch before it
+            }
+            (void) sink;
+        }
+        for (int it = 0; it < 24; ++it) {
+            const float k = float(1 + (round * 24 + it) % 9);
+            for (size_t i = size_t(it) % 5; i < N; i += 5) {
+                const float c = a.data[i] * k;
+                if (ds[size_t(it)].data[i] != c + 2.0f || es[size_t(it)].data[i] != c + b.data[i]) { ++bad; break; }
+            }
+        }
+    }
+    EXPECT_EQ(bad, 0);
+}
