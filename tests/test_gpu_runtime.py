@@ -722,3 +722,75 @@ def test_async_launches_queued_behind_a_long_kernel_keep_their_order(orc):
         smb.set_option(smb.OPT_SHARD_MIN_BYTES, old)
         lib.smb_free(big_a)
         lib.smb_free(big_o)
+
+
+def test_random_async_programs_match_sequential_evaluation(orc):
+    """Random programs of ~40 dependent operators over a handful of managed arrays -- binary / scalar / in-place / row-broadcast
+    / fused-chain operators, temporaries freed while in flight and their blocks handed out again -- enqueued in async mode
+    behind a long kernel (so that they really are in flight together), on one device and on device sets; every array is
+    compared with a sequential numpy evaluation (single float32 operations: the same bits)."""
+    lib = smb.lib()
+    rng = np.random.default_rng(105)
+    nbig = 1 << 28
+    big_a, big_o = lib.smb_alloc(nbig * 4, smb.MEM_MANAGED), lib.smb_alloc(nbig * 4, smb.MEM_MANAGED)
+    old = lib.smb_get_option(smb.OPT_SHARD_MIN_BYTES)
+    R, C = 256, 2048
+    n = R * C
+    f32 = np.float32
+    np_err = np.seterr(all="ignore")     # some programs overflow: inf / NaN are compared like everything else
+    try:
+        sets = [[], [0, 0]] + ([list(range(smb.device_count()))] if smb.device_count() >= 2 else [])
+        for devs in sets:
+            smb.set_option(smb.OPT_SHARD_MIN_BYTES, 0 if devs else old)
+            smb.set_devices(devs)
+            smb.contiguous_ptr(smb.OP_ADD, smb.F32, big_a, big_a, big_o, nbig)
+            smb.sync()
+            for prog in range(12):
+                host = [rng.uniform(0.5, 1.5, n).astype(f32) for _ in range(5)]
+                row = rng.uniform(0.5, 1.5, C).astype(f32)
+                arrs = [Managed(h) for h in host]
+                mrow = Managed(row)
+                smb.set_option(smb.OPT_ASYNC, 1)
+                try:
+                    smb.contiguous_ptr(smb.OP_ADD, smb.F32, big_a, big_a, big_o, nbig)       # ~0.5 ms: everything below queues up
+                    for step in range(40):
+                        kind = int(rng.integers(0, 6))
+                        i, j, k = (int(x) for x in rng.integers(0, 5, 3))
+                        op = ["add", "sub", "mul"][int(rng.integers(0, 3))]
+                        npop = {"add": np.add, "sub": np.subtract, "mul": np.multiply}[op]
+                        if kind == 0:      # k = i (op) j, possibly in place
+                            smb.contiguous_ptr(smb.OPS[op], smb.F32, arrs[i].ptr, arrs[j].ptr, arrs[k].ptr, n)
+                            host[k] = npop(host[i], host[j])
+                        elif kind == 1:    # k = i (op) constant
+                            cst = float(f32(rng.uniform(0.75, 1.25)))
+                            smb.array_scalar_ptr(smb.OPS[op], smb.F32, arrs[i].ptr, cst, n, arrs[k].ptr)
+                            host[k] = npop(host[i], f32(cst))
+                        elif kind == 2:    # through a temporary that is freed while in flight
+                            tmp = lib.smb_alloc(n * 4, smb.MEM_MANAGED)
+                            smb.contiguous_ptr(smb.OPS[op], smb.F32, arrs[i].ptr, arrs[j].ptr, tmp, n)
+                            smb.contiguous_ptr(smb.OP_MUL, smb.F32, tmp, arrs[i].ptr, arrs[k].ptr, n)
+                            lib.smb_free(tmp)
+                            host[k] = npop(host[i], host[j]) * host[i]
+                        elif kind == 3:    # row broadcast (k_row: a plain launch between the stream kernels)
+                            smb.elementwise_ptr(smb.OPS[op], smb.F32, arrs[i].ptr, [C, 1], mrow.ptr, [0, 1], [R, C], arrs[k].ptr)
+                            host[k] = npop(host[i].reshape(R, C), row.reshape(1, C)).reshape(-1)
+                        elif kind == 4 and k != i and k != j:    # fused chain (i + j) * i -> k
+                            leaves = [(None, False, (arrs[i].ptr, [1])), ("add", False, (arrs[j].ptr, [1])), ("mul", False, (arrs[i].ptr, [1]))]
+                            smb.chain_ptr(smb.F32, leaves, [n], arrs[k].ptr)
+                            host[k] = (host[i] + host[j]) * host[i]
+                        else:              # keep the values in range
+                            smb.array_scalar_ptr(smb.OP_MUL, smb.F32, arrs[k].ptr, 0.5, n, arrs[k].ptr)
+                            host[k] = host[k] * f32(0.5)
+                    smb._check(lib.smb_wait_pending())
+                finally:
+                    smb.set_option(smb.OPT_ASYNC, 0)
+                for idx in range(5):
+                    assert_same_bits(arrs[idx].np.copy(), host[idx], f"program {prog} on {devs}: array {idx}")
+                for m in arrs + [mrow]:
+                    m.free()
+    finally:
+        np.seterr(**np_err)
+        smb.set_devices([])
+        smb.set_option(smb.OPT_SHARD_MIN_BYTES, old)
+        lib.smb_free(big_a)
+        lib.smb_free(big_o)
