@@ -1102,7 +1102,9 @@ template<typename T> __device__ __noinline__ T chain_pow(T a, T b, bool lane) {
 // step codes: the four ops, the two non-commutative ones mirrored (leaf on the left), pow
 enum { CH_ADD = 0, CH_SUB = 1, CH_MUL = 2, CH_DIV = 3, CH_POW = 4, CH_RSUB = 5, CH_RDIV = 6, CH_SQR = 7, CH_SQRT = 8 };
 // pow(x, 0.5) exactly as the specialised sm::pow kernel computes it (PowSpecialFn<POWS_SQRT>); never reached for int32
-template<typename T> __device__ __forceinline__ T chain_sqrt(T a) {
+// (out of line, like chain_pow: inlined, the correctly rounded square root's fix-up path cost the plain arithmetic chains three
+// registers and 10 % -- 7.27 -> 6.50 TB/s on (a+b)*c)
+template<typename T> __device__ __noinline__ T chain_sqrt(T a) {
     if constexpr (std::is_floating_point<T>::value) {
         if (a == (T)0) return (T)0;                 // +-0 -> +0
         if (a == -(T)INFINITY) return (T)INFINITY;  // -inf -> +inf
@@ -1202,9 +1204,15 @@ __device__ __forceinline__ void chain_compute(const ChainTable &t, uint64_t tile
                 SMB_CHAIN_CASE(CH_DIV, (DevOp<OP_DIV, T>::apply(x, y)))
                 SMB_CHAIN_CASE(CH_RSUB, (DevOp<OP_SUB, T>::apply(y, x)))
                 SMB_CHAIN_CASE(CH_RDIV, (DevOp<OP_DIV, T>::apply(y, x)))
-                SMB_CHAIN_CASE(CH_SQR, ((void)y, DevOp<OP_MUL, T>::apply(x, x)))
-                SMB_CHAIN_CASE(CH_SQRT, ((void)y, chain_sqrt<T>(x)))
-                default: // CH_POW
+                default: // CH_POW and its two exact forms (rare: kept out of the compare chain of the arithmetic cases)
+                    if (t.op[s] == CH_SQR || t.op[s] == CH_SQRT) {
+                        const bool sq = t.op[s] == CH_SQR;
+#pragma unroll
+                        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                            for (int e = 0; e < EPV; ++e) acc[u][e] = sq ? DevOp<OP_MUL, T>::apply(acc[u][e], acc[u][e]) : chain_sqrt<T>(acc[u][e]);
+                        break;
+                    }
 #pragma unroll
                     for (int u = 0; u < UNROLL; ++u) {
                         const uint64_t lin = t.lin_base + (v0 + (uint64_t)u * kBlock) * EPV;
