@@ -119,9 +119,10 @@ enum {
     /* Table-driven pow kernels: how many CTAs at the END of the grid own a single tile (they fill the
      * ragged end the multi-tile CTAs leave).  0 (default): none -- measured no gain on B200. */
     SMB_OPT_POW_TAIL_CTAS = 10,
-    /* Fused chains with an f32 pow step and at most 3 leaves (sm::pow(a + b, e)).  4 (default): dense same-shape
-     * operands run the pow kernel itself with the operator applied to the loaded operands (bit-identical to the
-     * operator followed by sm::pow); everything else, and the values 0..3, use the general chain kernel --
+    /* Fused chains with a pow step and at most 3 leaves (sm::pow(a + b, e), sm::pow(a * c, e)).  4 (default): dense
+     * same-shape operands -- or one dense operand and a constant, for + - * -- run the pow kernel itself (float and
+     * double) with the operator applied to the loaded operands (bit-identical to the operator followed by sm::pow);
+     * everything else, and the values 0..3, use the general chain kernel --
      * 0: one vector per thread, no prefetch (round 1); 1: one vector + register prefetch of the next tile's
      * leaves; 2: two vectors; 3: two vectors + prefetch. */
     SMB_OPT_CHAIN_POW_VARIANT = 11,
