@@ -10,6 +10,8 @@
 #include <cstdint>
 #include <random>
 #include <thread>
+#include <memory>
+#include <cstring>
 #include "sm.h"
 
 namespace {
@@ -495,6 +497,68 @@ TEST(DropIn, AsyncDependentOperatorsQueuedBehindALongKernel) {
                 if (ds[size_t(it)].data[i] != c + 2.0f || es[size_t(it)].data[i] != c + b.data[i]) { ++bad; break; }
             }
         }
+    }
+    EXPECT_EQ(bad, 0);
+}
+
+// Random programs of dependent operators at the C++ launch rate inside an async scope, queued behind a long kernel: results
+// replace earlier arrays (whose blocks are freed while kernels that read them are in flight and handed out again), row
+// broadcasts (plain launches) and fused chains sit between the stream kernels.  Everything is checked against the same
+// program evaluated on the host, bit for bit, after the scope ends.
+TEST(DropIn, RandomAsyncProgramsAtTheFullLaunchRate) {
+    const size_t R = 128, C = 2048, N = R * C, NBIG = size_t(1) << 27;
+    auto big = sm::ones<float>(NBIG);
+    std::mt19937 rng(20261105);
+    int bad = 0;
+    for (int prog = 0; prog < 16; ++prog) {
+        std::vector<std::unique_ptr<sm::SMArray<float>>> v;
+        std::vector<std::vector<float>> h(5, std::vector<float>(N));
+        auto row = sm::empty<float>(1, C);
+        std::vector<float> hrow(C);
+        for (size_t j = 0; j < C; ++j) row.data[j] = hrow[j] = 0.25f * float(int(rng() % 9) - 4);
+        for (int a = 0; a < 5; ++a) {
+            v.push_back(std::make_unique<sm::SMArray<float>>(sm::empty<float>(R, C)));
+            for (size_t i = 0; i < N; ++i) v[size_t(a)]->data[i] = h[size_t(a)][i] = 0.5f + float((i * 7 + size_t(a) * 131 + size_t(prog)) % 1013) / 1013.0f;
+        }
+        {
+            sm::async_scope scope;
+            auto sink = big + big;                               // ~0.25 ms: the program below queues up behind it
+            for (int step = 0; step < 48; ++step) {
+                const size_t i = rng() % 5, j = rng() % 5, k = rng() % 5;
+                std::vector<float> out(N);
+                switch (rng() % 6) {
+                    case 0:
+                        v[k] = std::make_unique<sm::SMArray<float>>(*v[i] + *v[j]);
+                        for (size_t e = 0; e < N; ++e) out[e] = h[i][e] + h[j][e];
+                        break;
+                    case 1:
+                        v[k] = std::make_unique<sm::SMArray<float>>(*v[i] - *v[j]);
+                        for (size_t e = 0; e < N; ++e) out[e] = h[i][e] - h[j][e];
+                        break;
+                    case 2:
+                        v[k] = std::make_unique<sm::SMArray<float>>(*v[i] * 0.75f);
+                        for (size_t e = 0; e < N; ++e) out[e] = h[i][e] * 0.75f;
+                        break;
+                    case 3:
+                        v[k] = std::make_unique<sm::SMArray<float>>(*v[i] + row);
+                        for (size_t e = 0; e < N; ++e) out[e] = h[i][e] + hrow[e % C];
+                        break;
+                    case 4:
+                        v[k] = std::make_unique<sm::SMArray<float>>((sm::lazy(*v[i]) + *v[j]) * 0.25f);
+                        for (size_t e = 0; e < N; ++e) { const float t = h[i][e] + h[j][e]; out[e] = t * 0.25f; }
+                        break;
+                    default: {
+                        auto t = *v[i] - *v[j];                 // a temporary that dies while its consumer is in flight
+                        v[k] = std::make_unique<sm::SMArray<float>>(t + *v[i]);
+                        for (size_t e = 0; e < N; ++e) { const float d = h[i][e] - h[j][e]; out[e] = d + h[i][e]; }
+                    }
+                }
+                h[k].swap(out);
+            }
+            (void) sink;
+        }
+        for (size_t a = 0; a < 5; ++a)
+            if (std::memcmp(v[a]->data, h[a].data(), N * sizeof(float)) != 0) ++bad;
     }
     EXPECT_EQ(bad, 0);
 }

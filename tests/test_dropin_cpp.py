@@ -28,7 +28,7 @@ def test_reference_tests_pass_on_the_drop_in_headers():
 
 
 def test_own_cpp_acceptance():
-    assert _run("dropin_test") >= 24
+    assert _run("dropin_test") >= 25
 
 
 def test_user_defined_op_plugin():
